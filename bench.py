@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of the supervised-compression bottleneck path (encode + rANS + decode) on B200.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU path (restated oracle) on host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                # one rank per GPU, weak scaling
+
+Workload = BASELINE.json configs[1]: Entropic Student ResNet-50 bottleneck (FPBasedResNetBottleneck, 24 bottleneck /
+256 target channels, factorized-prior EntropyBottleneck), random init (seed 0), synthetic 3x224x224 images, batch 256
+PER GPU (weak scaling: images are independent units, no data-path collective; the only collective is one counter
+all-reduce after the timed region).  A step = bottleneck_layer.encode + bottleneck_layer.decode over one batch.
+
+One JSON line on stdout (rank 0):
+  value     images/s, inputs resident in HBM, device-timed (CUDA events), max over ranks
+  e2e       images/s through the public plugin API with HOST buffers: pinned images -> H2D -> encode() -> list[bytes]
+            on the host (D2H) -> decode(strings) (H2D) -> per-image feature means read back (D2H)
+  roofline  dominant kernel: algorithmic FLOPs per launch / its CUDA-event time inside the timed region, vs MEASURED_PEAKS.json
+  cpu_baseline  the restated reference (oracle/, "port": CompressAI is not installable here) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'images/s encode+rANS+decode @224^2 (FPBasedResNetBottleneck, Entropic Student ResNet-50)'
+UNIT = 'images/s'
+IMG = (3, 224, 224)
+LATENT = (24, 55, 55)
+# algorithmic FLOPs (2*MAC) per image
+FLOPS = {'conv2d_f32[3->96,k5,s2]': 180.6e6, 'gdn_f32[96]': 231.2e6, 'conv2d_f32[96->48,k5,s2]': 722.5e6,
+         'gdn_f32[48]': 14.5e6, 'conv2d_f32[48->24,k2,s1]': 27.9e6, 'conv2d_f32[24->512,k2,s1]': 308.3e6,
+         'gdn_f32[512,inv]': 1644.2e6, 'conv2d_f32[512->256,k2,s1]': 3172.0e6, 'gdn_f32[256,inv]': 396.5e6,
+         'conv2d_f32[256->256,k2,s1]': 1644.2e6}
+PATH_FLOPS_PER_IMAGE = 8.342e9
+PATH_BYTES_PER_IMAGE = 34.85e6
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'hbm_gbs': p['hbm_gbs'], 'tflops_burst': p['bf16_tflops'], 'tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'tflops_burst': 1590.0, 'tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, smmax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smmax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(smmax) if smmax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def build_product_layer(device):
+    import torch
+    import sc2bench_b200 as s2
+    torch.manual_seed(0)
+    layer = s2.get_layer('FPBasedResNetBottleneck', num_bottleneck_channels=24, num_target_channels=256)
+    layer.eval()
+    layer.update()
+    return layer.to(device)
+
+
+def cpu_reference_run(n_images, steps, warmup, state_dict=None):
+    """Times the restated reference path (oracle/) on the host cores: torch CPU convs (all threads) + the per-sample
+    CompressAI coder loop through Python lists (as EntropyModel.compress/decompress does).  Returns images/s etc."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import torch
+    import ref_models
+    torch.manual_seed(0)
+    layer = ref_models.build_fp_bottleneck(3, 24, 256)
+    if state_dict is not None:
+        layer.load_state_dict(state_dict)
+    layer.eval()
+    layer.update()
+    torch.manual_seed(1)
+    x = torch.randn(n_images, *IMG)
+    times, nbytes = [], 0
+    with torch.inference_mode():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            obj = layer.encode(x)
+            out = layer.decode(**obj)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+            nbytes = sum(len(s) for s in obj['strings'][0])
+    total = sum(times)
+    return {'images_per_s': n_images * len(times) / total, 'ms_per_step': 1e3 * total / len(times), 'threads': torch.get_num_threads(),
+            'cores': os.cpu_count(), 'bytes_per_image': nbytes / n_images, 'out_shape': list(out.shape)}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    n = args.cpu_images
+    r = cpu_reference_run(n, args.steps, args.warmup)
+    sample = '%d images of 3x224x224 per step (the B200 arm runs 256 per GPU per step); restated reference ' \
+             '(oracle/shim compressai restatement + C rANS, torch CPU convs); compressai itself is not installable here' % n
+    line = {'impl': 'reference', 'metric': METRIC, 'value': r['images_per_s'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'entropic-student-resnet50 FPBasedResNetBottleneck encode+decode, 3x224x224, random init',
+                       'images_per_step': n, 'device': 'cpu'},
+            'cpu_baseline': {'value': r['images_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port', 'sample': sample},
+            'e2e': {'value': r['images_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
+    ap.add_argument('--cpu-images', type=int, default=8, help='images per step of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'b200':
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        return run_reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import sc2bench_b200 as s2
+    from sc2bench_b200 import parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)')
+    rank, world, local_rank = parallel.init_distributed('nccl')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    peaks = load_peaks()
+    layer = build_product_layer(device)
+    B = args.batch
+    n_sym = LATENT[0] * LATENT[1] * LATENT[2]
+
+    # two distinct input batches (154 MB each, larger than the 126 MB L2) alternate between steps
+    gen = torch.Generator(device='cpu').manual_seed(1 + rank)
+    host_inputs = [torch.randn(B, *IMG, generator=gen).pin_memory() for _ in range(2)]
+    dev_inputs = [h.to(device) for h in host_inputs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(i):
+        streams, shape = layer.encode_packed(dev_inputs[i & 1])
+        return streams, layer.decode_packed(streams, shape)
+
+    # ---- device-resident throughput ("value") -------------------------------------------------
+    dominant = 'conv2d_f32[512->256,k2,s1]'
+    with torch.inference_mode():
+        for i in range(args.warmup):
+            device_step(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        s2.ops.profile_kernels({dominant})
+        launches0 = s2.ops.STATS['launches']
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            streams, out = device_step(i)
+        e1.record()
+        barrier()
+        launches = s2.ops.STATS['launches'] - launches0
+        ms = e0.elapsed_time(e1)
+        prof = s2.ops.profile_results()
+        s2.ops.profile_kernels(None)
+        clocks = sampler.stop()
+        total_bytes = streams.total_bytes()
+
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    counters = parallel.EvalCounters(device)
+    counters.add(images=B * args.steps, bytes=total_bytes * args.steps, symbols=B * n_sym * args.steps)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    counters.all_reduce()  # the path's only collective: one small counter vector per evaluation
+    ms = float(t.item())
+    c = counters.as_dict()
+    value = c['images'] / (ms / 1e3)
+
+    # ---- end-to-end through the public API with host buffers ("e2e") ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        with torch.inference_mode():
+            def e2e_step(i):
+                x = host_inputs[i & 1].to(device, non_blocking=True)
+                obj = layer.encode(x)                       # {'strings': [list[bytes]], 'shape'}: bitstreams land on the host
+                feat = layer.decode(**obj)                  # list[bytes] -> device -> features
+                return obj, feat.mean(dim=(1, 2, 3)).cpu()  # per-image result read back
+            for i in range(args.warmup):
+                e2e_step(i)
+            barrier()
+            t0 = time.perf_counter()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(args.steps):
+                obj, res = e2e_step(i)
+            f1.record()
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            e2e_ms = max(f0.elapsed_time(f1), wall_ms)  # host work (bytes objects) is part of the contract
+        te = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        stream_bytes = sum(len(s) for s in obj['strings'][0])
+        e2e = {'value': world * B * args.steps / (float(te.item()) / 1e3), 'unit': UNIT,
+               'h2d_bytes_per_step': B * IMG[0] * IMG[1] * IMG[2] * 4 + stream_bytes + 8 * (B + 1),
+               'd2h_bytes_per_step': stream_bytes + 8 * (B + 1) + 4 + B * 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------
+    k_ms = prof.get(dominant, [])
+    roofline = None
+    if k_ms:
+        avg_ms = sum(k_ms) / len(k_ms)
+        achieved = FLOPS[dominant] * B / (avg_ms / 1e3) / 1e12
+        roofline = {'kernel': dominant, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
+                    'frac': achieved / peaks['tflops_sustained'], 'traffic': None, 'peak_source': peaks['source'] + ', bf16 sustained',
+                    'avg_launch_ms': avg_ms, 'share_of_step': avg_ms / (ms / args.steps),
+                    'note': 'exact-fp32 CUDA-core implicit GEMM (round-1 path); algorithmic FLOPs = 2*MAC of SURVEY.md App. B x batch'}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sd = {k: v.detach().cpu() for k, v in layer.state_dict().items()}
+        r = cpu_reference_run(args.cpu_images, steps=2, warmup=1, state_dict=sd)
+        cpu_baseline = {'value': r['images_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port',
+                        'sample': '%d images per step x 2 steps of the same workload; restated reference (oracle/: CompressAI '
+                                  'restatement, torch CPU convs on %d threads, per-sample Python-list coder loop + C rANS)'
+                                  % (args.cpu_images, r['threads'])}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'configs[1]: entropic-student-resnet50 FPBasedResNetBottleneck(24,256) encode+rANS+decode, '
+                                   '3x224x224, random init, batch %d per GPU' % B,
+                       'images_per_gpu_per_step': B, 'global_images_per_step': B * world, 'symbols_per_image': n_sym,
+                       'l2_policy': 'two alternating 154 MB input batches (> 126 MB L2); activations are GBs per step',
+                       'parallelism': 'dp%d (batch sharded, one counter all-reduce per evaluation)' % world},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'bytes_per_image': c['bytes_per_image'], 'bits_per_symbol': c['bits_per_symbol'],
+            'path_tflops': value * PATH_FLOPS_PER_IMAGE / 1e12, 'path_hbm_gbs_algorithmic': value * PATH_BYTES_PER_IMAGE / 1e9}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,161 @@
+/*
+ * sc2b200.h -- C ABI of libsc2b200.so: the B200 (sm_100a) implementation of sc2bench's
+ * supervised-compression bottleneck path (g_a conv+GDN -> EntropyBottleneck quantise ->
+ * rANS encode -> rANS decode -> g_s IGDN+conv).
+ *
+ * Boundary rules:
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - the CALLER allocates every buffer; the library allocates nothing that outlives a call,
+ *     keeps no global state (apart from a lazily resolved driver entry point) and never frees
+ *     caller memory;
+ *   - every device entry point takes an explicit CUDA stream (cudaStream_t passed as void*),
+ *     only enqueues work on it and never synchronises the device;
+ *   - return value: 0 = ok, <0 = invalid argument / launch failure (SC2_ERR_*), device-side
+ *     faults (arena overflow, truncated stream) are reported asynchronously through the
+ *     caller-provided `status` words (SC2_FAULT_* bit flags);
+ *   - nothing throws across the boundary.
+ *
+ * What each entry point replaces in the reference stack (the reference itself is pure Python;
+ * the FFI underneath its hot path is CompressAI's two pybind modules):
+ *   compressai._CXX.pmf_to_quantized_cdf                 -> sc2_pmf_to_quantized_cdf
+ *       reached from sc2bench/models/layer.py:441 (BaseBottleneck.update)
+ *   compressai.ans.RansEncoder.encode_with_indexes       -> sc2_rans_encode_batch (+ sc2_rans_pack)
+ *       reached from sc2bench/models/layer.py:506 (entropy_bottleneck.compress), :647 (gaussian_conditional.compress)
+ *   compressai.ans.RansDecoder.decode_with_indexes       -> sc2_rans_decode_batch
+ *       reached from sc2bench/models/layer.py:520 (entropy_bottleneck.decompress), :665
+ *   EntropyModel.quantize("symbols") / dequantize        -> sc2_quantize_symbols / fused into decode
+ *       reached from sc2bench/models/layer.py:506,520,545-546
+ *   GaussianConditional.build_indexes                    -> sc2_gc_build_indexes
+ *       reached from sc2bench/models/layer.py:646,664
+ *   torch conv2d / conv_transpose2d + compressai.layers.GDN / GDN1 (library calls)
+ *                                                        -> sc2_conv2d_f32 / sc2_gdn_f32 (+ sc2_tc_* tensor-core path)
+ *       instantiated at sc2bench/models/layer.py:475-494
+ */
+#ifndef SC2B200_H
+#define SC2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC2_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SC2_API __attribute__((visibility("default")))
+#else
+#define SC2_API
+#endif
+
+/* return codes */
+#define SC2_OK 0
+#define SC2_ERR_INVALID_ARG (-1)
+#define SC2_ERR_UNSUPPORTED (-2)
+#define SC2_ERR_CUDA (-3)
+#define SC2_ERR_DOMAIN (-4) /* pmf has a negative / non-finite entry, or sums to zero */
+
+/* device-side fault flags written (OR-ed) into a caller-provided int32 status word */
+#define SC2_FAULT_ARENA_OVERFLOW 1   /* encoder ran out of its output slot */
+#define SC2_FAULT_STREAM_TRUNCATED 2 /* decoder would read past the end of a stream */
+#define SC2_FAULT_BAD_STREAM 4       /* stream shorter than 8 bytes or not a multiple of 4 */
+
+typedef void *sc2_stream_t; /* cudaStream_t */
+
+SC2_API int sc2_abi_version(void);
+SC2_API const char *sc2_error_string(int code);
+/* last CUDA error string seen by this thread inside the library (for SC2_ERR_CUDA) */
+SC2_API const char *sc2_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Host: CDF construction.  Bit-exact restatement of compressai._CXX.pmf_to_quantized_cdf.
+ * cdf_out has n + 1 entries.  Runs once per update(), never on the per-image path. */
+SC2_API int sc2_pmf_to_quantized_cdf(const float *pmf, int n, int precision, uint32_t *cdf_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Host: coder tables.  From CompressAI's three buffers (_quantized_cdf [n_rows x cdf_stride] int32,
+ * _cdf_length [n_rows], _offset [n_rows]) build the blob the kernels read:
+ * per-entry exact-division reciprocals for the encoder, sentinel-padded CDF rows for the decoder.
+ * The caller uploads the blob to device memory (any 16-byte aligned address). */
+SC2_API size_t sc2_rans_table_bytes(int n_rows, int cdf_stride);
+SC2_API int sc2_rans_build_tables(const int32_t *cdfs, const int32_t *cdf_sizes, const int32_t *offsets,
+                          int n_rows, int cdf_stride, void *blob_out);
+
+/* Bytes one stream can need in the worst case (every symbol escaped with 8 nibbles). */
+SC2_API int64_t sc2_rans_max_stream_bytes(int64_t n_symbols);
+
+/* ------------------------------------------------------------------------------------------
+ * Device: batched rANS encode, one CompressAI-compatible stream per sample.
+ *   symbols   [batch x n_per_stream] int32, C order within a sample (c, h, w)
+ *   indexes   [batch x n_per_stream] int32 CDF row per symbol, or NULL for "channel mode":
+ *             row = (i / spatial) for symbol i of a sample (EntropyBottleneck._build_indexes)
+ *   tables    device copy of the sc2_rans_build_tables blob built for (n_rows, cdf_stride)
+ *   arena     batch slots of slot_bytes (multiple of 4); stream b is written BACKWARDS from the end
+ *             of slot b and occupies its last lengths[b] bytes
+ *   lengths   [batch] int32 out, bytes
+ *   status    [1] int32, OR-ed fault flags (caller zeroes it) */
+SC2_API int sc2_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n_per_stream,
+                          int64_t spatial, const void *tables, int n_rows, int cdf_stride, uint8_t *arena,
+                          int64_t slot_bytes, int32_t *lengths, int32_t *status, sc2_stream_t stream);
+
+/* Device: compact the streams to the front of `packed`: offsets[b] = sum(lengths[:b]) (int64, batch+1
+ * entries, offsets[batch] = total).  One D2H copy of offsets[batch] bytes then carries all strings. */
+SC2_API int sc2_rans_pack(const uint8_t *arena, int64_t slot_bytes, const int32_t *lengths, int batch,
+                  uint8_t *packed, int64_t *offsets, sc2_stream_t stream);
+
+/* Device: batched rANS decode (+ fused dequantise).
+ *   packed/offsets  streams laid out as sc2_rans_pack produces them (offsets: batch+1 int64, device)
+ *   indexes/spatial as for encode
+ *   out_symbols     [batch x n_per_stream] int32 or NULL
+ *   out_values      [batch x n_per_stream] float32 or NULL: float(symbol) + means[row]   (means may be NULL -> +0)
+ *   means           [n_rows] float32 per-row medians (EntropyBottleneck) or NULL */
+SC2_API int sc2_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, int batch, int64_t n_per_stream,
+                          const int32_t *indexes, int64_t spatial, const void *tables, int n_rows, int cdf_stride,
+                          int32_t *out_symbols, float *out_values, const float *means,
+                          int32_t *status, sc2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device: EntropyModel.quantize(x, "symbols", means): int32(rint(x - mean[c])) over [batch, C, spatial].
+ * means may be NULL.  (Fused into the last g_a conv on the tensor-core path.) */
+SC2_API int sc2_quantize_symbols(const float *x, const float *means, int32_t *symbols, int batch, int channels,
+                         int64_t spatial, sc2_stream_t stream);
+
+/* Device: GaussianConditional.build_indexes: idx = #(table[:-1] < max(scale, bound)) per element. */
+SC2_API int sc2_gc_build_indexes(const float *scales, int64_t n, const float *scale_table, int n_levels,
+                         float scale_bound, int32_t *indexes, sc2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device: fp32 (CUDA-core) direct convolution, NCHW, with a fused epilogue.  Exact-fp32 path used by
+ * g_a (symbol exactness needs fp32-grade latents) and as the general fallback. */
+#define SC2_EPI_NONE 0
+#define SC2_EPI_RELU 1
+#define SC2_EPI_CLAMP01 2
+#define SC2_EPI_QUANTIZE 3 /* y -> int32(rint(y - aux[c])) written to out as int32 (aux = medians or NULL) */
+#define SC2_EPI_ABS 4
+
+typedef struct sc2_conv_desc {
+    int batch, c_in, h_in, w_in;
+    int c_out, kh, kw;
+    int stride, pad;
+    int transposed;     /* 0: Conv2d (weight [c_out, c_in, kh, kw]); 1: ConvTranspose2d (weight [c_in, c_out, kh, kw]) */
+    int output_padding; /* transposed only */
+    int epilogue;       /* SC2_EPI_* */
+} sc2_conv_desc;
+
+/* output spatial size for a descriptor */
+SC2_API int sc2_conv_out_size(const sc2_conv_desc *d, int *h_out, int *w_out);
+
+SC2_API int sc2_conv2d_f32(const sc2_conv_desc *d, const float *x, const float *weight, const float *bias /*nullable*/,
+                   const float *aux /*nullable*/, void *out, sc2_stream_t stream);
+
+/* Device: GDN family on NCHW fp32.  gamma [C x C] and beta [C] are the EFFECTIVE (reparametrised)
+ * values.  kind 0 = GDN1 (norm = beta + gamma.|x|; y = x / norm, inverse: x * norm)
+ *          kind 1 = GDN  (norm = beta + gamma.x^2; y = x * rsqrt(norm), inverse: x * sqrt(norm)) */
+SC2_API int sc2_gdn_f32(const float *x, const float *gamma, const float *beta, float *y, int batch, int channels,
+                int64_t spatial, int kind, int inverse, sc2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SC2B200_H */

@@ -1,0 +1,21 @@
+"""sc2bench_b200 -- B200-native (sm_100a) implementation of sc2bench's supervised-compression bottleneck path.
+
+The directory is called `sc2-benchmark_b200/` (repo layout contract); it is imported as `sc2bench_b200` through the
+thin alias package next to it.  Importing the package loads (and, if needed, builds) libsc2b200.so: the CUDA
+library is the product, there is no CPU fallback for the hot path.
+"""
+from . import _native
+
+_native.load()  # fail loudly right here if the native library is missing and cannot be built
+
+from . import ops  # noqa: E402
+from .backbone import (AnalyzableModule, FileSizeAnalyzer, SplittableResNet, UpdatableBackbone,  # noqa: E402,F401
+                       check_if_updatable, get_backbone, splittable_resnet)
+from .bottleneck import (LAYER_CLASS_DICT, BaseBottleneck, EntropyBottleneckLayer, FPBasedResNetBottleneck,  # noqa: E402,F401
+                         get_layer, register_layer_class, register_layer_func)
+from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional  # noqa: E402,F401
+from .layers import GDN, GDN1  # noqa: E402,F401
+from .models import (CompressionModel, FactorizedPrior, ScaleHyperprior, bmshj2018_factorized,  # noqa: E402,F401
+                     bmshj2018_hyperprior, get_scale_table, update_registered_buffers)
+
+__version__ = '0.1.0'

@@ -1,0 +1,80 @@
+"""ctypes binding of libsc2b200.so (declared in include/sc2b200.h).
+
+The library is the product: there is NO Python/CPU fallback for the hot path.  If the shared object is
+missing it is built in-tree with nvcc; if that is impossible, importing this module raises.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_c = ctypes
+vp, i32, i64, f32 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+
+class ConvDesc(_c.Structure):
+    """struct sc2_conv_desc"""
+    _fields_ = [(n, i32) for n in ('batch', 'c_in', 'h_in', 'w_in', 'c_out', 'kh', 'kw', 'stride', 'pad',
+                                    'transposed', 'output_padding', 'epilogue')]
+
+
+# name -> (restype, argtypes): every symbol include/sc2b200.h declares
+SIGNATURES = {
+    'sc2_abi_version': (i32, []),
+    'sc2_error_string': (_c.c_char_p, [i32]),
+    'sc2_last_cuda_error': (_c.c_char_p, []),
+    'sc2_pmf_to_quantized_cdf': (i32, [vp, i32, i32, vp]),
+    'sc2_rans_table_bytes': (_c.c_size_t, [i32, i32]),
+    'sc2_rans_build_tables': (i32, [vp, vp, vp, i32, i32, vp]),
+    'sc2_rans_max_stream_bytes': (i64, [i64]),
+    'sc2_rans_encode_batch': (i32, [vp, vp, i32, i64, i64, vp, i32, i32, vp, i64, vp, vp, vp]),
+    'sc2_rans_pack': (i32, [vp, i64, vp, i32, vp, vp, vp]),
+    'sc2_rans_decode_batch': (i32, [vp, vp, i32, i64, vp, i64, vp, i32, i32, vp, vp, vp, vp, vp]),
+    'sc2_quantize_symbols': (i32, [vp, vp, vp, i32, i32, i64, vp]),
+    'sc2_gc_build_indexes': (i32, [vp, i64, vp, i32, f32, vp, vp]),
+    'sc2_conv_out_size': (i32, [_c.POINTER(ConvDesc), _c.POINTER(i32), _c.POINTER(i32)]),
+    'sc2_conv2d_f32': (i32, [_c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]),
+    'sc2_gdn_f32': (i32, [vp, vp, vp, vp, i32, i32, i64, i32, i32, vp]),
+}
+
+SC2_OK = 0
+FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM = 1, 2, 4
+EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS = 0, 1, 2, 3, 4
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Loads (building first if needed) the native library; raises loudly when that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or os.environ.get('SC2B200_REBUILD'):
+        path = _build.build_native(force=bool(os.environ.get('SC2B200_REBUILD')))
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.sc2_abi_version() != 1:
+        raise ImportError('libsc2b200.so ABI version mismatch: rebuild with sc2-benchmark_b200/build.py --force')
+    _lib = lib
+    return lib
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != SC2_OK:
+        lib = load()
+        msg = lib.sc2_error_string(rc).decode()
+        if rc == -3:
+            msg += ': ' + lib.sc2_last_cuda_error().decode()
+        raise NativeError('%s failed: %s' % (what, msg))

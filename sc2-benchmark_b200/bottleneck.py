@@ -1,0 +1,160 @@
+"""Bottleneck layers of the supervised-compression path, mirroring `sc2bench.models.layer`.
+
+Same registry (`LAYER_CLASS_DICT`, `register_layer_class`, `get_layer`), class names, constructor arguments,
+child-module names (`encoder`, `decoder`, `entropy_bottleneck`) and `encode` / `decode` / `forward` / `update`
+contract as the reference, so YAML `bottleneck_config: {key, kwargs}` entries resolve unchanged:
+  - FPBasedResNetBottleneck  <- sc2bench/models/layer.py:444-550
+  - BaseBottleneck           <- sc2bench/models/layer.py:401-441
+  - EntropyBottleneckLayer   <- sc2bench/models/layer.py:346-398
+  - get_layer                <- sc2bench/models/layer.py:820-835
+The eval-time branch (`updated and not training`) is the hot path: g_a, quantisation, rANS encode / decode and
+g_s all run in libsc2b200.so.  The two training-time branches stay differentiable torch.
+"""
+import torch
+from torch import nn
+
+from . import _native, ops
+from .layers import GDN1
+from .models import CompressionModel, run_transform
+
+LAYER_CLASS_DICT = dict()
+LAYER_FUNC_DICT = dict()
+
+
+def register_layer_class(cls):
+    LAYER_CLASS_DICT[cls.__name__] = cls
+    return cls
+
+
+def register_layer_func(func):
+    LAYER_FUNC_DICT[func.__name__] = func
+    return func
+
+
+def get_layer(cls_or_func_name, **kwargs):
+    """Builds a registered layer; `None` for an unknown key, like the reference."""
+    if cls_or_func_name in LAYER_CLASS_DICT:
+        return LAYER_CLASS_DICT[cls_or_func_name](**kwargs)
+    if cls_or_func_name in LAYER_FUNC_DICT:
+        return LAYER_FUNC_DICT[cls_or_func_name](**kwargs)
+    return None
+
+
+class EntropyBottleneckLayer(CompressionModel):
+    """A bare EntropyBottleneck as a CompressionModel (dropped after a backbone stage by EntropicClassifier)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.updated = False
+
+    def forward(self, x):
+        return self.entropy_bottleneck(x)
+
+    def compress(self, x):
+        return {'strings': [self.entropy_bottleneck.compress(x)], 'shape': x.size()[-2:]}
+
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 1
+        return self.entropy_bottleneck.decompress(strings[0], shape)
+
+    def update(self, force=False):
+        self.updated = True
+        return super().update(force=force)
+
+
+class BaseBottleneck(CompressionModel):
+    """Entropy-bottleneck based encoder / decoder pair; subclasses provide encode() / decode() / forward()."""
+
+    def __init__(self, entropy_bottleneck_channels):
+        super().__init__(entropy_bottleneck_channels=entropy_bottleneck_channels)
+        self.updated = False
+
+    def encode(self, *args, **kwargs):
+        raise NotImplementedError()
+
+    def decode(self, *args, **kwargs):
+        raise NotImplementedError()
+
+    def forward(self, *args):
+        raise NotImplementedError()
+
+    def update(self, force=False):
+        self.updated = True
+        return super().update(force=force)
+
+
+@register_layer_class
+class FPBasedResNetBottleneck(BaseBottleneck):
+    """Factorized-prior bottleneck for ResNet-style students (Entropic Student, Matsubara et al. WACV 2022).
+
+    encoder: Conv(5x5, s2) - GDN1 - Conv(5x5, s2) - GDN1 - Conv(2x2)            3 -> 4b -> 2b -> b channels
+    decoder: Conv(2x2, p1) - IGDN1 - Conv(2x2) - IGDN1 - Conv(2x2, p1)          b -> 2t -> t -> t channels
+    with b = num_bottleneck_channels, t = num_target_channels; no conv has a bias.
+    """
+
+    def __init__(self, num_input_channels=3, num_bottleneck_channels=24, num_target_channels=256,
+                 encoder_channel_sizes=None, decoder_channel_sizes=None):
+        if encoder_channel_sizes is None:
+            b = num_bottleneck_channels
+            encoder_channel_sizes = [num_input_channels, b * 4, b * 2, b]
+        if decoder_channel_sizes is None:
+            t = num_target_channels
+            decoder_channel_sizes = [encoder_channel_sizes[-1], t * 2, t, t]
+        super().__init__(entropy_bottleneck_channels=num_bottleneck_channels)
+        e, d = encoder_channel_sizes, decoder_channel_sizes
+        self.encoder = nn.Sequential(
+            nn.Conv2d(e[0], e[1], kernel_size=5, stride=2, padding=2, bias=False), GDN1(e[1]),
+            nn.Conv2d(e[1], e[2], kernel_size=5, stride=2, padding=2, bias=False), GDN1(e[2]),
+            nn.Conv2d(e[2], e[3], kernel_size=2, stride=1, padding=0, bias=False))
+        self.decoder = nn.Sequential(
+            nn.Conv2d(d[0], d[1], kernel_size=2, stride=1, padding=1, bias=False), GDN1(d[1], inverse=True),
+            nn.Conv2d(d[1], d[2], kernel_size=2, stride=1, padding=0, bias=False), GDN1(d[2], inverse=True),
+            nn.Conv2d(d[2], d[3], kernel_size=2, stride=1, padding=1, bias=False))
+
+    # ---- hot path ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_packed(self, x):
+        """g_a + quantise + rANS, bitstreams left on the device: (PackedStreams, latent (H, W))."""
+        eb = self.entropy_bottleneck
+        medians = eb._get_medians().detach().reshape(-1)
+        symbols = run_transform(self.encoder, x, final_epilogue=_native.EPI_QUANTIZE, final_aux=medians)
+        return eb.compress_symbols(symbols, spatial=symbols[0, 0].numel()), symbols.size()[-2:]
+
+    @torch.no_grad()
+    def decode_packed(self, streams, shape):
+        latent_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape))
+        return run_transform(self.decoder, latent_hat)
+
+    def encode(self, x, **kwargs):
+        """-> {'strings': [list of B bytes objects], 'shape': latent (H, W)}  (reference contract, layer.py:496-507)"""
+        streams, shape = self.encode_packed(x)
+        return {'strings': [streams.tolist()], 'shape': shape}
+
+    def decode(self, strings, shape):
+        """strings[0]: list of B bytes objects (or a device-resident PackedStreams) -> decoder features."""
+        first = strings[0]
+        if not isinstance(first, ops.PackedStreams):
+            first = ops.PackedStreams.from_list(first, self.entropy_bottleneck._quantized_cdf.device)
+        return self.decode_packed(first, shape)
+
+    # ---- training-time branches (differentiable torch, off the hot path) ----------------------------
+    def _get_means(self, x):
+        medians = self.entropy_bottleneck._get_medians().detach()
+        spatial_dims = x.dim() - 2
+        medians = self.entropy_bottleneck._extend_ndims(medians, spatial_dims)
+        return medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
+
+    def _forward2train(self, x):
+        y_hat, _ = self.entropy_bottleneck(self.encoder(x))
+        return self.decoder(y_hat)
+
+    def forward(self, x):
+        if not self.updated:
+            return self._forward2train(x)
+        if not self.training:
+            return self.decode(**self.encode(x))
+        # fine-tuning after update(): hard rounding around the medians, no gradient through it
+        latent = self.encoder(x)
+        eb = self.entropy_bottleneck
+        rounded = eb.dequantize(eb.quantize(latent, 'dequantize', self._get_means(latent)))
+        return self.decoder(rounded.detach())

@@ -1,0 +1,66 @@
+"""Builds libsc2b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python sc2-benchmark_b200/build.py [--force]
+
+The .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import glob
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB_DIR = os.path.join(HERE, 'lib')
+LIB_PATH = os.path.join(LIB_DIR, 'libsc2b200.so')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--use_fast_math=false']
+NVCC_FLAGS.remove('--use_fast_math=false')  # never fast-math: bit-exactness matters on this path
+
+
+def _sources():
+    return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+
+
+def _fingerprint():
+    h = hashlib.sha256()
+    for path in _sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + \
+            [os.path.join(os.path.dirname(HERE), 'include', 'sc2b200.h'), os.path.abspath(__file__)]:
+        h.update(path.encode())
+        with open(path, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def build_native(force=False, verbose=False):
+    os.makedirs(LIB_DIR, exist_ok=True)
+    stamp = os.path.join(LIB_DIR, 'build.stamp')
+    fp = _fingerprint()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+        return LIB_PATH
+    if not os.path.exists(NVCC):
+        raise RuntimeError('nvcc not found at %s; libsc2b200.so cannot be built' % NVCC)
+    objs = []
+    procs = []
+    for src in _sources():
+        obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        cmd = [NVCC] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for cmd, proc in procs:
+        out, _ = proc.communicate()
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(out.decode())
+        if proc.returncode != 0:
+            raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
+    link = [NVCC, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC']
+    subprocess.check_call(link)
+    with open(stamp, 'w') as f:
+        f.write(fp)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    print(build_native(force='--force' in sys.argv, verbose='-v' in sys.argv))

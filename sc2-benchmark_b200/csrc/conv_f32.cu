@@ -1,0 +1,265 @@
+// conv_f32.cu -- exact-fp32 (CUDA-core FFMA) implicit-GEMM convolution with fused epilogues, NCHW.
+//
+// Role on the path: (1) g_a for symbol exactness -- round(y - median) flips with any latent error, so the
+// encoder needs fp32-grade arithmetic; (2) the general fallback for every conv / transposed conv /
+// GDN shape the tensor-core kernels (conv_tc.cu) do not cover; (3) the on-device fp32 reference the tensor-core
+// kernels are validated against at full size.
+//
+// Replaces the torch conv2d / conv_transpose2d + compressai GDN/GDN1 library calls instantiated at
+// sc2bench/models/layer.py:475-494 (GDN1.forward = abs -> 1x1 conv(gamma)+beta -> reciprocal -> mul, four ATen
+// passes, becomes one kernel: the 1x1 "gamma" GEMM with |x| applied on load and x/norm applied in the epilogue).
+//
+// GEMM view: M = output pixels of one image (oy*Wout + ox), N = output channels, K = (c_in, ky, kx).
+// A[m][k] is gathered from the input on the fly (zero outside the image), B[k][n] from the weights.
+#include "common.cuh"
+
+namespace sc2 {
+
+enum InTransform { IN_NONE = 0, IN_ABS = 1, IN_SQUARE = 2 };
+enum Epilogue {
+    EP_NONE = SC2_EPI_NONE,
+    EP_RELU = SC2_EPI_RELU,
+    EP_CLAMP01 = SC2_EPI_CLAMP01,
+    EP_QUANTIZE = SC2_EPI_QUANTIZE,
+    EP_ABS = SC2_EPI_ABS,
+    EP_GDN1_FWD = 16,  // out = x / (acc + beta)
+    EP_GDN1_INV = 17,  // out = x * (acc + beta)
+    EP_GDN_FWD = 18,   // out = x * rsqrt(acc + beta)
+    EP_GDN_INV = 19,   // out = x * sqrt(acc + beta)
+};
+
+struct ConvParams {
+    const float *x;
+    const float *w;
+    const float *bias;  // nullable; beta for the GDN epilogues
+    const float *aux;   // medians for EP_QUANTIZE (nullable)
+    void *out;
+    int batch, c_in, h_in, w_in, c_out, kh, kw, stride, pad, transposed;
+    int h_out, w_out;
+    int K;  // c_in * kh * kw
+    int in_transform, epilogue;
+};
+
+constexpr int BK = 16;
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+conv2d_f32_kernel(const ConvParams p) {
+    constexpr int kThreads = (BM / TM) * (BN / TN);
+    static_assert(kThreads == 256, "tile shape must give 256 threads");
+    static_assert((BM * BK) % kThreads == 0 && (BN * BK) % kThreads == 0, "loader shape");
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Bs[BK][BN];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int M = p.h_out * p.w_out;
+    const int KK = p.kh * p.kw;
+    const int64_t in_img = static_cast<int64_t>(p.c_in) * p.h_in * p.w_in;
+    const float *xb = p.x + static_cast<int64_t>(b) * in_img;
+
+    // ---- A loader mapping: thread -> one k column, (BM*BK/256) pixels ----
+    constexpr int A_PER_THREAD = BM * BK / kThreads;  // pixels per thread for its k
+    const int a_k = tid / (BM / A_PER_THREAD);         // 0..BK-1
+    const int a_m = (tid % (BM / A_PER_THREAD)) * A_PER_THREAD;
+    int a_oy[A_PER_THREAD], a_ox[A_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < A_PER_THREAD; ++i) {
+        const int m = m0 + a_m + i;
+        const int mm = m < M ? m : 0;
+        a_oy[i] = m < M ? mm / p.w_out : -100000;  // pushes the gather out of range
+        a_ox[i] = mm % p.w_out;
+    }
+    // ---- B loader mapping: thread -> one n, (BN*BK/256) consecutive k ----
+    constexpr int B_PER_THREAD = BN * BK / kThreads;
+    const int b_n = tid / (BK / B_PER_THREAD);
+    const int b_k = (tid % (BK / B_PER_THREAD)) * B_PER_THREAD;
+
+    // ---- compute mapping ----
+    const int tm = tid % (BM / TM);
+    const int tn = tid / (BM / TM);
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+        // gather A
+        {
+            const int k = k0 + a_k;
+            float v[A_PER_THREAD];
+#pragma unroll
+            for (int i = 0; i < A_PER_THREAD; ++i) v[i] = 0.0f;
+            if (k < p.K) {
+                const int c = k / KK;
+                const int r = k - c * KK;
+                const int ky = r / p.kw;
+                const int kx = r - ky * p.kw;
+                const float *xc = xb + static_cast<int64_t>(c) * p.h_in * p.w_in;
+#pragma unroll
+                for (int i = 0; i < A_PER_THREAD; ++i) {
+                    int iy, ix;
+                    bool ok;
+                    if (!p.transposed) {
+                        iy = a_oy[i] * p.stride - p.pad + ky;
+                        ix = a_ox[i] * p.stride - p.pad + kx;
+                        ok = iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in;
+                    } else {
+                        const int ty = a_oy[i] + p.pad - ky;
+                        const int tx = a_ox[i] + p.pad - kx;
+                        iy = ty / p.stride;
+                        ix = tx / p.stride;
+                        ok = ty >= 0 && tx >= 0 && (ty - iy * p.stride) == 0 && (tx - ix * p.stride) == 0 &&
+                             iy < p.h_in && ix < p.w_in;
+                    }
+                    if (ok) {
+                        float t = __ldg(xc + iy * p.w_in + ix);
+                        if (p.in_transform == IN_ABS) t = fabsf(t);
+                        else if (p.in_transform == IN_SQUARE) t = t * t;
+                        v[i] = t;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < A_PER_THREAD; ++i) As[a_k][a_m + i] = v[i];
+        }
+        // load B
+        {
+            const int n = n0 + b_n;
+#pragma unroll
+            for (int i = 0; i < B_PER_THREAD; ++i) {
+                const int k = k0 + b_k + i;
+                float t = 0.0f;
+                if (n < p.c_out && k < p.K) {
+                    if (!p.transposed) {
+                        t = __ldg(p.w + static_cast<int64_t>(n) * p.K + k);
+                    } else {
+                        const int c = k / KK;
+                        const int r = k - c * KK;
+                        t = __ldg(p.w + (static_cast<int64_t>(c) * p.c_out + n) * KK + r);
+                    }
+                }
+                Bs[b_k + i][b_n] = t;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], bb[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(&As[k][tm * TM + i]);
+                a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(&Bs[k][tn * TN + j]);
+                bb[j] = t.x; bb[j + 1] = t.y; bb[j + 2] = t.z; bb[j + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue ----
+    float *outf = static_cast<float *>(p.out) + static_cast<int64_t>(b) * p.c_out * M;
+    int32_t *outi = static_cast<int32_t *>(p.out) + static_cast<int64_t>(b) * p.c_out * M;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int n = n0 + tn * TN + j;
+        if (n >= p.c_out) continue;
+        const float bias = p.bias ? __ldg(p.bias + n) : 0.0f;
+        const float med = (p.epilogue == EP_QUANTIZE && p.aux) ? __ldg(p.aux + n) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int m = m0 + tm * TM + i;
+            if (m >= M) continue;
+            float v = acc[i][j] + bias;
+            const int64_t o = static_cast<int64_t>(n) * M + m;
+            switch (p.epilogue) {
+                case EP_RELU: v = fmaxf(v, 0.0f); break;
+                case EP_CLAMP01: v = fminf(fmaxf(v, 0.0f), 1.0f); break;
+                case EP_ABS: v = fabsf(v); break;
+                case EP_GDN1_FWD: v = __fdiv_rn(1.0f, v) * __ldg(xb + o); break;  // x * (1 / norm), as the reference
+                case EP_GDN1_INV: v = __ldg(xb + o) * v; break;
+                case EP_GDN_FWD: v = __ldg(xb + o) * __frsqrt_rn(v); break;
+                case EP_GDN_INV: v = __ldg(xb + o) * __fsqrt_rn(v); break;
+                default: break;
+            }
+            if (p.epilogue == EP_QUANTIZE) outi[o] = __float2int_rn(rintf(v - med));
+            else outf[o] = v;
+        }
+    }
+}
+
+static int launch_conv(const ConvParams &p, cudaStream_t st) {
+    const int M = p.h_out * p.w_out;
+    if (M <= 0 || p.batch <= 0) return SC2_OK;
+    if (p.batch > 65535) return SC2_ERR_UNSUPPORTED;
+    if (p.c_out > 32) {
+        dim3 grid((M + 127) / 128, (p.c_out + 63) / 64, p.batch);
+        conv2d_f32_kernel<128, 64, 8, 4><<<grid, 256, 0, st>>>(p);
+    } else {
+        dim3 grid((M + 127) / 128, (p.c_out + 31) / 32, p.batch);
+        conv2d_f32_kernel<128, 32, 4, 4><<<grid, 256, 0, st>>>(p);
+    }
+    SC2_LAUNCH_CHECK("conv2d_f32_kernel");
+    return SC2_OK;
+}
+
+}  // namespace sc2
+
+extern "C" {
+
+int sc2_conv_out_size(const sc2_conv_desc *d, int *h_out, int *w_out) {
+    if (!d || !h_out || !w_out || d->stride < 1 || d->kh < 1 || d->kw < 1) return SC2_ERR_INVALID_ARG;
+    if (!d->transposed) {
+        *h_out = (d->h_in + 2 * d->pad - d->kh) / d->stride + 1;
+        *w_out = (d->w_in + 2 * d->pad - d->kw) / d->stride + 1;
+    } else {
+        *h_out = (d->h_in - 1) * d->stride - 2 * d->pad + d->kh + d->output_padding;
+        *w_out = (d->w_in - 1) * d->stride - 2 * d->pad + d->kw + d->output_padding;
+    }
+    return (*h_out > 0 && *w_out > 0) ? SC2_OK : SC2_ERR_INVALID_ARG;
+}
+
+int sc2_conv2d_f32(const sc2_conv_desc *d, const float *x, const float *weight, const float *bias, const float *aux,
+                   void *out, sc2_stream_t stream) {
+    if (!d || !x || !weight || !out) return SC2_ERR_INVALID_ARG;
+    if (d->batch < 0 || d->c_in < 1 || d->c_out < 1 || d->pad < 0) return SC2_ERR_INVALID_ARG;
+    if (d->epilogue < SC2_EPI_NONE || d->epilogue > SC2_EPI_ABS) return SC2_ERR_INVALID_ARG;
+    sc2::ConvParams p;
+    int rc = sc2_conv_out_size(d, &p.h_out, &p.w_out);
+    if (rc != SC2_OK) return rc;
+    p.x = x; p.w = weight; p.bias = bias; p.aux = aux; p.out = out;
+    p.batch = d->batch; p.c_in = d->c_in; p.h_in = d->h_in; p.w_in = d->w_in; p.c_out = d->c_out;
+    p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.transposed = d->transposed ? 1 : 0;
+    p.K = d->c_in * d->kh * d->kw;
+    p.in_transform = sc2::IN_NONE;
+    p.epilogue = d->epilogue;
+    return sc2::launch_conv(p, sc2::as_stream(stream));
+}
+
+int sc2_gdn_f32(const float *x, const float *gamma, const float *beta, float *y, int batch, int channels,
+                int64_t spatial, int kind, int inverse, sc2_stream_t stream) {
+    if (!x || !gamma || !beta || !y || batch < 0 || channels < 1 || spatial < 0 || spatial > 0x7fffffff) return SC2_ERR_INVALID_ARG;
+    if (kind != 0 && kind != 1) return SC2_ERR_INVALID_ARG;
+    if (x == y) return SC2_ERR_INVALID_ARG;  // the epilogue re-reads x: not in-place
+    sc2::ConvParams p;
+    p.x = x; p.w = gamma; p.bias = beta; p.aux = nullptr; p.out = y;
+    p.batch = batch; p.c_in = channels; p.c_out = channels;
+    p.h_in = 1; p.w_in = static_cast<int>(spatial); p.h_out = 1; p.w_out = static_cast<int>(spatial);
+    p.kh = p.kw = 1; p.stride = 1; p.pad = 0; p.transposed = 0;
+    p.K = channels;
+    p.in_transform = kind == 0 ? sc2::IN_ABS : sc2::IN_SQUARE;
+    p.epilogue = kind == 0 ? (inverse ? sc2::EP_GDN1_INV : sc2::EP_GDN1_FWD) : (inverse ? sc2::EP_GDN_INV : sc2::EP_GDN_FWD);
+    return sc2::launch_conv(p, sc2::as_stream(stream));
+}
+
+}  // extern "C"

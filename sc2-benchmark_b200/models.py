@@ -1,0 +1,259 @@
+"""CompressionModel and the two CompressAI zoo architectures on the path, with the CompressAI contract.
+
+Drop-in for `compressai.models.CompressionModel` (sc2bench/models/layer.py:4,346,401; backbone.py:4,154,276),
+`compressai.models.google.get_scale_table` (layer.py:5), `compressai.models.utils.update_registered_buffers`
+(layer.py:6,714-719) and `compressai.zoo.image.{bmshj2018_factorized,bmshj2018_hyperprior,model_architectures}`
+(sc2bench/models/registry.py:2,12-14,73).  `compress()` / `decompress()` run g_a / g_s and the coder through
+libsc2b200.so; `forward()` (training) stays differentiable torch.
+"""
+import math
+import warnings
+
+import torch
+from torch import nn
+
+from . import _native, ops
+from .entropy_models import EntropyBottleneck, GaussianConditional
+from .layers import GDN
+
+SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+def _resize_registered_buffer(module, buffer_name, state_dict_key, state_dict, policy, dtype):
+    new_size = state_dict[state_dict_key].size()
+    current = dict(module.named_buffers()).get(buffer_name)
+    if policy in ('resize_if_empty', 'resize'):
+        if current is None:
+            raise RuntimeError(f'buffer "{buffer_name}" was not registered')
+        if policy == 'resize' or current.numel() == 0:
+            current.resize_(new_size)
+    elif policy == 'register':
+        if current is not None:
+            raise RuntimeError(f'buffer "{buffer_name}" was already registered')
+        module.register_buffer(buffer_name, torch.zeros(new_size, dtype=dtype))
+    else:
+        raise ValueError(f'Invalid policy "{policy}"')
+
+
+def update_registered_buffers(module, module_name, buffer_names, state_dict, policy='resize_if_empty', dtype=torch.int):
+    """Resizes the (initially empty) CDF buffers so that a checkpoint's tables can be loaded into them."""
+    if not module:
+        return
+    valid = [n for n, _ in module.named_buffers()]
+    for name in buffer_names:
+        if name not in valid:
+            raise ValueError(f'Invalid buffer name "{name}"')
+    for name in buffer_names:
+        _resize_registered_buffer(module, name, f'{module_name}.{name}', state_dict, policy, dtype)
+
+
+def conv(in_channels, out_channels, kernel_size=5, stride=2):
+    return nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=kernel_size // 2)
+
+
+def deconv(in_channels, out_channels, kernel_size=5, stride=2):
+    return nn.ConvTranspose2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
+                              output_padding=stride - 1, padding=kernel_size // 2)
+
+
+def _single(v):
+    if isinstance(v, (tuple, list)):
+        if len(set(v)) != 1:
+            raise NotImplementedError('anisotropic stride / padding is not on the bottleneck path')
+        return int(v[0])
+    return int(v)
+
+
+def run_transform(seq, x, final_epilogue=_native.EPI_NONE, final_aux=None):
+    """Inference executor for an analysis / synthesis transform (an nn.Sequential of Conv2d / ConvTranspose2d /
+    GDN / GDN1 / ReLU): every layer is one libsc2b200 launch, ReLU folds into the conv before it, and the last
+    conv can take a fused epilogue (quantise-to-symbols, clamp)."""
+    ops.require_cuda(x, 'run_transform')
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        last = i == len(mods) - 1
+        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            if m.groups != 1 or _single(m.dilation) != 1:
+                raise NotImplementedError('grouped / dilated convolutions are not on the bottleneck path')
+            epi, aux = _native.EPI_NONE, None
+            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                epi = _native.EPI_RELU
+                i += 1
+                last = i == len(mods) - 1
+            if last and final_epilogue != _native.EPI_NONE:
+                if epi != _native.EPI_NONE:
+                    raise NotImplementedError('cannot stack two epilogues')
+                epi, aux = final_epilogue, final_aux
+            tr = isinstance(m, nn.ConvTranspose2d)
+            x = ops.conv2d(x, m.weight, m.bias, stride=_single(m.stride), padding=_single(m.padding), transposed=tr,
+                           output_padding=_single(m.output_padding) if tr else 0, epilogue=epi, aux=aux)
+        elif isinstance(m, GDN):
+            x = m(x)
+        elif isinstance(m, nn.ReLU):
+            x = torch.relu_(x) if x.is_floating_point() else x
+        else:
+            x = m(x)
+        i += 1
+    return x
+
+
+class CompressionModel(nn.Module):
+    """Base class holding entropy models; `update()`, `aux_loss()`, table-aware `load_state_dict()`."""
+
+    def __init__(self, entropy_bottleneck_channels=None, init_weights=None):
+        super().__init__()
+        if entropy_bottleneck_channels is not None:
+            # deprecated in CompressAI 1.2 but relied on by sc2bench (layer.py:356,409)
+            self.entropy_bottleneck = EntropyBottleneck(entropy_bottleneck_channels)
+        if init_weights is not None:
+            warnings.warn('init_weights was removed.', DeprecationWarning, stacklevel=2)
+
+    def load_state_dict(self, state_dict, strict=True):
+        for name, module in self.named_modules():
+            if not any(k.startswith(name) for k in state_dict.keys()):
+                continue
+            if isinstance(module, EntropyBottleneck):
+                update_registered_buffers(module, name, ['_quantized_cdf', '_offset', '_cdf_length'], state_dict)
+            if isinstance(module, GaussianConditional):
+                update_registered_buffers(module, name, ['_quantized_cdf', '_offset', '_cdf_length', 'scale_table'], state_dict)
+        return nn.Module.load_state_dict(self, state_dict, strict=strict)
+
+    def update(self, scale_table=None, force=False):
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = False
+        for _, module in self.named_modules():
+            if isinstance(module, EntropyBottleneck):
+                updated |= module.update(force=force)
+            if isinstance(module, GaussianConditional):
+                updated |= module.update_scale_table(scale_table, force=force)
+        return updated
+
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+
+class FactorizedPrior(CompressionModel):
+    """bmshj2018-factorized: g_a (4 conv, 3 GDN) -> EntropyBottleneck -> g_s (4 deconv, 3 IGDN)."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__(**kwargs)
+        self.entropy_bottleneck = EntropyBottleneck(M)
+        self.g_a = nn.Sequential(conv(3, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
+        self.g_s = nn.Sequential(deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True),
+                                 deconv(N, N), GDN(N, inverse=True), deconv(N, 3))
+        self.N, self.M = N, M
+
+    @property
+    def downsampling_factor(self):
+        return 2 ** 4
+
+    def forward(self, x):
+        y = self.g_a(x)
+        y_hat, y_likelihoods = self.entropy_bottleneck(y)
+        return {'x_hat': self.g_s(y_hat), 'likelihoods': {'y': y_likelihoods}}
+
+    @torch.no_grad()
+    def compress_packed(self, x):
+        eb = self.entropy_bottleneck
+        medians = eb._get_medians().detach().reshape(-1)
+        symbols = run_transform(self.g_a, x, final_epilogue=_native.EPI_QUANTIZE, final_aux=medians)
+        return eb.compress_symbols(symbols, spatial=symbols[0, 0].numel()), symbols.size()[-2:]
+
+    def compress(self, x):
+        streams, shape = self.compress_packed(x)
+        return {'strings': [streams.tolist()], 'shape': shape}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 1
+        first = strings[0]
+        streams = first if isinstance(first, ops.PackedStreams) else \
+            ops.PackedStreams.from_list(first, self.entropy_bottleneck._quantized_cdf.device)
+        y_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape))
+        return {'x_hat': run_transform(self.g_s, y_hat, final_epilogue=_native.EPI_CLAMP01)}
+
+
+class ScaleHyperprior(CompressionModel):
+    """bmshj2018-hyperprior: adds h_a / h_s and a Gaussian conditional whose scales are decoded from z."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__(**kwargs)
+        self.entropy_bottleneck = EntropyBottleneck(N)
+        self.g_a = nn.Sequential(conv(3, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
+        self.g_s = nn.Sequential(deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True),
+                                 deconv(N, N), GDN(N, inverse=True), deconv(N, 3))
+        self.h_a = nn.Sequential(conv(M, N, stride=1, kernel_size=3), nn.ReLU(inplace=True), conv(N, N),
+                                 nn.ReLU(inplace=True), conv(N, N))
+        self.h_s = nn.Sequential(deconv(N, N), nn.ReLU(inplace=True), deconv(N, N), nn.ReLU(inplace=True),
+                                 conv(N, M, stride=1, kernel_size=3), nn.ReLU(inplace=True))
+        self.gaussian_conditional = GaussianConditional(None)
+        self.N, self.M = int(N), int(M)
+
+    @property
+    def downsampling_factor(self):
+        return 2 ** (4 + 2)
+
+    def forward(self, x):
+        y = self.g_a(x)
+        z = self.h_a(torch.abs(y))
+        z_hat, z_likelihoods = self.entropy_bottleneck(z)
+        scales_hat = self.h_s(z_hat)
+        y_hat, y_likelihoods = self.gaussian_conditional(y, scales_hat)
+        return {'x_hat': self.g_s(y_hat), 'likelihoods': {'y': y_likelihoods, 'z': z_likelihoods}}
+
+    @torch.no_grad()
+    def compress(self, x):
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y = run_transform(self.g_a, x)
+        z_symbols = run_transform(self.h_a, torch.abs(y), final_epilogue=_native.EPI_QUANTIZE,
+                                  final_aux=eb._get_medians().detach().reshape(-1))
+        z_streams = eb.compress_symbols(z_symbols, spatial=z_symbols[0, 0].numel())
+        # the encoder decodes z itself so that both sides derive the scales from identical values
+        z_hat = eb.decompress_packed(z_streams, tuple(z_symbols.size()[-2:]))
+        indexes = gc.build_indexes(run_transform(self.h_s, z_hat))
+        y_symbols = ops.quantize_symbols(y.reshape(y.size(0), 1, -1))
+        y_streams = ops.rans_encode(y_symbols, gc.coder_tables(), indexes=indexes)
+        return {'strings': [y_streams.tolist(), z_streams.tolist()], 'shape': z_symbols.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 2
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        device = eb._quantized_cdf.device
+        z_hat = eb.decompress_packed(ops.PackedStreams.from_list(strings[1], device), tuple(shape))
+        indexes = gc.build_indexes(run_transform(self.h_s, z_hat))
+        y_streams = ops.PackedStreams.from_list(strings[0], device)
+        y_hat = ops.rans_decode(y_streams, indexes[0].numel(), gc.coder_tables(), indexes=indexes, want='values')
+        return {'x_hat': run_transform(self.g_s, y_hat.view(indexes.size()), final_epilogue=_native.EPI_CLAMP01)}
+
+
+# ---- zoo (compressai.zoo.image) --------------------------------------------------------------------
+_QUALITY_TO_NM = {q: (128, 192) for q in range(1, 6)}
+_QUALITY_TO_NM.update({q: (192, 320) for q in range(6, 9)})
+model_architectures = {'bmshj2018-factorized': FactorizedPrior, 'bmshj2018-hyperprior': ScaleHyperprior}
+
+
+def _zoo(arch, quality, metric, pretrained, **kwargs):
+    if metric not in ('mse', 'ms-ssim'):
+        raise ValueError(f'Invalid metric "{metric}"')
+    if quality not in _QUALITY_TO_NM:
+        raise ValueError(f'Invalid quality "{quality}", should be between (1, 8)')
+    if pretrained:
+        raise RuntimeError('pretrained CompressAI weights have to be downloaded; load a local checkpoint with '
+                           'load_state_dict() instead (no network access here)')
+    return model_architectures[arch](*_QUALITY_TO_NM[quality], **kwargs)
+
+
+def bmshj2018_factorized(quality, metric='mse', pretrained=False, progress=True, **kwargs):
+    return _zoo('bmshj2018-factorized', quality, metric, pretrained, **kwargs)
+
+
+def bmshj2018_hyperprior(quality, metric='mse', pretrained=False, progress=True, **kwargs):
+    return _zoo('bmshj2018-hyperprior', quality, metric, pretrained, **kwargs)

@@ -1,0 +1,313 @@
+"""Tensor-level front-end of the C ABI (include/sc2b200.h).
+
+PyTorch is used here for device memory (caching allocator), streams and pinned host buffers only; every
+computation below is a call into libsc2b200.so on the current CUDA stream.  There is no CPU fallback:
+a non-CUDA tensor on the hot path raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import ConvDesc, check
+
+
+def _lib():
+    return _native.load()
+
+
+# ---- launch accounting (bench.py reads these; cheap enough to keep on) ----------------------------
+STATS = {'launches': 0}
+_PROFILE = {'tags': None, 'events': []}
+
+
+def profile_kernels(tags):
+    """Bracket launches whose tag is in `tags` (or every launch for tags == 'all') with CUDA events on the launching
+    stream.  `profile_kernels(None)` turns it off.  Read the result with `profile_results()`."""
+    _PROFILE['tags'] = tags
+    _PROFILE['events'] = []
+
+
+def profile_results():
+    """{tag: [ms, ...]} -- call after a synchronize."""
+    out = {}
+    for tag, e0, e1 in _PROFILE['events']:
+        out.setdefault(tag, []).append(e0.elapsed_time(e1))
+    return out
+
+
+class _launch:
+    def __init__(self, tag, kernels=1):
+        self.tag, self.kernels, self.e0 = tag, kernels, None
+
+    def __enter__(self):
+        STATS['launches'] += self.kernels
+        tags = _PROFILE['tags']
+        if tags is not None and (tags == 'all' or self.tag in tags):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROFILE['events'].append((self.tag, self.e0, e1))
+        return False
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def require_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError('%s: the sc2bench_b200 hot path runs on CUDA tensors only (got %s); there is no CPU fallback'
+                           % (what, t.device if isinstance(t, torch.Tensor) else type(t)))
+
+
+# ----------------------------------------------------------------------------------------------
+# host: CDF quantisation (compressai._CXX.pmf_to_quantized_cdf)
+# ----------------------------------------------------------------------------------------------
+def pmf_to_quantized_cdf(pmf, precision=16):
+    """float pmf (sequence / 1-D tensor) -> torch.IntTensor CDF of len(pmf) + 1 entries."""
+    arr = np.ascontiguousarray(np.asarray(pmf.detach().cpu() if isinstance(pmf, torch.Tensor) else pmf, dtype=np.float32)).reshape(-1)
+    out = np.empty(arr.size + 1, dtype=np.uint32)
+    rc = _lib().sc2_pmf_to_quantized_cdf(arr.ctypes.data, arr.size, int(precision), out.ctypes.data)
+    if rc == -4:
+        raise ValueError('Invalid `pmf`: negative, non-finite or all-zero.')
+    check(rc, 'sc2_pmf_to_quantized_cdf')
+    return torch.from_numpy(out.astype(np.int32))
+
+
+# ----------------------------------------------------------------------------------------------
+# coder tables
+# ----------------------------------------------------------------------------------------------
+class CoderTables:
+    """Device-side coder tables built from CompressAI's (_quantized_cdf, _cdf_length, _offset) buffers."""
+
+    def __init__(self, quantized_cdf, cdf_length, offset):
+        cdf = np.ascontiguousarray(quantized_cdf.detach().cpu().numpy().astype(np.int32))
+        sizes = np.ascontiguousarray(cdf_length.detach().cpu().numpy().astype(np.int32).reshape(-1))
+        offs = np.ascontiguousarray(offset.detach().cpu().numpy().astype(np.int32).reshape(-1))
+        if cdf.ndim != 2:
+            raise ValueError(f'Invalid CDF size {tuple(cdf.shape)}')
+        if sizes.shape[0] != cdf.shape[0] or offs.shape[0] != cdf.shape[0]:
+            raise ValueError('Invalid CDF lengths / offsets size')
+        self.n_rows, self.cdf_stride = int(cdf.shape[0]), int(cdf.shape[1])
+        self.max_size = int(sizes.max())
+        nbytes = _lib().sc2_rans_table_bytes(self.n_rows, self.cdf_stride)
+        blob = np.zeros(nbytes, dtype=np.uint8)
+        rc = _lib().sc2_rans_build_tables(cdf.ctypes.data, sizes.ctypes.data, offs.ctypes.data, self.n_rows,
+                                          self.cdf_stride, blob.ctypes.data)
+        if rc == -1:
+            raise ValueError('Invalid CDF table (each row must start at 0, end at 65536 and be strictly increasing)')
+        check(rc, 'sc2_rans_build_tables')
+        self._blob = torch.from_numpy(blob)
+        self._on_device = {}
+
+    def on(self, device):
+        device = torch.device(device)
+        t = self._on_device.get(device)
+        if t is None:
+            t = self._blob.to(device)
+            self._on_device[device] = t
+        return t
+
+
+# ----------------------------------------------------------------------------------------------
+# packed bitstreams
+# ----------------------------------------------------------------------------------------------
+class PackedStreams:
+    """B CompressAI bitstreams held back to back in one device buffer (+ int64 offsets[B + 1]).
+
+    `tolist()` materialises the reference contract's `list[bytes]` with ONE D2H copy."""
+
+    def __init__(self, packed, offsets, batch, status=None, capacity=None):
+        self.packed, self.offsets, self.batch, self.status = packed, offsets, batch, status
+        self._host = None
+
+    def _to_host(self):
+        if self._host is None:
+            offs = self.offsets.cpu()  # sync point
+            if self.status is not None:
+                st = int(self.status.item())
+                if st & _native.FAULT_ARENA_OVERFLOW:
+                    raise RuntimeError('rANS encoder ran out of arena space (device fault flag)')
+            total = int(offs[-1])
+            host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+            host.copy_(self.packed[:total], non_blocking=False)
+            self._host = (offs.numpy(), host.numpy())
+        return self._host
+
+    def lengths(self):
+        offs, _ = self._to_host()
+        return np.diff(offs)
+
+    def total_bytes(self):
+        return int(self._to_host()[0][-1])
+
+    def tolist(self):
+        offs, data = self._to_host()
+        raw = data.tobytes()
+        return [raw[offs[i]:offs[i + 1]] for i in range(self.batch)]
+
+    @staticmethod
+    def from_list(strings, device):
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError('Invalid `strings` parameter type.')
+        lens = np.fromiter((len(s) for s in strings), dtype=np.int64, count=len(strings))
+        if len(strings) and ((lens < 8).any() or (lens & 3).any()):
+            raise ValueError('Invalid bitstream: a CompressAI rANS stream is a multiple of 4 bytes and >= 8 bytes long')
+        offs = np.zeros(len(strings) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        total = int(offs[-1])
+        host = torch.empty(max(total, 4), dtype=torch.uint8, pin_memory=True)
+        host.numpy()[:total] = np.frombuffer(b''.join(strings), dtype=np.uint8)
+        packed = host.to(device, non_blocking=True)
+        offsets = torch.from_numpy(offs).pin_memory().to(device, non_blocking=True)
+        ps = PackedStreams(packed, offsets, len(strings))
+        ps._keepalive = host
+        return ps
+
+
+# ----------------------------------------------------------------------------------------------
+# device ops
+# ----------------------------------------------------------------------------------------------
+def quantize_symbols(x, means=None):
+    """EntropyModel.quantize(x, "symbols", means) for x [B, C, *spatial]; means: [C] tensor or None."""
+    require_cuda(x, 'quantize_symbols')
+    x = x.contiguous().float()
+    B, C = x.shape[0], x.shape[1]
+    spatial = x[0, 0].numel() if x.dim() > 2 else 1
+    out = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+    m = means.contiguous().float() if means is not None else None
+    with torch.cuda.device(x.device), _launch('quantize_symbols'):
+        check(_lib().sc2_quantize_symbols(_ptr(x), _ptr(m), _ptr(out), B, C, spatial, _stream_ptr()), 'sc2_quantize_symbols')
+    return out
+
+
+def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None):
+    """symbols: int32 [B, n] (or [B, C, ...]) CUDA tensor -> PackedStreams."""
+    require_cuda(symbols, 'rans_encode')
+    dev = symbols.device
+    B = symbols.shape[0]
+    sym = symbols.contiguous().view(B, -1)
+    if sym.dtype != torch.int32:
+        sym = sym.int()
+    n = sym.shape[1]
+    idx = None
+    if indexes is not None:
+        idx = indexes.contiguous().view(B, -1)
+        if idx.dtype != torch.int32:
+            idx = idx.int()
+        if idx.shape != sym.shape:
+            raise ValueError('`inputs` and `indexes` should have the same size.')
+    elif spatial is None:
+        raise ValueError('channel mode needs `spatial` (symbols per channel)')
+    lib = _lib()
+    if slot_bytes is None:
+        slot_bytes = int(lib.sc2_rans_max_stream_bytes(n))
+    arena = torch.empty(max(B, 1) * slot_bytes, dtype=torch.uint8, device=dev)
+    lengths = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    packed = torch.empty(max(B, 1) * slot_bytes, dtype=torch.uint8, device=dev)
+    offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    tab = tables.on(dev)
+    with torch.cuda.device(dev):
+        st = _stream_ptr()
+        with _launch('rans_encode', 1 if B else 0):
+            check(lib.sc2_rans_encode_batch(_ptr(sym), _ptr(idx), B, n, int(spatial or 0), _ptr(tab), tables.n_rows,
+                                            tables.cdf_stride, _ptr(arena), slot_bytes, _ptr(lengths), _ptr(status), st),
+                  'sc2_rans_encode_batch')
+        with _launch('rans_pack', 2 if B else 1):
+            check(lib.sc2_rans_pack(_ptr(arena), slot_bytes, _ptr(lengths), B, _ptr(packed), _ptr(offsets), st), 'sc2_rans_pack')
+    return PackedStreams(packed, offsets, B, status)
+
+
+def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means=None, want='values', check_status=True):
+    """PackedStreams -> [B, n] float32 (symbol + means[row]) or int32 symbols."""
+    dev = streams.packed.device
+    B = streams.batch
+    idx = None
+    if indexes is not None:
+        require_cuda(indexes, 'rans_decode')
+        idx = indexes.contiguous().view(B, -1)
+        if idx.dtype != torch.int32:
+            idx = idx.int()
+    elif spatial is None:
+        raise ValueError('channel mode needs `spatial` (symbols per channel)')
+    out_sym = torch.empty((B, n_per_stream), dtype=torch.int32, device=dev) if want == 'symbols' else None
+    out_val = torch.empty((B, n_per_stream), dtype=torch.float32, device=dev) if want == 'values' else None
+    m = means.contiguous().float() if means is not None else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    tab = tables.on(dev)
+    with torch.cuda.device(dev), _launch('rans_decode', 1 if B and n_per_stream else 0):
+        check(_lib().sc2_rans_decode_batch(_ptr(streams.packed), _ptr(streams.offsets), B, n_per_stream, _ptr(idx),
+                                           int(spatial or 0), _ptr(tab), tables.n_rows, tables.cdf_stride, _ptr(out_sym),
+                                           _ptr(out_val), _ptr(m), _ptr(status), _stream_ptr()), 'sc2_rans_decode_batch')
+    if check_status:
+        st = int(status.item())
+        if st:
+            raise ValueError('Invalid bitstream (device fault flags 0x%x: %s)' % (st, ', '.join(
+                name for bit, name in ((2, 'stream truncated'), (4, 'bad stream length')) if st & bit)))
+    return out_sym if want == 'symbols' else out_val
+
+
+def gc_build_indexes(scales, scale_table, scale_bound):
+    require_cuda(scales, 'gc_build_indexes')
+    s = scales.contiguous().float()
+    out = torch.empty(s.shape, dtype=torch.int32, device=s.device)
+    tab = scale_table.to(s.device).contiguous().float()
+    with torch.cuda.device(s.device), _launch('gc_build_indexes'):
+        check(_lib().sc2_gc_build_indexes(_ptr(s), s.numel(), _ptr(tab), tab.numel(), float(scale_bound), _ptr(out),
+                                          _stream_ptr()), 'sc2_gc_build_indexes')
+    return out
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_padding=0, epilogue=_native.EPI_NONE, aux=None):
+    """fp32 NCHW conv / transposed conv with a fused epilogue (sc2_conv2d_f32)."""
+    require_cuda(x, 'conv2d')
+    x = x.contiguous().float()
+    w = weight.detach().contiguous().float()
+    B, Cin, H, W = x.shape
+    if transposed:
+        if w.shape[0] != Cin:
+            raise ValueError('weight / input channel mismatch')
+        Cout = w.shape[1]
+    else:
+        if w.shape[1] != Cin:
+            raise ValueError('weight / input channel mismatch (groups are not supported)')
+        Cout = w.shape[0]
+    d = ConvDesc(B, Cin, H, W, Cout, w.shape[2], w.shape[3], int(stride), int(padding), int(bool(transposed)),
+                 int(output_padding), int(epilogue))
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    check(_lib().sc2_conv_out_size(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)), 'sc2_conv_out_size')
+    out = torch.empty((B, Cout, ho.value, wo.value), dtype=torch.int32 if epilogue == _native.EPI_QUANTIZE else torch.float32,
+                      device=x.device)
+    b = bias.detach().contiguous().float() if bias is not None else None
+    a = aux.detach().contiguous().float() if aux is not None else None
+    tag = 'conv2d_f32[%d->%d,k%d,s%d%s]' % (Cin, Cout, w.shape[2], int(stride), ',T' if transposed else '')
+    with torch.cuda.device(x.device), _launch(tag):
+        check(_lib().sc2_conv2d_f32(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(a), _ptr(out), _stream_ptr()), 'sc2_conv2d_f32')
+    return out
+
+
+def gdn(x, gamma, beta, kind=0, inverse=False):
+    """GDN1 (kind 0) / GDN (kind 1) on NCHW fp32 with EFFECTIVE gamma [C, C] and beta [C]."""
+    require_cuda(x, 'gdn')
+    x = x.contiguous().float()
+    B, C = x.shape[0], x.shape[1]
+    spatial = x[0, 0].numel()
+    g = gamma.detach().reshape(C, C).contiguous().float()
+    b = beta.detach().contiguous().float()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device), _launch('gdn_f32[%d%s]' % (C, ',inv' if inverse else '')):
+        check(_lib().sc2_gdn_f32(_ptr(x), _ptr(g), _ptr(b), _ptr(out), B, C, spatial, int(kind), int(bool(inverse)),
+                                 _stream_ptr()), 'sc2_gdn_f32')
+    return out

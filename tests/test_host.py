@@ -1,0 +1,218 @@
+"""CPU: host-side logic of the product and the C-ABI surface (no GPU compute)."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+import cref
+from helpers import load_golden, state_dict_from_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def s2():
+    import sc2bench_b200
+    return sc2bench_b200
+
+
+def test_library_exports_every_declared_symbol(s2):
+    header = open(os.path.join(ROOT, 'include', 'sc2b200.h')).read()
+    declared = set(re.findall(r'SC2_API\s+[\w\s\*]+?\b(sc2_\w+)\s*\(', header))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(s2._native.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(s2._native.SIGNATURES), declared ^ set(s2._native.SIGNATURES)
+    assert lib.sc2_abi_version() == 1
+
+
+def test_pmf_to_quantized_cdf_matches_oracle(s2):
+    g = load_golden('rans_cases.npz')
+    for i in range(int(g['n_pmfs'])):
+        got = s2.ops.pmf_to_quantized_cdf(g['pmf%d' % i]).numpy().astype(np.int64)
+        assert (got == g['pmf%d_cdf' % i]).all()
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        n = rng.randint(2, 400)
+        pmf = (np.abs(rng.randn(n)) ** rng.randint(1, 8)).astype(np.float32)
+        pmf /= pmf.sum()
+        assert (s2.ops.pmf_to_quantized_cdf(pmf).numpy().astype(np.uint32) == cref.pmf_to_quantized_cdf(pmf)).all()
+    with pytest.raises(ValueError):
+        s2.ops.pmf_to_quantized_cdf(np.array([0.2, -1.0], np.float32))
+    with pytest.raises(ValueError):
+        s2.ops.pmf_to_quantized_cdf(np.zeros(3, np.float32))
+
+
+def test_entropy_bottleneck_tables_match_oracle(s2, oracle_compressai):
+    from compressai.entropy_models import EntropyBottleneck as OracleEB
+    g = load_golden('rans_cases.npz')
+    torch.manual_seed(0)
+    eb = s2.EntropyBottleneck(24)
+    assert eb.update() is True and eb.update() is False
+    assert (eb._quantized_cdf.numpy() == g['eb24_cdf']).all()
+    assert (eb._cdf_length.numpy() == g['eb24_len']).all() and (eb._offset.numpy() == g['eb24_off']).all()
+    # a "trained-looking" model: ragged table lengths, non-zero medians
+    small = load_golden('fp_bottleneck_small.npz')
+    sd = {k[len('entropy_bottleneck.'):]: v for k, v in state_dict_from_golden(small).items() if k.startswith('entropy_bottleneck.')}
+    mine, ref = s2.EntropyBottleneck(8), OracleEB(8)
+    for m in (mine, ref):
+        m.load_state_dict({k: v for k, v in sd.items() if not k.startswith('_')}, strict=False)
+        assert m.update(force=True)
+    for name in ('_quantized_cdf', '_cdf_length', '_offset'):
+        assert torch.equal(getattr(mine, name), getattr(ref, name)), name
+        assert torch.equal(getattr(mine, name), sd[name]), name
+    assert float(mine.loss().detach()) == pytest.approx(float(ref.loss().detach()), rel=1e-6)
+
+
+def test_gaussian_conditional_tables_match_oracle(s2):
+    g = load_golden('rans_cases.npz')
+    gc = s2.GaussianConditional(None)
+    assert gc.update_scale_table(s2.get_scale_table()) is True
+    assert gc.update_scale_table(s2.get_scale_table()) is False
+    assert tuple(gc._quantized_cdf.shape) == tuple(g['gc_cdf_shape'])
+    assert (gc._cdf_length.numpy() == g['gc_len']).all() and (gc._offset.numpy() == g['gc_off']).all()
+    import hashlib
+    assert hashlib.sha256(np.ascontiguousarray(gc._quantized_cdf.numpy()).tobytes()).hexdigest() == str(g['gc_cdf_sha256'])
+
+
+def _parse_blob(blob):
+    magic, n_rows, cdf_stride, dec_stride, meta_off, enc_off, dec_off, total = struct.unpack_from('<8i', blob, 0)
+    assert magic == 0x54523253 and total == len(blob)
+    meta = np.frombuffer(blob, np.int32, 2 * n_rows, meta_off)
+    enc = np.frombuffer(blob, np.uint32, n_rows * cdf_stride * 4, enc_off).reshape(n_rows, cdf_stride, 4)
+    dec = np.frombuffer(blob, np.int32, n_rows * dec_stride, dec_off).reshape(n_rows, dec_stride)
+    return n_rows, cdf_stride, meta[:n_rows], meta[n_rows:], enc, dec
+
+
+def test_encoder_reciprocals_divide_exactly(s2):
+    """q = mulhi64(x, rcp) >> shift must equal x // freq for every reachable state x < 2^63 (checked with Python ints)."""
+    g = load_golden('rans_cases.npz')
+    gc = s2.GaussianConditional(None)
+    gc.update_scale_table(s2.get_scale_table())
+    rng = np.random.RandomState(3)
+    for cdf, ln, off in ((g['eb24_cdf'], g['eb24_len'], g['eb24_off']),
+                         (gc._quantized_cdf.numpy(), gc._cdf_length.numpy(), gc._offset.numpy())):
+        t = s2.ops.CoderTables(torch.from_numpy(cdf), torch.from_numpy(ln), torch.from_numpy(off))
+        n_rows, stride, sizes, offsets, enc, dec = _parse_blob(t._blob.numpy().tobytes())
+        assert (sizes == ln).all() and (offsets == off).all()
+        rows = range(n_rows) if n_rows <= 24 else (0, 17, 40, 63)
+        for r in rows:
+            assert (dec[r, :sizes[r]] == cdf[r, :sizes[r]]).all() and (dec[r, sizes[r]:] == 0x7fffffff).all()
+            vs = range(sizes[r] - 1) if sizes[r] < 64 else rng.randint(0, sizes[r] - 1, size=64)
+            for v in vs:
+                rcp = int(enc[r, v, 0]) | (int(enc[r, v, 1]) << 32)
+                bias, shift, freq = int(enc[r, v, 2]) & 0x1ffff, (int(enc[r, v, 2]) >> 24) & 15, int(enc[r, v, 3])
+                start = int(cdf[r, v])
+                assert freq == int(cdf[r, v + 1]) - start
+                # the division is applied after renormalisation: x in [2^31, freq << 47) (or x >> 32 of such a state)
+                x_max = freq << 47
+                xs = [1 << 31, x_max - 1, x_max - freq, x_max // 2 + 1, freq, max(freq - 1, 1), (1 << 32) - 1, 1 << 32, (1 << 31) - 1]
+                xs += [int(x) % x_max for x in rng.randint(0, 2 ** 62, size=20, dtype=np.int64) * 2 + 1]
+                for x in xs:
+                    if x <= 0 or x >= x_max:
+                        continue
+                    q = ((x * rcp) >> 64) >> shift
+                    new = (x + bias + q * (65536 - freq)) & ((1 << 64) - 1)
+                    assert new == ((x // freq) << 16) + (x % freq) + start, (r, v, x)
+
+
+def test_table_builder_rejects_bad_tables(s2):
+    bad = torch.tensor([[0, 5, 5, 65536]], dtype=torch.int32)  # zero-width bin
+    with pytest.raises(ValueError):
+        s2.ops.CoderTables(bad, torch.tensor([4], dtype=torch.int32), torch.tensor([0], dtype=torch.int32))
+    bad2 = torch.tensor([[1, 5, 9, 65536]], dtype=torch.int32)  # does not start at 0
+    with pytest.raises(ValueError):
+        s2.ops.CoderTables(bad2, torch.tensor([4], dtype=torch.int32), torch.tensor([0], dtype=torch.int32))
+
+
+def test_state_dict_is_interchangeable_with_the_reference_layout(s2, oracle_compressai):
+    """A checkpoint written by the reference stack (oracle-backed here) loads into the product and back."""
+    small = load_golden('fp_bottleneck_small.npz')
+    sd = state_dict_from_golden(small)
+    layer = s2.get_layer('FPBasedResNetBottleneck', num_input_channels=3, num_bottleneck_channels=8, num_target_channels=32)
+    assert layer.updated is False
+    assert set(layer.state_dict().keys()) | {'entropy_bottleneck._quantized_cdf', 'entropy_bottleneck._cdf_length', 'entropy_bottleneck._offset'} == set(sd.keys())
+    layer.load_state_dict(sd)  # strict; CDF buffers are resized on the fly
+    assert tuple(layer.entropy_bottleneck._quantized_cdf.shape) == tuple(sd['entropy_bottleneck._quantized_cdf'].shape)
+    assert layer.update() is False  # tables came from the checkpoint -> early return, but the flag flips
+    assert layer.updated is True
+    out = layer.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(out[k], v), k
+    # legacy CompressAI <= 1.1 parameter names
+    legacy = {}
+    for k, v in sd.items():
+        m = re.match(r'entropy_bottleneck\.(matrices|biases|factors)\.(\d)$', k)
+        legacy['entropy_bottleneck._%s%s' % ({'matrices': 'matrix', 'biases': 'bias', 'factors': 'factor'}[m.group(1)], m.group(2)) if m else k] = v
+    layer2 = s2.get_layer('FPBasedResNetBottleneck', num_input_channels=3, num_bottleneck_channels=8, num_target_channels=32)
+    layer2.load_state_dict(legacy)
+    assert torch.equal(layer2.entropy_bottleneck.matrices[2], sd['entropy_bottleneck.matrices.2'])
+
+
+def test_registry_and_contract_surface(s2):
+    assert s2.get_layer('no_such_layer') is None
+    assert 'FPBasedResNetBottleneck' in s2.LAYER_CLASS_DICT
+    layer = s2.get_layer('FPBasedResNetBottleneck')
+    assert isinstance(layer, s2.CompressionModel) and isinstance(layer, s2.BaseBottleneck)
+    assert [type(m).__name__ for m in layer.encoder] == ['Conv2d', 'GDN1', 'Conv2d', 'GDN1', 'Conv2d']
+    assert [type(m).__name__ for m in layer.decoder] == ['Conv2d', 'GDN1', 'Conv2d', 'GDN1', 'Conv2d']
+    assert [m.weight.shape for m in layer.encoder if hasattr(m, 'weight')] == [(96, 3, 5, 5), (48, 96, 5, 5), (24, 48, 2, 2)]
+    assert [m.weight.shape for m in layer.decoder if hasattr(m, 'weight')] == [(512, 24, 2, 2), (256, 512, 2, 2), (256, 256, 2, 2)]
+    assert sum(p.numel() for n, p in layer.named_parameters() if not n.startswith('entropy_bottleneck')) == 1302704
+    assert sum(p.numel() for p in layer.entropy_bottleneck.parameters()) == 24 * 61
+    with pytest.raises(ValueError, match='Uninitialized CDFs'):
+        layer.entropy_bottleneck.coder_tables()
+    m = s2.splittable_resnet(bottleneck_config={'key': 'FPBasedResNetBottleneck', 'kwargs': {}}, resnet_name='resnet18',
+                             skips_avgpool=False, skips_fc=False, weights=None,
+                             analysis_config={'analyzes_after_compress': True, 'analyzer_configs': [{'key': 'FileSizeAnalyzer', 'kwargs': {'unit': 'KB'}}]})
+    assert s2.check_if_updatable(m) and m.get_aux_module() is m.bottleneck_layer
+    assert not m.bottleneck_updated
+    m.update()
+    assert m.bottleneck_updated and m.bottleneck_layer.updated
+    m.activate_analysis()
+    m.analyze({'strings': [[b'12345678']], 'shape': (1, 1)})
+    assert len(m.analyzers[0].file_size_list) == 1
+
+
+def test_training_branches_run_on_cpu_and_hot_path_refuses_cpu(s2):
+    torch.manual_seed(0)
+    layer = s2.get_layer('FPBasedResNetBottleneck', num_bottleneck_channels=4, num_target_channels=8)
+    x = torch.randn(2, 3, 32, 32, requires_grad=True)
+    layer.train()
+    y = layer(x)  # noise / likelihood branch
+    assert y.shape == (2, 8, 8, 8)
+    (y.sum() + layer.aux_loss()).backward()
+    y_hat, lik = layer.entropy_bottleneck(layer.encoder(x))
+    assert lik.shape == y_hat.shape and float(lik.min()) > 0
+    layer.update()
+    y2 = layer(x)  # fine-tuning branch: rounding, detached
+    assert y2.shape == y.shape
+    layer.eval()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        layer(x.detach())
+    with pytest.raises(RuntimeError, match='CUDA'):
+        layer.entropy_bottleneck.decompress([b'\x00' * 8], (7, 7))
+
+
+def test_forward_matches_oracle_in_training_mode(s2, oracle_compressai):
+    """The differentiable (torch) branches agree with the reference stack bit for bit on CPU."""
+    from compressai.layers import GDN1 as OracleGDN1
+    torch.manual_seed(3)
+    a, b = s2.GDN1(6), OracleGDN1(6)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(2, 6, 5, 5, requires_grad=True)
+    assert torch.equal(a(x), b(x))
+    ai, bi = s2.GDN(6, inverse=True), oracle_compressai.layers.GDN(6, inverse=True)
+    bi.load_state_dict(ai.state_dict())
+    assert torch.equal(ai(x), bi(x))
+    eb_a, eb_b = s2.EntropyBottleneck(6), oracle_compressai.entropy_models.EntropyBottleneck(6)
+    eb_b.load_state_dict(eb_a.state_dict())
+    eb_a.eval(), eb_b.eval()
+    ya, la = eb_a(x)
+    yb, lb = eb_b(x)
+    assert torch.equal(ya, yb) and torch.allclose(la, lb, rtol=0, atol=0)
