@@ -424,7 +424,8 @@ extern "C" {
 int sc2_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n_per_stream,
                           int64_t spatial, const void *tables, int n_rows, int cdf_stride, uint8_t *arena,
                           int64_t slot_bytes, int32_t *lengths, int32_t *status, sc2_stream_t stream) {
-    if (!symbols || !tables || !arena || !lengths || !status) return SC2_ERR_INVALID_ARG;
+    if (batch == 0) return SC2_OK;
+    if ((!symbols && n_per_stream > 0) || !tables || !arena || !lengths || !status) return SC2_ERR_INVALID_ARG;
     if (batch < 0 || n_per_stream < 0 || n_per_stream > 0x7fffffff || slot_bytes < 8 || (slot_bytes & 3)) return SC2_ERR_INVALID_ARG;
     if (!indexes && spatial < 1) return SC2_ERR_INVALID_ARG;
     if (batch == 0) return SC2_OK;

@@ -68,6 +68,7 @@ def _single(v):
     return int(v)
 
 
+@torch.no_grad()
 def run_transform(seq, x, final_epilogue=_native.EPI_NONE, final_aux=None):
     """Inference executor for an analysis / synthesis transform (an nn.Sequential of Conv2d / ConvTranspose2d /
     GDN / GDN1 / ReLU): every layer is one libsc2b200 launch, ReLU folds into the conv before it, and the last
@@ -94,7 +95,8 @@ def run_transform(seq, x, final_epilogue=_native.EPI_NONE, final_aux=None):
             x = ops.conv2d(x, m.weight, m.bias, stride=_single(m.stride), padding=_single(m.padding), transposed=tr,
                            output_padding=_single(m.output_padding) if tr else 0, epilogue=epi, aux=aux)
         elif isinstance(m, GDN):
-            x = m(x)
+            gamma, beta = m.effective_params()
+            x = ops.gdn(x, gamma, beta, kind=m._kind, inverse=m.inverse)
         elif isinstance(m, nn.ReLU):
             x = torch.relu_(x) if x.is_floating_point() else x
         else:

@@ -197,13 +197,13 @@ def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None):
     require_cuda(symbols, 'rans_encode')
     dev = symbols.device
     B = symbols.shape[0]
-    sym = symbols.contiguous().view(B, -1)
+    n = symbols[0].numel() if B else (symbols.numel() if symbols.dim() < 2 else int(np.prod(symbols.shape[1:])))
+    sym = symbols.contiguous().view(B, n)
     if sym.dtype != torch.int32:
         sym = sym.int()
-    n = sym.shape[1]
     idx = None
     if indexes is not None:
-        idx = indexes.contiguous().view(B, -1)
+        idx = indexes.contiguous().view(B, n)
         if idx.dtype != torch.int32:
             idx = idx.int()
         if idx.shape != sym.shape:
@@ -237,7 +237,7 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
     idx = None
     if indexes is not None:
         require_cuda(indexes, 'rans_decode')
-        idx = indexes.contiguous().view(B, -1)
+        idx = indexes.contiguous().view(B, n_per_stream)
         if idx.dtype != torch.int32:
             idx = idx.int()
     elif spatial is None:
