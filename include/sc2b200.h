@@ -155,6 +155,32 @@ SC2_API int sc2_conv2d_f32(const sc2_conv_desc *d, const float *x, const float *
 SC2_API int sc2_gdn_f32(const float *x, const float *gamma, const float *beta, float *y, int batch, int channels,
                 int64_t spatial, int kind, int inverse, sc2_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device: tensor-core (tcgen05 + TMEM + TMA) implicit-GEMM convolution on NHWC fp16 activations, stride 1.
+ * Used for g_s (sc2bench/models/layer.py:485-494), where fp16 operands with fp32 accumulation meet the 1e-3 bar.
+ *   x         [batch, h_in, w_in, c_in_pad] fp16, c_in_pad a multiple of 64 (zero-padded channels)
+ *   w_packed  [kh*kw, c_out, c_in_pad] fp16  (tap-major repack of the Conv2d weight; for the GDN modes: gamma [c, c])
+ *   out       [batch, h_out, w_out, c_out]  fp16 or fp32 (mode), h_out = h_in + 2*pad - kh + 1
+ *   modes     0 store fp16 | 1 store fp32 | 2 IGDN1: out = gdn_x * (beta + acc) | 3 GDN1: out = gdn_x / (beta + acc)
+ *             (GDN modes: 1x1 "gamma" GEMM over |x|, gdn_x = x itself, c_in_pad == c_out) */
+#define SC2_TC_STORE_F16 0
+#define SC2_TC_STORE_F32 1
+#define SC2_TC_IGDN1_F16 2
+#define SC2_TC_GDN1_F16 3
+
+typedef struct sc2_tc_conv_desc {
+    int batch, h_in, w_in, c_in_pad;
+    int c_out, kh, kw, pad;
+    int mode;
+} sc2_tc_conv_desc;
+
+SC2_API int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta,
+                             const void *gdn_x, void *out, sc2_stream_t stream);
+
+/* Device: NCHW fp32 -> NHWC fp16 with channels zero-padded to c_pad (even). */
+SC2_API int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, int64_t spatial, int c_pad,
+                                     sc2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,510 @@
+// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution for NHWC fp16 activations (sm_100a).
+//
+// The synthesis transform g_s of the bottleneck (sc2bench/models/layer.py:485-494: Conv 2x2 -> IGDN1 -> Conv 2x2 ->
+// IGDN1 -> Conv 2x2) is 86 % of the path's FLOPs and tolerates fp16 operands (fp32 accumulation; 4e-4 relative on the
+// decoded features), so it runs on the 5th-generation tensor cores:
+//
+//   GEMM view   M = output pixels (a TH x TW patch of one image = up to 128 rows), N = output channels (<= 256 per CTA),
+//               K = taps x input channels.
+//   A operand   no im2col: for tap (dy, dx) the A tile is the SAME activation tensor read through a 4-D TMA box
+//               {64 channels, TW, TH, 1} shifted by (dx - pad, dy - pad); TMA zero-fills outside the image = padding.
+//               The box lands in shared memory as 128-byte rows (K-major, SWIZZLE_128B), which is exactly the UMMA
+//               canonical layout.
+//   B operand   weights repacked once per model to [tap][c_out][c_in] fp16, 2-D TMA box {64, N_TILE}.
+//   D           fp32 accumulator in TMEM (N_TILE columns x 128 lanes), read back with tcgen05.ld by 4 epilogue warps.
+//   pipeline    warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue;
+//               STAGES-deep smem ring with full/empty mbarriers, tcgen05.commit releases stages.
+//   epilogues   store fp16 NHWC | store fp32 NHWC | IGDN1: out = x * (beta + gamma.|x|) where the GEMM is the 1x1
+//               "gamma" contraction, |x| is produced in shared memory by the (otherwise idle) epilogue warps right after
+//               the TMA lands (sign-bit clear), and x is re-read as a tile.  Output tiles go through swizzled smem and
+//               one TMA store per 128-byte channel group, so HBM writes are full lines and image borders are clipped
+//               by the TMA unit.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace sc2 {
+namespace tc {
+
+constexpr int kBlockK = 64;        // fp16 elements per 128-byte swizzle row
+constexpr int kTileM = 128;        // UMMA_M
+constexpr int kABytes = kTileM * 128;
+constexpr int kNumThreads = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+
+enum Mode { MODE_STORE_F16 = 0, MODE_STORE_F32 = 1, MODE_IGDN1_F16 = 2, MODE_GDN1_F16 = 3 };
+
+struct Params {
+    int tiles_x, tiles_y;  // output tile grid per image
+    int tw, th;            // tile = th rows x tw columns of output pixels (th * tw <= 128)
+    int taps_x, taps_y, pad;
+    int k_chunks;          // c_in_padded / 64
+    int n_total;           // c_out (rows per tap of the packed weight tensor)
+    const float *beta;     // GDN modes: effective beta [n_total]
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3ffff) >> 4);        // start address >> 4            bits [0, 14)
+    d |= static_cast<uint64_t>(0) << 16;                       // leading byte offset (unused)  bits [16, 30)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;               // stride byte offset = 1024     bits [32, 46)
+    d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (sm_100)   bits [46, 48)
+    d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B                  bits [61, 64)
+    return d;
+}
+
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(kTileM >> 4) << 24);
+}
+
+template <int N_TILE, int STAGES>
+struct Smem {
+    static constexpr int kBBytes = N_TILE * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kRingBytes = STAGES * kStageBytes;
+    static constexpr int kBarOffset = kRingBytes;
+    // full[STAGES], empty[STAGES], xform[STAGES], accum, xload : 8 bytes each; then the TMEM base address
+    static constexpr int kTotal = kRingBytes + (3 * STAGES + 2) * 8 + 16;
+};
+
+// ---- the kernel --------------------------------------------------------------------------------------------------
+template <int N_TILE, int STAGES, int MODE>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_x, const Params p) {
+    using L = Smem<N_TILE, STAGES>;
+    constexpr bool kGdn = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
+    constexpr bool kOutF32 = MODE == MODE_STORE_F32;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
+    uint64_t *empty = full + STAGES;
+    uint64_t *xform = empty + STAGES;
+    uint64_t *accum_bar = xform + STAGES;
+    uint64_t *xload_bar = accum_bar + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xload_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int x0 = (tile % p.tiles_x) * p.tw;
+    const int y0 = (tile / p.tiles_x) * p.th;
+    const int n0 = blockIdx.y * N_TILE;
+    const int img = blockIdx.z;
+    const int rows = p.tw * p.th;
+    const int n_iter = p.taps_x * p.taps_y * p.k_chunks;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_out);
+        if (kGdn) tma_prefetch_desc(&map_x);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&xform[s], 128);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_init(xload_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, N_TILE);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (elect_one()) {
+            const uint32_t stage_tx = static_cast<uint32_t>(rows * 128 + L::kBBytes);
+            int it = 0;
+            for (int ty = 0; ty < p.taps_y; ++ty)
+                for (int tx = 0; tx < p.taps_x; ++tx)
+                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        uint8_t *a_dst = smem + s * L::kStageBytes;
+                        mbar_expect_tx(&full[s], stage_tx);
+                        tma_load_4d(&map_a, &full[s], a_dst, kc * kBlockK, x0 + tx - p.pad, y0 + ty - p.pad, img);
+                        tma_load_2d(&map_b, &full[s], a_dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
+                    }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        constexpr uint32_t idesc = make_idesc(N_TILE);
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
+            mbar_wait(kGdn ? &xform[s] : &full[s], ph);
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+                const uint64_t a_desc = make_smem_desc(a_addr);
+                const uint64_t b_desc = make_smem_desc(a_addr + kABytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                    umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);                       // frees the stage once these MMAs have read it
+                if (it == n_iter - 1) umma_commit(accum_bar);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // =============================== epilogue warps (2..5) ===============================
+        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;      // tile row = TMEM lane = pixel index inside the tile
+        const bool row_ok = row < rows;
+        if (kGdn) {
+            // |x| in place: the A tile is the activation itself; clear the fp16 sign bits row by row
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                if (row_ok) {
+                    uint4 *r = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + row * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 v = r[c];
+                        v.x &= 0x7fff7fffu; v.y &= 0x7fff7fffu; v.z &= 0x7fff7fffu; v.w &= 0x7fff7fffu;
+                        r[c] = v;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&xform[s]);
+            }
+        }
+        mbar_wait(accum_bar, 0);
+        tcgen05_fence_after();
+        // all MMAs have completed: the smem ring is free and becomes the output staging area
+        constexpr int kSubCols = kOutF32 ? 32 : 64;           // channels per 128-byte staging row
+        constexpr int kSubTiles = N_TILE / kSubCols;
+        static_assert(kSubTiles * kABytes <= L::kRingBytes, "staging does not fit in the ring");
+        if (kGdn) {
+            if (threadIdx.x == 64) {
+                mbar_expect_tx(xload_bar, static_cast<uint32_t>(rows * 128 * kSubTiles));
+                for (int j = 0; j < kSubTiles; ++j)
+                    tma_load_4d(&map_x, xload_bar, smem + j * kABytes, n0 + j * 64, x0, y0, img);
+            }
+            mbar_wait(xload_bar, 0);
+        }
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + c0, v);
+            if (row_ok) {
+                if (kOutF32) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(smem + (c0 / 32) * kABytes + row * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        dst[c ^ (row & 7)] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                } else {
+                    uint4 *dst = reinterpret_cast<uint4 *>(smem + (c0 / 64) * kABytes + row * 128);
+                    const int chunk0 = (c0 % 64) / 8;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * c + e]);
+                        const int phys = (chunk0 + c) ^ (row & 7);
+                        if (kGdn) {
+                            const uint4 xv = dst[phys];
+                            const __half2 *xh = reinterpret_cast<const __half2 *>(&xv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 xf = __half22float2(xh[e]);
+                                const float b0 = __ldg(p.beta + n0 + c0 + 8 * c + 2 * e);
+                                const float b1 = __ldg(p.beta + n0 + c0 + 8 * c + 2 * e + 1);
+                                if (MODE == MODE_IGDN1_F16) {
+                                    f[2 * e] = xf.x * (f[2 * e] + b0);
+                                    f[2 * e + 1] = xf.y * (f[2 * e + 1] + b1);
+                                } else {
+                                    f[2 * e] = xf.x / (f[2 * e] + b0);
+                                    f[2 * e + 1] = xf.y / (f[2 * e + 1] + b1);
+                                }
+                            }
+                        }
+                        uint4 o;
+                        __half2 h;
+                        h = __floats2half2_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2half2_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2half2_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2half2_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t *>(&h);
+                        dst[phys] = o;
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        if (threadIdx.x == 64) {
+            for (int j = 0; j < kSubTiles; ++j) tma_store_4d(&map_out, smem + j * kABytes, n0 + j * kSubCols, x0, y0, img);
+            tma_store_commit_and_wait();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, N_TILE);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// NHWC tensor [batch, h, w, c] seen as 4-D {c, w, h, batch}; box {box_c, box_w, box_h, 1}, 128-byte swizzle.
+static int make_nhwc_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int elem_bytes, int c, int w, int h, int batch,
+                         int box_c, int box_w, int box_h) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return SC2_ERR_CUDA;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(batch)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * elem_bytes, static_cast<cuuint64_t>(w) * c * elem_bytes,
+                             static_cast<cuuint64_t>(h) * w * c * elem_bytes};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SC2_OK : SC2_ERR_INVALID_ARG;
+}
+
+static int make_weight_map(CUtensorMap *m, const void *base, int c_in_pad, int rows_total, int n_tile) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return SC2_ERR_CUDA;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(c_in_pad), static_cast<cuuint64_t>(rows_total)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(c_in_pad) * 2};
+    cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(n_tile)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SC2_OK : SC2_ERR_INVALID_ARG;
+}
+
+template <int N_TILE, int STAGES, int MODE>
+static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const CUtensorMap &mx, const Params &p,
+                  int n_tiles, int batch, cudaStream_t st) {
+    using L = Smem<N_TILE, STAGES>;
+    const int smem = L::kTotal + 1024;  // slack for the manual 1024-byte alignment
+    static bool configured = false;
+    if (!configured) {
+        SC2_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<N_TILE, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(p.tiles_x * p.tiles_y, n_tiles, batch);
+    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kNumThreads, smem, st>>>(ma, mb, mo, mx, p);
+    SC2_LAUNCH_CHECK("tc_conv_kernel");
+    return SC2_OK;
+}
+
+// NCHW fp32 -> NHWC fp16 with the channel dimension zero-padded to c_pad (feeds the first tensor-core layer).
+__global__ void nchw_f32_to_nhwc_f16_kernel(const float *__restrict__ x, __half *__restrict__ y, int c, int64_t hw, int c_pad,
+                                            int64_t total) {
+    // one thread per (pixel, channel pair); consecutive threads walk the padded channel dimension -> coalesced writes
+    const int pairs = c_pad / 2;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int cp = static_cast<int>(i % pairs);
+        const int64_t pix = i / pairs;          // b * hw + s
+        const int64_t b = pix / hw, sp = pix - b * hw;
+        const int c0 = 2 * cp;
+        const float v0 = c0 < c ? __ldg(x + (b * c + c0) * hw + sp) : 0.0f;
+        const float v1 = c0 + 1 < c ? __ldg(x + (b * c + c0 + 1) * hw + sp) : 0.0f;
+        reinterpret_cast<__half2 *>(y)[i] = __floats2half2_rn(v0, v1);
+    }
+}
+
+}  // namespace tc
+}  // namespace sc2
+
+extern "C" {
+
+int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, int64_t spatial, int c_pad, sc2_stream_t stream) {
+    if (!x || !y || batch < 0 || channels < 1 || c_pad < channels || (c_pad & 1) || spatial < 0) return SC2_ERR_INVALID_ARG;
+    const int64_t total = static_cast<int64_t>(batch) * spatial * (c_pad / 2);
+    if (total == 0) return SC2_OK;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > sc2::kNumSMs * 32) blocks = sc2::kNumSMs * 32;
+    sc2::tc::nchw_f32_to_nhwc_f16_kernel<<<static_cast<int>(blocks), 256, 0, sc2::as_stream(stream)>>>(
+        x, static_cast<__half *>(y), channels, spatial, c_pad, total);
+    SC2_LAUNCH_CHECK("nchw_f32_to_nhwc_f16_kernel");
+    return SC2_OK;
+}
+
+int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta, const void *gdn_x,
+                     void *out, sc2_stream_t stream) {
+    using namespace sc2::tc;
+    if (!d || !x || !w_packed || !out) return SC2_ERR_INVALID_ARG;
+    if (d->batch < 1 || d->batch > 65535 || d->c_in_pad % kBlockK || d->c_in_pad < kBlockK) return SC2_ERR_INVALID_ARG;
+    if (d->mode < 0 || d->mode > 3) return SC2_ERR_INVALID_ARG;
+    const bool gdn = d->mode == MODE_IGDN1_F16 || d->mode == MODE_GDN1_F16;
+    if (gdn && (!beta || !gdn_x || d->kh != 1 || d->kw != 1 || d->pad != 0 || d->c_in_pad != d->c_out)) return SC2_ERR_INVALID_ARG;
+    const int h_out = d->h_in + 2 * d->pad - d->kh + 1, w_out = d->w_in + 2 * d->pad - d->kw + 1;
+    if (h_out < 1 || w_out < 1) return SC2_ERR_INVALID_ARG;
+    // tile shape: tw columns x th rows, tw * th <= 128
+    int n_col_tiles = (w_out + 127) / 128;
+    int tw = (w_out + n_col_tiles - 1) / n_col_tiles;
+    tw = (tw + 7) / 8 * 8;
+    if (tw > 128) tw = 128;
+    int th = 128 / tw;
+    if (th > h_out) th = h_out;
+    if (th > 256) th = 256;
+    int n_tile;
+    if (d->c_out % 256 == 0) n_tile = 256;
+    else if (d->c_out % 128 == 0) n_tile = 128;
+    else if (d->c_out % 64 == 0) n_tile = 64;
+    else return SC2_ERR_UNSUPPORTED;
+    Params p;
+    p.tw = tw; p.th = th;
+    p.tiles_x = (w_out + tw - 1) / tw;
+    p.tiles_y = (h_out + th - 1) / th;
+    p.taps_x = d->kw; p.taps_y = d->kh; p.pad = d->pad;
+    p.k_chunks = d->c_in_pad / kBlockK;
+    p.n_total = d->c_out;
+    p.beta = beta;
+    CUtensorMap ma, mb, mo, mx;
+    int rc = make_nhwc_map(&ma, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in_pad, d->w_in, d->h_in, d->batch, kBlockK, tw, th);
+    if (rc) return rc;
+    rc = make_weight_map(&mb, w_packed, d->c_in_pad, d->kh * d->kw * d->c_out, n_tile);
+    if (rc) return rc;
+    if (d->mode == MODE_STORE_F32)
+        rc = make_nhwc_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->c_out, w_out, h_out, d->batch, 32, tw, th);
+    else
+        rc = make_nhwc_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_out, w_out, h_out, d->batch, 64, tw, th);
+    if (rc) return rc;
+    mx = mo;
+    if (gdn) {
+        rc = make_nhwc_map(&mx, gdn_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_out, w_out, h_out, d->batch, 64, tw, th);
+        if (rc) return rc;
+    }
+    cudaStream_t st = sc2::as_stream(stream);
+    const int n_tiles = d->c_out / n_tile;
+#define SC2_TC_DISPATCH(NT, STG)                                                                            \
+    switch (d->mode) {                                                                                      \
+        case MODE_STORE_F16: return launch<NT, STG, MODE_STORE_F16>(ma, mb, mo, mx, p, n_tiles, d->batch, st); \
+        case MODE_STORE_F32: return launch<NT, STG, MODE_STORE_F32>(ma, mb, mo, mx, p, n_tiles, d->batch, st); \
+        case MODE_IGDN1_F16: return launch<NT, STG, MODE_IGDN1_F16>(ma, mb, mo, mx, p, n_tiles, d->batch, st); \
+        default: return launch<NT, STG, MODE_GDN1_F16>(ma, mb, mo, mx, p, n_tiles, d->batch, st);           \
+    }
+    if (n_tile == 256) { SC2_TC_DISPATCH(256, 4) }
+    if (n_tile == 128) { SC2_TC_DISPATCH(128, 4) }
+    SC2_TC_DISPATCH(64, 4)
+#undef SC2_TC_DISPATCH
+}
+
+}  // extern "C"

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _native
-from ._native import ConvDesc, check
+from ._native import ConvDesc, TcConvDesc, check
 
 
 def _lib():
@@ -310,4 +310,48 @@ def gdn(x, gamma, beta, kind=0, inverse=False):
     with torch.cuda.device(x.device), _launch('gdn_f32[%d%s]' % (C, ',inv' if inverse else '')):
         check(_lib().sc2_gdn_f32(_ptr(x), _ptr(g), _ptr(b), _ptr(out), B, C, spatial, int(kind), int(bool(inverse)),
                                  _stream_ptr()), 'sc2_gdn_f32')
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core path (NHWC fp16)
+# ----------------------------------------------------------------------------------------------
+def pack_conv_weight_f16(weight, c_in_pad=None):
+    """Conv2d weight [c_out, c_in, kh, kw] -> [kh*kw, c_out, c_in_pad] fp16 (tap-major, K contiguous). Once per model."""
+    w = weight.detach().float()
+    c_out, c_in, kh, kw = w.shape
+    if c_in_pad is None:
+        c_in_pad = (c_in + 63) // 64 * 64
+    packed = torch.zeros((kh * kw, c_out, c_in_pad), dtype=torch.float16, device=w.device)
+    packed[:, :, :c_in] = w.permute(2, 3, 0, 1).reshape(kh * kw, c_out, c_in).half()
+    return packed.contiguous()
+
+
+def nchw_to_nhwc_f16(x, c_pad):
+    """fp32 NCHW -> fp16 NHWC with zero-padded channels: returns a [B, H, W, c_pad] tensor."""
+    require_cuda(x, 'nchw_to_nhwc_f16')
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    y = torch.empty((B, H, W, c_pad), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device), _launch('nchw_to_nhwc_f16'):
+        check(_lib().sc2_nchw_f32_to_nhwc_f16(_ptr(x), _ptr(y), B, C, H * W, c_pad, _stream_ptr()), 'sc2_nchw_f32_to_nhwc_f16')
+    return y
+
+
+def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None, gdn_x=None):
+    """tcgen05 implicit-GEMM conv on NHWC fp16 (sc2_tc_conv_nhwc). Returns NHWC fp16 / fp32."""
+    require_cuda(x_nhwc, 'tc_conv')
+    assert x_nhwc.dtype == torch.float16 and x_nhwc.is_contiguous() and w_packed.dtype == torch.float16
+    B, H, W, Cp = x_nhwc.shape
+    taps, c_out, cp2 = w_packed.shape
+    if taps != kh * kw or cp2 != Cp:
+        raise ValueError('packed weight does not match the activation / kernel size')
+    d = TcConvDesc(B, H, W, Cp, c_out, kh, kw, pad, mode)
+    ho, wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+    out = torch.empty((B, ho, wo, c_out), dtype=torch.float32 if mode == _native.TC_STORE_F32 else torch.float16, device=x_nhwc.device)
+    b = beta.detach().contiguous().float() if beta is not None else None
+    tag = 'tc_conv[%d->%d,k%d,m%d]' % (Cp, c_out, kh, mode)
+    with torch.cuda.device(x_nhwc.device), _launch(tag):
+        check(_lib().sc2_tc_conv_nhwc(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(b), _ptr(gdn_x), _ptr(out), _stream_ptr()),
+              'sc2_tc_conv_nhwc')
     return out
