@@ -38,7 +38,13 @@ LATENT = (24, 55, 55)
 FLOPS = {'conv2d_f32[3->96,k5,s2]': 180.6e6, 'gdn_f32[96]': 231.2e6, 'conv2d_f32[96->48,k5,s2]': 722.5e6,
          'gdn_f32[48]': 14.5e6, 'conv2d_f32[48->24,k2,s1]': 27.9e6, 'conv2d_f32[24->512,k2,s1]': 308.3e6,
          'gdn_f32[512,inv]': 1644.2e6, 'conv2d_f32[512->256,k2,s1]': 3172.0e6, 'gdn_f32[256,inv]': 396.5e6,
-         'conv2d_f32[256->256,k2,s1]': 1644.2e6}
+         'conv2d_f32[256->256,k2,s1]': 1644.2e6,
+         # tensor-core g_s (tags carry the PADDED input channels; FLOPs are the algorithmic ones)
+         'tc_conv[64->512,k2,m0]': 308.3e6, 'tc_conv[512->512,k1,m2]': 1644.2e6, 'tc_conv[512->256,k2,m0]': 3172.0e6,
+         'tc_conv[256->256,k1,m2]': 396.5e6, 'tc_conv[256->256,k2,m1]': 1644.2e6}
+# algorithmic HBM bytes per image of the non-GEMM kernels
+BYTES = {'rans_encode': 290400 + 49240, 'rans_decode': 49240 + 290400, 'rans_pack': 2 * 49240,
+         'nchw_to_nhwc_f16': 290400 + 55 * 55 * 64 * 2}
 PATH_FLOPS_PER_IMAGE = 8.342e9
 PATH_BYTES_PER_IMAGE = 34.85e6
 
@@ -200,14 +206,13 @@ def main():
         return streams, layer.decode_packed(streams, shape)
 
     # ---- device-resident throughput ("value") -------------------------------------------------
-    dominant = 'conv2d_f32[512->256,k2,s1]'
     with torch.inference_mode():
         for i in range(args.warmup):
             device_step(i)
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        s2.ops.profile_kernels({dominant})
+        s2.ops.profile_kernels('all')  # two event records per launch: ~30 launches per multi-ms step
         launches0 = s2.ops.STATS['launches']
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -266,16 +271,35 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel --------------------------------------------------------
-    k_ms = prof.get(dominant, [])
+    # ---- per-kernel accounting and the roofline of the dominant kernel ---------------------------
+    step_ms = ms / args.steps
+    kernels = []
+    for tag, times in prof.items():
+        avg = sum(times) / len(times)
+        per_step = sum(times) / args.steps
+        k = {'kernel': tag, 'launches_per_step': len(times) / args.steps, 'avg_launch_ms': avg, 'share_of_step': per_step / step_ms}
+        if tag in FLOPS:
+            k.update(bound='tensor', achieved=FLOPS[tag] * B / (avg / 1e3) / 1e12, unit='TFLOP/s', peak=peaks['tflops_sustained'])
+        elif tag in BYTES:
+            k.update(bound='hbm', achieved=BYTES[tag] * B / (avg / 1e3) / 1e9, unit='GB/s', peak=peaks['hbm_gbs'])
+        if 'achieved' in k:
+            k['frac'] = k['achieved'] / k['peak']
+        if tag in ('rans_encode', 'rans_decode'):
+            k['symbols_per_s_per_stream'] = n_sym / (avg / 1e3)
+            k['symbols_per_s_aggregate'] = n_sym * B / (avg / 1e3)
+            k['note'] = 'serial rANS state chain per stream: latency-bound, neither roofline applies (SURVEY.md H1)'
+        kernels.append(k)
+    kernels.sort(key=lambda k: -k['share_of_step'])
     roofline = None
-    if k_ms:
-        avg_ms = sum(k_ms) / len(k_ms)
-        achieved = FLOPS[dominant] * B / (avg_ms / 1e3) / 1e12
-        roofline = {'kernel': dominant, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': achieved / peaks['tflops_sustained'], 'traffic': None, 'peak_source': peaks['source'] + ', bf16 sustained',
-                    'avg_launch_ms': avg_ms, 'share_of_step': avg_ms / (ms / args.steps),
-                    'note': 'exact-fp32 CUDA-core implicit GEMM (round-1 path); algorithmic FLOPs = 2*MAC of SURVEY.md App. B x batch'}
+    if kernels:
+        top = kernels[0]
+        roofline = {'kernel': top['kernel'], 'bound': top.get('bound'), 'achieved': top.get('achieved'), 'peak': top.get('peak'),
+                    'unit': top.get('unit'), 'frac': top.get('frac'), 'traffic': None,
+                    'peak_source': peaks['source'] + (', bf16 sustained' if top.get('bound') == 'tensor' else ', copy bandwidth'),
+                    'avg_launch_ms': top['avg_launch_ms'], 'share_of_step': top['share_of_step'], 'note': top.get('note')}
+        gemm = [k for k in kernels if k.get('bound') == 'tensor']
+        if gemm and gemm[0] is not top:
+            roofline['dominant_gemm'] = {kk: gemm[0][kk] for kk in ('kernel', 'achieved', 'unit', 'peak', 'frac', 'avg_launch_ms', 'share_of_step')}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -287,7 +311,8 @@ def main():
                                   % (args.cpu_images, r['threads'])}
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (g_a, exact) / f16 operands with f32 accumulate (g_s) / u64 (coder)',
             'data': 'synthetic',
             'config': {'workload': 'configs[1]: entropic-student-resnet50 FPBasedResNetBottleneck(24,256) encode+rANS+decode, '
                                    '3x224x224, random init, batch %d per GPU' % B,
@@ -295,6 +320,7 @@ def main():
                        'l2_policy': 'two alternating 154 MB input batches (> 126 MB L2); activations are GBs per step',
                        'parallelism': 'dp%d (batch sharded, one counter all-reduce per evaluation)' % world},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'kernels': kernels,
             'bytes_per_image': c['bytes_per_image'], 'bits_per_symbol': c['bits_per_symbol'],
             'path_tflops': value * PATH_FLOPS_PER_IMAGE / 1e12, 'path_hbm_gbs_algorithmic': value * PATH_BYTES_PER_IMAGE / 1e9}
     print(json.dumps(line), flush=True)

@@ -17,6 +17,65 @@ from . import _native, ops
 from .layers import GDN1
 from .models import CompressionModel, run_transform
 
+
+
+class TensorCoreTransform:
+    """Execution plan that runs a stride-1 `Conv2d / GDN1` transform (the bottleneck's synthesis transform g_s) on the
+    tcgen05 kernels: activations NHWC fp16 between layers, fp32 accumulation in TMEM, GDN1 fused with its 1x1 gamma
+    GEMM, last layer written as fp32.  Weights are repacked once and re-packed when the parameters change."""
+
+    def __init__(self, seq):
+        self.seq = seq
+        self._key = None
+        self._steps = None
+
+    @staticmethod
+    def supports(seq):
+        mods = list(seq)
+        if not mods or not isinstance(mods[-1], nn.Conv2d):
+            return False
+        for m in mods:
+            if isinstance(m, nn.Conv2d):
+                k = m.kernel_size
+                if (m.bias is not None or m.groups != 1 or tuple(m.stride) != (1, 1) or tuple(m.dilation) != (1, 1)
+                        or k[0] != k[1] or m.padding[0] != m.padding[1] or isinstance(m.padding, str) or m.out_channels % 64):
+                    return False
+            elif type(m) is GDN1:
+                if m.beta.numel() % 64:
+                    return False
+            else:
+                return False
+        return True
+
+    def _prepare(self):
+        params = [p for p in self.seq.parameters()]
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        if key == self._key:
+            return
+        steps, mods = [], list(self.seq)
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Conv2d):
+                c_in_pad = (m.in_channels + 63) // 64 * 64
+                mode = _native.TC_STORE_F32 if i == len(mods) - 1 else _native.TC_STORE_F16
+                steps.append(('conv', ops.pack_conv_weight_f16(m.weight, c_in_pad), m.kernel_size[0], m.padding[0], mode, None))
+            else:
+                gamma, beta = m.effective_params()
+                C = beta.numel()
+                mode = _native.TC_IGDN1_F16 if m.inverse else _native.TC_GDN1_F16
+                steps.append(('gdn', gamma.detach().reshape(1, C, C).half().contiguous(), 1, 0, mode, beta.detach().float().contiguous()))
+        self._steps, self._key = steps, key
+        self.c_in_pad = (mods[0].in_channels + 63) // 64 * 64
+
+    @torch.no_grad()
+    def __call__(self, x_nchw):
+        """fp32 NCHW in -> fp32 output, logically NCHW (physically channels-last: what cuDNN prefers for the tail)."""
+        self._prepare()
+        x = ops.nchw_to_nhwc_f16(x_nchw, self.c_in_pad)
+        for kind, w, k, pad, mode, beta in self._steps:
+            x = ops.tc_conv(x, w, k, k, pad, mode=mode, beta=beta, gdn_x=x if kind == 'gdn' else None)
+        return x.permute(0, 3, 1, 2)
+
+
 LAYER_CLASS_DICT = dict()
 LAYER_FUNC_DICT = dict()
 
@@ -110,6 +169,10 @@ class FPBasedResNetBottleneck(BaseBottleneck):
             nn.Conv2d(d[0], d[1], kernel_size=2, stride=1, padding=1, bias=False), GDN1(d[1], inverse=True),
             nn.Conv2d(d[1], d[2], kernel_size=2, stride=1, padding=0, bias=False), GDN1(d[2], inverse=True),
             nn.Conv2d(d[2], d[3], kernel_size=2, stride=1, padding=1, bias=False))
+        # 'fp16-tc': tcgen05 tensor-core kernels (fp16 operands, fp32 accumulate; the 1e-3 feature tolerance);
+        # 'fp32': exact-fp32 CUDA-core kernels.  Shapes the tensor-core kernels do not cover use 'fp32'.
+        self.decoder_precision = 'fp16-tc'
+        self._tc_decoder = None
 
     # ---- hot path ---------------------------------------------------------------------------------
     @torch.no_grad()
@@ -121,9 +184,18 @@ class FPBasedResNetBottleneck(BaseBottleneck):
         return eb.compress_symbols(symbols, spatial=symbols[0, 0].numel()), symbols.size()[-2:]
 
     @torch.no_grad()
+    def synthesize(self, latent_hat):
+        """g_s on the device: dequantised latent (fp32 NCHW) -> decoder features."""
+        if self.decoder_precision == 'fp16-tc' and TensorCoreTransform.supports(self.decoder):
+            if self._tc_decoder is None:
+                self._tc_decoder = TensorCoreTransform(self.decoder)
+            return self._tc_decoder(latent_hat)
+        return run_transform(self.decoder, latent_hat)
+
+    @torch.no_grad()
     def decode_packed(self, streams, shape):
         latent_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape))
-        return run_transform(self.decoder, latent_hat)
+        return self.synthesize(latent_hat)
 
     def encode(self, x, **kwargs):
         """-> {'strings': [list of B bytes objects], 'shape': latent (H, W)}  (reference contract, layer.py:496-507)"""

@@ -432,6 +432,9 @@ int sc2_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int ba
     cudaStream_t st = sc2::as_stream(stream);
     if (n_rows < 1 || cdf_stride < 2) return SC2_ERR_INVALID_ARG;
     if (!indexes && (n_per_stream + spatial - 1) / spatial > n_rows) return SC2_ERR_INVALID_ARG;
+    if (!indexes && spatial <= 0x7fffffff)
+        return sc2::launch_rans_encode_fast(symbols, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, arena, slot_bytes,
+                                            lengths, status, st);
     const size_t chunk = sc2::kWarpsPerBlock * (32 * 16 + 32 * 4);
     size_t smem = chunk;
     const size_t table_bytes = static_cast<size_t>(n_rows) * cdf_stride * 16;
@@ -477,6 +480,9 @@ int sc2_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, int bat
     cudaStream_t st = sc2::as_stream(stream);
     if (n_rows < 1 || cdf_stride < 2) return SC2_ERR_INVALID_ARG;
     if (!indexes && (n_per_stream + spatial - 1) / spatial > n_rows) return SC2_ERR_INVALID_ARG;
+    if (!indexes && spatial <= 0x7fffffff)
+        return sc2::launch_rans_decode_fast(packed, offsets, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, out_symbols,
+                                            out_values, means, status, st);
     size_t smem = sc2::kWarpsPerBlock * sc2::kRing * 4;
     const size_t table_bytes = static_cast<size_t>(n_rows) * ((cdf_stride + 31) / 32 * 32) * 4;
     if (table_bytes + smem <= 96 * 1024) smem += table_bytes;

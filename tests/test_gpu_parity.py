@@ -334,8 +334,13 @@ def test_batch256_path_properties(s2, dev):
         assert torch.equal(back.view_as(symbols), symbols)
         out = layer.decode_packed(streams, shape)
         assert out.shape == (256, 256, 56, 56)
-        direct = s2.models.run_transform(layer.decoder, symbols.float() + med.view(1, -1, 1, 1))
+        direct = layer.synthesize(symbols.float() + med.view(1, -1, 1, 1))
         assert torch.equal(out, direct)
+        # the tensor-core g_s (fp16 operands) against the exact-fp32 CUDA-core g_s at full size
+        layer.decoder_precision = 'fp32'
+        exact = layer.synthesize(symbols[:32].float() + med.view(1, -1, 1, 1))
+        layer.decoder_precision = 'fp16-tc'
+        assert rel_err(out[:32], exact) < FEATURE_TOL
         # sample 17 alone gives the same bytes and features as inside the batch
         s17, _ = layer.encode_packed(x[17:18])
         assert s17.tolist()[0] == streams.tolist()[17]
