@@ -177,6 +177,36 @@ typedef struct sc2_tc_conv_desc {
 SC2_API int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta,
                              const void *gdn_x, void *out, sc2_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device: fp32-grade tensor-core convolution ("split fp16", three tcgen05 passes; conv_tc_split.cu) for g_a
+ * (sc2bench/models/layer.py:475-484).  Every tensor is a pair of fp16 planes (hi, lo): value = hi + lo / 2048.
+ *   x_hi/x_lo   stride 1: [images, h_in, w_in, c_in]; stride 2: PARITY PLANES [images * 4, h_in, w_in, c_in] where
+ *               plane py*2+px holds input pixel (2Y+py, 2X+px) at (Y, X)   (h_in, w_in = plane geometry)
+ *   w_hi/w_lo   [kh*kw, n_tile, c_in] tap-major packed weights, n_tile = sc2_tc_split_n_tile(c_out), extra rows zero
+ *   modes       0 store split planes [images, h_out, w_out, out_c] | 1 GDN1 forward (1x1: w = gamma, gdn_x = x itself)
+ *               | 2 quantise: int32(rint(y - medians[c])) to out_sym in NCHW (coder) order
+ *   c_in        multiple of 16 (zero-pad the patches / weights) */
+#define SC2_TCS_STORE 0
+#define SC2_TCS_GDN1 1
+#define SC2_TCS_QUANT 2
+
+typedef struct sc2_tc_split_desc {
+    int images, h_in, w_in, c_in;
+    int c_out, kh, kw, stride, pad;
+    int mode;
+    int h_out, w_out, out_c;
+} sc2_tc_split_desc;
+
+SC2_API int sc2_tc_split_n_tile(int c_out);
+SC2_API int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *x_lo, const void *w_hi,
+                              const void *w_lo, const float *beta, const float *medians, const void *gdn_x_hi,
+                              const void *gdn_x_lo, void *out_hi, void *out_lo, int32_t *out_sym, sc2_stream_t stream);
+
+/* Device: im2col of an fp32 NCHW image for the first (c_in = 3) layer: split fp16 patches, K = (c, dy, dx) zero-padded
+ * to k_pad, pixels in parity-plane order [batch * 4, h_out/2, w_out/2, k_pad] (h_out, w_out must be even). */
+SC2_API int sc2_patchify_split(const float *x, void *out_hi, void *out_lo, int batch, int c_in, int h_in, int w_in,
+                               int kh, int kw, int stride, int pad, int k_pad, sc2_stream_t stream);
+
 /* Device: NCHW fp32 -> NHWC fp16 with channels zero-padded to c_pad (even). */
 SC2_API int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, int64_t spatial, int c_pad,
                                      sc2_stream_t stream);

@@ -23,6 +23,12 @@ class TcConvDesc(_c.Structure):
     _fields_ = [(n, i32) for n in ('batch', 'h_in', 'w_in', 'c_in_pad', 'c_out', 'kh', 'kw', 'pad', 'mode')]
 
 
+class TcSplitDesc(_c.Structure):
+    """struct sc2_tc_split_desc"""
+    _fields_ = [(n, i32) for n in ('images', 'h_in', 'w_in', 'c_in', 'c_out', 'kh', 'kw', 'stride', 'pad', 'mode',
+                                    'h_out', 'w_out', 'out_c')]
+
+
 # name -> (restype, argtypes): every symbol include/sc2b200.h declares
 SIGNATURES = {
     'sc2_abi_version': (i32, []),
@@ -42,12 +48,16 @@ SIGNATURES = {
     'sc2_gdn_f32': (i32, [vp, vp, vp, vp, i32, i32, i64, i32, i32, vp]),
     'sc2_tc_conv_nhwc': (i32, [_c.POINTER(TcConvDesc), vp, vp, vp, vp, vp, vp]),
     'sc2_nchw_f32_to_nhwc_f16': (i32, [vp, vp, i32, i32, i64, i32, vp]),
+    'sc2_tc_split_n_tile': (i32, [i32]),
+    'sc2_tc_split_conv': (i32, [_c.POINTER(TcSplitDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sc2_patchify_split': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
 }
 
 SC2_OK = 0
 FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM = 1, 2, 4
 EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS = 0, 1, 2, 3, 4
 TC_STORE_F16, TC_STORE_F32, TC_IGDN1_F16, TC_GDN1_F16 = 0, 1, 2, 3
+TCS_STORE, TCS_GDN1, TCS_QUANT = 0, 1, 2
 
 _lib = None
 

@@ -1,0 +1,438 @@
+// conv_tc_split.cu -- fp32-grade implicit-GEMM convolution on the tcgen05 tensor cores ("split fp16", 3 MMA passes).
+//
+// The analysis transform g_a (sc2bench/models/layer.py:475-484) feeds round(y - median): a latent error flips symbols,
+// so g_a needs fp32-grade arithmetic while fp16/bf16/tf32 single-pass tensor-core math is 1e-3..1e-4.
+// Here every operand a is carried as two fp16 numbers, a = hi + lo / 2048 with hi = fp16(a), lo = fp16((a - hi) * 2048)
+// (22 mantissa bits; the 2^11 scale keeps lo in fp16's normal range), and a product sum is evaluated as
+//     D0 = sum hi_a hi_b,   D1 = sum (hi_a lo_b + lo_a hi_b),   result = D0 + D1 / 2048        (lo_a lo_b ~ 2^-22 dropped)
+// with three tcgen05.mma (kind::f16, fp32 accumulation in TMEM) per K step into two accumulators.  A CPU emulation
+// gives 1.8e-7 latent error on the Entropic-Student encoder (torch's own fp32: 3.6e-7) and no symbol mismatch.
+//
+// Same structure as conv_tc.cu: A tiles are shifted 4-D TMA boxes of the NHWC activation planes (hi and lo),
+// B tiles are 2-D boxes of the tap-major packed weights (hi and lo), one elected thread issues the MMAs.
+// Stride-2 convolutions read PARITY PLANES: the producer of their input writes pixel (2Y+py, 2X+px) to plane py*2+px at
+// (Y, X), so tap (dy, dx) of a stride-2 conv is again a unit-stride shifted box of one plane.
+// Epilogues (thread = output pixel, straight from TMEM): store split | GDN1 (x / (beta + gamma.|x|), |x| formed in smem
+// by the epilogue warps on both halves) | quantise to int32 symbols in coder (NCHW) order.
+#include "tc_common.cuh"
+
+namespace sc2 {
+namespace tcs {
+
+using namespace sc2::tc;
+
+constexpr int kNumThreads = 192;
+constexpr int kMaxTaps = 25;
+constexpr float kLoScale = 2048.0f;
+constexpr float kLoInv = 1.0f / 2048.0f;
+// TMEM: 512 columns.  The hi*hi sum D0 is spread over up to 6 accumulators ("groups" of taps) that are added in fp32 by the
+// epilogue: tcgen05 accumulation truncates, so one accumulator over K = 2400 (150 K-steps) loses ~3e-6; chunked
+// summation brings it back to FFMA-grade.  The cross terms D1 are 2^-11 smaller and share one accumulator.
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kD1Col = 384;
+
+enum Mode { MODE_STORE_SPLIT = 0, MODE_GDN1_SPLIT = 1, MODE_QUANT = 2 };
+
+struct Tap {
+    int8_t plane, dx, dy, pad_;
+};
+
+struct Params {
+    int tiles_x, tiles_y, tw, th;
+    int n_taps;
+    Tap taps[kMaxTaps];
+    int k_chunks, k_steps_last;
+    int groups;        // D0 accumulator groups (taps are dealt to groups in order)
+    int planes;        // input planes per output image (1, or 4 parity planes)
+    int c_out;         // valid output channels (<= N_TILE)
+    int h_out, w_out;
+    const float *beta;
+    const float *medians;
+    __half *out_hi, *out_lo;
+    int out_c;         // channel pitch of the output planes
+    int32_t *out_sym;
+    const __half *x_hi, *x_lo;
+};
+
+template <int N_TILE, int STAGES>
+struct Smem {
+    static constexpr int kBBytes = N_TILE * 128;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr int kRingBytes = STAGES * kStageBytes;
+    static constexpr int kTotal = kRingBytes + (3 * STAGES + 1) * 8 + 16;
+};
+
+__device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr, __half *lo_ptr) {
+    uint4 h, l;
+    uint32_t *hw = reinterpret_cast<uint32_t *>(&h), *lw = reinterpret_cast<uint32_t *>(&l);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn((f[2 * e] - back.x) * kLoScale, (f[2 * e + 1] - back.y) * kLoScale);
+        hw[e] = *reinterpret_cast<const uint32_t *>(&hh);
+        lw[e] = *reinterpret_cast<const uint32_t *>(&ll);
+    }
+    *reinterpret_cast<uint4 *>(hi_ptr) = h;
+    *reinterpret_cast<uint4 *>(lo_ptr) = l;
+}
+
+template <int N_TILE, int STAGES, int MODE>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                     const __grid_constant__ Params p) {
+    using L = Smem<N_TILE, STAGES>;
+    constexpr bool kGdn = MODE == MODE_GDN1_SPLIT;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kRingBytes);
+    uint64_t *empty = full + STAGES;
+    uint64_t *xform = empty + STAGES;
+    uint64_t *accum_bar = xform + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int x0 = (tile % p.tiles_x) * p.tw;
+    const int y0 = (tile / p.tiles_x) * p.th;
+    const int img = blockIdx.z;
+    const int rows = p.tw * p.th;
+    const int n_iter = p.n_taps * p.k_chunks;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&xform[s], 128);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (elect_one()) {
+            const uint32_t stage_tx = static_cast<uint32_t>(2 * rows * 128 + 2 * L::kBBytes);
+            int it = 0;
+            for (int t = 0; t < p.n_taps; ++t) {
+                const Tap tap = p.taps[t];
+                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    uint8_t *dst = smem + s * L::kStageBytes;
+                    mbar_expect_tx(&full[s], stage_tx);
+                    const int cx = x0 + tap.dx, cy = y0 + tap.dy, cz = img * p.planes + tap.plane;
+                    tma_load_4d(&map_a_hi, &full[s], dst, kc * kBlockK, cx, cy, cz);
+                    tma_load_4d(&map_a_lo, &full[s], dst + kABytes, kc * kBlockK, cx, cy, cz);
+                    tma_load_2d(&map_b_hi, &full[s], dst + 2 * kABytes, kc * kBlockK, t * N_TILE);
+                    tma_load_2d(&map_b_lo, &full[s], dst + 2 * kABytes + L::kBBytes, kc * kBlockK, t * N_TILE);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        constexpr uint32_t idesc = make_idesc(N_TILE);
+        constexpr uint32_t kSlot = N_TILE <= 64 ? 64 : 128;
+        int it = 0;
+        uint32_t started = 0;  // bit g: group g's accumulator holds data; bit 31: D1 does
+        for (int t = 0; t < p.n_taps; ++t)
+            for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                const uint32_t g = static_cast<uint32_t>(t * p.groups / p.n_taps);
+                const int s = it % STAGES;
+                const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
+                mbar_wait(kGdn ? &xform[s] : &full[s], ph);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t base = smem_u32(smem + s * L::kStageBytes);
+                    const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + kABytes);
+                    const uint64_t b_hi = make_smem_desc(base + 2 * kABytes), b_lo = make_smem_desc(base + 2 * kABytes + L::kBBytes);
+                    const int k_steps = (kc == p.k_chunks - 1) ? p.k_steps_last : kBlockK / 16;
+                    for (int k = 0; k < k_steps; ++k) {
+                        const uint32_t acc0 = k > 0 ? 1u : ((started >> g) & 1u), acc1 = k > 0 ? 1u : (started >> 31);
+                        umma_f16(tmem_base + g * kSlot, a_hi + 2 * k, b_hi + 2 * k, idesc, acc0);  // D0[g] += hi * hi
+                        umma_f16(tmem_base + kD1Col, a_hi + 2 * k, b_lo + 2 * k, idesc, acc1);    // D1 += hi * lo
+                        umma_f16(tmem_base + kD1Col, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);      // D1 += lo * hi
+                    }
+                    umma_commit(&empty[s]);
+                    if (it == n_iter - 1) umma_commit(accum_bar);
+                }
+                started |= (1u << g) | 0x80000000u;  // tracked by every lane: whichever lane is elected next sees it
+                __syncwarp();
+            }
+    } else {
+        // =============================== epilogue warps (2..5) ===============================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const bool row_in_tile = row < rows;
+        if (kGdn) {
+            // |x| on both halves, in place: |a| = |hi| + sign(hi) * lo / 2048
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                if (row_in_tile) {
+                    uint4 *rh = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + row * 128);
+                    uint4 *rl = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + kABytes + row * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 h = rh[c], l = rl[c];
+                        l.x ^= h.x & 0x80008000u; l.y ^= h.y & 0x80008000u; l.z ^= h.z & 0x80008000u; l.w ^= h.w & 0x80008000u;
+                        h.x &= 0x7fff7fffu; h.y &= 0x7fff7fffu; h.z &= 0x7fff7fffu; h.w &= 0x7fff7fffu;
+                        rh[c] = h;
+                        rl[c] = l;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&xform[s]);
+            }
+        }
+        mbar_wait(accum_bar, 0);
+        tcgen05_fence_after();
+        const int ty = row / p.tw, tx = row - ty * p.tw;
+        const int oy = y0 + ty, ox = x0 + tx;
+        const bool valid = row_in_tile && oy < p.h_out && ox < p.w_out;
+        const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        constexpr uint32_t kSlot = N_TILE <= 64 ? 64 : 128;
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+            uint32_t d0[32], d1[32];
+            tmem_ld32(lane_addr + c0, d0);
+            for (int g = 1; g < p.groups; ++g) {  // chunked summation of the hi*hi partial sums, in fp32 (round to nearest)
+                uint32_t dg[32];
+                tmem_ld32(lane_addr + g * kSlot + c0, dg);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) d0[e] = __float_as_uint(__uint_as_float(d0[e]) + __uint_as_float(dg[e]));
+            }
+            tmem_ld32(lane_addr + kD1Col + c0, d1);
+            if (!valid) continue;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int c = c0 + 8 * g;
+                if (c >= p.c_out) break;
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(d0[8 * g + e]) + __uint_as_float(d1[8 * g + e]) * kLoInv;
+                if (MODE == MODE_QUANT) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        if (c + e < p.c_out) {
+                            const float med = p.medians ? __ldg(p.medians + c + e) : 0.0f;
+                            p.out_sym[((static_cast<int64_t>(img) * p.c_out + c + e) * p.h_out + oy) * p.w_out + ox] =
+                                __float2int_rn(rintf(f[e] - med));
+                        }
+                    }
+                } else {
+                    if (kGdn) {
+                        const uint4 xh = *reinterpret_cast<const uint4 *>(p.x_hi + pix * p.out_c + c);
+                        const uint4 xl = *reinterpret_cast<const uint4 *>(p.x_lo + pix * p.out_c + c);
+                        const __half2 *xhh = reinterpret_cast<const __half2 *>(&xh), *xlh = reinterpret_cast<const __half2 *>(&xl);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 a = __half22float2(xhh[e]), b = __half22float2(xlh[e]);
+                            const float x0f = a.x + b.x * kLoInv, x1f = a.y + b.y * kLoInv;
+                            const float n0 = f[2 * e] + __ldg(p.beta + c + 2 * e), n1 = f[2 * e + 1] + __ldg(p.beta + c + 2 * e + 1);
+                            f[2 * e] = x0f * __fdiv_rn(1.0f, n0);      // x * (1 / norm), like the reference
+                            f[2 * e + 1] = x1f * __fdiv_rn(1.0f, n1);
+                        }
+                    }
+                    split_store8(f, p.out_hi + pix * p.out_c + c, p.out_lo + pix * p.out_c + c);
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- im2col for the first layer (c_in = 3): fp32 NCHW image -> split fp16 patches in parity-plane pixel order -------
+// out planes [batch * 4, H/2... ] are indexed (b, py, px, Y, X) with output pixel (oy, ox) = (2Y + py, 2X + px);
+// K index = (c * kh + dy) * kw + dx, zero padded to k_pad.
+__global__ void patchify_split_kernel(const float *__restrict__ x, __half *__restrict__ out_hi, __half *__restrict__ out_lo,
+                                      int c_in, int h_in, int w_in, int kh, int kw, int stride, int pad, int hp, int wp,
+                                      int k_pad, int64_t total_groups) {
+    const int groups = k_pad / 8;
+    const int K = c_in * kh * kw;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total_groups;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % groups);
+        int64_t pixel = i / groups;  // ((b * 4 + parity) * hp + Y) * wp + X
+        const int X = static_cast<int>(pixel % wp);
+        pixel /= wp;
+        const int Y = static_cast<int>(pixel % hp);
+        pixel /= hp;
+        const int parity = static_cast<int>(pixel & 3);
+        const int64_t b = pixel >> 2;
+        const int oy = 2 * Y + (parity >> 1), ox = 2 * X + (parity & 1);
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = g * 8 + e;
+            float v = 0.0f;
+            if (k < K) {
+                const int c = k / (kh * kw);
+                const int r = k - c * kh * kw;
+                const int dy = r / kw, dx = r - dy * kw;
+                const int iy = oy * stride - pad + dy, ix = ox * stride - pad + dx;
+                if (iy >= 0 && iy < h_in && ix >= 0 && ix < w_in) v = __ldg(x + ((b * c_in + c) * h_in + iy) * w_in + ix);
+            }
+            f[e] = v;
+        }
+        split_store8(f, out_hi + i * 8, out_lo + i * 8);
+    }
+}
+
+template <int N_TILE, int STAGES, int MODE>
+static int launch(const CUtensorMap &mah, const CUtensorMap &mal, const CUtensorMap &mbh, const CUtensorMap &mbl, const Params &p,
+                  int images, cudaStream_t st) {
+    using L = Smem<N_TILE, STAGES>;
+    const int smem = L::kTotal + 1024;
+    static bool configured = false;
+    if (!configured) {
+        SC2_CUDA_TRY(cudaFuncSetAttribute(tc_split_conv_kernel<N_TILE, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(p.tiles_x * p.tiles_y, 1, images);
+    tc_split_conv_kernel<N_TILE, STAGES, MODE><<<grid, kNumThreads, smem, st>>>(mah, mal, mbh, mbl, p);
+    SC2_LAUNCH_CHECK("tc_split_conv_kernel");
+    return SC2_OK;
+}
+
+template <int N_TILE, int STAGES>
+static int dispatch_mode(int mode, const CUtensorMap &mah, const CUtensorMap &mal, const CUtensorMap &mbh, const CUtensorMap &mbl,
+                         const Params &p, int images, cudaStream_t st) {
+    switch (mode) {
+        case MODE_STORE_SPLIT: return launch<N_TILE, STAGES, MODE_STORE_SPLIT>(mah, mal, mbh, mbl, p, images, st);
+        case MODE_GDN1_SPLIT: return launch<N_TILE, STAGES, MODE_GDN1_SPLIT>(mah, mal, mbh, mbl, p, images, st);
+        default: return launch<N_TILE, STAGES, MODE_QUANT>(mah, mal, mbh, mbl, p, images, st);
+    }
+}
+
+}  // namespace tcs
+}  // namespace sc2
+
+extern "C" {
+
+int sc2_tc_split_n_tile(int c_out) {
+    const int tiles[] = {32, 48, 64, 96, 128};
+    for (int t : tiles)
+        if (c_out <= t) return t;
+    return 0;
+}
+
+int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo,
+                      const float *beta, const float *medians, const void *gdn_x_hi, const void *gdn_x_lo, void *out_hi,
+                      void *out_lo, int32_t *out_sym, sc2_stream_t stream) {
+    using namespace sc2::tcs;
+    if (!d || !x_hi || !x_lo || !w_hi || !w_lo) return SC2_ERR_INVALID_ARG;
+    if (d->images < 1 || d->images > 65535 || d->c_in < 16 || d->c_in % 16 || d->c_out < 1) return SC2_ERR_INVALID_ARG;
+    if (d->stride != 1 && d->stride != 2) return SC2_ERR_UNSUPPORTED;
+    if (d->kh * d->kw > kMaxTaps || d->kh < 1 || d->kw < 1) return SC2_ERR_UNSUPPORTED;
+    if ((d->c_in * 2) % 16) return SC2_ERR_INVALID_ARG;
+    const int n_tile = sc2_tc_split_n_tile(d->c_out);
+    if (!n_tile) return SC2_ERR_UNSUPPORTED;
+    if (d->mode == MODE_GDN1_SPLIT && (!beta || !gdn_x_hi || !gdn_x_lo || d->kh != 1 || d->kw != 1 || d->stride != 1)) return SC2_ERR_INVALID_ARG;
+    if (d->mode == MODE_QUANT ? !out_sym : (!out_hi || !out_lo)) return SC2_ERR_INVALID_ARG;
+    if (d->mode != MODE_QUANT && (d->out_c % 8 || d->out_c < d->c_out)) return SC2_ERR_INVALID_ARG;
+    Params p;
+    const int planes = d->stride == 2 ? 4 : 1;
+    p.planes = planes;
+    p.h_out = d->h_out; p.w_out = d->w_out;
+    int n_col_tiles = (d->w_out + 127) / 128;
+    int tw = (d->w_out + n_col_tiles - 1) / n_col_tiles;
+    tw = (tw + 7) / 8 * 8;
+    if (tw > 128) tw = 128;
+    int th = 128 / tw;
+    if (th > d->h_out) th = d->h_out;
+    p.tw = tw; p.th = th;
+    p.tiles_x = (d->w_out + tw - 1) / tw;
+    p.tiles_y = (d->h_out + th - 1) / th;
+    p.n_taps = d->kh * d->kw;
+    for (int dy = 0; dy < d->kh; ++dy)
+        for (int dx = 0; dx < d->kw; ++dx) {
+            Tap t;
+            const int sy = dy - d->pad, sx = dx - d->pad;
+            if (d->stride == 2) {
+                const int py = ((sy % 2) + 2) % 2, px = ((sx % 2) + 2) % 2;
+                t.plane = static_cast<int8_t>(py * 2 + px);
+                t.dy = static_cast<int8_t>((sy - py) / 2);
+                t.dx = static_cast<int8_t>((sx - px) / 2);
+            } else {
+                t.plane = 0;
+                t.dy = static_cast<int8_t>(sy);
+                t.dx = static_cast<int8_t>(sx);
+            }
+            t.pad_ = 0;
+            p.taps[dy * d->kw + dx] = t;
+        }
+    p.k_chunks = (d->c_in + kBlockK - 1) / kBlockK;
+    const int rem = d->c_in - (p.k_chunks - 1) * kBlockK;
+    p.k_steps_last = rem / 16;
+    {   // one D0 accumulator per ~24 K-steps, as many as TMEM holds (6 for N <= 64, 3 for N <= 128)
+        const int steps = p.n_taps * ((p.k_chunks - 1) * 4 + p.k_steps_last);
+        int groups = (steps + 23) / 24;
+        const int max_groups = n_tile <= 64 ? 6 : 3;
+        if (groups > max_groups) groups = max_groups;
+        if (groups > p.n_taps) groups = p.n_taps;
+        if (groups < 1) groups = 1;
+        p.groups = groups;
+    }
+    p.c_out = d->c_out;
+    p.beta = beta; p.medians = medians;
+    p.out_hi = static_cast<__half *>(out_hi); p.out_lo = static_cast<__half *>(out_lo);
+    p.out_c = d->out_c;
+    p.out_sym = out_sym;
+    p.x_hi = static_cast<const __half *>(gdn_x_hi); p.x_lo = static_cast<const __half *>(gdn_x_lo);
+    CUtensorMap mah, mal, mbh, mbl;
+    // input planes: [images * planes, h_in, w_in, c_in] (h_in, w_in = plane geometry)
+    int rc = make_nhwc_map(&mah, x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * planes, kBlockK, tw, th);
+    if (rc) return rc;
+    rc = make_nhwc_map(&mal, x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * planes, kBlockK, tw, th);
+    if (rc) return rc;
+    // packed weights: [taps * n_tile, c_in] (rows beyond c_out are zero)
+    rc = make_weight_map(&mbh, w_hi, d->c_in, p.n_taps * n_tile, n_tile);
+    if (rc) return rc;
+    rc = make_weight_map(&mbl, w_lo, d->c_in, p.n_taps * n_tile, n_tile);
+    if (rc) return rc;
+    cudaStream_t st = sc2::as_stream(stream);
+    switch (n_tile) {
+        case 32: return dispatch_mode<32, 4>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        case 48: return dispatch_mode<48, 4>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        case 64: return dispatch_mode<64, 4>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        case 96: return dispatch_mode<96, 3>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        default: return dispatch_mode<128, 3>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+    }
+}
+
+int sc2_patchify_split(const float *x, void *out_hi, void *out_lo, int batch, int c_in, int h_in, int w_in, int kh, int kw,
+                       int stride, int pad, int k_pad, sc2_stream_t stream) {
+    if (!x || !out_hi || !out_lo || batch < 1 || k_pad % 16 || k_pad < c_in * kh * kw) return SC2_ERR_INVALID_ARG;
+    const int h_out = (h_in + 2 * pad - kh) / stride + 1, w_out = (w_in + 2 * pad - kw) / stride + 1;
+    if (h_out < 2 || w_out < 2 || (h_out & 1) || (w_out & 1)) return SC2_ERR_UNSUPPORTED;
+    const int hp = h_out / 2, wp = w_out / 2;
+    const int64_t total = static_cast<int64_t>(batch) * 4 * hp * wp * (k_pad / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > sc2::kNumSMs * 32) blocks = sc2::kNumSMs * 32;
+    sc2::tcs::patchify_split_kernel<<<static_cast<int>(blocks), 256, 0, sc2::as_stream(stream)>>>(
+        x, static_cast<__half *>(out_hi), static_cast<__half *>(out_lo), c_in, h_in, w_in, kh, kw, stride, pad, hp, wp, k_pad, total);
+    SC2_LAUNCH_CHECK("patchify_split_kernel");
+    return SC2_OK;
+}
+
+}  // extern "C"

@@ -63,14 +63,36 @@ __device__ __forceinline__ void enc_emit_checked(EncChain &s) {
     s.x >>= 32;
 }
 
-// cold path: nibbles of an escaped symbol in coder order (high nibble first, then the nibble count).
-// State goes in and out BY VALUE so that the hot loop keeps it in registers (a by-reference call would pin it to the stack).
-__device__ __noinline__ EncChain enc_escape(EncChain s, uint32_t raw) {
-    const int n_bypass = raw == 0 ? 0 : (35 - __clz(raw)) >> 2;
-    for (int k = n_bypass - 1; k >= -1; --k) {
-        const uint32_t val = k >= 0 ? ((raw >> (4 * k)) & kMaxBypassVal) : static_cast<uint32_t>(n_bypass);
-        if (s.x >= (1ull << 59)) enc_emit_checked(s);
-        s.x = (s.x << kBypassPrecision) | val;
+// one regular symbol, unchecked (caller guarantees s.pw > 0): the dependent chain is
+//   ISETP -> SEL -> IMAD.WIDE x3 (mul.hi.u64) -> SHF -> IMAD.WIDE -> IADD
+__device__ __forceinline__ void enc_step(EncChain &s, const uint4 a, const uint4 b) {
+    const uint32_t xl = static_cast<uint32_t>(s.x), xh = static_cast<uint32_t>(s.x >> 32);
+    const bool ren = xh >= a.z;  // x >= freq << 47
+    if (ren) s.words[s.pw - 1] = xl;
+    s.pw -= ren ? 1u : 0u;
+    const uint64_t y = ren ? static_cast<uint64_t>(xh) : s.x;
+    const uint64_t rcp = (static_cast<uint64_t>(a.y) << 32) | a.x;
+    const uint64_t q = __umul64hi(y, rcp) >> b.y;
+    s.x = y + b.x + q * static_cast<uint64_t>(a.w);
+}
+
+// cold path: a chunk that contains escapes, is the (short) last chunk, or runs close to the end of the arena slot
+__device__ __noinline__ EncChain enc_chunk_careful(EncChain s, const uint4 *sA, const uint4 *sB, int cnt) {
+    for (int j = 0; j < cnt; ++j) {
+        const uint4 a = sA[j], b = sB[j];
+        if (b.z) {
+            const uint32_t raw = b.w;
+            const int n_bypass = raw == 0 ? 0 : (35 - __clz(raw)) >> 2;
+            for (int k = n_bypass - 1; k >= -1; --k) {
+                const uint32_t val = k >= 0 ? ((raw >> (4 * k)) & kMaxBypassVal) : static_cast<uint32_t>(n_bypass);
+                if (s.x >= (1ull << 59)) enc_emit_checked(s);
+                s.x = (s.x << kBypassPrecision) | val;
+            }
+        }
+        if (static_cast<uint32_t>(s.x >> 32) >= a.z) enc_emit_checked(s);
+        const uint64_t rcp = (static_cast<uint64_t>(a.y) << 32) | a.x;
+        const uint64_t q = __umul64hi(s.x, rcp) >> b.y;
+        s.x = s.x + b.x + q * static_cast<uint64_t>(a.w);
     }
     return s;
 }
@@ -112,6 +134,7 @@ rans_encode_fast_kernel(const int32_t *__restrict__ symbols, int batch, uint32_t
             const uint32_t hn = hi - 32;
             nxt = (static_cast<uint32_t>(lane) < hn) ? __ldg(sym + (hn - 1 - lane)) : 0;
         }
+        uint32_t my_esc = 0;
         if (lane < cnt) {
             const uint32_t i = hi - 1 - lane;
             const int row = static_cast<int>(i / spatial);
@@ -126,33 +149,32 @@ rans_encode_fast_kernel(const int32_t *__restrict__ symbols, int batch, uint32_t
                 value = max_value;
             }
             if (value == max_value) esc = 1;
+            my_esc = esc;
             const int eidx = row * t.cdf_stride + value;
             const uint4 e = staged ? s_enc[eidx] : __ldg(t.enc + eidx);
             // unpack here, in parallel across lanes, so the chain only sees ready-to-use operands
             sA[lane] = make_uint4(e.x, e.y, e.w << 15, 65536u - e.w);               // rcp_lo, rcp_hi, renorm threshold, 2^16 - freq
             sB[lane] = make_uint4(e.z & 0x1ffffu, (e.z >> 24) & 15u, esc, raw);     // bias, shift, escape?, raw
         }
+        // does any symbol of this chunk escape?  (uniform; computed off the chain)
+        const bool any_escape = __any_sync(0xffffffffu, my_esc != 0u);
         __syncwarp();
-        uint4 A = sA[0], B = sB[0];
-#pragma unroll 2
-        for (int j = 0; j < cnt; ++j) {
-            const uint4 a = A, bb = B;
-            if (j + 1 < cnt) {  // software prefetch of the next entry
-                A = sA[j + 1];
-                B = sB[j + 1];
+        if (cnt == 32 && !any_escape && s.pw >= 40u) {
+            // ---- fast chain: 32 regular symbols, no escapes, room for 32 words guaranteed -> no checks inside.
+            // Two register sets alternate so that the next entry is already loaded when a step starts.
+            uint4 a0 = sA[0], b0 = sB[0];
+#pragma unroll 1
+            for (int j = 0; j < 32; j += 2) {
+                const uint4 a1 = sA[j + 1], b1 = sB[j + 1];
+                enc_step(s, a0, b0);
+                if (j + 2 < 32) {
+                    a0 = sA[j + 2];
+                    b0 = sB[j + 2];
+                }
+                enc_step(s, a1, b1);
             }
-            if (__builtin_expect(bb.z != 0u, 0)) s = enc_escape(s, bb.w);
-            // ---- the chain ----
-            const uint32_t xl = static_cast<uint32_t>(s.x), xh = static_cast<uint32_t>(s.x >> 32);
-            const bool ren = xh >= a.z;                 // x >= freq << 47
-            const bool can = s.pw != 0u;
-            if (ren && can) s.words[s.pw - 1] = xl;
-            s.pw -= (ren && can) ? 1u : 0u;
-            s.overflow |= (ren && !can) ? 1u : 0u;
-            const uint64_t y = ren ? static_cast<uint64_t>(xh) : s.x;
-            const uint64_t rcp = (static_cast<uint64_t>(a.y) << 32) | a.x;
-            const uint64_t q = __umul64hi(y, rcp) >> bb.y;
-            s.x = y + bb.x + q * static_cast<uint64_t>(a.w);
+        } else {
+            s = enc_chunk_careful(s, sA, sB, cnt);
         }
         __syncwarp();
     }
@@ -176,75 +198,123 @@ rans_encode_fast_kernel(const int32_t *__restrict__ symbols, int batch, uint32_t
 // ---------------------------------------------------------------------------------------------------------------
 struct DecChain {
     uint64_t x;
-    uint32_t p;        // index of the word held in `next_w`
+    uint32_t p;        // index of the word held in `next_w` (= number of words consumed so far)
     uint32_t next_w;   // words[p], already in a register
-    uint32_t n_words;
-    const uint32_t *words;
-    uint32_t *ring;
-    uint32_t truncated;
 };
 
-__device__ __forceinline__ void ring_fill(const DecChain &s, uint32_t first, int lane) {
+struct DecStream {
+    const uint32_t *words;
+    uint32_t n_words;
+    uint32_t *ring;
+};
+
+__device__ __forceinline__ void ring_fill(const DecStream &st, uint32_t first, int lane) {
     const uint32_t w = first + lane;
-    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s.ring + (w & (kRingWords - 1))));
-    const bool ok = w < s.n_words;
-    const uint32_t *src = ok ? s.words + w : s.words;
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(st.ring + (w & (kRingWords - 1))));
+    const bool ok = w < st.n_words;
+    const uint32_t *src = ok ? st.words + w : st.words;
     const int src_bytes = ok ? 4 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// cold path: ring refill when the word index crosses a half
+// cold path: the word index crossed a ring half: wait for the previous refill, reuse the half that was just left
 __device__ __noinline__ void dec_refill(const uint32_t *words, uint32_t n_words, uint32_t *ring, uint32_t first, int lane) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    DecChain t;
-    t.words = words;
-    t.n_words = n_words;
-    t.ring = ring;
-    ring_fill(t, first, lane);
+    DecStream st;
+    st.words = words;
+    st.n_words = n_words;
+    st.ring = ring;
+    ring_fill(st, first, lane);
 }
 
-// consume next_w and fetch the following word from the ring (refilling the ring half that was just left)
-__device__ __forceinline__ void dec_advance_word(DecChain &s, int lane) {
-    s.truncated |= (s.p >= s.n_words) ? 1u : 0u;
+// consume next_w and fetch the following word from the ring
+__device__ __forceinline__ void dec_advance_word(DecChain &s, const DecStream &st, int lane) {
     ++s.p;
-    if (__builtin_expect((s.p & 31u) == 0u, 0)) dec_refill(s.words, s.n_words, s.ring, s.p + 32u, lane);
-    s.next_w = s.ring[s.p & (kRingWords - 1)];
+    if (__builtin_expect((s.p & 31u) == 0u, 0)) dec_refill(st.words, st.n_words, st.ring, s.p + 32u, lane);
+    s.next_w = st.ring[s.p & (kRingWords - 1)];
 }
 
-__device__ __forceinline__ uint32_t dec_get_nibble(DecChain &s, int lane) {
+__device__ __forceinline__ uint32_t dec_get_nibble(DecChain &s, const DecStream &st, int lane) {
     const uint32_t val = static_cast<uint32_t>(s.x) & kMaxBypassVal;
     s.x >>= kBypassPrecision;
     if (s.x < kL) {
         s.x = (s.x << 32) | s.next_w;
-        dec_advance_word(s, lane);
+        dec_advance_word(s, st, lane);
     }
     return val;
 }
 
-struct DecEscapeResult {
+struct DecMissResult {
     DecChain s;
+    uint32_t sp_start, sp_freq;
+    int32_t sp_value;
     int32_t value;
 };
 
-// cold path: the bypass-coded magnitude of an escaped symbol (state by value: see enc_escape)
-__device__ __noinline__ DecEscapeResult dec_escape(DecChain s, int32_t max_value, int lane) {
-    uint32_t val = dec_get_nibble(s, lane);
-    int n_bypass = static_cast<int>(val);
-    while (val == kMaxBypassVal) {
-        val = dec_get_nibble(s, lane);
-        n_bypass += static_cast<int>(val);
+// cold path (by value, see enc_chunk_careful): the speculation missed.  Warp-wide search (lane l compares CDF entries
+// l and l + 32, further 32-entry groups from memory), then the COMPLETE symbol step including escapes.
+__device__ __noinline__ DecMissResult dec_miss(DecChain s, const uint32_t *words, uint32_t n_words, uint32_t *ring,
+                                               const int32_t *drow, int32_t c0, int32_t c1, int32_t max_value,
+                                               uint32_t sp_start, uint32_t sp_freq, int32_t sp_value, int lane) {
+    DecStream st;
+    st.words = words;
+    st.n_words = n_words;
+    st.ring = ring;
+    const int32_t cum = static_cast<int32_t>(static_cast<uint32_t>(s.x) & 0xffffu);
+    int k;
+    uint32_t m = __ballot_sync(0xffffffffu, c0 > cum);
+    if (m) {
+        k = __ffs(m) - 1;
+    } else {
+        m = __ballot_sync(0xffffffffu, c1 > cum);
+        if (m) {
+            k = 32 + __ffs(m) - 1;
+        } else {
+            k = 64;
+            for (;; k += 32) {
+                const uint32_t mm = __ballot_sync(0xffffffffu, drow[k + lane] > cum);
+                if (mm) {
+                    k += __ffs(mm) - 1;
+                    break;
+                }
+            }
+        }
     }
-    uint32_t raw = 0;
-    for (int q = 0; q < n_bypass; ++q) {
-        const uint32_t nib = dec_get_nibble(s, lane);
-        if (q < 8) raw |= nib << (4 * q);
+    const uint32_t start = static_cast<uint32_t>(drow[k - 1]);
+    const uint32_t freq = static_cast<uint32_t>(drow[k]) - start;
+    int32_t value = k - 1;
+    s.x = static_cast<uint64_t>(freq) * (s.x >> kRansPrecision) + (static_cast<uint32_t>(cum) - start);
+    if (s.x < kL) {
+        s.x = (s.x << 32) | s.next_w;
+        dec_advance_word(s, st, lane);
     }
-    const int32_t v = static_cast<int32_t>(raw >> 1);
-    DecEscapeResult r;
+    DecMissResult r;
+    r.sp_start = sp_start;
+    r.sp_freq = sp_freq;
+    r.sp_value = sp_value;
+    if (value != max_value) {
+        r.sp_start = start;
+        r.sp_freq = freq;
+        r.sp_value = value;
+    } else {
+        uint32_t val = dec_get_nibble(s, st, lane);
+        int n_bypass = static_cast<int>(val);
+        while (val == kMaxBypassVal) {
+            val = dec_get_nibble(s, st, lane);
+            n_bypass += static_cast<int>(val);
+        }
+        uint32_t raw = 0;
+        for (int q = 0; q < n_bypass; ++q) {
+            const uint32_t nib = dec_get_nibble(s, st, lane);
+            if (q < 8) raw |= nib << (4 * q);
+        }
+        const int32_t v = static_cast<int32_t>(raw >> 1);
+        value = (raw & 1u) ? -v - 1 : v + max_value;
+    }
     r.s = s;
-    r.value = (raw & 1u) ? -v - 1 : v + max_value;
+    r.value = value;
     return r;
 }
 
@@ -275,18 +345,18 @@ rans_decode_fast_kernel(const uint8_t *__restrict__ packed, const int64_t *__res
         if (lane == 0) atomicOr(status, SC2_FAULT_BAD_STREAM);
         return;
     }
-    DecChain s;
-    s.words = reinterpret_cast<const uint32_t *>(packed + off);
-    s.n_words = static_cast<uint32_t>(n_bytes >> 2);
-    s.ring = s_ring;
-    s.truncated = 0u;
-    ring_fill(s, 0, lane);
-    ring_fill(s, 32, lane);
+    DecStream st;
+    st.words = reinterpret_cast<const uint32_t *>(packed + off);
+    st.n_words = static_cast<uint32_t>(n_bytes >> 2);
+    st.ring = s_ring;
+    ring_fill(st, 0, lane);
+    ring_fill(st, 32, lane);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    s.x = static_cast<uint64_t>(s.ring[0]) | (static_cast<uint64_t>(s.ring[1]) << 32);
+    DecChain s;
+    s.x = static_cast<uint64_t>(s_ring[0]) | (static_cast<uint64_t>(s_ring[1]) << 32);
     s.p = 2;
-    s.next_w = s.ring[2];
+    s.next_w = s_ring[2];
 
     int32_t *osym = out_symbols ? out_symbols + static_cast<int64_t>(b) * n : nullptr;
     float *oval = out_values ? out_values + static_cast<int64_t>(b) * n : nullptr;
@@ -300,62 +370,68 @@ rans_decode_fast_kernel(const uint8_t *__restrict__ packed, const int64_t *__res
         const int32_t max_value = __ldg(t.sizes + row) - 2;
         const int32_t offset = __ldg(t.offsets + row);
         const float mean = means ? __ldg(means + row) : 0.0f;
-        // speculation state: the last regular symbol decoded in this row
+        // speculation state: the last regular symbol decoded in this row (freq 0 = nothing yet -> first symbol misses)
         uint32_t sp_start = 0, sp_freq = 0;
         int32_t sp_value = 0;
         for (uint32_t base = 0; base < row_n; base += 32) {
             const int cnt = (row_n - base) >= 32 ? 32 : static_cast<int>(row_n - base);
-#pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                // ---- the chain ----
-                const uint32_t cum = static_cast<uint32_t>(s.x) & 0xffffu;
-                uint32_t d = cum - sp_start;
-                uint32_t freq = sp_freq;
-                int32_t value = sp_value;
-                if (__builtin_expect(!(d < sp_freq), 0)) {
-                    // miss: warp-wide search, lane l compares CDF entry l (and l + 32)
-                    int k;
-                    uint32_t m = __ballot_sync(0xffffffffu, c0 > static_cast<int32_t>(cum));
-                    if (m) {
-                        k = __ffs(m) - 1;
-                    } else {
-                        m = __ballot_sync(0xffffffffu, c1 > static_cast<int32_t>(cum));
-                        if (m) {
-                            k = 32 + __ffs(m) - 1;
-                        } else {
-                            k = 64;
-                            for (;; k += 32) {
-                                const uint32_t mm = __ballot_sync(0xffffffffu, drow[k + lane] > static_cast<int32_t>(cum));
-                                if (mm) {
-                                    k += __ffs(mm) - 1;
-                                    break;
-                                }
-                            }
-                        }
-                    }
-                    const uint32_t start = static_cast<uint32_t>(drow[k - 1]);
-                    freq = static_cast<uint32_t>(drow[k]) - start;
-                    d = cum - start;
-                    value = k - 1;
-                    if (value != max_value) {
-                        sp_start = start;
-                        sp_freq = freq;
-                        sp_value = value;
-                    }
-                }
-                uint64_t xn = static_cast<uint64_t>(freq) * (s.x >> kRansPrecision) + d;
-                if (xn < kL) {
-                    xn = (xn << 32) | s.next_w;
-                    dec_advance_word(s, lane);
-                }
-                s.x = xn;
-                if (__builtin_expect(value == max_value, 0)) {
-                    const DecEscapeResult r = dec_escape(s, max_value, lane);
-                    s = r.s;
-                    value = r.value;
-                }
-                s_out[j] = value;  // uniform value, one shared-memory word
+            // ---- hot loop: nothing but the hit chain on 32-bit halves of the state; a rare event (speculation miss,
+            // ring half consumed) jumps out, is handled, and the loop resumes.  Chain per symbol:
+            //   LOP -> IADD -> ISETP(miss?) -> IMAD.WIDE -> IMAD -> SHF/LOP -> ISETP(renorm?) -> SEL
+            uint32_t xl = static_cast<uint32_t>(s.x), xh = static_cast<uint32_t>(s.x >> 32);
+            int j = 0;
+#define SC2_DEC_STEP(K)                                                                              \
+    {                                                                                                \
+        const uint32_t d = (xl & 0xffffu) - sp_start;                                                \
+        if (d >= sp_freq) { j += (K); goto miss_event; }                                             \
+        const uint64_t prod = static_cast<uint64_t>(sp_freq) * __funnelshift_r(xl, xh, 16) + d;      \
+        const uint32_t nl = static_cast<uint32_t>(prod);                                             \
+        const uint32_t nh = static_cast<uint32_t>(prod >> 32) + sp_freq * (xh >> 16);                \
+        const bool ren = (nh | (nl >> 31)) == 0u; /* x < 2^31 */                                     \
+        xl = ren ? s.next_w : nl;                                                                    \
+        xh = ren ? nl : nh;                                                                          \
+        s_out[j + (K)] = sp_value;                                                                   \
+        if (ren) {                                                                                   \
+            ++s.p;                                                                                   \
+            s.next_w = s_ring[s.p & (kRingWords - 1)];                                               \
+            if ((s.p & 31u) == 0u) { j += (K) + 1; goto refill_event; }                              \
+        }                                                                                            \
+    }
+        resume:
+            while (j + 4 <= cnt) {
+                SC2_DEC_STEP(0)
+                SC2_DEC_STEP(1)
+                SC2_DEC_STEP(2)
+                SC2_DEC_STEP(3)
+                j += 4;
             }
+            while (j < cnt) {
+                SC2_DEC_STEP(0)
+                j += 1;
+            }
+            goto chunk_done;
+        refill_event:
+            // the word index crossed a ring half: top up the half that was just left, then re-read next_w
+            dec_refill(st.words, st.n_words, st.ring, s.p + 32u, lane);
+            s.next_w = s_ring[s.p & (kRingWords - 1)];
+            goto resume;
+        miss_event : {
+            s.x = (static_cast<uint64_t>(xh) << 32) | xl;
+            const DecMissResult r = dec_miss(s, st.words, st.n_words, st.ring, drow, c0, c1, max_value, sp_start, sp_freq,
+                                             sp_value, lane);
+            s = r.s;
+            xl = static_cast<uint32_t>(s.x);
+            xh = static_cast<uint32_t>(s.x >> 32);
+            sp_start = r.sp_start;
+            sp_freq = r.sp_freq;
+            sp_value = r.sp_value;
+            s_out[j] = r.value;
+            ++j;
+            goto resume;
+        }
+        chunk_done:
+#undef SC2_DEC_STEP
+            s.x = (static_cast<uint64_t>(xh) << 32) | xl;
             __syncwarp();
             if (lane < cnt) {
                 const int32_t v = s_out[lane] + offset;
@@ -367,7 +443,8 @@ rans_decode_fast_kernel(const uint8_t *__restrict__ packed, const int64_t *__res
         }
         done += row_n;
     }
-    if (s.truncated && lane == 0) atomicOr(status, SC2_FAULT_STREAM_TRUNCATED);
+    // a well-formed stream is consumed exactly; reading past the end (zero-filled) means it was truncated
+    if (s.p > st.n_words && lane == 0) atomicOr(status, SC2_FAULT_STREAM_TRUNCATED);
 }
 
 }  // namespace

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _native
-from ._native import ConvDesc, TcConvDesc, check
+from ._native import ConvDesc, TcConvDesc, TcSplitDesc, check
 
 
 def _lib():
@@ -355,3 +355,85 @@ def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None,
         check(_lib().sc2_tc_conv_nhwc(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(b), _ptr(gdn_x), _ptr(out), _stream_ptr()),
               'sc2_tc_conv_nhwc')
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# fp32-grade tensor-core path ("split fp16": value = hi + lo / 2048)
+# ----------------------------------------------------------------------------------------------
+LO_SCALE = 2048.0
+
+
+def split_f16(t):
+    """fp32 tensor -> (hi, lo) fp16 pair with t ~= hi + lo / 2048 (22 mantissa bits). Host-side prep of weights."""
+    t = t.detach().float()
+    hi = t.half()
+    lo = ((t - hi.float()) * LO_SCALE).half()
+    return hi.contiguous(), lo.contiguous()
+
+
+def pack_conv_weight_split(weight, c_in_pad=None, as_patches=False):
+    """Conv2d weight [c_out, c_in, kh, kw] -> (hi, lo) of shape [taps, n_tile, c_in_pad], rows beyond c_out zero.
+    as_patches=True packs the whole receptive field into ONE tap with K = (c, dy, dx) (first layer, after im2col)."""
+    w = weight.detach().float()
+    c_out, c_in, kh, kw = w.shape
+    n_tile = _lib().sc2_tc_split_n_tile(c_out)
+    if n_tile == 0:
+        raise ValueError('c_out %d is not supported by the split tensor-core kernel' % c_out)
+    if as_patches:
+        k = c_in * kh * kw
+        c_in_pad = c_in_pad or (k + 15) // 16 * 16
+        packed = torch.zeros((1, n_tile, c_in_pad), dtype=torch.float32, device=w.device)
+        packed[0, :c_out, :k] = w.reshape(c_out, k)
+    else:
+        c_in_pad = c_in_pad or (c_in + 15) // 16 * 16
+        packed = torch.zeros((kh * kw, n_tile, c_in_pad), dtype=torch.float32, device=w.device)
+        packed[:, :c_out, :c_in] = w.permute(2, 3, 0, 1).reshape(kh * kw, c_out, c_in)
+    return split_f16(packed)
+
+
+def patchify_split(x, kh, kw, stride, pad, k_pad):
+    """fp32 NCHW image -> split fp16 patches [B * 4, h_out/2, w_out/2, k_pad] in parity-plane pixel order."""
+    require_cuda(x, 'patchify_split')
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    ho, wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    hi = torch.empty((B * 4, ho // 2, wo // 2, k_pad), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(x.device), _launch('patchify_split'):
+        check(_lib().sc2_patchify_split(_ptr(x), _ptr(hi), _ptr(lo), B, C, H, W, kh, kw, stride, pad, k_pad, _stream_ptr()),
+              'sc2_patchify_split')
+    return hi, lo
+
+
+def tc_split_conv(x_hi, x_lo, w_hi, w_lo, c_out, kh, kw, stride, pad, mode, beta=None, medians=None, gdn=False):
+    """sc2_tc_split_conv.  x planes: stride 1 [images, H, W, C]; stride 2 parity planes [images * 4, H, W, C].
+    Returns (hi, lo) planes [images, h_out, w_out, c_out] or int32 symbols [images, c_out, h_out, w_out] (mode QUANT)."""
+    require_cuda(x_hi, 'tc_split_conv')
+    n_img_planes, H, W, C = x_hi.shape
+    planes = 4 if stride == 2 else 1
+    images = n_img_planes // planes
+    if stride == 2:
+        ho, wo = (2 * H + 2 * pad - kh) // 2 + 1, (2 * W + 2 * pad - kw) // 2 + 1
+    else:
+        ho, wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+    dev = x_hi.device
+    out_hi = out_lo = out_sym = None
+    if mode == _native.TCS_QUANT:
+        out_sym = torch.empty((images, c_out, ho, wo), dtype=torch.int32, device=dev)
+        out_c = c_out
+    else:
+        out_c = (c_out + 7) // 8 * 8
+        out_hi = torch.empty((images, ho, wo, out_c), dtype=torch.float16, device=dev)
+        out_lo = torch.empty_like(out_hi)
+        if out_c != c_out:
+            out_hi.zero_()
+            out_lo.zero_()
+    d = TcSplitDesc(images, H, W, C, c_out, kh, kw, stride, pad, mode, ho, wo, out_c)
+    b = beta.detach().contiguous().float() if beta is not None else None
+    m = medians.detach().contiguous().float() if medians is not None else None
+    tag = 'tc_split[%d->%d,k%d,s%d,m%d]' % (C, c_out, kh, stride, mode)
+    with torch.cuda.device(dev), _launch(tag):
+        check(_lib().sc2_tc_split_conv(ctypes.byref(d), _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(b), _ptr(m),
+                                       _ptr(x_hi) if gdn else None, _ptr(x_lo) if gdn else None, _ptr(out_hi), _ptr(out_lo),
+                                       _ptr(out_sym), _stream_ptr()), 'sc2_tc_split_conv')
+    return out_sym if mode == _native.TCS_QUANT else (out_hi, out_lo)

@@ -63,3 +63,88 @@ def test_tc_gdn1_matches_torch(s2, C, inverse, H, W):
                          beta=beta.to(dev), gdn_x=x_nhwc)
     got = out.float().permute(0, 3, 1, 2).cpu()
     assert rel_err(got, ref) < 1.5e-3, rel_err(got, ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fp32-grade "split fp16" tensor-core kernels (g_a)
+# ---------------------------------------------------------------------------------------------------
+SPLIT_TOL = 3e-6  # max-abs / max-abs vs an fp64 reference of the SAME fp32 operands
+
+
+def _planes(s2, x, dev, parity=False):
+    """fp32 NCHW -> split NHWC planes on the device; parity=True gives the [B * 4, H/2, W/2, C] parity-plane layout."""
+    if parity:
+        B, C, H, W = x.shape
+        x = torch.stack([x[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)], dim=1).reshape(B * 4, C, H // 2, W // 2)
+    hi, lo = s2.ops.split_f16(x.permute(0, 2, 3, 1).contiguous())
+    return hi.to(dev), lo.to(dev)
+
+
+def _unsplit(hi, lo):
+    return (hi.float() + lo.float() / 2048.0).permute(0, 3, 1, 2).cpu()
+
+
+def test_patchify_matches_unfold(s2):
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 36, 44)
+    hi, lo = s2.ops.patchify_split(x.to(dev), 5, 5, 2, 2, 80)
+    got = hi.float() + lo.float() / 2048.0                      # [B*4, 9, 11, 80]
+    cols = F.unfold(x, 5, padding=2, stride=2).view(2, 75, 18, 22)  # K order (c, dy, dx), like the weight
+    want = torch.stack([cols[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)], dim=1).reshape(8, 75, 9, 11).permute(0, 2, 3, 1)
+    assert got.shape == (8, 9, 11, 80)
+    assert float((got[..., :75].cpu() - want).abs().max()) < 1e-6 and float(got[..., 75:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,pad,H,W', [(96, 48, 5, 2, 2, 112, 112), (48, 24, 2, 1, 0, 56, 56), (32, 16, 5, 2, 2, 24, 40),
+                                                       (16, 8, 2, 1, 0, 9, 13), (64, 128, 3, 1, 1, 12, 20)])
+def test_tc_split_conv_matches_fp64(s2, cin, cout, k, stride, pad, H, W):
+    dev = torch.device('cuda:0')
+    torch.manual_seed(cin + cout + H)
+    x = torch.randn(2, cin, H, W) * 2
+    w = torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5
+    ref = F.conv2d(x.double(), w.double(), None, stride, pad)
+    xh, xl = _planes(s2, x, dev, parity=stride == 2)
+    wh, wl = s2.ops.pack_conv_weight_split(w.to(dev), c_in_pad=cin)
+    oh, ol = s2.ops.tc_split_conv(xh, xl, wh, wl, cout, k, k, stride, pad, s2._native.TCS_STORE)
+    got = _unsplit(oh, ol)[:, :cout]
+    assert got.shape == ref.shape
+    assert rel_err(got, ref.float()) < SPLIT_TOL, rel_err(got, ref.float())
+    med = torch.randn(cout)
+    sym = s2.ops.tc_split_conv(xh, xl, wh, wl, cout, k, k, stride, pad, s2._native.TCS_QUANT, medians=med.to(dev))
+    want = torch.round(ref.float() - med.view(1, -1, 1, 1)).int()
+    assert sym.shape == want.shape
+    assert int((sym.cpu() != want).sum()) <= max(1, want.numel() // 100000)  # ties at fp32 resolution only
+
+
+def test_tc_split_first_layer_via_patches(s2):
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    x = torch.randn(2, 3, 64, 48)
+    w = torch.randn(96, 3, 5, 5) / 75 ** 0.5
+    ref = F.conv2d(x.double(), w.double(), None, 2, 2)           # [2, 96, 32, 24]
+    ph, pl = s2.ops.patchify_split(x.to(dev), 5, 5, 2, 2, 80)
+    wh, wl = s2.ops.pack_conv_weight_split(w.to(dev), as_patches=True)
+    assert wh.shape == (1, 96, 80)
+    oh, ol = s2.ops.tc_split_conv(ph, pl, wh, wl, 96, 1, 1, 1, 0, s2._native.TCS_STORE)  # parity-plane output [8, 16, 12, 96]
+    got = _unsplit(oh, ol).view(2, 2, 2, 96, 16, 12)
+    full = torch.zeros(2, 96, 32, 24)
+    for py in (0, 1):
+        for px in (0, 1):
+            full[:, :, py::2, px::2] = got[:, py, px]
+    assert rel_err(full, ref.float()) < SPLIT_TOL
+
+
+@pytest.mark.parametrize('C,H,W', [(96, 20, 28), (48, 56, 56), (32, 7, 9), (16, 5, 5)])
+def test_tc_split_gdn1_matches_fp64(s2, C, H, W):
+    dev = torch.device('cuda:0')
+    torch.manual_seed(C)
+    x = torch.randn(2, C, H, W) * 3
+    gamma = 0.1 * torch.eye(C) + 0.02 * torch.rand(C, C)
+    beta = 0.5 + torch.rand(C)
+    norm = F.conv2d(x.abs().double(), gamma.double().view(C, C, 1, 1), beta.double())
+    ref = (x.double() / norm).float()
+    xh, xl = _planes(s2, x, dev)
+    gh, gl = s2.ops.pack_conv_weight_split(gamma.view(C, C, 1, 1).to(dev), c_in_pad=C)
+    oh, ol = s2.ops.tc_split_conv(xh, xl, gh, gl, C, 1, 1, 1, 0, s2._native.TCS_GDN1, beta=beta.to(dev), gdn=True)
+    assert rel_err(_unsplit(oh, ol)[:, :C], ref) < SPLIT_TOL
