@@ -76,6 +76,74 @@ class TensorCoreTransform:
         return x.permute(0, 3, 1, 2)
 
 
+class TensorCoreAnalysis:
+    """Execution plan for the bottleneck's analysis transform g_a (Conv s2 - GDN1 - Conv s2 - GDN1 - Conv s1) on the
+    fp32-grade "split fp16" tcgen05 kernels, ending in the fused quantise-to-symbols epilogue:
+
+        image (fp32 NCHW) --patchify--> patches (parity-plane order) --1x1 GEMM--> x1 --GDN1--> y1 (parity planes)
+        --5x5 s2 conv as 25 shifted boxes--> x2 --GDN1--> y2 --2x2 conv + round(y - median)--> int32 symbols (NCHW)
+
+    Every intermediate is a (hi, lo) pair of NHWC fp16 planes.  Weights / gammas are split and packed once."""
+
+    def __init__(self, seq):
+        self.seq = seq
+        self._key = None
+
+    @staticmethod
+    def supports(seq, x_shape):
+        mods = list(seq)
+        if len(mods) != 5 or not all(isinstance(mods[i], nn.Conv2d) for i in (0, 2, 4)) or not all(type(mods[i]) is GDN1 for i in (1, 3)):
+            return False
+        c1, c2, c3 = mods[0], mods[2], mods[4]
+        for c in (c1, c2, c3):
+            if (c.bias is not None or c.groups != 1 or tuple(c.dilation) != (1, 1) or c.kernel_size[0] != c.kernel_size[1]
+                    or isinstance(c.padding, str) or c.padding[0] != c.padding[1] or c.stride[0] != c.stride[1]):
+                return False
+        if c1.stride[0] != 2 or c2.stride[0] != 2 or c3.stride[0] != 1 or mods[1].inverse or mods[3].inverse:
+            return False
+        if c1.in_channels * c1.kernel_size[0] ** 2 > 128 or c2.kernel_size[0] ** 2 > 25 or c3.kernel_size[0] ** 2 > 25:
+            return False
+        if c1.out_channels % 16 or c2.out_channels % 16 or max(c1.out_channels, c2.out_channels, c3.out_channels) > 128:
+            return False
+        H, W = x_shape[-2:]
+        k, p = c1.kernel_size[0], c1.padding[0]
+        h1, w1 = (H + 2 * p - k) // 2 + 1, (W + 2 * p - k) // 2 + 1
+        return h1 >= 2 and w1 >= 2 and h1 % 2 == 0 and w1 % 2 == 0
+
+    def _prepare(self):
+        params = list(self.seq.parameters())
+        key = tuple((q.data_ptr(), q._version, q.device) for q in params)
+        if key == self._key:
+            return
+        c1, g1, c2, g2, c3 = list(self.seq)
+        self.k1_pad = (c1.in_channels * c1.kernel_size[0] ** 2 + 15) // 16 * 16
+        self.w1 = ops.pack_conv_weight_split(c1.weight, c_in_pad=self.k1_pad, as_patches=True)
+        self.w2 = ops.pack_conv_weight_split(c2.weight)
+        self.w3 = ops.pack_conv_weight_split(c3.weight)
+        self.gdn = []
+        for g in (g1, g2):
+            gamma, beta = g.effective_params()
+            C = beta.numel()
+            self.gdn.append((ops.pack_conv_weight_split(gamma.detach().reshape(C, C, 1, 1)), beta.detach().float().contiguous()))
+        self._key = key
+
+    @torch.no_grad()
+    def __call__(self, x, medians):
+        self._prepare()
+        c1, _, c2, _, c3 = list(self.seq)
+        T = _native
+        ph, pl = ops.patchify_split(x, c1.kernel_size[0], c1.kernel_size[0], 2, c1.padding[0], self.k1_pad)
+        h, l = ops.tc_split_conv(ph, pl, self.w1[0], self.w1[1], c1.out_channels, 1, 1, 1, 0, T.TCS_STORE)
+        (gh, gl), beta = self.gdn[0]
+        h, l = ops.tc_split_conv(h, l, gh, gl, c1.out_channels, 1, 1, 1, 0, T.TCS_GDN1, beta=beta, gdn=True)
+        h, l = ops.tc_split_conv(h, l, self.w2[0], self.w2[1], c2.out_channels, c2.kernel_size[0], c2.kernel_size[0], 2,
+                                 c2.padding[0], T.TCS_STORE)
+        (gh, gl), beta = self.gdn[1]
+        h, l = ops.tc_split_conv(h, l, gh, gl, c2.out_channels, 1, 1, 1, 0, T.TCS_GDN1, beta=beta, gdn=True)
+        return ops.tc_split_conv(h, l, self.w3[0], self.w3[1], c3.out_channels, c3.kernel_size[0], c3.kernel_size[0], 1,
+                                 c3.padding[0], T.TCS_QUANT, medians=medians)
+
+
 LAYER_CLASS_DICT = dict()
 LAYER_FUNC_DICT = dict()
 
@@ -173,15 +241,28 @@ class FPBasedResNetBottleneck(BaseBottleneck):
         # 'fp32': exact-fp32 CUDA-core kernels.  Shapes the tensor-core kernels do not cover use 'fp32'.
         self.decoder_precision = 'fp16-tc'
         self._tc_decoder = None
+        # 'split-tc': fp32-grade split-fp16 tensor-core kernels (three MMA passes); 'fp32': exact-fp32 CUDA-core kernels.
+        self.encoder_precision = 'split-tc'
+        self._tc_encoder = None
 
     # ---- hot path ---------------------------------------------------------------------------------
     @torch.no_grad()
     def encode_packed(self, x):
         """g_a + quantise + rANS, bitstreams left on the device: (PackedStreams, latent (H, W))."""
         eb = self.entropy_bottleneck
-        medians = eb._get_medians().detach().reshape(-1)
-        symbols = run_transform(self.encoder, x, final_epilogue=_native.EPI_QUANTIZE, final_aux=medians)
+        symbols = self.analyze_to_symbols(x)
         return eb.compress_symbols(symbols, spatial=symbols[0, 0].numel()), symbols.size()[-2:]
+
+    @torch.no_grad()
+    def analyze_to_symbols(self, x):
+        """g_a + round(y - median) on the device: image batch -> int32 symbols [B, C, H, W] (coder order)."""
+        ops.require_cuda(x, 'FPBasedResNetBottleneck.encode')
+        medians = self.entropy_bottleneck._get_medians().detach().reshape(-1)
+        if self.encoder_precision == 'split-tc' and TensorCoreAnalysis.supports(self.encoder, x.shape):
+            if self._tc_encoder is None:
+                self._tc_encoder = TensorCoreAnalysis(self.encoder)
+            return self._tc_encoder(x, medians)
+        return run_transform(self.encoder, x, final_epilogue=_native.EPI_QUANTIZE, final_aux=medians)
 
     @torch.no_grad()
     def synthesize(self, latent_hat):
