@@ -274,8 +274,8 @@ class FPBasedResNetBottleneck(BaseBottleneck):
         return run_transform(self.decoder, latent_hat)
 
     @torch.no_grad()
-    def decode_packed(self, streams, shape):
-        latent_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape))
+    def decode_packed(self, streams, shape, check_status=False):
+        latent_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape), check_status=check_status)
         return self.synthesize(latent_hat)
 
     def encode(self, x, **kwargs):
@@ -286,9 +286,10 @@ class FPBasedResNetBottleneck(BaseBottleneck):
     def decode(self, strings, shape):
         """strings[0]: list of B bytes objects (or a device-resident PackedStreams) -> decoder features."""
         first = strings[0]
-        if not isinstance(first, ops.PackedStreams):
+        from_host = not isinstance(first, ops.PackedStreams)
+        if from_host:
             first = ops.PackedStreams.from_list(first, self.entropy_bottleneck._quantized_cdf.device)
-        return self.decode_packed(first, shape)
+        return self.decode_packed(first, shape, check_status=from_host)  # bytes from outside are validated eagerly
 
     # ---- training-time branches (differentiable torch, off the hot path) ----------------------------
     def _get_means(self, x):

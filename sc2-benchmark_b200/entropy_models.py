@@ -294,13 +294,22 @@ class EntropyBottleneck(EntropyModel):
     def compress(self, x):
         return self.compress_packed(x).tolist()
 
-    def decompress_packed(self, streams, size, want='values'):
+    def decompress_packed(self, streams, size, want='values', check_status=False):
+        """Device-resident decode.  With check_status=False (default) nothing synchronises: device fault flags
+        (truncated / malformed stream) stay in `self.last_decode_status` and are raised by `check_faults()`."""
         tables = self.coder_tables()
         C = self._quantized_cdf.size(0)
         spatial = int(np.prod(size)) if len(size) else 1
         medians = self._get_medians().detach().reshape(-1)
-        out = ops.rans_decode(streams, C * spatial, tables, spatial=spatial, means=medians, want=want)
+        out, self.last_decode_status = ops.rans_decode(streams, C * spatial, tables, spatial=spatial, means=medians, want=want,
+                                                       check_status=check_status, return_status=True)
         return out.view(streams.batch, C, *size)
+
+    def check_faults(self):
+        """Synchronises and raises if the last device-resident decode flagged a truncated or malformed stream."""
+        st = getattr(self, 'last_decode_status', None)
+        if st is not None:
+            ops.raise_on_decode_fault(int(st.item()))
 
     def decompress(self, strings, size):
         if not isinstance(strings, (tuple, list)):
@@ -309,7 +318,7 @@ class EntropyBottleneck(EntropyModel):
         device = self._quantized_cdf.device
         if device.type != 'cuda':
             raise RuntimeError('EntropyBottleneck.decompress: the sc2bench_b200 coder runs on CUDA only; move the model to a GPU')
-        return self.decompress_packed(ops.PackedStreams.from_list(strings, device), tuple(size))
+        return self.decompress_packed(ops.PackedStreams.from_list(strings, device), tuple(size), check_status=True)
 
 
 class GaussianConditional(EntropyModel):

@@ -178,7 +178,7 @@ class FactorizedPrior(CompressionModel):
         first = strings[0]
         streams = first if isinstance(first, ops.PackedStreams) else \
             ops.PackedStreams.from_list(first, self.entropy_bottleneck._quantized_cdf.device)
-        y_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape))
+        y_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape), check_status=not isinstance(first, ops.PackedStreams))
         return {'x_hat': run_transform(self.g_s, y_hat, final_epilogue=_native.EPI_CLAMP01)}
 
 
@@ -229,7 +229,7 @@ class ScaleHyperprior(CompressionModel):
         assert isinstance(strings, list) and len(strings) == 2
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         device = eb._quantized_cdf.device
-        z_hat = eb.decompress_packed(ops.PackedStreams.from_list(strings[1], device), tuple(shape))
+        z_hat = eb.decompress_packed(ops.PackedStreams.from_list(strings[1], device), tuple(shape), check_status=True)
         indexes = gc.build_indexes(run_transform(self.h_s, z_hat))
         y_streams = ops.PackedStreams.from_list(strings[0], device)
         y_hat = ops.rans_decode(y_streams, indexes[0].numel(), gc.coder_tables(), indexes=indexes, want='values')

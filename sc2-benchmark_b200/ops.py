@@ -230,7 +230,14 @@ def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None):
     return PackedStreams(packed, offsets, B, status)
 
 
-def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means=None, want='values', check_status=True):
+def raise_on_decode_fault(st):
+    if st:
+        raise ValueError('Invalid bitstream (device fault flags 0x%x: %s)' % (st, ', '.join(
+            name for bit, name in ((2, 'stream truncated'), (4, 'bad stream length')) if st & bit)))
+
+
+def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means=None, want='values', check_status=True,
+                return_status=False):
     """PackedStreams -> [B, n] float32 (symbol + means[row]) or int32 symbols."""
     dev = streams.packed.device
     B = streams.batch
@@ -252,11 +259,9 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
                                            int(spatial or 0), _ptr(tab), tables.n_rows, tables.cdf_stride, _ptr(out_sym),
                                            _ptr(out_val), _ptr(m), _ptr(status), _stream_ptr()), 'sc2_rans_decode_batch')
     if check_status:
-        st = int(status.item())
-        if st:
-            raise ValueError('Invalid bitstream (device fault flags 0x%x: %s)' % (st, ', '.join(
-                name for bit, name in ((2, 'stream truncated'), (4, 'bad stream length')) if st & bit)))
-    return out_sym if want == 'symbols' else out_val
+        raise_on_decode_fault(int(status.item()))
+    out = out_sym if want == 'symbols' else out_val
+    return (out, status) if return_status else out
 
 
 def gc_build_indexes(scales, scale_table, scale_bound):
