@@ -29,6 +29,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# keep stdout clean for the single JSON line: NCCL's version / debug banner goes to a file
+os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/sc2b200_nccl.%h.%p.log')
 
 METRIC = 'images/s encode+rANS+decode @224^2 (FPBasedResNetBottleneck, Entropic Student ResNet-50)'
 UNIT = 'images/s'
@@ -167,6 +169,7 @@ def main():
     ap.add_argument('--cpu-images', type=int, default=8, help='images per step of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-threads', type=int, default=3, help='host threads (one CUDA stream each) driving the e2e steps')
     ap.add_argument('--inflight', type=int, default=3, help='batches in flight (CUDA streams): the serial rANS chain of one batch overlaps the convolutions of the next')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
@@ -255,33 +258,42 @@ def main():
     value = c['images'] / (ms / 1e3)
 
     # ---- end-to-end through the public API with host buffers ("e2e") ---------------------------
+    # Each step is the reference-facing call sequence on HOST data: pinned images -> H2D -> layer.encode(x) (returns the
+    # contract object with real `bytes` on the host) -> layer.decode(**obj) (bytes -> H2D -> features) -> a per-image
+    # result read back.  `e2e_threads` host threads each drive their own CUDA stream (like the reference's
+    # nn.DataParallel replicas are host threads), so the PCIe copies and the host-side bytes handling of one batch overlap
+    # the GPU work of another; every step still runs entirely inside the timed region.
     e2e = None
     if not args.no_e2e:
-        with torch.inference_mode():
-            def e2e_step(i):
+        import concurrent.futures
+
+        def e2e_step(i):
+            with torch.inference_mode(), torch.cuda.stream(e2e_streams[i % len(e2e_streams)]):
                 x = host_inputs[i & 1].to(device, non_blocking=True)
                 obj = layer.encode(x)                       # {'strings': [list[bytes]], 'shape'}: bitstreams land on the host
                 feat = layer.decode(**obj)                  # list[bytes] -> device -> features
-                return obj, feat.mean(dim=(1, 2, 3)).cpu()  # per-image result read back
-            for i in range(args.warmup):
-                e2e_step(i)
+                res = feat.mean(dim=(1, 2, 3)).cpu()        # per-image result read back (synchronises this stream)
+            return obj, res
+
+        n_thr = max(1, args.e2e_threads)
+        e2e_streams = [torch.cuda.Stream(device=device) for _ in range(n_thr)]
+        with concurrent.futures.ThreadPoolExecutor(max_workers=n_thr) as pool:
+            list(pool.map(e2e_step, range(args.warmup)))
             barrier()
             t0 = time.perf_counter()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for i in range(args.steps):
-                obj, res = e2e_step(i)
-            f1.record()
+            results = list(pool.map(e2e_step, range(args.warmup, args.warmup + args.steps)))
+            torch.cuda.synchronize()
+            e2e_ms = (time.perf_counter() - t0) * 1e3  # host wall clock: host work is part of this contract
             barrier()
-            wall_ms = (time.perf_counter() - t0) * 1e3
-            e2e_ms = max(f0.elapsed_time(f1), wall_ms)  # host work (bytes objects) is part of the contract
+        obj, res = results[-1]
         te = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         stream_bytes = sum(len(s) for s in obj['strings'][0])
         e2e = {'value': world * B * args.steps / (float(te.item()) / 1e3), 'unit': UNIT,
                'h2d_bytes_per_step': B * IMG[0] * IMG[1] * IMG[2] * 4 + stream_bytes + 8 * (B + 1),
-               'd2h_bytes_per_step': stream_bytes + 8 * (B + 1) + 4 + B * 4}
+               'd2h_bytes_per_step': stream_bytes + 8 * (B + 1) + 4 + B * 4, 'host_threads': n_thr,
+               'ms_per_step': float(te.item()) / args.steps}
 
     if rank != 0:
         if world > 1:

@@ -1,30 +1,28 @@
-// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution for NHWC fp16 activations (sm_100a).
+// conv_tc.cu -- persistent tcgen05 / TMEM / TMA implicit-GEMM convolution for NHWC fp16 activations (sm_100a).
 //
 // The synthesis transform g_s of the bottleneck (sc2bench/models/layer.py:485-494: Conv 2x2 -> IGDN1 -> Conv 2x2 ->
 // IGDN1 -> Conv 2x2) is 86 % of the path's FLOPs and tolerates fp16 operands (fp32 accumulation; 4e-4 relative on the
 // decoded features), so it runs on the 5th-generation tensor cores:
 //
-//   GEMM view   M = output pixels (a TH x TW patch of one image = up to 128 rows), N = output channels (<= 256 per CTA),
+//   GEMM view   M = output pixels (a TH x TW patch of one image = up to 128 rows), N = output channels (<= 256 per tile),
 //               K = taps x input channels.
 //   A operand   no im2col: for tap (dy, dx) the A tile is the SAME activation tensor read through a 4-D TMA box
 //               {64 channels, TW, TH, 1} shifted by (dx - pad, dy - pad); TMA zero-fills outside the image = padding.
-//               The box lands in shared memory as 128-byte rows (K-major, SWIZZLE_128B), which is exactly the UMMA
-//               canonical layout.
+//               The box lands in shared memory as 128-byte rows (K-major, SWIZZLE_128B) = the UMMA canonical layout.
 //   B operand   weights repacked once per model to [tap][c_out][c_in] fp16, 2-D TMA box {64, N_TILE}.
-//   D           fp32 accumulator in TMEM (N_TILE columns x 128 lanes), read back with tcgen05.ld by 4 epilogue warps.
-//   pipeline    warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue;
-//               STAGES-deep smem ring with full/empty mbarriers, tcgen05.commit releases stages.
-//   epilogues   store fp16 NHWC | store fp32 NHWC | IGDN1: out = x * (beta + gamma.|x|) where the GEMM is the 1x1
-//               "gamma" contraction, |x| is produced in shared memory by the (otherwise idle) epilogue warps right after
-//               the TMA lands (sign-bit clear), and x is re-read as a tile.  Output tiles go through swizzled smem and
-//               one TMA store per 128-byte channel group, so HBM writes are full lines and image borders are clipped
-//               by the TMA unit.
+//   D           fp32 accumulators in TMEM, DOUBLE BUFFERED (2 x N_TILE columns): the epilogue of tile i overlaps the
+//               MMAs of tile i + 1.
+//   schedule    persistent: one CTA per SM walks the tile list (stride gridDim.x); barrier / TMEM / descriptor set-up
+//               is paid once per CTA instead of once per tile (it dominated the small-K layers).
+//   roles       warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM -> registers
+//               -> global, thread = output pixel), warps 6..9 (GDN modes) = |x| transform of the landed A tiles.
+//   epilogues   store fp16 | store fp32 | IGDN1: out = x * (beta + gamma.|x|) | GDN1: out = x / (beta + gamma.|x|),
+//               where the GEMM is the 1x1 "gamma" contraction over |x| (sign bits cleared in shared memory right after
+//               the TMA lands) and x is re-read by the epilogue.
 #include "tc_common.cuh"
 
 namespace sc2 {
 namespace tc {
-
-constexpr int kNumThreads = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 
 enum Mode { MODE_STORE_F16 = 0, MODE_STORE_F32 = 1, MODE_IGDN1_F16 = 2, MODE_GDN1_F16 = 3 };
 
@@ -34,7 +32,12 @@ struct Params {
     int taps_x, taps_y, pad;
     int k_chunks;          // c_in_padded / 64
     int n_total;           // c_out (rows per tap of the packed weight tensor)
+    int n_tiles;           // c_out / N_TILE
+    int batch;
+    int h_out, w_out;
     const float *beta;     // GDN modes: effective beta [n_total]
+    const __half *gdn_x;   // GDN modes: x itself, NHWC [batch, h_out, w_out, n_total]
+    void *out;             // NHWC [batch, h_out, w_out, n_total], fp16 or fp32
 };
 
 template <int N_TILE, int STAGES>
@@ -42,53 +45,49 @@ struct Smem {
     static constexpr int kBBytes = N_TILE * 128;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kRingBytes = STAGES * kStageBytes;
-    static constexpr int kBarOffset = kRingBytes;
-    // full[STAGES], empty[STAGES], xform[STAGES], accum, xload : 8 bytes each; then the TMEM base address
-    static constexpr int kTotal = kRingBytes + (3 * STAGES + 2) * 8 + 16;
+    // full[STAGES], empty[STAGES], xform[STAGES], acc_full[2], acc_empty[2] : 8 bytes each; then the TMEM base address
+    static constexpr int kTotal = kRingBytes + (3 * STAGES + 4) * 8 + 16;
 };
 
-// ---- the kernel --------------------------------------------------------------------------------------------------
 template <int N_TILE, int STAGES, int MODE>
-__global__ void __launch_bounds__(kNumThreads, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_x, const Params p) {
+__global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16) ? 320 : 192, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params p) {
     using L = Smem<N_TILE, STAGES>;
     constexpr bool kGdn = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
     constexpr bool kOutF32 = MODE == MODE_STORE_F32;
+    constexpr uint32_t kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
+    static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "two accumulator stages must fit TMEM");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kRingBytes);
     uint64_t *empty = full + STAGES;
     uint64_t *xform = empty + STAGES;
-    uint64_t *accum_bar = xform + STAGES;
-    uint64_t *xload_bar = accum_bar + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xload_bar + 1);
+    uint64_t *acc_full = xform + STAGES;
+    uint64_t *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int x0 = (tile % p.tiles_x) * p.tw;
-    const int y0 = (tile / p.tiles_x) * p.th;
-    const int n0 = blockIdx.y * N_TILE;
-    const int img = blockIdx.z;
     const int rows = p.tw * p.th;
-    const int n_iter = p.taps_x * p.taps_y * p.k_chunks;
+    const int k_iters = p.taps_x * p.taps_y * p.k_chunks;
+    const int tiles_xy = p.tiles_x * p.tiles_y;
+    const int total_tiles = tiles_xy * p.n_tiles * p.batch;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
-        tma_prefetch_desc(&map_out);
-        if (kGdn) tma_prefetch_desc(&map_x);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
             mbar_init(&xform[s], 128);
         }
-        mbar_init(accum_bar, 1);
-        mbar_init(xload_bar, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 128);
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, N_TILE);
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -98,101 +97,85 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // =============================== TMA producer ===============================
         if (elect_one()) {
             const uint32_t stage_tx = static_cast<uint32_t>(rows * 128 + L::kBBytes);
-            int it = 0;
-            for (int ty = 0; ty < p.taps_y; ++ty)
-                for (int tx = 0; tx < p.taps_x; ++tx)
-                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                        const int s = it % STAGES;
-                        const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
-                        mbar_wait(&empty[s], ph ^ 1u);
-                        uint8_t *a_dst = smem + s * L::kStageBytes;
-                        mbar_expect_tx(&full[s], stage_tx);
-                        tma_load_4d(&map_a, &full[s], a_dst, kc * kBlockK, x0 + tx - p.pad, y0 + ty - p.pad, img);
-                        tma_load_2d(&map_b, &full[s], a_dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
-                    }
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int sp = tile % tiles_xy, rest = tile / tiles_xy;
+                const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
+                const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
+                for (int ty = 0; ty < p.taps_y; ++ty)
+                    for (int tx = 0; tx < p.taps_x; ++tx)
+                        for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                            mbar_wait(&empty[s], ph ^ 1u);
+                            uint8_t *dst = smem + s * L::kStageBytes;
+                            mbar_expect_tx(&full[s], stage_tx);
+                            tma_load_4d(&map_a, &full[s], dst, kc * kBlockK, x0 + tx - p.pad, y0 + ty - p.pad, img);
+                            tma_load_2d(&map_b, &full[s], dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
+                        }
+            }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         constexpr uint32_t idesc = make_idesc(N_TILE);
-        for (int it = 0; it < n_iter; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
-            mbar_wait(kGdn ? &xform[s] : &full[s], ph);
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+            mbar_wait(&acc_empty[as], aph ^ 1u);  // the epilogue has drained this accumulator stage
             tcgen05_fence_after();
-            if (elect_one()) {
-                const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-                const uint64_t a_desc = make_smem_desc(a_addr);
-                const uint64_t b_desc = make_smem_desc(a_addr + kABytes);
+            for (int k_it = 0; k_it < k_iters; ++k_it, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                mbar_wait(kGdn ? &xform[s] : &full[s], ph);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+                    const uint64_t a_desc = make_smem_desc(a_addr);
+                    const uint64_t b_desc = make_smem_desc(a_addr + kABytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                    umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_f16(tmem_base + as * N_TILE, a_desc + 2 * k, b_desc + 2 * k, idesc, (k_it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[s]);                               // frees the smem stage once these MMAs have read it
+                    if (k_it == k_iters - 1) umma_commit(&acc_full[as]);  // accumulator complete
                 }
-                umma_commit(&empty[s]);                       // frees the stage once these MMAs have read it
-                if (it == n_iter - 1) umma_commit(accum_bar);  // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
-    } else {
+    } else if (warp < 6) {
         // =============================== epilogue warps (2..5) ===============================
-        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-        const int row = quarter * 32 + lane;      // tile row = TMEM lane = pixel index inside the tile
-        const bool row_ok = row < rows;
-        if (kGdn) {
-            // |x| in place: the A tile is the activation itself; clear the fp16 sign bits row by row
-            for (int it = 0; it < n_iter; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
-                mbar_wait(&full[s], ph);
-                if (row_ok) {
-                    uint4 *r = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + row * 128);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4 v = r[c];
-                        v.x &= 0x7fff7fffu; v.y &= 0x7fff7fffu; v.z &= 0x7fff7fffu; v.w &= 0x7fff7fffu;
-                        r[c] = v;
-                    }
-                }
-                fence_proxy_async();
-                mbar_arrive(&xform[s]);
-            }
-        }
-        mbar_wait(accum_bar, 0);
-        tcgen05_fence_after();
-        // all MMAs have completed: the smem ring is free and becomes the output staging area
-        constexpr int kSubCols = kOutF32 ? 32 : 64;           // channels per 128-byte staging row
-        constexpr int kSubTiles = N_TILE / kSubCols;
-        static_assert(kSubTiles * kABytes <= L::kRingBytes, "staging does not fit in the ring");
-        if (kGdn) {
-            if (threadIdx.x == 64) {
-                mbar_expect_tx(xload_bar, static_cast<uint32_t>(rows * 128 * kSubTiles));
-                for (int j = 0; j < kSubTiles; ++j)
-                    tma_load_4d(&map_x, xload_bar, smem + j * kABytes, n0 + j * 64, x0, y0, img);
-            }
-            mbar_wait(xload_bar, 0);
-        }
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;  // tile row = TMEM lane = pixel index inside the tile
+        const int ty = row / p.tw, tx = row - ty * p.tw;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+            const int sp = tile % tiles_xy, rest = tile / tiles_xy;
+            const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
+            const int oy = (sp / p.tiles_x) * p.th + ty, ox = (sp % p.tiles_x) * p.tw + tx;
+            const bool valid = row < rows && oy < p.h_out && ox < p.w_out;
+            const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
+            mbar_wait(&acc_full[as], aph);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + as * N_TILE + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + c0, v);
-            if (row_ok) {
+            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                if (!valid) continue;
+                const int64_t o = pix * p.n_total + n0 + c0;
                 if (kOutF32) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(smem + (c0 / 32) * kABytes + row * 128);
+                    float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + o);
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
-                        dst[c ^ (row & 7)] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        dst[c] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                             __uint_as_float(v[4 * c + 3]));
                 } else {
-                    uint4 *dst = reinterpret_cast<uint4 *>(smem + (c0 / 64) * kABytes + row * 128);
-                    const int chunk0 = (c0 % 64) / 8;
+                    uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__half *>(p.out) + o);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * c + e]);
-                        const int phys = (chunk0 + c) ^ (row & 7);
                         if (kGdn) {
-                            const uint4 xv = dst[phys];
+                            const uint4 xv = __ldg(reinterpret_cast<const uint4 *>(p.gdn_x + o) + c);
                             const __half2 *xh = reinterpret_cast<const __half2 *>(&xv);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -208,45 +191,61 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 }
                             }
                         }
-                        uint4 o;
+                        uint4 ov;
                         __half2 h;
-                        h = __floats2half2_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2half2_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2half2_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2half2_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t *>(&h);
-                        dst[phys] = o;
+                        h = __floats2half2_rn(f[0], f[1]); ov.x = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2half2_rn(f[2], f[3]); ov.y = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2half2_rn(f[4], f[5]); ov.z = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2half2_rn(f[6], f[7]); ov.w = *reinterpret_cast<uint32_t *>(&h);
+                        dst[c] = ov;
                     }
                 }
             }
+            tcgen05_fence_before();
+            mbar_arrive(&acc_empty[as]);  // 128 arrivals release the accumulator stage to the MMA warp
         }
-        tcgen05_fence_before();
-        fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-        if (threadIdx.x == 64) {
-            for (int j = 0; j < kSubTiles; ++j) tma_store_4d(&map_out, smem + j * kABytes, n0 + j * kSubCols, x0, y0, img);
-            tma_store_commit_and_wait();
+    } else if (kGdn) {
+        // =============================== |x| transform warps (6..9, GDN modes) ===============================
+        const int row = (warp - 6) * 32 + lane;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int k_it = 0; k_it < k_iters; ++k_it, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                if (row < rows) {
+                    uint4 *r = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + row * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 v = r[c];
+                        v.x &= 0x7fff7fffu; v.y &= 0x7fff7fffu; v.z &= 0x7fff7fffu; v.w &= 0x7fff7fffu;
+                        r[c] = v;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&xform[s]);
+            }
         }
     }
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, N_TILE);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
-// ---- host side ----------------------------------------------------------------------------------------------------
 template <int N_TILE, int STAGES, int MODE>
-static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const CUtensorMap &mx, const Params &p,
-                  int n_tiles, int batch, cudaStream_t st) {
+static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const Params &p, cudaStream_t st) {
     using L = Smem<N_TILE, STAGES>;
+    constexpr bool kGdn = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
     const int smem = L::kTotal + 1024;  // slack for the manual 1024-byte alignment
     static bool configured = false;
     if (!configured) {
         SC2_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<N_TILE, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid(p.tiles_x * p.tiles_y, n_tiles, batch);
-    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kNumThreads, smem, st>>>(ma, mb, mo, mx, p);
+    const int total = p.tiles_x * p.tiles_y * p.n_tiles * p.batch;
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kGdn ? 320 : 192, smem, st>>>(ma, mb, p);
     SC2_LAUNCH_CHECK("tc_conv_kernel");
     return SC2_OK;
 }
@@ -289,7 +288,7 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
                      void *out, sc2_stream_t stream) {
     using namespace sc2::tc;
     if (!d || !x || !w_packed || !out) return SC2_ERR_INVALID_ARG;
-    if (d->batch < 1 || d->batch > 65535 || d->c_in_pad % kBlockK || d->c_in_pad < kBlockK) return SC2_ERR_INVALID_ARG;
+    if (d->batch < 1 || d->c_in_pad % kBlockK || d->c_in_pad < kBlockK) return SC2_ERR_INVALID_ARG;
     if (d->mode < 0 || d->mode > 3) return SC2_ERR_INVALID_ARG;
     const bool gdn = d->mode == MODE_IGDN1_F16 || d->mode == MODE_GDN1_F16;
     if (gdn && (!beta || !gdn_x || d->kh != 1 || d->kw != 1 || d->pad != 0 || d->c_in_pad != d->c_out)) return SC2_ERR_INVALID_ARG;
@@ -315,34 +314,29 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
     p.taps_x = d->kw; p.taps_y = d->kh; p.pad = d->pad;
     p.k_chunks = d->c_in_pad / kBlockK;
     p.n_total = d->c_out;
+    p.n_tiles = d->c_out / n_tile;
+    p.batch = d->batch;
+    p.h_out = h_out; p.w_out = w_out;
     p.beta = beta;
-    CUtensorMap ma, mb, mo, mx;
+    p.gdn_x = static_cast<const __half *>(gdn_x);
+    p.out = out;
+    if (static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.n_tiles * p.batch > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
+    CUtensorMap ma, mb;
     int rc = make_nhwc_map(&ma, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in_pad, d->w_in, d->h_in, d->batch, kBlockK, tw, th);
     if (rc) return rc;
     rc = make_weight_map(&mb, w_packed, d->c_in_pad, d->kh * d->kw * d->c_out, n_tile);
     if (rc) return rc;
-    if (d->mode == MODE_STORE_F32)
-        rc = make_nhwc_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->c_out, w_out, h_out, d->batch, 32, tw, th);
-    else
-        rc = make_nhwc_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_out, w_out, h_out, d->batch, 64, tw, th);
-    if (rc) return rc;
-    mx = mo;
-    if (gdn) {
-        rc = make_nhwc_map(&mx, gdn_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_out, w_out, h_out, d->batch, 64, tw, th);
-        if (rc) return rc;
-    }
     cudaStream_t st = sc2::as_stream(stream);
-    const int n_tiles = d->c_out / n_tile;
-#define SC2_TC_DISPATCH(NT, STG)                                                                            \
-    switch (d->mode) {                                                                                      \
-        case MODE_STORE_F16: return launch<NT, STG, MODE_STORE_F16>(ma, mb, mo, mx, p, n_tiles, d->batch, st); \
-        case MODE_STORE_F32: return launch<NT, STG, MODE_STORE_F32>(ma, mb, mo, mx, p, n_tiles, d->batch, st); \
-        case MODE_IGDN1_F16: return launch<NT, STG, MODE_IGDN1_F16>(ma, mb, mo, mx, p, n_tiles, d->batch, st); \
-        default: return launch<NT, STG, MODE_GDN1_F16>(ma, mb, mo, mx, p, n_tiles, d->batch, st);           \
+#define SC2_TC_DISPATCH(NT, STG)                                                   \
+    switch (d->mode) {                                                             \
+        case MODE_STORE_F16: return launch<NT, STG, MODE_STORE_F16>(ma, mb, p, st);  \
+        case MODE_STORE_F32: return launch<NT, STG, MODE_STORE_F32>(ma, mb, p, st);  \
+        case MODE_IGDN1_F16: return launch<NT, STG, MODE_IGDN1_F16>(ma, mb, p, st);  \
+        default: return launch<NT, STG, MODE_GDN1_F16>(ma, mb, p, st);             \
     }
     if (n_tile == 256) { SC2_TC_DISPATCH(256, 4) }
-    if (n_tile == 128) { SC2_TC_DISPATCH(128, 4) }
-    SC2_TC_DISPATCH(64, 4)
+    if (n_tile == 128) { SC2_TC_DISPATCH(128, 6) }
+    SC2_TC_DISPATCH(64, 8)
 #undef SC2_TC_DISPATCH
 }
 

@@ -154,8 +154,8 @@ class PackedStreams:
 
     def tolist(self):
         offs, data = self._to_host()
-        raw = data.tobytes()
-        return [raw[offs[i]:offs[i + 1]] for i in range(self.batch)]
+        view = memoryview(data)  # one copy per stream, straight out of the pinned staging buffer
+        return [bytes(view[offs[i]:offs[i + 1]]) for i in range(self.batch)]
 
     @staticmethod
     def from_list(strings, device):
@@ -168,7 +168,9 @@ class PackedStreams:
         np.cumsum(lens, out=offs[1:])
         total = int(offs[-1])
         host = torch.empty(max(total, 4), dtype=torch.uint8, pin_memory=True)
-        host.numpy()[:total] = np.frombuffer(b''.join(strings), dtype=np.uint8)
+        dst = memoryview(host.numpy())
+        for i, s in enumerate(strings):  # one copy per stream, straight into the pinned staging buffer
+            dst[offs[i]:offs[i + 1]] = s
         packed = host.to(device, non_blocking=True)
         offsets = torch.from_numpy(offs).pin_memory().to(device, non_blocking=True)
         ps = PackedStreams(packed, offsets, len(strings))
