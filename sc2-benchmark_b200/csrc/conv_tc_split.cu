@@ -44,6 +44,7 @@ struct Params {
     int k_chunks, k_steps_last;
     int groups;        // D0 accumulator groups (taps are dealt to groups in order)
     int planes;        // input planes per output image (1, or 4 parity planes)
+    int images;        // output images (grid-stride tile loop covers tiles_x * tiles_y * images tiles)
     int c_out;         // valid output channels (<= N_TILE)
     int h_out, w_out;
     const float *beta;
@@ -59,7 +60,7 @@ struct Smem {
     static constexpr int kBBytes = N_TILE * 128;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kRingBytes = STAGES * kStageBytes;
-    static constexpr int kTotal = kRingBytes + (3 * STAGES + 1) * 8 + 16;
+    static constexpr int kTotal = kRingBytes + (3 * STAGES + 4) * 8 + 16;
 };
 
 __device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr, __half *lo_ptr) {
@@ -78,28 +79,32 @@ __device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr
 }
 
 template <int N_TILE, int STAGES, int MODE>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(MODE == MODE_GDN1_SPLIT ? 320 : 192, 1)
 tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                      const __grid_constant__ Params p) {
+    // Persistent: the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  With one D0 group the two 256-column
+    // halves of TMEM alternate between tiles (epilogue of tile i overlaps the MMAs of tile i + 1); with several D0
+    // groups (long K) the whole TMEM belongs to one tile at a time.
     using L = Smem<N_TILE, STAGES>;
     constexpr bool kGdn = MODE == MODE_GDN1_SPLIT;
+    constexpr uint32_t kSlot = N_TILE <= 64 ? 64 : 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kRingBytes);
     uint64_t *empty = full + STAGES;
     uint64_t *xform = empty + STAGES;
-    uint64_t *accum_bar = xform + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+    uint64_t *acc_full = xform + STAGES;
+    uint64_t *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int x0 = (tile % p.tiles_x) * p.tw;
-    const int y0 = (tile / p.tiles_x) * p.th;
-    const int img = blockIdx.z;
     const int rows = p.tw * p.th;
-    const int n_iter = p.n_taps * p.k_chunks;
+    const int k_iters = p.n_taps * p.k_chunks;
+    const int tiles_xy = p.tiles_x * p.tiles_y;
+    const int total_tiles = tiles_xy * p.images;
+    const uint32_t acc_stages = p.groups == 1 ? 2u : 1u;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a_hi);
@@ -111,7 +116,10 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             mbar_init(&empty[s], 1);
             mbar_init(&xform[s], 128);
         }
-        mbar_init(accum_bar, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 128);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -124,65 +132,137 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         // =============================== TMA producer ===============================
         if (elect_one()) {
             const uint32_t stage_tx = static_cast<uint32_t>(2 * rows * 128 + 2 * L::kBBytes);
-            int it = 0;
-            for (int t = 0; t < p.n_taps; ++t) {
-                const Tap tap = p.taps[t];
-                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    uint8_t *dst = smem + s * L::kStageBytes;
-                    mbar_expect_tx(&full[s], stage_tx);
-                    const int cx = x0 + tap.dx, cy = y0 + tap.dy, cz = img * p.planes + tap.plane;
-                    tma_load_4d(&map_a_hi, &full[s], dst, kc * kBlockK, cx, cy, cz);
-                    tma_load_4d(&map_a_lo, &full[s], dst + kABytes, kc * kBlockK, cx, cy, cz);
-                    tma_load_2d(&map_b_hi, &full[s], dst + 2 * kABytes, kc * kBlockK, t * N_TILE);
-                    tma_load_2d(&map_b_lo, &full[s], dst + 2 * kABytes + L::kBBytes, kc * kBlockK, t * N_TILE);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int sp = tile % tiles_xy, img = tile / tiles_xy;
+                const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
+                for (int t = 0; t < p.n_taps; ++t) {
+                    const Tap tap = p.taps[t];
+                    for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        uint8_t *dst = smem + s * L::kStageBytes;
+                        mbar_expect_tx(&full[s], stage_tx);
+                        const int cx = x0 + tap.dx, cy = y0 + tap.dy, cz = img * p.planes + tap.plane;
+                        tma_load_4d(&map_a_hi, &full[s], dst, kc * kBlockK, cx, cy, cz);
+                        tma_load_4d(&map_a_lo, &full[s], dst + kABytes, kc * kBlockK, cx, cy, cz);
+                        tma_load_2d(&map_b_hi, &full[s], dst + 2 * kABytes, kc * kBlockK, t * N_TILE);
+                        tma_load_2d(&map_b_lo, &full[s], dst + 2 * kABytes + L::kBBytes, kc * kBlockK, t * N_TILE);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         constexpr uint32_t idesc = make_idesc(N_TILE);
-        constexpr uint32_t kSlot = N_TILE <= 64 ? 64 : 128;
-        int it = 0;
-        uint32_t started = 0;  // bit g: group g's accumulator holds data; bit 31: D1 does
-        for (int t = 0; t < p.n_taps; ++t)
-            for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                const uint32_t g = static_cast<uint32_t>(t * p.groups / p.n_taps);
-                const int s = it % STAGES;
-                const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
-                mbar_wait(kGdn ? &xform[s] : &full[s], ph);
-                tcgen05_fence_after();
-                if (elect_one()) {
-                    const uint32_t base = smem_u32(smem + s * L::kStageBytes);
-                    const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + kABytes);
-                    const uint64_t b_hi = make_smem_desc(base + 2 * kABytes), b_lo = make_smem_desc(base + 2 * kABytes + L::kBBytes);
-                    const int k_steps = (kc == p.k_chunks - 1) ? p.k_steps_last : kBlockK / 16;
-                    for (int k = 0; k < k_steps; ++k) {
-                        const uint32_t acc0 = k > 0 ? 1u : ((started >> g) & 1u), acc1 = k > 0 ? 1u : (started >> 31);
-                        umma_f16(tmem_base + g * kSlot, a_hi + 2 * k, b_hi + 2 * k, idesc, acc0);  // D0[g] += hi * hi
-                        umma_f16(tmem_base + kD1Col, a_hi + 2 * k, b_lo + 2 * k, idesc, acc1);    // D1 += hi * lo
-                        umma_f16(tmem_base + kD1Col, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);      // D1 += lo * hi
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t as = lt % acc_stages, aph = (lt / acc_stages) & 1u;
+            mbar_wait(&acc_empty[as], aph ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t d1_col = p.groups == 1 ? as * 256u + 128u : kD1Col;
+            uint32_t started = 0;  // bit g: D0 group g holds data; bit 31: D1 does (tracked by every lane)
+            for (int t = 0; t < p.n_taps; ++t)
+                for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                    const uint32_t g = static_cast<uint32_t>(t * p.groups / p.n_taps);
+                    const uint32_t d0_col = p.groups == 1 ? as * 256u : g * kSlot;
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(kGdn ? &xform[s] : &full[s], ph);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint32_t base = smem_u32(smem + s * L::kStageBytes);
+                        const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + kABytes);
+                        const uint64_t b_hi = make_smem_desc(base + 2 * kABytes), b_lo = make_smem_desc(base + 2 * kABytes + L::kBBytes);
+                        const int k_steps = (kc == p.k_chunks - 1) ? p.k_steps_last : kBlockK / 16;
+                        for (int k = 0; k < k_steps; ++k) {
+                            const uint32_t acc0 = k > 0 ? 1u : ((started >> g) & 1u), acc1 = k > 0 ? 1u : (started >> 31);
+                            umma_f16(tmem_base + d0_col, a_hi + 2 * k, b_hi + 2 * k, idesc, acc0);  // D0[g] += hi * hi
+                            umma_f16(tmem_base + d1_col, a_hi + 2 * k, b_lo + 2 * k, idesc, acc1);  // D1 += hi * lo
+                            umma_f16(tmem_base + d1_col, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);    // D1 += lo * hi
+                        }
+                        umma_commit(&empty[s]);
+                        if (t == p.n_taps - 1 && kc == p.k_chunks - 1) umma_commit(&acc_full[as]);
                     }
-                    umma_commit(&empty[s]);
-                    if (it == n_iter - 1) umma_commit(accum_bar);
+                    started |= (1u << g) | 0x80000000u;
+                    __syncwarp();
                 }
-                started |= (1u << g) | 0x80000000u;  // tracked by every lane: whichever lane is elected next sees it
-                __syncwarp();
-            }
-    } else {
+        }
+    } else if (warp < 6) {
         // =============================== epilogue warps (2..5) ===============================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const bool row_in_tile = row < rows;
-        if (kGdn) {
-            // |x| on both halves, in place: |a| = |hi| + sign(hi) * lo / 2048
-            for (int it = 0; it < n_iter; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = static_cast<uint32_t>(it / STAGES) & 1u;
+        const int ty = row / p.tw, tx = row - ty * p.tw;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t as = lt % acc_stages, aph = (lt / acc_stages) & 1u;
+            const int sp = tile % tiles_xy, img = tile / tiles_xy;
+            const int oy = (sp / p.tiles_x) * p.th + ty, ox = (sp % p.tiles_x) * p.tw + tx;
+            const bool valid = row < rows && oy < p.h_out && ox < p.w_out;
+            const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
+            mbar_wait(&acc_full[as], aph);
+            tcgen05_fence_after();
+            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+            const uint32_t d0_base = p.groups == 1 ? as * 256u : 0u;
+            const uint32_t d1_col = p.groups == 1 ? as * 256u + 128u : kD1Col;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                uint32_t d0[32], d1[32];
+                tmem_ld32(lane_addr + d0_base + c0, d0);
+                for (int g = 1; g < p.groups; ++g) {  // chunked summation of the hi*hi partial sums, fp32 round-to-nearest
+                    uint32_t dg[32];
+                    tmem_ld32(lane_addr + g * kSlot + c0, dg);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) d0[e] = __float_as_uint(__uint_as_float(d0[e]) + __uint_as_float(dg[e]));
+                }
+                tmem_ld32(lane_addr + d1_col + c0, d1);
+                if (!valid) continue;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int c = c0 + 8 * g;
+                    if (c >= p.c_out) break;
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(d0[8 * g + e]) + __uint_as_float(d1[8 * g + e]) * kLoInv;
+                    if (MODE == MODE_QUANT) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (c + e < p.c_out) {
+                                const float med = p.medians ? __ldg(p.medians + c + e) : 0.0f;
+                                p.out_sym[((static_cast<int64_t>(img) * p.c_out + c + e) * p.h_out + oy) * p.w_out + ox] =
+                                    __float2int_rn(rintf(f[e] - med));
+                            }
+                        }
+                    } else {
+                        if (kGdn) {
+                            const uint4 xh = __ldg(reinterpret_cast<const uint4 *>(p.x_hi + pix * p.out_c + c));
+                            const uint4 xl = __ldg(reinterpret_cast<const uint4 *>(p.x_lo + pix * p.out_c + c));
+                            const __half2 *xhh = reinterpret_cast<const __half2 *>(&xh), *xlh = reinterpret_cast<const __half2 *>(&xl);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 a = __half22float2(xhh[e]), b = __half22float2(xlh[e]);
+                                const float x0f = a.x + b.x * kLoInv, x1f = a.y + b.y * kLoInv;
+                                const float n0 = f[2 * e] + __ldg(p.beta + c + 2 * e), n1 = f[2 * e + 1] + __ldg(p.beta + c + 2 * e + 1);
+                                f[2 * e] = x0f * __fdiv_rn(1.0f, n0);      // x * (1 / norm), like the reference
+                                f[2 * e + 1] = x1f * __fdiv_rn(1.0f, n1);
+                            }
+                        }
+                        split_store8(f, p.out_hi + pix * p.out_c + c, p.out_lo + pix * p.out_c + c);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(&acc_empty[as]);
+        }
+    } else if (kGdn) {
+        // =============================== |x| transform warps (6..9) ===============================
+        // |a| = |hi| + sign(hi) * lo / 2048: clear hi's sign bits, flip lo's where hi was negative
+        const int row = (warp - 6) * 32 + lane;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+            for (int k_it = 0; k_it < k_iters; ++k_it, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&full[s], ph);
-                if (row_in_tile) {
+                if (row < rows) {
                     uint4 *rh = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + row * 128);
                     uint4 *rl = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + kABytes + row * 128);
 #pragma unroll
@@ -197,62 +277,6 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 fence_proxy_async();
                 mbar_arrive(&xform[s]);
             }
-        }
-        mbar_wait(accum_bar, 0);
-        tcgen05_fence_after();
-        const int ty = row / p.tw, tx = row - ty * p.tw;
-        const int oy = y0 + ty, ox = x0 + tx;
-        const bool valid = row_in_tile && oy < p.h_out && ox < p.w_out;
-        const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-        constexpr uint32_t kSlot = N_TILE <= 64 ? 64 : 128;
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-            uint32_t d0[32], d1[32];
-            tmem_ld32(lane_addr + c0, d0);
-            for (int g = 1; g < p.groups; ++g) {  // chunked summation of the hi*hi partial sums, in fp32 (round to nearest)
-                uint32_t dg[32];
-                tmem_ld32(lane_addr + g * kSlot + c0, dg);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) d0[e] = __float_as_uint(__uint_as_float(d0[e]) + __uint_as_float(dg[e]));
-            }
-            tmem_ld32(lane_addr + kD1Col + c0, d1);
-            if (!valid) continue;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int c = c0 + 8 * g;
-                if (c >= p.c_out) break;
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(d0[8 * g + e]) + __uint_as_float(d1[8 * g + e]) * kLoInv;
-                if (MODE == MODE_QUANT) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        if (c + e < p.c_out) {
-                            const float med = p.medians ? __ldg(p.medians + c + e) : 0.0f;
-                            p.out_sym[((static_cast<int64_t>(img) * p.c_out + c + e) * p.h_out + oy) * p.w_out + ox] =
-                                __float2int_rn(rintf(f[e] - med));
-                        }
-                    }
-                } else {
-                    if (kGdn) {
-                        const uint4 xh = *reinterpret_cast<const uint4 *>(p.x_hi + pix * p.out_c + c);
-                        const uint4 xl = *reinterpret_cast<const uint4 *>(p.x_lo + pix * p.out_c + c);
-                        const __half2 *xhh = reinterpret_cast<const __half2 *>(&xh), *xlh = reinterpret_cast<const __half2 *>(&xl);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 a = __half22float2(xhh[e]), b = __half22float2(xlh[e]);
-                            const float x0f = a.x + b.x * kLoInv, x1f = a.y + b.y * kLoInv;
-                            const float n0 = f[2 * e] + __ldg(p.beta + c + 2 * e), n1 = f[2 * e + 1] + __ldg(p.beta + c + 2 * e + 1);
-                            f[2 * e] = x0f * __fdiv_rn(1.0f, n0);      // x * (1 / norm), like the reference
-                            f[2 * e + 1] = x1f * __fdiv_rn(1.0f, n1);
-                        }
-                    }
-                    split_store8(f, p.out_hi + pix * p.out_c + c, p.out_lo + pix * p.out_c + c);
-                }
-            }
-        }
-        tcgen05_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
@@ -308,8 +332,10 @@ static int launch(const CUtensorMap &mah, const CUtensorMap &mal, const CUtensor
         SC2_CUDA_TRY(cudaFuncSetAttribute(tc_split_conv_kernel<N_TILE, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid(p.tiles_x * p.tiles_y, 1, images);
-    tc_split_conv_kernel<N_TILE, STAGES, MODE><<<grid, kNumThreads, smem, st>>>(mah, mal, mbh, mbl, p);
+    const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * images;
+    if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
+    const int grid = total < kNumSMs ? static_cast<int>(total) : kNumSMs;
+    tc_split_conv_kernel<N_TILE, STAGES, MODE><<<grid, MODE == MODE_GDN1_SPLIT ? 320 : 192, smem, st>>>(mah, mal, mbh, mbl, p);
     SC2_LAUNCH_CHECK("tc_split_conv_kernel");
     return SC2_OK;
 }
@@ -341,7 +367,7 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
                       void *out_lo, int32_t *out_sym, sc2_stream_t stream) {
     using namespace sc2::tcs;
     if (!d || !x_hi || !x_lo || !w_hi || !w_lo) return SC2_ERR_INVALID_ARG;
-    if (d->images < 1 || d->images > 65535 || d->c_in < 16 || d->c_in % 16 || d->c_out < 1) return SC2_ERR_INVALID_ARG;
+    if (d->images < 1 || d->c_in < 16 || d->c_in % 16 || d->c_out < 1) return SC2_ERR_INVALID_ARG;
     if (d->stride != 1 && d->stride != 2) return SC2_ERR_UNSUPPORTED;
     if (d->kh * d->kw > kMaxTaps || d->kh < 1 || d->kw < 1) return SC2_ERR_UNSUPPORTED;
     if ((d->c_in * 2) % 16) return SC2_ERR_INVALID_ARG;
@@ -353,6 +379,7 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     Params p;
     const int planes = d->stride == 2 ? 4 : 1;
     p.planes = planes;
+    p.images = d->images;
     p.h_out = d->h_out; p.w_out = d->w_out;
     int n_col_tiles = (d->w_out + 127) / 128;
     int tw = (d->w_out + n_col_tiles - 1) / n_col_tiles;
