@@ -14,8 +14,9 @@
 //               MMAs of tile i + 1.
 //   schedule    persistent: one CTA per SM walks the tile list (stride gridDim.x); barrier / TMEM / descriptor set-up
 //               is paid once per CTA instead of once per tile (it dominated the small-K layers).
-//   roles       warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM -> registers
-//               -> global, thread = output pixel), warps 6..9 (GDN modes) = |x| transform of the landed A tiles.
+//   roles       warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = epilogue (TMEM -> registers
+//               -> global, thread = output pixel, the two warpgroups take alternate 32-column chunks),
+//               warps 10..13 (GDN modes) = |x| transform of the landed A tiles.
 //   epilogues   store fp16 | store fp32 | IGDN1: out = x * (beta + gamma.|x|) | GDN1: out = x / (beta + gamma.|x|),
 //               where the GEMM is the 1x1 "gamma" contraction over |x| (sign bits cleared in shared memory right after
 //               the TMA lands) and x is re-read by the epilogue.
@@ -50,7 +51,7 @@ struct Smem {
 };
 
 template <int N_TILE, int STAGES, int MODE>
-__global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16) ? 320 : 192, 1)
+__global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16) ? 448 : 320, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params p) {
     using L = Smem<N_TILE, STAGES>;
     constexpr bool kGdn = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
@@ -83,7 +84,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128);
+            mbar_init(&acc_empty[s], 256);
         }
         fence_barrier_init();
     }
@@ -139,8 +140,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 __syncwarp();
             }
         }
-    } else if (warp < 6) {
-        // =============================== epilogue warps (2..5) ===============================
+    } else if (warp < 10) {
+        // =============================== epilogue warps (2..9) ===============================
+        const int half = (warp - 2) >> 2;     // warpgroup 0 / 1: even / odd 32-column chunks
         const int quarter = warp & 3;         // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;  // tile row = TMEM lane = pixel index inside the tile
         const int ty = row / p.tw, tx = row - ty * p.tw;
@@ -156,7 +158,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + as * N_TILE + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+            for (int c0 = half * 32; c0 < N_TILE; c0 += 64) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 if (!valid) continue;
@@ -202,11 +204,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
             tcgen05_fence_before();
-            mbar_arrive(&acc_empty[as]);  // 128 arrivals release the accumulator stage to the MMA warp
+            mbar_arrive(&acc_empty[as]);  // 256 arrivals release the accumulator stage to the MMA warp
         }
     } else if (kGdn) {
-        // =============================== |x| transform warps (6..9, GDN modes) ===============================
-        const int row = (warp - 6) * 32 + lane;
+        // =============================== |x| transform warps (10..13, GDN modes) ===============================
+        const int row = (warp - 10) * 32 + lane;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int k_it = 0; k_it < k_iters; ++k_it, ++it) {
@@ -216,9 +218,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     uint4 *r = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + row * 128);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        uint4 v = r[c];
+                        // rotate the 16-byte chunk with the row: 8 neighbouring rows hit 8 different bank groups
+                        const int cc = (c + row) & 7;
+                        uint4 v = r[cc];
                         v.x &= 0x7fff7fffu; v.y &= 0x7fff7fffu; v.z &= 0x7fff7fffu; v.w &= 0x7fff7fffu;
-                        r[c] = v;
+                        r[cc] = v;
                     }
                 }
                 fence_proxy_async();
@@ -245,7 +249,7 @@ static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const Params &p,
     }
     const int total = p.tiles_x * p.tiles_y * p.n_tiles * p.batch;
     const int grid = total < kNumSMs ? total : kNumSMs;
-    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kGdn ? 320 : 192, smem, st>>>(ma, mb, p);
+    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kGdn ? 448 : 320, smem, st>>>(ma, mb, p);
     SC2_LAUNCH_CHECK("tc_conv_kernel");
     return SC2_OK;
 }

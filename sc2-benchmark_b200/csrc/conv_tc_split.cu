@@ -79,7 +79,7 @@ __device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr
 }
 
 template <int N_TILE, int STAGES, int MODE>
-__global__ void __launch_bounds__(MODE == MODE_GDN1_SPLIT ? 320 : 192, 1)
+__global__ void __launch_bounds__(MODE == MODE_GDN1_SPLIT ? 448 : 320, 1)
 tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                      const __grid_constant__ Params p) {
@@ -118,7 +118,7 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128);
+            mbar_init(&acc_empty[s], 256);
         }
         fence_barrier_init();
     }
@@ -187,8 +187,9 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     __syncwarp();
                 }
         }
-    } else if (warp < 6) {
-        // =============================== epilogue warps (2..5) ===============================
+    } else if (warp < 10) {
+        // =============================== epilogue warps (2..9): two warpgroups, alternate 32-column chunks ===============================
+        const int half = (warp - 2) >> 2;
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int ty = row / p.tw, tx = row - ty * p.tw;
@@ -205,7 +206,7 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             const uint32_t d0_base = p.groups == 1 ? as * 256u : 0u;
             const uint32_t d1_col = p.groups == 1 ? as * 256u + 128u : kD1Col;
 #pragma unroll 1
-            for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+            for (int c0 = half * 32; c0 < N_TILE; c0 += 64) {
                 uint32_t d0[32], d1[32];
                 tmem_ld32(lane_addr + d0_base + c0, d0);
                 for (int g = 1; g < p.groups; ++g) {  // chunked summation of the hi*hi partial sums, fp32 round-to-nearest
@@ -254,9 +255,9 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             mbar_arrive(&acc_empty[as]);
         }
     } else if (kGdn) {
-        // =============================== |x| transform warps (6..9) ===============================
+        // =============================== |x| transform warps (10..13) ===============================
         // |a| = |hi| + sign(hi) * lo / 2048: clear hi's sign bits, flip lo's where hi was negative
-        const int row = (warp - 6) * 32 + lane;
+        const int row = (warp - 10) * 32 + lane;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
             for (int k_it = 0; k_it < k_iters; ++k_it, ++it) {
@@ -267,11 +268,13 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     uint4 *rl = reinterpret_cast<uint4 *>(smem + s * L::kStageBytes + kABytes + row * 128);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        uint4 h = rh[c], l = rl[c];
+                        // rotate the 16-byte chunk with the row: 8 neighbouring rows hit 8 different bank groups
+                        const int cc = (c + row) & 7;
+                        uint4 h = rh[cc], l = rl[cc];
                         l.x ^= h.x & 0x80008000u; l.y ^= h.y & 0x80008000u; l.z ^= h.z & 0x80008000u; l.w ^= h.w & 0x80008000u;
                         h.x &= 0x7fff7fffu; h.y &= 0x7fff7fffu; h.z &= 0x7fff7fffu; h.w &= 0x7fff7fffu;
-                        rh[c] = h;
-                        rl[c] = l;
+                        rh[cc] = h;
+                        rl[cc] = l;
                     }
                 }
                 fence_proxy_async();
@@ -335,7 +338,7 @@ static int launch(const CUtensorMap &mah, const CUtensorMap &mal, const CUtensor
     const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * images;
     if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
     const int grid = total < kNumSMs ? static_cast<int>(total) : kNumSMs;
-    tc_split_conv_kernel<N_TILE, STAGES, MODE><<<grid, MODE == MODE_GDN1_SPLIT ? 320 : 192, smem, st>>>(mah, mal, mbh, mbl, p);
+    tc_split_conv_kernel<N_TILE, STAGES, MODE><<<grid, MODE == MODE_GDN1_SPLIT ? 448 : 320, smem, st>>>(mah, mal, mbh, mbl, p);
     SC2_LAUNCH_CHECK("tc_split_conv_kernel");
     return SC2_OK;
 }
