@@ -55,12 +55,17 @@ struct Params {
     const __half *x_hi, *x_lo;
 };
 
-template <int N_TILE, int STAGES>
+// B_RES: 1x1 convolutions (one tap, <= 2 K chunks) keep the whole weight matrix resident in shared memory for the life of
+// the persistent CTA and stream only A tiles through the ring (re-loading B per tile made those layers L2-bound).
+template <int N_TILE, int STAGES, bool B_RES>
 struct Smem {
     static constexpr int kBBytes = N_TILE * 128;
-    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr int kResBytes = B_RES ? 2 * 2 * kBBytes : 0;          // [chunk][hi, lo]
+    static constexpr int kStageBytes = 2 * kABytes + (B_RES ? 0 : 2 * kBBytes);
     static constexpr int kRingBytes = STAGES * kStageBytes;
-    static constexpr int kTotal = kRingBytes + (3 * STAGES + 4) * 8 + 16;
+    static constexpr int kBarOffset = kResBytes + kRingBytes;
+    static constexpr int kTotal = kBarOffset + (3 * STAGES + 5) * 8 + 16;
+    static_assert(kTotal + 1024 <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr, __half *lo_ptr) {
@@ -78,7 +83,7 @@ __device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr
     *reinterpret_cast<uint4 *>(lo_ptr) = l;
 }
 
-template <int N_TILE, int STAGES, int MODE>
+template <int N_TILE, int STAGES, int MODE, bool B_RES>
 __global__ void __launch_bounds__(MODE == MODE_GDN1_SPLIT ? 448 : 320, 1)
 tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -86,17 +91,19 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     // Persistent: the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  With one D0 group the two 256-column
     // halves of TMEM alternate between tiles (epilogue of tile i overlaps the MMAs of tile i + 1); with several D0
     // groups (long K) the whole TMEM belongs to one tile at a time.
-    using L = Smem<N_TILE, STAGES>;
+    using L = Smem<N_TILE, STAGES, B_RES>;
     constexpr bool kGdn = MODE == MODE_GDN1_SPLIT;
     constexpr uint32_t kSlot = N_TILE <= 64 ? 64 : 128;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kRingBytes);
+    uint8_t *smem_res = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *smem = smem_res + L::kResBytes;  // the ring
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_res + L::kBarOffset);
     uint64_t *empty = full + STAGES;
     uint64_t *xform = empty + STAGES;
     uint64_t *acc_full = xform + STAGES;
     uint64_t *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *b_full = acc_empty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -120,6 +127,7 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 256);
         }
+        mbar_init(b_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -131,7 +139,14 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (warp == 0) {
         // =============================== TMA producer ===============================
         if (elect_one()) {
-            const uint32_t stage_tx = static_cast<uint32_t>(2 * rows * 128 + 2 * L::kBBytes);
+            const uint32_t stage_tx = static_cast<uint32_t>(2 * rows * 128 + (B_RES ? 0 : 2 * L::kBBytes));
+            if (B_RES) {  // the whole (single-tap) weight matrix, once per CTA
+                mbar_expect_tx(b_full, static_cast<uint32_t>(p.k_chunks * 2 * L::kBBytes));
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    tma_load_2d(&map_b_hi, b_full, smem_res + (2 * kc) * L::kBBytes, kc * kBlockK, 0);
+                    tma_load_2d(&map_b_lo, b_full, smem_res + (2 * kc + 1) * L::kBBytes, kc * kBlockK, 0);
+                }
+            }
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int sp = tile % tiles_xy, img = tile / tiles_xy;
@@ -146,8 +161,10 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         const int cx = x0 + tap.dx, cy = y0 + tap.dy, cz = img * p.planes + tap.plane;
                         tma_load_4d(&map_a_hi, &full[s], dst, kc * kBlockK, cx, cy, cz);
                         tma_load_4d(&map_a_lo, &full[s], dst + kABytes, kc * kBlockK, cx, cy, cz);
-                        tma_load_2d(&map_b_hi, &full[s], dst + 2 * kABytes, kc * kBlockK, t * N_TILE);
-                        tma_load_2d(&map_b_lo, &full[s], dst + 2 * kABytes + L::kBBytes, kc * kBlockK, t * N_TILE);
+                        if (!B_RES) {
+                            tma_load_2d(&map_b_hi, &full[s], dst + 2 * kABytes, kc * kBlockK, t * N_TILE);
+                            tma_load_2d(&map_b_lo, &full[s], dst + 2 * kABytes + L::kBBytes, kc * kBlockK, t * N_TILE);
+                        }
                     }
                 }
             }
@@ -156,6 +173,7 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         // =============================== MMA issuer ===============================
         constexpr uint32_t idesc = make_idesc(N_TILE);
         uint32_t it = 0, lt = 0;
+        if (B_RES) mbar_wait(b_full, 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             const uint32_t as = lt % acc_stages, aph = (lt / acc_stages) & 1u;
             mbar_wait(&acc_empty[as], aph ^ 1u);
@@ -172,7 +190,8 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     if (elect_one()) {
                         const uint32_t base = smem_u32(smem + s * L::kStageBytes);
                         const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + kABytes);
-                        const uint64_t b_hi = make_smem_desc(base + 2 * kABytes), b_lo = make_smem_desc(base + 2 * kABytes + L::kBBytes);
+                        const uint32_t b_base = B_RES ? smem_u32(smem_res + (2 * kc) * L::kBBytes) : base + 2 * kABytes;
+                        const uint64_t b_hi = make_smem_desc(b_base), b_lo = make_smem_desc(b_base + L::kBBytes);
                         const int k_steps = (kc == p.k_chunks - 1) ? p.k_steps_last : kBlockK / 16;
                         for (int k = 0; k < k_steps; ++k) {
                             const uint32_t acc0 = k > 0 ? 1u : ((started >> g) & 1u), acc1 = k > 0 ? 1u : (started >> 31);
@@ -325,31 +344,38 @@ __global__ void patchify_split_kernel(const float *__restrict__ x, __half *__res
     }
 }
 
-template <int N_TILE, int STAGES, int MODE>
+template <int N_TILE, int STAGES, int MODE, bool B_RES>
 static int launch(const CUtensorMap &mah, const CUtensorMap &mal, const CUtensorMap &mbh, const CUtensorMap &mbl, const Params &p,
                   int images, cudaStream_t st) {
-    using L = Smem<N_TILE, STAGES>;
+    using L = Smem<N_TILE, STAGES, B_RES>;
     const int smem = L::kTotal + 1024;
     static bool configured = false;
     if (!configured) {
-        SC2_CUDA_TRY(cudaFuncSetAttribute(tc_split_conv_kernel<N_TILE, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SC2_CUDA_TRY(cudaFuncSetAttribute(tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * images;
     if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
     const int grid = total < kNumSMs ? static_cast<int>(total) : kNumSMs;
-    tc_split_conv_kernel<N_TILE, STAGES, MODE><<<grid, MODE == MODE_GDN1_SPLIT ? 448 : 320, smem, st>>>(mah, mal, mbh, mbl, p);
+    tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES><<<grid, MODE == MODE_GDN1_SPLIT ? 448 : 320, smem, st>>>(mah, mal, mbh, mbl, p);
     SC2_LAUNCH_CHECK("tc_split_conv_kernel");
     return SC2_OK;
 }
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int STAGES_RES>
 static int dispatch_mode(int mode, const CUtensorMap &mah, const CUtensorMap &mal, const CUtensorMap &mbh, const CUtensorMap &mbl,
                          const Params &p, int images, cudaStream_t st) {
+    const bool res = p.n_taps == 1 && p.k_chunks <= 2;
     switch (mode) {
-        case MODE_STORE_SPLIT: return launch<N_TILE, STAGES, MODE_STORE_SPLIT>(mah, mal, mbh, mbl, p, images, st);
-        case MODE_GDN1_SPLIT: return launch<N_TILE, STAGES, MODE_GDN1_SPLIT>(mah, mal, mbh, mbl, p, images, st);
-        default: return launch<N_TILE, STAGES, MODE_QUANT>(mah, mal, mbh, mbl, p, images, st);
+        case MODE_STORE_SPLIT:
+            return res ? launch<N_TILE, STAGES_RES, MODE_STORE_SPLIT, true>(mah, mal, mbh, mbl, p, images, st)
+                       : launch<N_TILE, STAGES, MODE_STORE_SPLIT, false>(mah, mal, mbh, mbl, p, images, st);
+        case MODE_GDN1_SPLIT:
+            return res ? launch<N_TILE, STAGES_RES, MODE_GDN1_SPLIT, true>(mah, mal, mbh, mbl, p, images, st)
+                       : launch<N_TILE, STAGES, MODE_GDN1_SPLIT, false>(mah, mal, mbh, mbl, p, images, st);
+        default:
+            return res ? launch<N_TILE, STAGES_RES, MODE_QUANT, true>(mah, mal, mbh, mbl, p, images, st)
+                       : launch<N_TILE, STAGES, MODE_QUANT, false>(mah, mal, mbh, mbl, p, images, st);
     }
 }
 
@@ -442,11 +468,11 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     if (rc) return rc;
     cudaStream_t st = sc2::as_stream(stream);
     switch (n_tile) {
-        case 32: return dispatch_mode<32, 4>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
-        case 48: return dispatch_mode<48, 4>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
-        case 64: return dispatch_mode<64, 4>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
-        case 96: return dispatch_mode<96, 3>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
-        default: return dispatch_mode<128, 3>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        case 32: return dispatch_mode<32, 4, 5>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        case 48: return dispatch_mode<48, 4, 5>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        case 64: return dispatch_mode<64, 4, 5>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        case 96: return dispatch_mode<96, 3, 5>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        default: return dispatch_mode<128, 3, 4>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
     }
 }
 
