@@ -134,6 +134,57 @@ def check_if_updatable(model):
 
 
 @register_backbone_class
+class FeatureExtractionBackbone(UpdatableBackbone):
+    """Runs the children of `model` in order up to the last requested layer and returns {out_name: feature}
+    (detection / segmentation bodies; sc2bench/models/backbone.py:90-172).  The child named `analyzable_layer_key` is the
+    bottleneck: once updated and in eval mode it goes through encode -> analyze -> decode, i.e. the hot path."""
+
+    def __init__(self, model, return_layer_dict, analyzer_configs, analyzes_after_compress=False, analyzable_layer_key=None):
+        children = OrderedDict(model.named_children())
+        if not set(return_layer_dict).issubset(children):
+            raise ValueError('return_layer_dict are not present in model')
+        super().__init__(analyzer_configs)
+        wanted = {str(k) for k in return_layer_dict}
+        for name, module in children.items():  # layers after the last requested one are pruned
+            self.add_module(name, module)
+            wanted.discard(name)
+            if not wanted:
+                break
+        self.return_layer_dict = return_layer_dict
+        self.analyzable_layer_key = analyzable_layer_key
+        self.analyzes_after_compress = analyzes_after_compress
+
+    def forward(self, x):
+        out = OrderedDict()
+        for key, module in self.named_children():
+            if key == self.analyzable_layer_key and self.bottleneck_updated and not self.training:
+                compressed = module.encode(x)
+                if self.analyzes_after_compress:
+                    self.analyze(compressed)
+                x = module.decode(**compressed)
+            else:
+                x = module(x)
+            if key in self.return_layer_dict:
+                out[self.return_layer_dict[key]] = x
+        return out
+
+    def check_if_updatable(self):
+        key = self.analyzable_layer_key
+        return key is not None and key in self._modules and isinstance(self._modules[key], CompressionModel)
+
+    def update(self):
+        if self.analyzable_layer_key is None:
+            return
+        if not self.check_if_updatable():
+            raise KeyError(f'`analyzable_layer_key` ({self.analyzable_layer_key}) does not name an updatable bottleneck in {type(self).__name__}')
+        self._modules[self.analyzable_layer_key].update()
+        self.bottleneck_updated = True
+
+    def get_aux_module(self, **kwargs):
+        return self._modules[self.analyzable_layer_key] if self.check_if_updatable() else None
+
+
+@register_backbone_class
 class SplittableResNet(UpdatableBackbone):
     """ResNet whose stem + layer1 are replaced by a bottleneck layer (encoder | entropy bottleneck | decoder)."""
 

@@ -1,0 +1,120 @@
+"""GPU: the callers either side of the path at the shapes BASELINE.json names (configs[2..4]): the input-compression
+wrapper with the CompressAI zoo models at quality 8 (N=192, M=320; 224 -> AdaptivePad(64) -> 256), and the detection-style
+FeatureExtractionBackbone at COCO shape (3x800x1344, one 1.6 M-symbol stream per image).  Checked against the oracle
+(restated CompressAI on CPU torch + C rANS) on the same seeded weights and inputs."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+import cref
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+FEATURE_TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def s2():
+    import sc2bench_b200
+    return sc2bench_b200
+
+
+def _decode_symbols(strings, cdf, ln, off, idx):
+    return np.stack([cref.decode_with_indexes(s, idx, cdf, ln, off) for s in strings])
+
+
+@pytest.mark.parametrize('arch', ['bmshj2018_factorized', 'bmshj2018_hyperprior'])
+def test_neural_input_compression_classifier_q8(s2, oracle_compressai, arch):
+    import compressai.zoo as ozoo
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    ref = getattr(ozoo, arch)(quality=8, pretrained=False).eval()
+    ref.update()
+    codec = s2.get_compression_model({'key': arch, 'kwargs': {'quality': 8, 'pretrained': False}}, 'cpu')
+    codec.load_state_dict(ref.state_dict())
+    codec.update()
+    assert torch.equal(codec.entropy_bottleneck._quantized_cdf, ref.entropy_bottleneck._quantized_cdf)
+    classifier = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(3, 10))
+    model = s2.NeuralInputCompressionClassifier(classifier, pre_transform=s2.AdaptivePad(fill=0, factor=64), compression_model=codec,
+                                                post_transform=None,
+                                                analysis_config={'analyzes_after_compress': True,
+                                                                 'analyzer_configs': [{'key': 'FileSizeAnalyzer', 'kwargs': {'unit': 'KB'}}]})
+    model.eval().to(dev)
+    model.activate_analysis()
+    torch.manual_seed(1)
+    x = torch.rand(2, 3, 224, 224)
+    with torch.inference_mode():
+        xp = s2.AdaptivePad(fill=0, factor=64)(x)
+        assert xp.shape == (2, 3, 256, 256)
+        want_obj = ref.compress(xp)
+        want = ref.decompress(**want_obj)['x_hat']
+        got_obj = codec.compress(xp.to(dev))
+        got = codec.decompress(**got_obj)['x_hat']
+        logits = model(x.to(dev))
+    assert logits.shape == (2, 10) and len(model.analyzers[0].file_size_list) == 1
+    assert len(got_obj['strings']) == len(want_obj['strings']) and tuple(got_obj['shape']) == tuple(want_obj['shape'])
+    # the last string list is the EntropyBottleneck stream (y for factorized, z for the hyperprior): decode both sides' bytes
+    eb = ref.entropy_bottleneck
+    cdf, ln, off = eb._quantized_cdf.numpy(), eb._cdf_length.numpy(), eb._offset.numpy()
+    C = cdf.shape[0]
+    hw = int(np.prod(tuple(want_obj['shape'])))
+    idx = np.repeat(np.arange(C, dtype=np.int32), hw)
+    s_want = _decode_symbols(want_obj['strings'][-1], cdf, ln, off, idx)
+    s_got = _decode_symbols(got_obj['strings'][-1], cdf, ln, off, idx)
+    mism = int((s_want != s_got).sum())
+    assert mism <= max(2, s_want.size // 100000), 'symbol mismatches vs oracle: %d of %d' % (mism, s_want.size)
+    if mism == 0:
+        assert got_obj['strings'][-1] == want_obj['strings'][-1]  # identical symbols -> identical bytes
+    if arch.endswith('factorized'):
+        assert rel_err(got.cpu(), want) < FEATURE_TOL
+    else:
+        # a flipped z symbol changes the scales of a whole neighbourhood: compare only when z agrees exactly
+        if mism == 0:
+            assert rel_err(got.cpu(), want) < 5e-3
+        assert float(got.min()) >= 0 and float(got.max()) <= 1
+    # the decoder side accepts the ORACLE's bytes (cross-implementation decode)
+    with torch.inference_mode():
+        cross = codec.decompress(**want_obj)['x_hat']
+    assert rel_err(cross.cpu(), want) < FEATURE_TOL
+
+
+def test_feature_extraction_backbone_coco_shape(s2):
+    """configs[4]: splittable ResNet-50 body for Faster R-CNN at 3x800x1344 (GeneralizedRCNNTransform batching):
+    latent 24x199x335 = 1,599,960 symbols in ONE stream per image."""
+    import ref_models
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    body = s2.splittable_resnet(bottleneck_config={'key': 'FPBasedResNetBottleneck', 'kwargs': {'num_bottleneck_channels': 24, 'num_target_channels': 256}},
+                                resnet_name='resnet50', skips_avgpool=True, skips_fc=True, weights=None)
+    fx = s2.FeatureExtractionBackbone(body, {'bottleneck_layer': '1', 'layer2': '2', 'layer3': '3', 'layer4': '4'},
+                                      [{'key': 'FileSizeAnalyzer', 'kwargs': {'unit': 'KB'}}], analyzes_after_compress=True,
+                                      analyzable_layer_key='bottleneck_layer')
+    assert [n for n, _ in fx.named_children()] == ['bottleneck_layer', 'layer2', 'layer3', 'layer4']
+    fx.eval()
+    fx.update()
+    fx.activate_analysis()
+    oracle = ref_models.build_fp_bottleneck(3, 24, 256)
+    oracle.load_state_dict(fx.bottleneck_layer.state_dict())
+    oracle.eval()
+    fx.to(dev)
+    torch.manual_seed(1)
+    x = torch.rand(1, 3, 800, 1344)
+    with torch.inference_mode():
+        feats = fx(x.to(dev))
+        enc = fx.bottleneck_layer.encode(x.to(dev))
+        latent, want_sym = oracle.symbols(x)
+    assert list(feats.keys()) == ['1', '2', '3', '4'] and feats['1'].shape == (1, 256, 200, 336) and feats['4'].shape == (1, 2048, 25, 42)
+    assert tuple(enc['shape']) == (199, 335) and len(fx.analyzers[0].file_size_list) == 1
+    eb = oracle.entropy_bottleneck
+    cdf, ln, off = eb._quantized_cdf.numpy(), eb._cdf_length.numpy(), eb._offset.numpy()
+    idx = np.repeat(np.arange(24, dtype=np.int32), 199 * 335)
+    got_sym = cref.decode_with_indexes(enc['strings'][0][0], idx, cdf, ln, off).reshape(1, 24, 199, 335)
+    mism = int((got_sym != want_sym.numpy()).sum())
+    assert mism <= 2, 'symbol mismatches vs oracle at COCO shape: %d of %d' % (mism, got_sym.size)
+    if mism == 0:
+        assert enc['strings'][0][0] == cref.encode_with_indexes(want_sym.numpy().reshape(-1), idx, cdf, ln, off)
+    with torch.inference_mode():
+        med = eb._get_medians().detach().reshape(1, -1, 1, 1)
+        want_feat = oracle.decoder(torch.from_numpy(got_sym).float() + med)
+    assert rel_err(feats['1'].cpu(), want_feat) < FEATURE_TOL
