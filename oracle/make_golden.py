@@ -258,6 +258,42 @@ def small_zoo_models(torch):
         print(name, 'y', tuple(y.shape), 'bytes', [[len(s) for s in l] for l in obj['strings']])
 
 
+def small_shp_bottleneck(torch):
+    """The reference's SHPBasedResNetBottleneck (sc2bench/models/layer.py:553-720) at a tiny size, weights stored."""
+    from sc2bench.models.layer import get_layer
+    torch.manual_seed(31)
+    layer = get_layer('SHPBasedResNetBottleneck', num_input_channels=3, num_latent_channels=8, num_bottleneck_channels=8,
+                      num_target_channels=32)
+    with torch.no_grad():
+        for mod in list(layer.g_a) + list(layer.g_s):
+            if hasattr(mod, 'gamma'):
+                C = mod.gamma.shape[0]
+                mod.gamma.copy_(mod.gamma_reparam.init(0.1 * torch.eye(C) + 0.02 * torch.rand(C, C)))
+                mod.beta.copy_(mod.beta_reparam.init(0.5 + torch.rand(C)))
+        for mod in layer.g_a:
+            if isinstance(mod, torch.nn.Conv2d):
+                mod.weight.mul_(3.0)
+        for mod in list(layer.h_a) + list(layer.h_s):
+            if hasattr(mod, 'weight'):
+                mod.weight.mul_(2.0)
+    perturb_entropy_bottleneck(torch, layer.entropy_bottleneck, 13)
+    layer.eval()
+    layer.update(force=True)
+    torch.manual_seed(32)
+    x = torch.randn(2, 3, 96, 80) * 1.5
+    with torch.inference_mode():
+        enc = layer.encode(x)
+        dec = layer.decode(**enc)
+        y = layer.g_a(x)
+    out = {'x': x.numpy(), 'y': y.numpy(), 'decoded': dec.numpy(), 'shape': np.array(tuple(enc['shape']))}
+    for li, strings in enumerate(enc['strings']):
+        out['streams%d' % li], out['stream_offsets%d' % li] = _pack_strings(strings)
+    for k, v in layer.state_dict().items():
+        out['sd/' + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, 'shp_bottleneck_small.npz'), **out)
+    print('shp_bottleneck_small.npz: y', tuple(y.shape), 'z shape', tuple(enc['shape']), 'bytes', [[len(s) for s in l] for l in enc['strings']])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--real-compressai', action='store_true')
@@ -268,7 +304,7 @@ def main():
     import torch
     torch.set_num_threads(1)  # bit-reproducible reductions
     os.makedirs(GOLD, exist_ok=True)
-    jobs = {'rans': rans_cases, 'small_fp': small_fp_bottleneck, 'config1': config1, 'zoo': small_zoo_models}
+    jobs = {'rans': rans_cases, 'small_fp': small_fp_bottleneck, 'config1': config1, 'zoo': small_zoo_models, 'shp': small_shp_bottleneck}
     for k, fn in jobs.items():
         if args.only in (None, k):
             fn(torch)

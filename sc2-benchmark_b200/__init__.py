@@ -12,7 +12,7 @@ from . import ops  # noqa: E402
 from .backbone import (AnalyzableModule, FeatureExtractionBackbone, FileSizeAnalyzer, SplittableResNet,  # noqa: E402,F401
                        UpdatableBackbone, check_if_updatable, get_backbone, splittable_resnet)
 from .bottleneck import (LAYER_CLASS_DICT, BaseBottleneck, EntropyBottleneckLayer, FPBasedResNetBottleneck,  # noqa: E402,F401
-                         get_layer, register_layer_class, register_layer_func)
+                         SHPBasedResNetBottleneck, get_layer, register_layer_class, register_layer_func)
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional  # noqa: E402,F401
 from .layers import GDN, GDN1  # noqa: E402,F401
 from .models import (CompressionModel, FactorizedPrior, ScaleHyperprior, bmshj2018_factorized,  # noqa: E402,F401

@@ -14,8 +14,9 @@ import torch
 from torch import nn
 
 from . import _native, ops
+from .entropy_models import GaussianConditional
 from .layers import GDN1
-from .models import CompressionModel, run_transform
+from .models import CompressionModel, get_scale_table, run_transform, update_registered_buffers
 
 
 
@@ -312,3 +313,113 @@ class FPBasedResNetBottleneck(BaseBottleneck):
         eb = self.entropy_bottleneck
         rounded = eb.dequantize(eb.quantize(latent, 'dequantize', self._get_means(latent)))
         return self.decoder(rounded.detach())
+
+
+@register_layer_class
+class SHPBasedResNetBottleneck(BaseBottleneck):
+    """Scale-hyperprior bottleneck for ResNet-style students (mirrors sc2bench/models/layer.py:553-720).
+
+    y = g_a(x); z = h_a(|y|) is coded with the factorized EntropyBottleneck; both sides decode z, derive per-element scales
+    with h_s and code y with the Gaussian conditional (explicit CDF index per element).  strings = [y_strings, z_strings],
+    shape = z's spatial size.  The transforms run on the exact-fp32 kernels; the coder on the generic (indexed) rANS kernels."""
+
+    def __init__(self, num_input_channels=3, num_latent_channels=16, num_bottleneck_channels=24, num_target_channels=256,
+                 h_a=None, h_s=None, g_a_channel_sizes=None, g_s_channel_sizes=None):
+        if g_a_channel_sizes is None:
+            b = num_bottleneck_channels
+            g_a_channel_sizes = [num_input_channels, b * 4, b * 2, b]
+        else:
+            num_bottleneck_channels = g_a_channel_sizes[3]
+        if g_s_channel_sizes is None:
+            t = num_target_channels
+            g_s_channel_sizes = [g_a_channel_sizes[-1], t * 2, t, t]
+        super().__init__(entropy_bottleneck_channels=num_latent_channels)
+        a, g, L, b = g_a_channel_sizes, g_s_channel_sizes, num_latent_channels, num_bottleneck_channels
+        self.g_a = nn.Sequential(
+            nn.Conv2d(a[0], a[1], kernel_size=5, stride=2, padding=2, bias=False), GDN1(a[1]),
+            nn.Conv2d(a[1], a[2], kernel_size=5, stride=2, padding=2, bias=False), GDN1(a[2]),
+            nn.Conv2d(a[2], a[3], kernel_size=2, stride=1, padding=0, bias=False))
+        self.g_s = nn.Sequential(
+            nn.Conv2d(g[0], g[1], kernel_size=2, stride=1, padding=1, bias=False), GDN1(g[1], inverse=True),
+            nn.Conv2d(g[1], g[2], kernel_size=2, stride=1, padding=0, bias=False), GDN1(g[2], inverse=True),
+            nn.Conv2d(g[2], g[3], kernel_size=2, stride=1, padding=1, bias=False))
+        self.h_a = h_a if h_a is not None else nn.Sequential(
+            nn.Conv2d(b, L, kernel_size=5, stride=2, padding=1, bias=False), nn.ReLU(inplace=True),
+            nn.Conv2d(L, L, kernel_size=5, stride=2, padding=2, bias=False))
+        self.h_s = h_s if h_s is not None else nn.Sequential(
+            nn.ConvTranspose2d(L, L, kernel_size=5, stride=2, padding=1, bias=False), nn.LeakyReLU(inplace=True),
+            nn.ConvTranspose2d(L, L, kernel_size=5, stride=2, padding=1, bias=False), nn.LeakyReLU(inplace=True),
+            nn.Conv2d(L, b, kernel_size=5, stride=1, padding=0, bias=False))
+        self.gaussian_conditional = GaussianConditional(None)
+        self.num_latent_channels = L
+        self.num_bottleneck_channels = b
+        self.decoder_precision = 'fp16-tc'
+        self._tc_decoder = None
+
+    @torch.no_grad()
+    def _scales_to_indexes(self, z_hat):
+        return self.gaussian_conditional.build_indexes(run_transform(self.h_s, z_hat))
+
+    @torch.no_grad()
+    def encode(self, x, **kwargs):
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y = run_transform(self.g_a, x)
+        z_symbols = run_transform(self.h_a, torch.abs(y), final_epilogue=_native.EPI_QUANTIZE,
+                                  final_aux=eb._get_medians().detach().reshape(-1))
+        z_shape = z_symbols.size()[-2:]
+        z_streams = eb.compress_symbols(z_symbols, spatial=z_symbols[0, 0].numel())
+        z_hat = eb.decompress_packed(z_streams, tuple(z_shape))  # the encoder decodes z itself, like the decoder will
+        indexes = self._scales_to_indexes(z_hat)
+        y_symbols = ops.quantize_symbols(y.reshape(y.size(0), 1, -1))
+        y_streams = ops.rans_encode(y_symbols, gc.coder_tables(), indexes=indexes)
+        return {'strings': [y_streams.tolist(), z_streams.tolist()], 'shape': z_shape}
+
+    @torch.no_grad()
+    def decode(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 2
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        device = eb._quantized_cdf.device
+        z_hat = eb.decompress_packed(ops.PackedStreams.from_list(strings[1], device), tuple(shape), check_status=True)
+        indexes = self._scales_to_indexes(z_hat)
+        y_hat = ops.rans_decode(ops.PackedStreams.from_list(strings[0], device), indexes[0].numel(), gc.coder_tables(),
+                                indexes=indexes, want='values').view(indexes.size())
+        if self.decoder_precision == 'fp16-tc' and TensorCoreTransform.supports(self.g_s):
+            if self._tc_decoder is None:
+                self._tc_decoder = TensorCoreTransform(self.g_s)
+            return self._tc_decoder(y_hat)
+        return run_transform(self.g_s, y_hat)
+
+    def _get_means(self, x):
+        medians = self.entropy_bottleneck._get_medians().detach()
+        spatial_dims = x.dim() - 2
+        medians = self.entropy_bottleneck._extend_ndims(medians, spatial_dims)
+        return medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
+
+    def _forward2train(self, x):
+        y = self.g_a(x)
+        z_hat, _ = self.entropy_bottleneck(self.h_a(torch.abs(y)))
+        y_hat, _ = self.gaussian_conditional(y, self.h_s(z_hat))
+        return self.g_s(y_hat)
+
+    def forward(self, x):
+        if not self.updated:
+            return self._forward2train(x)
+        if not self.training:
+            return self.decode(**self.encode(x))
+        y = self.g_a(x)
+        gc = self.gaussian_conditional
+        y_hat = gc.dequantize(gc.quantize(y, 'dequantize', self._get_means(y)))
+        return self.g_s(y_hat.detach())
+
+    def update(self, scale_table=None, force=False):
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= super().update(force=force)
+        self.updated = True
+        return updated
+
+    def load_state_dict(self, state_dict, **kwargs):
+        update_registered_buffers(self.gaussian_conditional, 'gaussian_conditional',
+                                  ['_quantized_cdf', '_offset', '_cdf_length', 'scale_table'], state_dict)
+        return super().load_state_dict(state_dict)

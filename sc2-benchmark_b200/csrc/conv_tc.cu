@@ -154,11 +154,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int oy = (sp / p.tiles_x) * p.th + ty, ox = (sp % p.tiles_x) * p.tw + tx;
             const bool valid = row < rows && oy < p.h_out && ox < p.w_out;
             const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
+            // GDN modes: request this thread's x values BEFORE waiting for the accumulator (their latency hides behind the MMAs)
+            constexpr int kMaxChunks = (N_TILE + 63) / 64;
+            uint4 xpre[kGdn ? kMaxChunks : 1][4];
+            if (kGdn && valid) {
+#pragma unroll
+                for (int ci = 0; ci < kMaxChunks; ++ci) {
+                    const int c0 = half * 32 + ci * 64;
+                    if (c0 < N_TILE) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) xpre[ci][c] = __ldg(reinterpret_cast<const uint4 *>(p.gdn_x + pix * p.n_total + n0 + c0) + c);
+                    }
+                }
+            }
             mbar_wait(&acc_full[as], aph);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + as * N_TILE + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-            for (int c0 = half * 32; c0 < N_TILE; c0 += 64) {
+#pragma unroll
+            for (int ci = 0; ci < kMaxChunks; ++ci) {
+                const int c0 = half * 32 + ci * 64;
+                if (c0 >= N_TILE) break;
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 if (!valid) continue;
@@ -177,7 +192,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * c + e]);
                         if (kGdn) {
-                            const uint4 xv = __ldg(reinterpret_cast<const uint4 *>(p.gdn_x + o) + c);
+                            const uint4 xv = xpre[kGdn ? ci : 0][c];
                             const __half2 *xh = reinterpret_cast<const __half2 *>(&xv);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {

@@ -118,3 +118,64 @@ def test_feature_extraction_backbone_coco_shape(s2):
         med = eb._get_medians().detach().reshape(1, -1, 1, 1)
         want_feat = oracle.decoder(torch.from_numpy(got_sym).float() + med)
     assert rel_err(feats['1'].cpu(), want_feat) < FEATURE_TOL
+
+
+def test_shp_bottleneck_and_entropy_bottleneck_layer_vs_reference(s2, oracle_compressai):
+    """the scale-hyperprior bottleneck (GaussianConditional coder with per-element indexes) against
+    the REFERENCE'S OWN class when /root/reference is present (build container), else structure + round trip only; and
+    EntropyBottleneckLayer on a large latent (256 x 56 x 56 = 802,816 symbols per image, 256 CDF rows)."""
+    import os
+    import sys
+    dev = torch.device('cuda:0')
+    # ---- EntropyBottleneckLayer at ResNet layer1 size ----
+    from compressai.entropy_models import EntropyBottleneck as OracleEB
+    torch.manual_seed(0)
+    layer = s2.EntropyBottleneckLayer(entropy_bottleneck_channels=256)
+    layer.update()
+    oeb = OracleEB(256)
+    oeb.load_state_dict({k: v for k, v in layer.entropy_bottleneck.state_dict().items() if not k.startswith('_')}, strict=False)
+    oeb.update()
+    assert torch.equal(oeb._quantized_cdf, layer.entropy_bottleneck._quantized_cdf)
+    layer.eval().to(dev)
+    torch.manual_seed(1)
+    x = torch.randn(2, 256, 56, 56) * 3
+    obj = layer.compress(x.to(dev))
+    assert tuple(obj['shape']) == (56, 56) and len(obj['strings'][0]) == 2
+    cdf, ln, off = oeb._quantized_cdf.numpy(), oeb._cdf_length.numpy(), oeb._offset.numpy()
+    idx = np.repeat(np.arange(256, dtype=np.int32), 56 * 56)
+    med = oeb._get_medians().detach().reshape(1, -1, 1, 1)
+    want_sym = torch.round(x - med).int().numpy()
+    for b in range(2):
+        assert obj['strings'][0][b] == cref.encode_with_indexes(want_sym[b].reshape(-1), idx, cdf, ln, off)
+    back = layer.decompress(**obj)
+    assert torch.equal(back.cpu(), torch.from_numpy(want_sym).float() + med)
+    # ---- SHP bottleneck ----
+    torch.manual_seed(3)
+    shp = s2.get_layer('SHPBasedResNetBottleneck', num_latent_channels=16, num_bottleneck_channels=24, num_target_channels=256)
+    shp.eval()
+    shp.update()
+    assert shp.updated and tuple(shp.gaussian_conditional._quantized_cdf.shape) == (64, 3133)
+    ref = None
+    if os.path.isdir('/root/reference'):
+        sys.path.insert(0, '/root/reference')
+        sys.path.append(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', 'shim'))
+        from sc2bench.models.layer import get_layer as ref_get_layer
+        ref = ref_get_layer('SHPBasedResNetBottleneck', num_latent_channels=16, num_bottleneck_channels=24, num_target_channels=256)
+        ref.load_state_dict(shp.state_dict())
+        ref.eval()
+        ref.update()
+    shp.to(dev)
+    torch.manual_seed(4)
+    x = torch.randn(2, 3, 224, 224)
+    with torch.inference_mode():
+        enc = shp.encode(x.to(dev))
+        dec = shp.decode(**enc)
+    assert len(enc['strings']) == 2 and all(len(l) == 2 for l in enc['strings']) and dec.shape == (2, 256, 56, 56)
+    if ref is not None:
+        with torch.inference_mode():
+            want = ref.encode(x)
+            want_dec = ref.decode(**want)
+        assert tuple(want['shape']) == tuple(enc['shape'])
+        if want['strings'][1] == enc['strings'][1]:  # identical z -> identical scales -> y must match too
+            assert want['strings'][0] == enc['strings'][0]
+            assert rel_err(dec.cpu(), want_dec) < FEATURE_TOL

@@ -353,3 +353,27 @@ def test_batch256_path_properties(s2, dev):
         assert torch.equal(layer.decode_packed(s17, shape)[0], out[17])
         total_bytes = streams.total_bytes()
         assert 256 * 8 < total_bytes < 256 * 24 * 55 * 55 * 2
+
+
+def test_shp_bottleneck_small_golden(s2, dev):
+    """golden vectors from the reference's own SHPBasedResNetBottleneck (layer.py:553-720)."""
+    gs = load_golden('shp_bottleneck_small.npz')
+    layer = s2.get_layer('SHPBasedResNetBottleneck', num_input_channels=3, num_latent_channels=8, num_bottleneck_channels=8,
+                         num_target_channels=32)
+    layer.load_state_dict(state_dict_from_golden(gs))
+    layer.update()
+    layer.eval().to(dev)
+    x = torch.from_numpy(gs['x']).to(dev)
+    y = s2.models.run_transform(layer.g_a, x)
+    assert rel_err(y.cpu(), torch.from_numpy(gs['y'])) < LATENT_TOL
+    enc = layer.encode(x)
+    assert tuple(enc['shape']) == tuple(gs['shape']) and len(enc['strings']) == 2
+    want_y = unpack_streams(gs['streams0'], gs['stream_offsets0'])
+    want_z = unpack_streams(gs['streams1'], gs['stream_offsets1'])
+    assert enc['strings'][1] == want_z, 'z streams differ'
+    assert enc['strings'][0] == want_y, 'y streams differ'
+    dec = layer.decode(**enc)
+    assert rel_err(dec.cpu(), torch.from_numpy(gs['decoded'])) < FEATURE_TOL
+    # cross decode: the golden bytes through our decoder
+    dec2 = layer.decode([want_y, want_z], tuple(gs['shape']))
+    assert rel_err(dec2.cpu(), torch.from_numpy(gs['decoded'])) < FEATURE_TOL
