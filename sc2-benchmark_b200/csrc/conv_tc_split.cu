@@ -63,8 +63,13 @@ struct Smem {
     static constexpr int kResBytes = B_RES ? 2 * 2 * kBBytes : 0;          // [chunk][hi, lo]
     static constexpr int kStageBytes = 2 * kABytes + (B_RES ? 0 : 2 * kBBytes);
     static constexpr int kRingBytes = STAGES * kStageBytes;
-    static constexpr int kBarOffset = kResBytes + kRingBytes;
-    static constexpr int kTotal = kBarOffset + (3 * STAGES + 5) * 8 + 16;
+    // output staging: dense [128 rows][N_TILE channels] fp16 for the hi and the lo plane (TMA store source; in the GDN
+    // mode the x tile is TMA-loaded into it first and y overwrites x in place)
+    static constexpr int kStagePlane = kTileM * N_TILE * 2;
+    static constexpr int kStagingBytes = 2 * kStagePlane;
+    static constexpr int kStagingOffset = kResBytes + kRingBytes;
+    static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
+    static constexpr int kTotal = kBarOffset + (3 * STAGES + 6) * 8 + 16;
     static_assert(kTotal + 1024 <= 227 * 1024, "shared memory budget");
 };
 
@@ -87,6 +92,8 @@ template <int N_TILE, int STAGES, int MODE, bool B_RES>
 __global__ void __launch_bounds__(MODE == MODE_GDN1_SPLIT ? 448 : 320, 1)
 tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                     const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                     const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                      const __grid_constant__ Params p) {
     // Persistent: the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  With one D0 group the two 256-column
     // halves of TMEM alternate between tiles (epilogue of tile i overlaps the MMAs of tile i + 1); with several D0
@@ -103,7 +110,9 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     uint64_t *acc_full = xform + STAGES;
     uint64_t *acc_empty = acc_full + 2;
     uint64_t *b_full = acc_empty + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 1);
+    uint64_t *x_full = b_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(x_full + 1);
+    uint8_t *staging = smem_res + L::kStagingOffset;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -128,6 +137,11 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             mbar_init(&acc_empty[s], 256);
         }
         mbar_init(b_full, 1);
+        mbar_init(x_full, 1);
+        if (MODE != MODE_QUANT) {
+            tma_prefetch_desc(&map_o_hi);
+            tma_prefetch_desc(&map_o_lo);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -212,13 +226,28 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int ty = row / p.tw, tx = row - ty * p.tw;
+        const bool issuer = threadIdx.x == 64;  // first epilogue thread: owns the bulk-store group and the x-tile loads
+        __half *st_hi = reinterpret_cast<__half *>(staging), *st_lo = reinterpret_cast<__half *>(staging + L::kStagePlane);
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             const uint32_t as = lt % acc_stages, aph = (lt / acc_stages) & 1u;
             const int sp = tile % tiles_xy, img = tile / tiles_xy;
-            const int oy = (sp / p.tiles_x) * p.th + ty, ox = (sp % p.tiles_x) * p.tw + tx;
+            const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
+            const int oy = y0 + ty, ox = x0 + tx;
             const bool valid = row < rows && oy < p.h_out && ox < p.w_out;
-            const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
+            if (MODE != MODE_QUANT) {
+                // the staging buffer is free once the previous tile's bulk stores have read it
+                if (issuer) {
+                    tma_store_wait_read();
+                    if (kGdn) {  // x tile (hi, lo) -> staging; y will overwrite it in place
+                        mbar_expect_tx(x_full, static_cast<uint32_t>(2 * rows * p.out_c * 2));
+                        tma_load_4d(&map_x_hi, x_full, st_hi, 0, x0, y0, img);
+                        tma_load_4d(&map_x_lo, x_full, st_lo, 0, x0, y0, img);
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (kGdn) mbar_wait(x_full, lt & 1u);
+            }
             mbar_wait(&acc_full[as], aph);
             tcgen05_fence_after();
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -235,44 +264,59 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     for (int e = 0; e < 32; ++e) d0[e] = __float_as_uint(__uint_as_float(d0[e]) + __uint_as_float(dg[e]));
                 }
                 tmem_ld32(lane_addr + d1_col + c0, d1);
-                if (!valid) continue;
+                if (MODE == MODE_QUANT) {
+                    if (!valid) continue;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int c = c0 + 8 * g;
-                    if (c >= p.c_out) break;
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(d0[8 * g + e]) + __uint_as_float(d1[8 * g + e]) * kLoInv;
-                    if (MODE == MODE_QUANT) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            if (c + e < p.c_out) {
-                                const float med = p.medians ? __ldg(p.medians + c + e) : 0.0f;
-                                p.out_sym[((static_cast<int64_t>(img) * p.c_out + c + e) * p.h_out + oy) * p.w_out + ox] =
-                                    __float2int_rn(rintf(f[e] - med));
-                            }
+                    for (int e = 0; e < 32; ++e) {
+                        const int c = c0 + e;
+                        if (c < p.c_out) {
+                            const float v = __uint_as_float(d0[e]) + __uint_as_float(d1[e]) * kLoInv;
+                            const float med = p.medians ? __ldg(p.medians + c) : 0.0f;
+                            p.out_sym[((static_cast<int64_t>(img) * p.c_out + c) * p.h_out + oy) * p.w_out + ox] =
+                                __float2int_rn(rintf(v - med));
                         }
-                    } else {
+                    }
+                } else if (row < rows) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int c = c0 + 8 * g;
+                        if (c >= p.out_c) continue;
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            f[e] = (c + e < p.c_out) ? __uint_as_float(d0[8 * g + e]) + __uint_as_float(d1[8 * g + e]) * kLoInv : 0.0f;
+                        __half *ph = st_hi + row * p.out_c + c, *pl = st_lo + row * p.out_c + c;
                         if (kGdn) {
-                            const uint4 xh = __ldg(reinterpret_cast<const uint4 *>(p.x_hi + pix * p.out_c + c));
-                            const uint4 xl = __ldg(reinterpret_cast<const uint4 *>(p.x_lo + pix * p.out_c + c));
+                            const uint4 xh = *reinterpret_cast<const uint4 *>(ph);
+                            const uint4 xl = *reinterpret_cast<const uint4 *>(pl);
                             const __half2 *xhh = reinterpret_cast<const __half2 *>(&xh), *xlh = reinterpret_cast<const __half2 *>(&xl);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 a = __half22float2(xhh[e]), b = __half22float2(xlh[e]);
                                 const float x0f = a.x + b.x * kLoInv, x1f = a.y + b.y * kLoInv;
-                                const float n0 = f[2 * e] + __ldg(p.beta + c + 2 * e), n1 = f[2 * e + 1] + __ldg(p.beta + c + 2 * e + 1);
-                                f[2 * e] = x0f * __fdiv_rn(1.0f, n0);      // x * (1 / norm), like the reference
-                                f[2 * e + 1] = x1f * __fdiv_rn(1.0f, n1);
+                                const float b0 = (c + 2 * e < p.c_out) ? __ldg(p.beta + c + 2 * e) : 1.0f;
+                                const float b1 = (c + 2 * e + 1 < p.c_out) ? __ldg(p.beta + c + 2 * e + 1) : 1.0f;
+                                f[2 * e] = x0f * __fdiv_rn(1.0f, f[2 * e] + b0);      // x * (1 / norm), like the reference
+                                f[2 * e + 1] = x1f * __fdiv_rn(1.0f, f[2 * e + 1] + b1);
                             }
                         }
-                        split_store8(f, p.out_hi + pix * p.out_c + c, p.out_lo + pix * p.out_c + c);
+                        split_store8(f, ph, pl);
                     }
                 }
             }
             tcgen05_fence_before();
             mbar_arrive(&acc_empty[as]);
+            if (MODE != MODE_QUANT) {
+                fence_proxy_async();
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (issuer) {
+                    tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
+                    tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
+                    tma_store_commit();
+                }
+            }
         }
+        if (MODE != MODE_QUANT && issuer) tma_store_wait_all();
     } else if (kGdn) {
         // =============================== |x| transform warps (10..13) ===============================
         // |a| = |hi| + sign(hi) * lo / 2048: clear hi's sign bits, flip lo's where hi was negative
@@ -345,8 +389,8 @@ __global__ void patchify_split_kernel(const float *__restrict__ x, __half *__res
 }
 
 template <int N_TILE, int STAGES, int MODE, bool B_RES>
-static int launch(const CUtensorMap &mah, const CUtensorMap &mal, const CUtensorMap &mbh, const CUtensorMap &mbl, const Params &p,
-                  int images, cudaStream_t st) {
+static int launch(const CUtensorMap *maps, const Params &p, int images, cudaStream_t st) {
+    const CUtensorMap &mah = maps[0], &mal = maps[1], &mbh = maps[2], &mbl = maps[3];
     using L = Smem<N_TILE, STAGES, B_RES>;
     const int smem = L::kTotal + 1024;
     static bool configured = false;
@@ -357,25 +401,24 @@ static int launch(const CUtensorMap &mah, const CUtensorMap &mal, const CUtensor
     const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * images;
     if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
     const int grid = total < kNumSMs ? static_cast<int>(total) : kNumSMs;
-    tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES><<<grid, MODE == MODE_GDN1_SPLIT ? 448 : 320, smem, st>>>(mah, mal, mbh, mbl, p);
+    tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES><<<grid, MODE == MODE_GDN1_SPLIT ? 448 : 320, smem, st>>>(mah, mal, mbh, mbl, maps[4], maps[5], maps[6], maps[7], p);
     SC2_LAUNCH_CHECK("tc_split_conv_kernel");
     return SC2_OK;
 }
 
 template <int N_TILE, int STAGES, int STAGES_RES>
-static int dispatch_mode(int mode, const CUtensorMap &mah, const CUtensorMap &mal, const CUtensorMap &mbh, const CUtensorMap &mbl,
-                         const Params &p, int images, cudaStream_t st) {
+static int dispatch_mode(int mode, const CUtensorMap *maps, const Params &p, int images, cudaStream_t st) {
     const bool res = p.n_taps == 1 && p.k_chunks <= 2;
     switch (mode) {
         case MODE_STORE_SPLIT:
-            return res ? launch<N_TILE, STAGES_RES, MODE_STORE_SPLIT, true>(mah, mal, mbh, mbl, p, images, st)
-                       : launch<N_TILE, STAGES, MODE_STORE_SPLIT, false>(mah, mal, mbh, mbl, p, images, st);
+            return res ? launch<N_TILE, STAGES_RES, MODE_STORE_SPLIT, true>(maps, p, images, st)
+                       : launch<N_TILE, STAGES, MODE_STORE_SPLIT, false>(maps, p, images, st);
         case MODE_GDN1_SPLIT:
-            return res ? launch<N_TILE, STAGES_RES, MODE_GDN1_SPLIT, true>(mah, mal, mbh, mbl, p, images, st)
-                       : launch<N_TILE, STAGES, MODE_GDN1_SPLIT, false>(mah, mal, mbh, mbl, p, images, st);
+            return res ? launch<N_TILE, STAGES_RES, MODE_GDN1_SPLIT, true>(maps, p, images, st)
+                       : launch<N_TILE, STAGES, MODE_GDN1_SPLIT, false>(maps, p, images, st);
         default:
-            return res ? launch<N_TILE, STAGES_RES, MODE_QUANT, true>(mah, mal, mbh, mbl, p, images, st)
-                       : launch<N_TILE, STAGES, MODE_QUANT, false>(mah, mal, mbh, mbl, p, images, st);
+            return res ? launch<N_TILE, STAGES_RES, MODE_QUANT, true>(maps, p, images, st)
+                       : launch<N_TILE, STAGES, MODE_QUANT, false>(maps, p, images, st);
     }
 }
 
@@ -455,7 +498,8 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     p.out_c = d->out_c;
     p.out_sym = out_sym;
     p.x_hi = static_cast<const __half *>(gdn_x_hi); p.x_lo = static_cast<const __half *>(gdn_x_lo);
-    CUtensorMap mah, mal, mbh, mbl;
+    CUtensorMap maps[8];
+    CUtensorMap &mah = maps[0], &mal = maps[1], &mbh = maps[2], &mbl = maps[3];
     // input planes: [images * planes, h_in, w_in, c_in] (h_in, w_in = plane geometry)
     int rc = make_nhwc_map(&mah, x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * planes, kBlockK, tw, th);
     if (rc) return rc;
@@ -466,13 +510,32 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     if (rc) return rc;
     rc = make_weight_map(&mbl, w_lo, d->c_in, p.n_taps * n_tile, n_tile);
     if (rc) return rc;
+    maps[4] = maps[5] = maps[6] = maps[7] = mah;
+    if (d->mode != MODE_QUANT) {
+        // dense (unswizzled) boxes {out_c, tw, th, 1}: bulk-store sources / x-tile destinations in the staging buffer
+        if (d->out_c > n_tile) return SC2_ERR_INVALID_ARG;
+        rc = make_nhwc_map(&maps[4], out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, d->out_c, tw, th,
+                           CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        rc = make_nhwc_map(&maps[5], out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, d->out_c, tw, th,
+                           CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        if (d->mode == MODE_GDN1_SPLIT) {
+            rc = make_nhwc_map(&maps[6], gdn_x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, d->out_c, tw,
+                               th, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+            rc = make_nhwc_map(&maps[7], gdn_x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, d->out_c, tw,
+                               th, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+        }
+    }
     cudaStream_t st = sc2::as_stream(stream);
     switch (n_tile) {
-        case 32: return dispatch_mode<32, 4, 5>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
-        case 48: return dispatch_mode<48, 4, 5>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
-        case 64: return dispatch_mode<64, 4, 5>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
-        case 96: return dispatch_mode<96, 3, 5>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
-        default: return dispatch_mode<128, 3, 4>(d->mode, mah, mal, mbh, mbl, p, d->images, st);
+        case 32: return dispatch_mode<32, 4, 5>(d->mode, maps, p, d->images, st);
+        case 48: return dispatch_mode<48, 4, 5>(d->mode, maps, p, d->images, st);
+        case 64: return dispatch_mode<64, 3, 4>(d->mode, maps, p, d->images, st);
+        case 96: return dispatch_mode<96, 2, 3>(d->mode, maps, p, d->images, st);
+        default: return dispatch_mode<128, 2, 2>(d->mode, maps, p, d->images, st);
     }
 }
 

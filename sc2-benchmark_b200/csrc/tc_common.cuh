@@ -70,6 +70,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *s
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all previously committed bulk stores have finished READING shared memory (the staging buffer may be reused)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_commit_and_wait() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -142,7 +146,7 @@ inline EncodeTiledFn get_encode_fn() {
 
 // NHWC tensor [batch, h, w, c] seen as 4-D {c, w, h, batch}; box {box_c, box_w, box_h, 1}, 128-byte swizzle.
 inline int make_nhwc_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int elem_bytes, int c, int w, int h, int batch,
-                         int box_c, int box_w, int box_h) {
+                         int box_c, int box_w, int box_h, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return SC2_ERR_CUDA;
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(batch)};
@@ -151,7 +155,7 @@ inline int make_nhwc_map(CUtensorMap *m, const void *base, CUtensorMapDataType d
     cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SC2_OK : SC2_ERR_INVALID_ARG;
 }
 
