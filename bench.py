@@ -44,11 +44,28 @@ FLOPS = {'conv2d_f32[3->96,k5,s2]': 180.6e6, 'gdn_f32[96]': 231.2e6, 'conv2d_f32
          # tensor-core g_s (tags carry the PADDED input channels; FLOPs are the algorithmic ones)
          'tc_conv[64->512,k2,m0]': 308.3e6, 'tc_conv[512->512,k1,m2]': 1644.2e6, 'tc_conv[512->256,k2,m0]': 3172.0e6,
          'tc_conv[256->256,k1,m2]': 396.5e6, 'tc_conv[256->256,k2,m1]': 1644.2e6}
-# algorithmic HBM bytes per image of the non-GEMM kernels
+# algorithmic HBM bytes per image of the HBM-bound kernels (every kernel reads its input once and writes its
+# output once, 4 bytes per activation -- the split fp16 (hi, lo) pairs of g_a are 4 bytes per value as well)
 BYTES = {'rans_encode': 290400 + 49240, 'rans_decode': 49240 + 290400, 'rans_pack': 2 * 49240,
-         'nchw_to_nhwc_f16': 290400 + 55 * 55 * 64 * 2}
+         'nchw_to_nhwc_f16': 290400 + 55 * 55 * 64 * 2,
+         'patchify_split': 602112 + 4 * 12544 * 80,            # image in, im2col patches out (to be fused into the next kernel)
+         'tc_split[80->96,k1,s1,m0]': 4 * 12544 * 80 + 4816896,  # K1: patches in, x1 out
+         'tc_split[96->96,k1,s1,m1]': 2 * 4816896,               # GDN1(96): x1 in, y1 out
+         'tc_split[96->48,k5,s2,m0]': 4816896 + 602112,          # K3
+         'tc_split[48->48,k1,s1,m1]': 2 * 602112,                # GDN1(48)
+         'tc_split[48->24,k2,s1,m2]': 602112 + 290400}           # K5 + quantise: y2 in, int32 symbols out
 PATH_FLOPS_PER_IMAGE = 8.342e9
 PATH_BYTES_PER_IMAGE = 34.85e6
+
+
+def load_traffic():
+    """DRAM bytes per launch per kernel from the newest ncu --set full capture summarised under profiles/ (batch 256)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')))
+    if not files:
+        return {}, None
+    with open(files[-1]) as f:
+        return json.load(f), os.path.basename(files[-1])
 
 
 def load_peaks():
@@ -302,6 +319,7 @@ def main():
 
     # ---- per-kernel accounting and the roofline of the dominant kernel ---------------------------
     step_ms = ms / args.steps
+    traffic, traffic_src = load_traffic()
     kernels = []
     for tag, times in prof.items():
         avg = sum(times) / len(times)
@@ -313,6 +331,8 @@ def main():
             k.update(bound='hbm', achieved=BYTES[tag] * B / (avg / 1e3) / 1e9, unit='GB/s', peak=peaks['hbm_gbs'])
         if 'achieved' in k:
             k['frac'] = k['achieved'] / k['peak']
+        if tag in traffic:  # measured DRAM bytes of one launch (ncu), scaled to this batch size
+            k['traffic'] = traffic[tag]['dram_bytes_per_launch'] * B / traffic[tag].get('batch', 256)
         if tag in ('rans_encode', 'rans_decode'):
             k['symbols_per_s_per_stream'] = n_sym / (avg / 1e3)
             k['symbols_per_s_aggregate'] = n_sym * B / (avg / 1e3)
@@ -323,12 +343,12 @@ def main():
     if kernels:
         top = kernels[0]
         roofline = {'kernel': top['kernel'], 'bound': top.get('bound'), 'achieved': top.get('achieved'), 'peak': top.get('peak'),
-                    'unit': top.get('unit'), 'frac': top.get('frac'), 'traffic': None,
+                    'unit': top.get('unit'), 'frac': top.get('frac'), 'traffic': top.get('traffic'), 'traffic_source': traffic_src,
                     'peak_source': peaks['source'] + (', bf16 sustained' if top.get('bound') == 'tensor' else ', copy bandwidth'),
                     'avg_launch_ms': top['avg_launch_ms'], 'share_of_step': top['share_of_step'], 'note': top.get('note')}
         gemm = [k for k in kernels if k.get('bound') == 'tensor']
         if gemm and gemm[0] is not top:
-            roofline['dominant_gemm'] = {kk: gemm[0][kk] for kk in ('kernel', 'achieved', 'unit', 'peak', 'frac', 'avg_launch_ms', 'share_of_step')}
+            roofline['dominant_gemm'] = {kk: gemm[0].get(kk) for kk in ('kernel', 'bound', 'achieved', 'unit', 'peak', 'frac', 'traffic', 'avg_launch_ms', 'share_of_step')}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
