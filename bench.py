@@ -186,8 +186,8 @@ def main():
     ap.add_argument('--cpu-images', type=int, default=8, help='images per step of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-threads', type=int, default=3, help='host threads (one CUDA stream each) driving the e2e steps')
-    ap.add_argument('--inflight', type=int, default=6, help='batches in flight (CUDA streams): the serial rANS chain of one batch overlaps the convolutions of the next')
+    ap.add_argument('--e2e-threads', type=int, default=8, help='host threads (one CUDA stream each) driving the e2e steps')
+    ap.add_argument('--inflight', type=int, default=8, help='batches in flight (CUDA streams): the serial rANS chain of one batch overlaps the convolutions of the next')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
