@@ -207,6 +207,12 @@ SC2_API int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, cons
 SC2_API int sc2_patchify_split(const float *x, void *out_hi, void *out_lo, int batch, int c_in, int h_in, int w_in,
                                int kh, int kw, int stride, int pad, int k_pad, sc2_stream_t stream);
 
+/* Device: first layer of g_a with the im2col fused into the tensor-core kernel (conv_tc_first.cu): stride-2 Conv2d on an fp32
+ * NCHW image with c_in*kh*kw <= 128 and c_out <= 96, fp32-grade (split fp16), output as split parity planes
+ * [batch * 4, h_out/2, w_out/2, out_c].  w_hi/w_lo: [1, n_tile, ceil16(c_in*kh*kw)] as for sc2_tc_split_conv. */
+SC2_API int sc2_tc_first_layer(const float *image, int batch, int c_in, int h_in, int w_in, int kh, int kw, int pad, int c_out,
+                               const void *w_hi, const void *w_lo, void *out_hi, void *out_lo, int out_c, sc2_stream_t stream);
+
 /* Device: NCHW fp32 -> NHWC fp16 with channels zero-padded to c_pad (even). */
 SC2_API int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, int64_t spatial, int c_pad,
                                      sc2_stream_t stream);

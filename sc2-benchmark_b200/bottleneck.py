@@ -89,6 +89,7 @@ class TensorCoreAnalysis:
     def __init__(self, seq):
         self.seq = seq
         self._key = None
+        self.fuse_first_layer = True
 
     @staticmethod
     def supports(seq, x_shape):
@@ -133,8 +134,12 @@ class TensorCoreAnalysis:
         self._prepare()
         c1, _, c2, _, c3 = list(self.seq)
         T = _native
-        ph, pl = ops.patchify_split(x, c1.kernel_size[0], c1.kernel_size[0], 2, c1.padding[0], self.k1_pad)
-        h, l = ops.tc_split_conv(ph, pl, self.w1[0], self.w1[1], c1.out_channels, 1, 1, 1, 0, T.TCS_STORE)
+        if c1.out_channels <= 96 and self.fuse_first_layer:
+            # im2col fused into the kernel: no patch tensor in HBM
+            h, l = ops.tc_first_layer(x, self.w1[0], self.w1[1], c1.out_channels, c1.kernel_size[0], c1.kernel_size[0], c1.padding[0])
+        else:
+            ph, pl = ops.patchify_split(x, c1.kernel_size[0], c1.kernel_size[0], 2, c1.padding[0], self.k1_pad)
+            h, l = ops.tc_split_conv(ph, pl, self.w1[0], self.w1[1], c1.out_channels, 1, 1, 1, 0, T.TCS_STORE)
         (gh, gl), beta = self.gdn[0]
         h, l = ops.tc_split_conv(h, l, gh, gl, c1.out_channels, 1, 1, 1, 0, T.TCS_GDN1, beta=beta, gdn=True)
         h, l = ops.tc_split_conv(h, l, self.w2[0], self.w2[1], c2.out_channels, c2.kernel_size[0], c2.kernel_size[0], 2,

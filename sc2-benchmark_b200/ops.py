@@ -444,3 +444,19 @@ def tc_split_conv(x_hi, x_lo, w_hi, w_lo, c_out, kh, kw, stride, pad, mode, beta
                                        _ptr(x_hi) if gdn else None, _ptr(x_lo) if gdn else None, _ptr(out_hi), _ptr(out_lo),
                                        _ptr(out_sym), _stream_ptr()), 'sc2_tc_split_conv')
     return out_sym if mode == _native.TCS_QUANT else (out_hi, out_lo)
+
+
+def tc_first_layer(x, w_hi, w_lo, c_out, kh, kw, pad):
+    """Stride-2 first conv on an fp32 NCHW image with the im2col fused into the tensor-core kernel (sc2_tc_first_layer).
+    Returns split parity planes (hi, lo) of shape [B * 4, h_out/2, w_out/2, c_out rounded up to 8]."""
+    require_cuda(x, 'tc_first_layer')
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    ho, wo = (H + 2 * pad - kh) // 2 + 1, (W + 2 * pad - kw) // 2 + 1
+    out_c = (c_out + 7) // 8 * 8
+    hi = torch.empty((B * 4, ho // 2, wo // 2, out_c), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(x.device), _launch('tc_first[%d->%d,k%d,s2]' % (C, c_out, kh)):
+        check(_lib().sc2_tc_first_layer(_ptr(x), B, C, H, W, kh, kw, pad, c_out, _ptr(w_hi), _ptr(w_lo), _ptr(hi), _ptr(lo), out_c,
+                                        _stream_ptr()), 'sc2_tc_first_layer')
+    return hi, lo

@@ -148,3 +148,25 @@ def test_tc_split_gdn1_matches_fp64(s2, C, H, W):
     gh, gl = s2.ops.pack_conv_weight_split(gamma.view(C, C, 1, 1).to(dev), c_in_pad=C)
     oh, ol = s2.ops.tc_split_conv(xh, xl, gh, gl, C, 1, 1, 1, 0, s2._native.TCS_GDN1, beta=beta.to(dev), gdn=True)
     assert rel_err(_unsplit(oh, ol)[:, :C], ref) < SPLIT_TOL
+
+
+@pytest.mark.parametrize('cout,H,W', [(96, 64, 48), (96, 224, 224), (32, 36, 44), (48, 20, 28)])
+def test_tc_first_layer_fused_im2col(s2, cout, H, W):
+    dev = torch.device('cuda:0')
+    torch.manual_seed(cout + H)
+    x = torch.randn(2, 3, H, W) * 1.5
+    w = torch.randn(cout, 3, 5, 5) / 75 ** 0.5
+    ref = F.conv2d(x.double(), w.double(), None, 2, 2)
+    wh, wl = s2.ops.pack_conv_weight_split(w.to(dev), as_patches=True)
+    oh, ol = s2.ops.tc_first_layer(x.to(dev), wh, wl, cout, 5, 5, 2)
+    hp, wp = ref.shape[2] // 2, ref.shape[3] // 2
+    got = _unsplit(oh, ol)[:, :cout].view(2, 2, 2, cout, hp, wp)
+    full = torch.zeros_like(ref, dtype=torch.float32)
+    for py in (0, 1):
+        for px in (0, 1):
+            full[:, :, py::2, px::2] = got[:, py, px]
+    assert rel_err(full, ref.float()) < SPLIT_TOL
+    # identical to the unfused route (patchify + 1x1 GEMM)
+    ph, pl = s2.ops.patchify_split(x.to(dev), 5, 5, 2, 2, 80)
+    uh, ul = s2.ops.tc_split_conv(ph, pl, wh, wl, cout, 1, 1, 1, 0, s2._native.TCS_STORE)
+    assert torch.equal(uh, oh) and torch.equal(ul, ol)
