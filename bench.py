@@ -48,7 +48,8 @@ FLOPS = {'conv2d_f32[3->96,k5,s2]': 180.6e6, 'gdn_f32[96]': 231.2e6, 'conv2d_f32
 # output once, 4 bytes per activation -- the split fp16 (hi, lo) pairs of g_a are 4 bytes per value as well)
 BYTES = {'rans_encode': 290400 + 49240, 'rans_decode': 49240 + 290400, 'rans_pack': 2 * 49240,
          'nchw_to_nhwc_f16': 290400 + 55 * 55 * 64 * 2,
-         'patchify_split': 602112 + 4 * 12544 * 80,            # image in, im2col patches out (to be fused into the next kernel)
+         'tc_first[3->96,k5,s2]': 602112 + 4816896,              # K1 with fused im2col: image in, x1 out
+         'patchify_split': 602112 + 4 * 12544 * 80,            # (unfused route) image in, im2col patches out
          'tc_split[80->96,k1,s1,m0]': 4 * 12544 * 80 + 4816896,  # K1: patches in, x1 out
          'tc_split[96->96,k1,s1,m1]': 2 * 4816896,               # GDN1(96): x1 in, y1 out
          'tc_split[96->48,k5,s2,m0]': 4816896 + 602112,          # K3

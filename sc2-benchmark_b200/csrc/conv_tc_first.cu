@@ -56,6 +56,32 @@ __device__ __forceinline__ void split8(const float *f, uint4 &h, uint4 &l) {
     }
 }
 
+// One row segment of KW = 5 input floats starting at column ix0 (may stick out of the image).  Interior segments use vector
+// loads: ix0 = 4X + 2px - 2 is 16-byte aligned for px = 1 and 8-byte aligned for px = 0, and neighbouring threads read
+// neighbouring 16-byte pieces, so a warp's loads are contiguous.
+__device__ __forceinline__ void load_row5(const float *row, int ix0, int w_in, bool row_ok, bool vec_ok, float *out) {
+    if (!row_ok) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) out[i] = 0.0f;
+    } else if (vec_ok && ix0 >= 0 && ix0 + 4 < w_in) {
+        if ((ix0 & 3) == 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(row + ix0));
+            out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+        } else {
+            const float2 a = __ldg(reinterpret_cast<const float2 *>(row + ix0));
+            const float2 b = __ldg(reinterpret_cast<const float2 *>(row + ix0 + 2));
+            out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+        }
+        out[4] = __ldg(row + ix0 + 4);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int ix = ix0 + i;
+            out[i] = (ix >= 0 && ix < w_in) ? __ldg(row + ix) : 0.0f;
+        }
+    }
+}
+
 template <int N_TILE>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_first_layer_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -206,7 +232,30 @@ tc_first_layer_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid
             const float *img_base = p.image + static_cast<int64_t>(b) * p.c_in * p.h_in * p.w_in;
             mbar_wait(&empty[s], ph ^ 1u);
             uint8_t *stage = ring + s * L::kStageBytes;
-            if (row < rows) {
+            if (row < rows && p.c_in == 3 && p.kh == 5 && p.kw == 5) {
+                // specialised 3 x 5 x 5 patch: fully unrolled, vector row loads, K index known at compile time
+                float f[80];
+                const bool vec_ok = (p.w_in & 3) == 0 && ((ix0 & 1) == 0);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dy = 0; dy < 5; ++dy) {
+                        const int iy = iy0 + dy;
+                        load_row5(img_base + (static_cast<int64_t>(c) * p.h_in + iy) * p.w_in, ix0, p.w_in,
+                                  valid && iy >= 0 && iy < p.h_in, vec_ok, &f[(c * 5 + dy) * 5]);
+                    }
+#pragma unroll
+                for (int k = 75; k < 80; ++k) f[k] = 0.0f;
+#pragma unroll
+                for (int g = 0; g < 10; ++g) {
+                    uint4 h, l;
+                    split8(&f[g * 8], h, l);
+                    const int kc = g >> 3, j = g & 7;
+                    const int phys = j ^ (row & 7);
+                    *reinterpret_cast<uint4 *>(stage + (2 * kc) * kABytes + row * 128 + phys * 16) = h;
+                    *reinterpret_cast<uint4 *>(stage + (2 * kc + 1) * kABytes + row * 128 + phys * 16) = l;
+                }
+            } else if (row < rows) {
                 const int n_groups = p.k_steps * 2;  // 16-byte groups of 8 K values
 #pragma unroll 1
                 for (int g = 0; g < n_groups; ++g) {
