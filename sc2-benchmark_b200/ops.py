@@ -5,6 +5,7 @@ computation below is a call into libsc2b200.so on the current CUDA stream.  Ther
 a non-CUDA tensor on the hot path raises.
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -123,6 +124,32 @@ class CoderTables:
 # ----------------------------------------------------------------------------------------------
 # packed bitstreams
 # ----------------------------------------------------------------------------------------------
+class _PinnedPool(threading.local):
+    """Per-thread, grow-only pinned staging buffers (cudaHostAlloc per call costs milliseconds)."""
+
+    def __init__(self):
+        self.d2h = None
+        self.h2d = None
+        self.h2d_event = None
+
+    def get_d2h(self, nbytes):
+        if self.d2h is None or self.d2h.numel() < nbytes:
+            with torch.inference_mode(False):  # a plain tensor: it outlives the caller's inference_mode block
+                self.d2h = torch.empty(max(nbytes, 1 << 20) * 5 // 4, dtype=torch.uint8, pin_memory=True)
+        return self.d2h[:nbytes]
+
+    def get_h2d(self, nbytes):
+        if self.h2d_event is not None:
+            self.h2d_event.synchronize()  # the previous upload from this buffer has finished
+        if self.h2d is None or self.h2d.numel() < nbytes:
+            with torch.inference_mode(False):
+                self.h2d = torch.empty(max(nbytes, 1 << 20) * 5 // 4, dtype=torch.uint8, pin_memory=True)
+        return self.h2d[:nbytes]
+
+
+_PINNED = _PinnedPool()
+
+
 class PackedStreams:
     """B CompressAI bitstreams held back to back in one device buffer (+ int64 offsets[B + 1]).
 
@@ -135,27 +162,28 @@ class PackedStreams:
     def _to_host(self):
         if self._host is None:
             offs = self.offsets.cpu()  # sync point
-            if self.status is not None:
-                st = int(self.status.item())
-                if st & _native.FAULT_ARENA_OVERFLOW:
-                    raise RuntimeError('rANS encoder ran out of arena space (device fault flag)')
+            if self.status is not None and int(self.status.item()) & _native.FAULT_ARENA_OVERFLOW:
+                raise RuntimeError('rANS encoder ran out of arena space (device fault flag)')
             total = int(offs[-1])
-            host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+            host = _PINNED.get_d2h(total)
             host.copy_(self.packed[:total], non_blocking=False)
             self._host = (offs.numpy(), host.numpy())
         return self._host
 
+    def tolist(self):
+        offs, data = self._to_host()
+        view = memoryview(data)  # one copy per stream, straight out of the (per-thread, reused) pinned staging buffer
+        out = [bytes(view[offs[i]:offs[i + 1]]) for i in range(self.batch)]
+        self._host = (offs, None)  # the staging buffer is reused by the next call
+        return out
+
     def lengths(self):
-        offs, _ = self._to_host()
+        offs = self._host[0] if self._host is not None else self.offsets.cpu().numpy()
         return np.diff(offs)
 
     def total_bytes(self):
-        return int(self._to_host()[0][-1])
-
-    def tolist(self):
-        offs, data = self._to_host()
-        view = memoryview(data)  # one copy per stream, straight out of the pinned staging buffer
-        return [bytes(view[offs[i]:offs[i + 1]]) for i in range(self.batch)]
+        offs = self._host[0] if self._host is not None else self.offsets.cpu().numpy()
+        return int(offs[-1])
 
     @staticmethod
     def from_list(strings, device):
@@ -167,15 +195,19 @@ class PackedStreams:
         offs = np.zeros(len(strings) + 1, dtype=np.int64)
         np.cumsum(lens, out=offs[1:])
         total = int(offs[-1])
-        host = torch.empty(max(total, 4), dtype=torch.uint8, pin_memory=True)
+        # one pinned staging buffer per thread: [streams ... | pad to 8 | int64 offsets], uploaded with ONE H2D copy
+        off_pos = (max(total, 4) + 7) // 8 * 8
+        host = _PINNED.get_h2d(off_pos + offs.nbytes)
         dst = memoryview(host.numpy())
         for i, s in enumerate(strings):  # one copy per stream, straight into the pinned staging buffer
             dst[offs[i]:offs[i + 1]] = s
-        packed = host.to(device, non_blocking=True)
-        offsets = torch.from_numpy(offs).pin_memory().to(device, non_blocking=True)
-        ps = PackedStreams(packed, offsets, len(strings))
-        ps._keepalive = host
-        return ps
+        host.numpy()[off_pos:off_pos + offs.nbytes] = offs.view(np.uint8)
+        blob = host.to(device, non_blocking=True)
+        _PINNED.h2d_event = torch.cuda.Event()
+        _PINNED.h2d_event.record()
+        packed = blob[:max(total, 4)]
+        offsets = blob[off_pos:off_pos + offs.nbytes].view(torch.int64)
+        return PackedStreams(packed, offsets, len(strings))
 
 
 # ----------------------------------------------------------------------------------------------
