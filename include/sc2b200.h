@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 1
+#define SC2_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -121,6 +121,10 @@ SC2_API int sc2_rans_decode_batch(const uint8_t *packed, const int64_t *offsets,
 SC2_API int sc2_quantize_symbols(const float *x, const float *means, int32_t *symbols, int batch, int channels,
                          int64_t spatial, sc2_stream_t stream);
 
+/* Device: EntropyModel.dequantize(symbols, means) with one mean per ELEMENT (mean-scale hyperprior,
+ * sc2bench/models/layer.py:785): out[i] = float(symbols[i]) + means[i].  means may be NULL. */
+SC2_API int sc2_dequantize(const int32_t *symbols, const float *means, float *out, int64_t n, sc2_stream_t stream);
+
 /* Device: GaussianConditional.build_indexes: idx = #(table[:-1] < max(scale, bound)) per element. */
 SC2_API int sc2_gc_build_indexes(const float *scales, int64_t n, const float *scale_table, int n_levels,
                          float scale_bound, int32_t *indexes, sc2_stream_t stream);
@@ -133,6 +137,9 @@ SC2_API int sc2_gc_build_indexes(const float *scales, int64_t n, const float *sc
 #define SC2_EPI_CLAMP01 2
 #define SC2_EPI_QUANTIZE 3 /* y -> int32(rint(y - aux[c])) written to out as int32 (aux = medians or NULL) */
 #define SC2_EPI_ABS 4
+#define SC2_EPI_LEAKY_RELU 5 /* y > 0 ? y : y * epi_param (nn.LeakyReLU; sc2bench/models/layer.py:611-616,760-770) */
+#define SC2_IN_NONE 0
+#define SC2_IN_ABS 1 /* the convolution reads |x| (h_a(torch.abs(y)), sc2bench/models/layer.py:642) */
 
 typedef struct sc2_conv_desc {
     int batch, c_in, h_in, w_in;
@@ -141,6 +148,8 @@ typedef struct sc2_conv_desc {
     int transposed;     /* 0: Conv2d (weight [c_out, c_in, kh, kw]); 1: ConvTranspose2d (weight [c_in, c_out, kh, kw]) */
     int output_padding; /* transposed only */
     int epilogue;       /* SC2_EPI_* */
+    int in_transform;   /* SC2_IN_* */
+    float epi_param;    /* negative slope for SC2_EPI_LEAKY_RELU */
 } sc2_conv_desc;
 
 /* output spatial size for a descriptor */

@@ -258,11 +258,12 @@ def small_zoo_models(torch):
         print(name, 'y', tuple(y.shape), 'bytes', [[len(s) for s in l] for l in obj['strings']])
 
 
-def small_shp_bottleneck(torch):
-    """The reference's SHPBasedResNetBottleneck (sc2bench/models/layer.py:553-720) at a tiny size, weights stored."""
+def small_shp_bottleneck(torch, key='SHPBasedResNetBottleneck', fname='shp_bottleneck_small.npz', seed=31):
+    """The reference's SHPBasedResNetBottleneck / MSHPBasedResNetBottleneck (sc2bench/models/layer.py:553-817) at a tiny
+    size, weights stored."""
     from sc2bench.models.layer import get_layer
-    torch.manual_seed(31)
-    layer = get_layer('SHPBasedResNetBottleneck', num_input_channels=3, num_latent_channels=8, num_bottleneck_channels=8,
+    torch.manual_seed(seed)
+    layer = get_layer(key, num_input_channels=3, num_latent_channels=8, num_bottleneck_channels=8,
                       num_target_channels=32)
     with torch.no_grad():
         for mod in list(layer.g_a) + list(layer.g_s):
@@ -279,7 +280,7 @@ def small_shp_bottleneck(torch):
     perturb_entropy_bottleneck(torch, layer.entropy_bottleneck, 13)
     layer.eval()
     layer.update(force=True)
-    torch.manual_seed(32)
+    torch.manual_seed(seed + 1)
     x = torch.randn(2, 3, 96, 80) * 1.5
     with torch.inference_mode():
         enc = layer.encode(x)
@@ -290,8 +291,12 @@ def small_shp_bottleneck(torch):
         out['streams%d' % li], out['stream_offsets%d' % li] = _pack_strings(strings)
     for k, v in layer.state_dict().items():
         out['sd/' + k] = v.numpy()
-    np.savez_compressed(os.path.join(GOLD, 'shp_bottleneck_small.npz'), **out)
-    print('shp_bottleneck_small.npz: y', tuple(y.shape), 'z shape', tuple(enc['shape']), 'bytes', [[len(s) for s in l] for l in enc['strings']])
+    np.savez_compressed(os.path.join(GOLD, fname), **out)
+    print(fname, ': y', tuple(y.shape), 'z shape', tuple(enc['shape']), 'bytes', [[len(s) for s in l] for l in enc['strings']])
+
+
+def small_mshp_bottleneck(torch):
+    small_shp_bottleneck(torch, 'MSHPBasedResNetBottleneck', 'mshp_bottleneck_small.npz', seed=41)
 
 
 def main():
@@ -304,7 +309,8 @@ def main():
     import torch
     torch.set_num_threads(1)  # bit-reproducible reductions
     os.makedirs(GOLD, exist_ok=True)
-    jobs = {'rans': rans_cases, 'small_fp': small_fp_bottleneck, 'config1': config1, 'zoo': small_zoo_models, 'shp': small_shp_bottleneck}
+    jobs = {'rans': rans_cases, 'small_fp': small_fp_bottleneck, 'config1': config1, 'zoo': small_zoo_models, 'shp': small_shp_bottleneck,
+            'mshp': small_mshp_bottleneck}
     for k, fn in jobs.items():
         if args.only in (None, k):
             fn(torch)

@@ -12,13 +12,15 @@ from . import ops  # noqa: E402
 from .backbone import (AnalyzableModule, FeatureExtractionBackbone, FileSizeAnalyzer, SplittableResNet,  # noqa: E402,F401
                        UpdatableBackbone, check_if_updatable, get_backbone, splittable_resnet)
 from .bottleneck import (LAYER_CLASS_DICT, BaseBottleneck, EntropyBottleneckLayer, FPBasedResNetBottleneck,  # noqa: E402,F401
+                         MSHPBasedResNetBottleneck,
                          SHPBasedResNetBottleneck, get_layer, register_layer_class, register_layer_func)
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional  # noqa: E402,F401
 from .layers import GDN, GDN1  # noqa: E402,F401
 from .models import (CompressionModel, FactorizedPrior, ScaleHyperprior, bmshj2018_factorized,  # noqa: E402,F401
                      bmshj2018_hyperprior, get_scale_table, update_registered_buffers)
 
-from .wrapper import (COMPRESSAI_DICT, AdaptivePad, NeuralInputCompressionClassifier, get_compression_model,  # noqa: E402,F401
-                      register_compressai_model)
+from . import backbone, wrapper  # noqa: E402,F401
+from .wrapper import (COMPRESSAI_DICT, WRAPPER_CLASS_DICT, AdaptivePad, EntropicClassifier,  # noqa: E402,F401
+                      NeuralInputCompressionClassifier, get_compression_model, redesign_model, register_compressai_model)
 
 __version__ = '0.1.0'

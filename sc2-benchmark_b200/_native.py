@@ -15,7 +15,7 @@ vp, i32, i64, f32 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
 class ConvDesc(_c.Structure):
     """struct sc2_conv_desc"""
     _fields_ = [(n, i32) for n in ('batch', 'c_in', 'h_in', 'w_in', 'c_out', 'kh', 'kw', 'stride', 'pad',
-                                    'transposed', 'output_padding', 'epilogue')]
+                                    'transposed', 'output_padding', 'epilogue', 'in_transform')] + [('epi_param', _c.c_float)]
 
 
 class TcConvDesc(_c.Structure):
@@ -42,6 +42,7 @@ SIGNATURES = {
     'sc2_rans_pack': (i32, [vp, i64, vp, i32, vp, vp, vp]),
     'sc2_rans_decode_batch': (i32, [vp, vp, i32, i64, vp, i64, vp, i32, i32, vp, vp, vp, vp, vp]),
     'sc2_quantize_symbols': (i32, [vp, vp, vp, i32, i32, i64, vp]),
+    'sc2_dequantize': (i32, [vp, vp, vp, i64, vp]),
     'sc2_gc_build_indexes': (i32, [vp, i64, vp, i32, f32, vp, vp]),
     'sc2_conv_out_size': (i32, [_c.POINTER(ConvDesc), _c.POINTER(i32), _c.POINTER(i32)]),
     'sc2_conv2d_f32': (i32, [_c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]),
@@ -56,7 +57,8 @@ SIGNATURES = {
 
 SC2_OK = 0
 FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM = 1, 2, 4
-EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS = 0, 1, 2, 3, 4
+EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2, 3, 4, 5
+IN_NONE, IN_ABS = 0, 1
 TC_STORE_F16, TC_STORE_F32, TC_IGDN1_F16, TC_GDN1_F16 = 0, 1, 2, 3
 TCS_STORE, TCS_GDN1, TCS_QUANT = 0, 1, 2
 
@@ -80,7 +82,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sc2_abi_version() != 1:
+    if lib.sc2_abi_version() != 2:
         raise ImportError('libsc2b200.so ABI version mismatch: rebuild with sc2-benchmark_b200/build.py --force')
     _lib = lib
     return lib

@@ -369,8 +369,8 @@ class SHPBasedResNetBottleneck(BaseBottleneck):
     def encode(self, x, **kwargs):
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         y = run_transform(self.g_a, x)
-        z_symbols = run_transform(self.h_a, torch.abs(y), final_epilogue=_native.EPI_QUANTIZE,
-                                  final_aux=eb._get_medians().detach().reshape(-1))
+        z_symbols = run_transform(self.h_a, y, final_epilogue=_native.EPI_QUANTIZE,
+                                  final_aux=eb._get_medians().detach().reshape(-1), in_abs=True)  # h_a(|y|), |.| on load
         z_shape = z_symbols.size()[-2:]
         z_streams = eb.compress_symbols(z_symbols, spatial=z_symbols[0, 0].numel())
         z_hat = eb.decompress_packed(z_streams, tuple(z_shape))  # the encoder decodes z itself, like the decoder will
@@ -428,3 +428,80 @@ class SHPBasedResNetBottleneck(BaseBottleneck):
         update_registered_buffers(self.gaussian_conditional, 'gaussian_conditional',
                                   ['_quantized_cdf', '_offset', '_cdf_length', 'scale_table'], state_dict)
         return super().load_state_dict(state_dict)
+
+
+@register_layer_class
+class MSHPBasedResNetBottleneck(SHPBasedResNetBottleneck):
+    """Mean-scale hyperprior bottleneck (mirrors sc2bench/models/layer.py:723-817).
+
+    As the scale hyperprior, except: h_a reads y itself (not |y|) through LeakyReLU; h_s emits 2·C channels that split into
+    (scales_hat, means_hat); y is quantised around means_hat (one mean per element) and dequantised by adding it back."""
+
+    def __init__(self, num_input_channels=3, num_latent_channels=16, num_bottleneck_channels=24, num_target_channels=256,
+                 g_a_channel_sizes=None, g_s_channel_sizes=None):
+        L, b = num_latent_channels, num_bottleneck_channels
+        h_a = nn.Sequential(
+            nn.Conv2d(b, L, kernel_size=5, stride=2, padding=1, bias=False), nn.LeakyReLU(inplace=True),
+            nn.Conv2d(L, L, kernel_size=5, stride=2, padding=2, bias=False))
+        h_s = nn.Sequential(
+            nn.ConvTranspose2d(L, L, kernel_size=5, stride=2, padding=1, bias=False), nn.LeakyReLU(inplace=True),
+            nn.ConvTranspose2d(L, L * 3 // 2, kernel_size=5, stride=2, padding=1, bias=False), nn.LeakyReLU(inplace=True),
+            nn.Conv2d(L * 3 // 2, b * 2, kernel_size=5, stride=1, padding=0, bias=False))
+        super().__init__(num_input_channels=num_input_channels, num_latent_channels=L, num_bottleneck_channels=b,
+                         num_target_channels=num_target_channels, h_a=h_a, h_s=h_s,
+                         g_a_channel_sizes=g_a_channel_sizes, g_s_channel_sizes=g_s_channel_sizes)
+
+    @torch.no_grad()
+    def _gaussian_params(self, z_hat):
+        scales_hat, means_hat = run_transform(self.h_s, z_hat).chunk(2, 1)
+        return self.gaussian_conditional.build_indexes(scales_hat), means_hat.contiguous()
+
+    @torch.no_grad()
+    def encode(self, x, **kwargs):
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y = run_transform(self.g_a, x)
+        z_symbols = run_transform(self.h_a, y, final_epilogue=_native.EPI_QUANTIZE,
+                                  final_aux=eb._get_medians().detach().reshape(-1))
+        z_shape = z_symbols.size()[-2:]
+        z_streams = eb.compress_symbols(z_symbols, spatial=z_symbols[0, 0].numel())
+        z_hat = eb.decompress_packed(z_streams, tuple(z_shape))
+        indexes, means_hat = self._gaussian_params(z_hat)
+        y_symbols = ops.quantize_symbols(y, means_hat)
+        y_streams = ops.rans_encode(y_symbols, gc.coder_tables(), indexes=indexes)
+        return {'strings': [y_streams.tolist(), z_streams.tolist()], 'shape': z_shape}
+
+    @torch.no_grad()
+    def decode(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 2
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        device = eb._quantized_cdf.device
+        z_hat = eb.decompress_packed(ops.PackedStreams.from_list(strings[1], device), tuple(shape), check_status=True)
+        indexes, means_hat = self._gaussian_params(z_hat)
+        y_symbols = ops.rans_decode(ops.PackedStreams.from_list(strings[0], device), indexes[0].numel(), gc.coder_tables(),
+                                    indexes=indexes, want='symbols').view(indexes.size())
+        y_hat = ops.dequantize(y_symbols, means_hat)
+        if self.decoder_precision == 'fp16-tc' and TensorCoreTransform.supports(self.g_s):
+            if self._tc_decoder is None:
+                self._tc_decoder = TensorCoreTransform(self.g_s)
+            return self._tc_decoder(y_hat)
+        return run_transform(self.g_s, y_hat)
+
+    def _forward2train(self, x):
+        y = self.g_a(x)
+        z_hat, _ = self.entropy_bottleneck(self.h_a(y))
+        scales_hat, means_hat = self.h_s(z_hat).chunk(2, 1)
+        y_hat, _ = self.gaussian_conditional(y, scales_hat, means=means_hat)
+        return self.g_s(y_hat)
+
+    def forward(self, x):
+        if not self.updated:
+            return self._forward2train(x)
+        if not self.training:
+            return self.decode(**self.encode(x))
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y = self.g_a(x)
+        z = self.h_a(y)
+        z_hat = eb.dequantize(eb.quantize(z, 'dequantize', self._get_means(z)))
+        scales_hat, means_hat = self.h_s(z_hat).chunk(2, 1)
+        y_hat = gc.dequantize(gc.quantize(y, 'dequantize', means_hat))
+        return self.g_s(y_hat.detach())

@@ -22,6 +22,7 @@ enum Epilogue {
     EP_CLAMP01 = SC2_EPI_CLAMP01,
     EP_QUANTIZE = SC2_EPI_QUANTIZE,
     EP_ABS = SC2_EPI_ABS,
+    EP_LEAKY = SC2_EPI_LEAKY_RELU,
     EP_GDN1_FWD = 16,  // out = x / (acc + beta)
     EP_GDN1_INV = 17,  // out = x * (acc + beta)
     EP_GDN_FWD = 18,   // out = x * rsqrt(acc + beta)
@@ -38,6 +39,7 @@ struct ConvParams {
     int h_out, w_out;
     int K;  // c_in * kh * kw
     int in_transform, epilogue;
+    float epi_param;
 };
 
 constexpr int BK = 16;
@@ -186,6 +188,7 @@ conv2d_f32_kernel(const ConvParams p) {
                 case EP_RELU: v = fmaxf(v, 0.0f); break;
                 case EP_CLAMP01: v = fminf(fmaxf(v, 0.0f), 1.0f); break;
                 case EP_ABS: v = fabsf(v); break;
+                case EP_LEAKY: v = v > 0.0f ? v : v * p.epi_param; break;
                 case EP_GDN1_FWD: v = __fdiv_rn(1.0f, v) * __ldg(xb + o); break;  // x * (1 / norm), as the reference
                 case EP_GDN1_INV: v = __ldg(xb + o) * v; break;
                 case EP_GDN_FWD: v = __ldg(xb + o) * __frsqrt_rn(v); break;
@@ -233,7 +236,7 @@ int sc2_conv2d_f32(const sc2_conv_desc *d, const float *x, const float *weight, 
                    void *out, sc2_stream_t stream) {
     if (!d || !x || !weight || !out) return SC2_ERR_INVALID_ARG;
     if (d->batch < 0 || d->c_in < 1 || d->c_out < 1 || d->pad < 0) return SC2_ERR_INVALID_ARG;
-    if (d->epilogue < SC2_EPI_NONE || d->epilogue > SC2_EPI_ABS) return SC2_ERR_INVALID_ARG;
+    if (d->epilogue < SC2_EPI_NONE || d->epilogue > SC2_EPI_LEAKY_RELU) return SC2_ERR_INVALID_ARG;
     sc2::ConvParams p;
     int rc = sc2_conv_out_size(d, &p.h_out, &p.w_out);
     if (rc != SC2_OK) return rc;
@@ -241,8 +244,10 @@ int sc2_conv2d_f32(const sc2_conv_desc *d, const float *x, const float *weight, 
     p.batch = d->batch; p.c_in = d->c_in; p.h_in = d->h_in; p.w_in = d->w_in; p.c_out = d->c_out;
     p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.transposed = d->transposed ? 1 : 0;
     p.K = d->c_in * d->kh * d->kw;
-    p.in_transform = sc2::IN_NONE;
+    if (d->in_transform != SC2_IN_NONE && d->in_transform != SC2_IN_ABS) return SC2_ERR_INVALID_ARG;
+    p.in_transform = d->in_transform == SC2_IN_ABS ? sc2::IN_ABS : sc2::IN_NONE;
     p.epilogue = d->epilogue;
+    p.epi_param = d->epi_param;
     return sc2::launch_conv(p, sc2::as_stream(stream));
 }
 
@@ -257,6 +262,7 @@ int sc2_gdn_f32(const float *x, const float *gamma, const float *beta, float *y,
     p.h_in = 1; p.w_in = static_cast<int>(spatial); p.h_out = 1; p.w_out = static_cast<int>(spatial);
     p.kh = p.kw = 1; p.stride = 1; p.pad = 0; p.transposed = 0;
     p.K = channels;
+    p.epi_param = 0.0f;
     p.in_transform = kind == 0 ? sc2::IN_ABS : sc2::IN_SQUARE;
     p.epilogue = kind == 0 ? (inverse ? sc2::EP_GDN1_INV : sc2::EP_GDN1_FWD) : (inverse ? sc2::EP_GDN_INV : sc2::EP_GDN_FWD);
     return sc2::launch_conv(p, sc2::as_stream(stream));

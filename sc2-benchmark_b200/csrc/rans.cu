@@ -395,6 +395,13 @@ __global__ void quantize_symbols_kernel(const float *__restrict__ x, const float
     }
 }
 
+__global__ void dequantize_kernel(const int32_t *__restrict__ symbols, const float *__restrict__ means,
+                                  float *__restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = static_cast<float>(symbols[i]) + (means ? means[i] : 0.0f);
+}
+
 __global__ void gc_build_indexes_kernel(const float *__restrict__ scales, int64_t n,
                                         const float *__restrict__ table, int n_levels, float bound,
                                         int32_t *__restrict__ indexes) {
@@ -509,6 +516,16 @@ int sc2_quantize_symbols(const float *x, const float *means, int32_t *symbols, i
     if (blocks > sc2::kNumSMs * 16) blocks = sc2::kNumSMs * 16;
     sc2::quantize_symbols_kernel<<<static_cast<int>(blocks), 256, 0, sc2::as_stream(stream)>>>(x, means, symbols, channels, spatial, total);
     SC2_LAUNCH_CHECK("quantize_symbols_kernel");
+    return SC2_OK;
+}
+
+int sc2_dequantize(const int32_t *symbols, const float *means, float *out, int64_t n, sc2_stream_t stream) {
+    if (!symbols || !out || n < 0) return SC2_ERR_INVALID_ARG;
+    if (n == 0) return SC2_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > sc2::kNumSMs * 16) blocks = sc2::kNumSMs * 16;
+    sc2::dequantize_kernel<<<static_cast<int>(blocks), 256, 0, sc2::as_stream(stream)>>>(symbols, means, out, n);
+    SC2_LAUNCH_CHECK("dequantize_kernel");
     return SC2_OK;
 }
 

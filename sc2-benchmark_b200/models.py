@@ -69,12 +69,14 @@ def _single(v):
 
 
 @torch.no_grad()
-def run_transform(seq, x, final_epilogue=_native.EPI_NONE, final_aux=None):
+def run_transform(seq, x, final_epilogue=_native.EPI_NONE, final_aux=None, in_abs=False):
     """Inference executor for an analysis / synthesis transform (an nn.Sequential of Conv2d / ConvTranspose2d /
-    GDN / GDN1 / ReLU): every layer is one libsc2b200 launch, ReLU folds into the conv before it, and the last
-    conv can take a fused epilogue (quantise-to-symbols, clamp)."""
+    GDN / GDN1 / ReLU / LeakyReLU): every layer is one libsc2b200 launch, the activation folds into the conv before
+    it, the last conv can take a fused epilogue (quantise-to-symbols, clamp) and the first can read |x| (in_abs)."""
     ops.require_cuda(x, 'run_transform')
     mods = list(seq)
+    if in_abs and not (mods and isinstance(mods[0], (nn.Conv2d, nn.ConvTranspose2d))):
+        x, in_abs = torch.abs(x), False
     i = 0
     while i < len(mods):
         m = mods[i]
@@ -82,9 +84,14 @@ def run_transform(seq, x, final_epilogue=_native.EPI_NONE, final_aux=None):
         if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
             if m.groups != 1 or _single(m.dilation) != 1:
                 raise NotImplementedError('grouped / dilated convolutions are not on the bottleneck path')
-            epi, aux = _native.EPI_NONE, None
+            epi, aux, slope = _native.EPI_NONE, None, 0.0
+            first = i == 0
             if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
                 epi = _native.EPI_RELU
+                i += 1
+                last = i == len(mods) - 1
+            elif i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU):
+                epi, slope = _native.EPI_LEAKY_RELU, mods[i + 1].negative_slope
                 i += 1
                 last = i == len(mods) - 1
             if last and final_epilogue != _native.EPI_NONE:
@@ -93,7 +100,8 @@ def run_transform(seq, x, final_epilogue=_native.EPI_NONE, final_aux=None):
                 epi, aux = final_epilogue, final_aux
             tr = isinstance(m, nn.ConvTranspose2d)
             x = ops.conv2d(x, m.weight, m.bias, stride=_single(m.stride), padding=_single(m.padding), transposed=tr,
-                           output_padding=_single(m.output_padding) if tr else 0, epilogue=epi, aux=aux)
+                           output_padding=_single(m.output_padding) if tr else 0, epilogue=epi, aux=aux,
+                           in_abs=in_abs and first, epi_param=slope)
         elif isinstance(m, GDN):
             gamma, beta = m.effective_params()
             x = ops.gdn(x, gamma, beta, kind=m._kind, inverse=m.inverse)

@@ -214,11 +214,18 @@ class PackedStreams:
 # device ops
 # ----------------------------------------------------------------------------------------------
 def quantize_symbols(x, means=None):
-    """EntropyModel.quantize(x, "symbols", means) for x [B, C, *spatial]; means: [C] tensor or None."""
+    """EntropyModel.quantize(x, "symbols", means) for x [B, C, *spatial]; means: [C] tensor, a tensor of x's shape
+    (one mean per element, mean-scale hyperprior) or None."""
     require_cuda(x, 'quantize_symbols')
     x = x.contiguous().float()
     B, C = x.shape[0], x.shape[1]
     spatial = x[0, 0].numel() if x.dim() > 2 else 1
+    if means is not None and means.numel() != C:
+        if means.shape != x.shape:
+            raise ValueError('means must have one value per channel or per element')
+        B, C, spatial = 1, x.numel(), 1  # flat: element i takes means[i]
+        if C >= 2 ** 31:
+            raise ValueError('tensor too large for per-element means')
     out = torch.empty(x.shape, dtype=torch.int32, device=x.device)
     m = means.contiguous().float() if means is not None else None
     with torch.cuda.device(x.device), _launch('quantize_symbols'):
@@ -298,6 +305,23 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
     return (out, status) if return_status else out
 
 
+def dequantize(symbols, means=None):
+    """EntropyModel.dequantize(symbols, means) with one mean per element: float(symbols) + means."""
+    require_cuda(symbols, 'dequantize')
+    sym = symbols.contiguous()
+    if sym.dtype != torch.int32:
+        sym = sym.int()
+    m = None
+    if means is not None:
+        if means.shape != sym.shape:
+            raise ValueError('means must have the shape of symbols')
+        m = means.contiguous().float()
+    out = torch.empty(sym.shape, dtype=torch.float32, device=sym.device)
+    with torch.cuda.device(sym.device), _launch('dequantize', 1 if sym.numel() else 0):
+        check(_lib().sc2_dequantize(_ptr(sym), _ptr(m), _ptr(out), sym.numel(), _stream_ptr()), 'sc2_dequantize')
+    return out
+
+
 def gc_build_indexes(scales, scale_table, scale_bound):
     require_cuda(scales, 'gc_build_indexes')
     s = scales.contiguous().float()
@@ -309,8 +333,9 @@ def gc_build_indexes(scales, scale_table, scale_bound):
     return out
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_padding=0, epilogue=_native.EPI_NONE, aux=None):
-    """fp32 NCHW conv / transposed conv with a fused epilogue (sc2_conv2d_f32)."""
+def conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_padding=0, epilogue=_native.EPI_NONE, aux=None,
+           in_abs=False, epi_param=0.0):
+    """fp32 NCHW conv / transposed conv with a fused epilogue (sc2_conv2d_f32); in_abs convolves |x|."""
     require_cuda(x, 'conv2d')
     x = x.contiguous().float()
     w = weight.detach().contiguous().float()
@@ -324,7 +349,7 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_p
             raise ValueError('weight / input channel mismatch (groups are not supported)')
         Cout = w.shape[0]
     d = ConvDesc(B, Cin, H, W, Cout, w.shape[2], w.shape[3], int(stride), int(padding), int(bool(transposed)),
-                 int(output_padding), int(epilogue))
+                 int(output_padding), int(epilogue), _native.IN_ABS if in_abs else _native.IN_NONE, float(epi_param))
     ho, wo = ctypes.c_int(), ctypes.c_int()
     check(_lib().sc2_conv_out_size(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)), 'sc2_conv_out_size')
     out = torch.empty((B, Cout, ho.value, wo.value), dtype=torch.int32 if epilogue == _native.EPI_QUANTIZE else torch.float32,

@@ -179,3 +179,49 @@ def test_shp_bottleneck_and_entropy_bottleneck_layer_vs_reference(s2, oracle_com
         if want['strings'][1] == enc['strings'][1]:  # identical z -> identical scales -> y must match too
             assert want['strings'][0] == enc['strings'][0]
             assert rel_err(dec.cpu(), want_dec) < FEATURE_TOL
+
+
+def test_entropic_classifier_wrapper(s2, oracle_compressai):
+    """EntropicClassifier (wrapper.py:196-264) built the way the fine-tuning configs build it
+    (encoder = the classifier's modules up to layer1, EntropyBottleneckLayer(256), decoder = the rest, classifier = fc).
+    The analysed strings must equal the oracle coder's on the encoder features; logits must equal running the tail on the
+    dequantised features."""
+    import torchvision
+    from compressai.entropy_models import EntropyBottleneck as OracleEB
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    net = torchvision.models.resnet50(weights=None)
+    model = s2.wrapper.EntropicClassifier(
+        net, encoder_config={'sequential': ['conv1', 'bn1', 'relu', 'maxpool', 'layer1']},
+        compression_model_kwargs={'entropy_bottleneck_channels': 256},
+        decoder_config={'sequential': ['layer2', 'layer3', 'layer4', 'avgpool']}, classifier_config={'sequential': ['fc']},
+        analysis_config={'analyzes_after_compress': True, 'analyzer_configs': [{'key': 'FileSizeAnalyzer', 'kwargs': {'unit': 'KB'}}]})
+    assert list(dict(model.encoder.named_children())) == ['conv1', 'bn1', 'relu', 'maxpool', 'layer1']
+    assert s2.backbone.check_if_updatable(model) and model.get_aux_module() is model.entropy_bottleneck
+    sd = model.state_dict()
+    model.load_state_dict(sd)  # the reference's split load path
+    model.update()
+    assert model.bottleneck_updated
+    model.eval().to(dev)
+    captured = []
+    model.analyzers.append(type('Grab', (), {'analyze': lambda self, o: captured.append(o), 'summarize': lambda self: None,
+                                             'clear': lambda self: None})())
+    model.activate_analysis()
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, 128, 96).to(dev)
+    with torch.inference_mode():
+        logits = model(x)
+        feats = model.encoder(x)
+    assert logits.shape == (2, 1000) and len(captured) == 1 and len(model.analyzers[0].file_size_list) == 1
+    obj = captured[0]
+    assert tuple(obj['shape']) == tuple(feats.shape[-2:])
+    eb = model.entropy_bottleneck.entropy_bottleneck
+    oeb = OracleEB(256)
+    oeb.load_state_dict({k: v.cpu() for k, v in eb.state_dict().items() if not k.startswith('_')}, strict=False)
+    oeb.update()
+    want = oeb.compress(feats.cpu())
+    assert obj['strings'][0] == want
+    with torch.inference_mode():
+        f_hat = oeb.decompress(want, feats.shape[-2:]).to(dev)
+        want_logits = model.classifier(torch.flatten(model.decoder(f_hat), 1))
+    assert torch.equal(logits, want_logits)

@@ -355,10 +355,13 @@ def test_batch256_path_properties(s2, dev):
         assert 256 * 8 < total_bytes < 256 * 24 * 55 * 55 * 2
 
 
-def test_shp_bottleneck_small_golden(s2, dev):
-    """golden vectors from the reference's own SHPBasedResNetBottleneck (layer.py:553-720)."""
-    gs = load_golden('shp_bottleneck_small.npz')
-    layer = s2.get_layer('SHPBasedResNetBottleneck', num_input_channels=3, num_latent_channels=8, num_bottleneck_channels=8,
+@pytest.mark.parametrize('key,fname', [('SHPBasedResNetBottleneck', 'shp_bottleneck_small.npz'),
+                                       ('MSHPBasedResNetBottleneck', 'mshp_bottleneck_small.npz')])
+def test_shp_bottleneck_small_golden(s2, dev, key, fname):
+    """golden vectors from the reference's own SHPBasedResNetBottleneck / MSHPBasedResNetBottleneck
+    (layer.py:553-817)."""
+    gs = load_golden(fname)
+    layer = s2.get_layer(key, num_input_channels=3, num_latent_channels=8, num_bottleneck_channels=8,
                          num_target_channels=32)
     layer.load_state_dict(state_dict_from_golden(gs))
     layer.update()
@@ -377,3 +380,28 @@ def test_shp_bottleneck_small_golden(s2, dev):
     # cross decode: the golden bytes through our decoder
     dec2 = layer.decode([want_y, want_z], tuple(gs['shape']))
     assert rel_err(dec2.cpu(), torch.from_numpy(gs['decoded'])) < FEATURE_TOL
+
+
+def test_conv_leaky_relu_abs_and_dequantize(s2, dev):
+    """LeakyReLU epilogue / |x| on load (h_a, h_s of the hyperprior bottlenecks, layer.py:606-617,755-770) and the
+    per-element dequantise (layer.py:785) against torch on the CPU."""
+    torch.manual_seed(5)
+    x = torch.randn(2, 6, 13, 11)
+    conv = torch.nn.Conv2d(6, 10, 5, stride=2, padding=1, bias=False)
+    tconv = torch.nn.ConvTranspose2d(6, 9, 5, stride=2, padding=1, bias=False)
+    with torch.no_grad():
+        want = torch.nn.functional.leaky_relu(conv(torch.abs(x)), 0.01)
+        want_t = torch.nn.functional.leaky_relu(tconv(x), 0.2)
+    got = s2.ops.conv2d(x.to(dev), conv.weight.to(dev), stride=2, padding=1, epilogue=s2._native.EPI_LEAKY_RELU,
+                        epi_param=0.01, in_abs=True)
+    got_t = s2.ops.conv2d(x.to(dev), tconv.weight.to(dev), stride=2, padding=1, transposed=True,
+                          epilogue=s2._native.EPI_LEAKY_RELU, epi_param=0.2)
+    assert rel_err(got.cpu(), want) < 5e-6 and rel_err(got_t.cpu(), want_t) < 5e-6
+    seq = torch.nn.Sequential(conv, torch.nn.LeakyReLU(inplace=True)).to(dev)
+    assert torch.equal(s2.models.run_transform(seq, x.to(dev), in_abs=True), got)
+    sym = torch.randint(-40, 40, (3, 5, 7), dtype=torch.int32)
+    means = torch.randn(3, 5, 7)
+    assert torch.equal(s2.ops.dequantize(sym.to(dev), means.to(dev)).cpu(), sym.float() + means)
+    assert torch.equal(s2.ops.dequantize(sym.to(dev)).cpu(), sym.float())
+    y = torch.randn(3, 5, 7) * 4
+    assert torch.equal(s2.ops.quantize_symbols(y.to(dev), means.to(dev)).cpu(), torch.round(y - means).int())
