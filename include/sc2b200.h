@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 2
+#define SC2_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -183,8 +183,11 @@ typedef struct sc2_tc_conv_desc {
     int mode;
 } sc2_tc_conv_desc;
 
+/* tile_counter (all sc2_tc_* kernels): the kernels are persistent (one CTA per SM).  With a caller-provided int32 that is
+ * ZERO at launch (one per launch; stream-ordered reuse is fine) the CTAs claim tiles dynamically, so a CTA that is placed
+ * late -- its SM busy with another stream's blocks -- does not delay the kernel; NULL selects the static schedule. */
 SC2_API int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta,
-                             const void *gdn_x, void *out, sc2_stream_t stream);
+                             const void *gdn_x, void *out, int32_t *tile_counter, sc2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Device: fp32-grade tensor-core convolution ("split fp16", three tcgen05 passes; conv_tc_split.cu) for g_a
@@ -209,7 +212,8 @@ typedef struct sc2_tc_split_desc {
 SC2_API int sc2_tc_split_n_tile(int c_out);
 SC2_API int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *x_lo, const void *w_hi,
                               const void *w_lo, const float *beta, const float *medians, const void *gdn_x_hi,
-                              const void *gdn_x_lo, void *out_hi, void *out_lo, int32_t *out_sym, sc2_stream_t stream);
+                              const void *gdn_x_lo, void *out_hi, void *out_lo, int32_t *out_sym, int32_t *tile_counter,
+                              sc2_stream_t stream);
 
 /* Device: im2col of an fp32 NCHW image for the first (c_in = 3) layer: split fp16 patches, K = (c, dy, dx) zero-padded
  * to k_pad, pixels in parity-plane order [batch * 4, h_out/2, w_out/2, k_pad] (h_out, w_out must be even). */
@@ -220,11 +224,20 @@ SC2_API int sc2_patchify_split(const float *x, void *out_hi, void *out_lo, int b
  * NCHW image with c_in*kh*kw <= 128 and c_out <= 96, fp32-grade (split fp16), output as split parity planes
  * [batch * 4, h_out/2, w_out/2, out_c].  w_hi/w_lo: [1, n_tile, ceil16(c_in*kh*kw)] as for sc2_tc_split_conv. */
 SC2_API int sc2_tc_first_layer(const float *image, int batch, int c_in, int h_in, int w_in, int kh, int kw, int pad, int c_out,
-                               const void *w_hi, const void *w_lo, void *out_hi, void *out_lo, int out_c, sc2_stream_t stream);
+                               const void *w_hi, const void *w_lo, void *out_hi, void *out_lo, int out_c, int32_t *tile_counter,
+                               sc2_stream_t stream);
 
 /* Device: NCHW fp32 -> NHWC fp16 with channels zero-padded to c_pad (even). */
 SC2_API int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, int64_t spatial, int c_pad,
                                      sc2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics: per-CTA trace.  While a (caller-allocated, zeroed) device buffer is installed, every CTA of the coder and
+ * tensor-core kernels appends a 32-byte record {u64 start_ns, u64 end_ns, i32 kind, i32 sm, i32 aux, i32 block} after a
+ * 16-byte header whose first u32 counts records (kind: 1 conv_tc 2 conv_split 3 conv_first 4 rans_encode 5 rans_decode;
+ * aux: tiles the CTA processed).  Not thread-safe against concurrent start/stop; off by default. */
+SC2_API int sc2_trace_start(void *device_buffer, int64_t bytes);
+SC2_API int sc2_trace_stop(void);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,8 @@ class TcSplitDesc(_c.Structure):
 # name -> (restype, argtypes): every symbol include/sc2b200.h declares
 SIGNATURES = {
     'sc2_abi_version': (i32, []),
+    'sc2_trace_start': (i32, [vp, i64]),
+    'sc2_trace_stop': (i32, []),
     'sc2_error_string': (_c.c_char_p, [i32]),
     'sc2_last_cuda_error': (_c.c_char_p, []),
     'sc2_pmf_to_quantized_cdf': (i32, [vp, i32, i32, vp]),
@@ -47,12 +49,12 @@ SIGNATURES = {
     'sc2_conv_out_size': (i32, [_c.POINTER(ConvDesc), _c.POINTER(i32), _c.POINTER(i32)]),
     'sc2_conv2d_f32': (i32, [_c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]),
     'sc2_gdn_f32': (i32, [vp, vp, vp, vp, i32, i32, i64, i32, i32, vp]),
-    'sc2_tc_conv_nhwc': (i32, [_c.POINTER(TcConvDesc), vp, vp, vp, vp, vp, vp]),
+    'sc2_tc_conv_nhwc': (i32, [_c.POINTER(TcConvDesc), vp, vp, vp, vp, vp, vp, vp]),
     'sc2_nchw_f32_to_nhwc_f16': (i32, [vp, vp, i32, i32, i64, i32, vp]),
     'sc2_tc_split_n_tile': (i32, [i32]),
-    'sc2_tc_split_conv': (i32, [_c.POINTER(TcSplitDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sc2_tc_split_conv': (i32, [_c.POINTER(TcSplitDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'sc2_patchify_split': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
-    'sc2_tc_first_layer': (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
+    'sc2_tc_first_layer': (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
 }
 
 SC2_OK = 0
@@ -82,7 +84,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sc2_abi_version() != 2:
+    if lib.sc2_abi_version() != 3:
         raise ImportError('libsc2b200.so ABI version mismatch: rebuild with sc2-benchmark_b200/build.py --force')
     _lib = lib
     return lib

@@ -250,13 +250,51 @@ class FPBasedResNetBottleneck(BaseBottleneck):
         # 'split-tc': fp32-grade split-fp16 tensor-core kernels (three MMA passes); 'fp32': exact-fp32 CUDA-core kernels.
         self.encoder_precision = 'split-tc'
         self._tc_encoder = None
+        self._transform_stream = None
 
     # ---- hot path ---------------------------------------------------------------------------------
+    def use_transform_stream(self, stream=True, host_wait=False):
+        """Throughput mode for callers that keep several batches in flight (one CUDA stream, or one host thread, per batch).
+
+        The transforms are persistent tensor-core kernels that fill the GPU; the coder of a batch is a handful of warps that
+        run for milliseconds.  Issued on per-batch streams, the batches drift into lock-step -- all in their transforms, then
+        all in their coders with the tensor cores idle (measured with the per-CTA trace, scripts/diag_trace.py).  With a
+        transform stream every g_a / g_s runs on that ONE stream in call order (event-ordered against the caller's current
+        stream), and only the coders stay on the callers' streams: calling encode for batch i + d before decode for batch i
+        is then a software pipeline of depth d.  `stream`: a torch.cuda.Stream, True (create one) or None / False (off).
+        host_wait: for one-host-thread-per-batch callers -- the calling thread waits (GIL released) until its own stream has
+        produced the transform's input before it queues the transform, so that a batch whose copy or coder is still running
+        does not hold up the transforms of the other threads' batches."""
+        self._transform_host_wait = bool(host_wait)
+        if stream is True:
+            stream = torch.cuda.Stream(device=self.entropy_bottleneck._quantized_cdf.device)
+        self._transform_stream = stream or None
+        return self._transform_stream
+
+    def _on_transform_stream(self, fn, *tensors):
+        """Runs fn() on the transform stream, ordered after the current stream's work on `tensors` and before whatever the
+        current stream does next with the result."""
+        ts = self._transform_stream
+        cur = torch.cuda.current_stream()
+        if ts is None or ts == cur:
+            return fn()
+        if getattr(self, '_transform_host_wait', False):
+            cur.synchronize()
+        else:
+            ts.wait_stream(cur)
+        for t in tensors:
+            t.record_stream(ts)
+        with torch.cuda.stream(ts):
+            out = fn()
+        out.record_stream(cur)
+        cur.wait_stream(ts)
+        return out
+
     @torch.no_grad()
     def encode_packed(self, x):
         """g_a + quantise + rANS, bitstreams left on the device: (PackedStreams, latent (H, W))."""
         eb = self.entropy_bottleneck
-        symbols = self.analyze_to_symbols(x)
+        symbols = self._on_transform_stream(lambda: self.analyze_to_symbols(x), x)
         return eb.compress_symbols(symbols, spatial=symbols[0, 0].numel()), symbols.size()[-2:]
 
     @torch.no_grad()
@@ -282,7 +320,7 @@ class FPBasedResNetBottleneck(BaseBottleneck):
     @torch.no_grad()
     def decode_packed(self, streams, shape, check_status=False):
         latent_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape), check_status=check_status)
-        return self.synthesize(latent_hat)
+        return self._on_transform_stream(lambda: self.synthesize(latent_hat), latent_hat)
 
     def encode(self, x, **kwargs):
         """-> {'strings': [list of B bytes objects], 'shape': latent (H, W)}  (reference contract, layer.py:496-507)"""

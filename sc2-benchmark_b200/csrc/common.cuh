@@ -26,6 +26,45 @@ static inline cudaStream_t as_stream(sc2_stream_t s) { return reinterpret_cast<c
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- diagnostics: per-CTA trace (sc2_trace_start / sc2_trace_stop) -------------------------------------------------
+// When a trace buffer is installed every CTA of the long-running kernels appends {start, end (globaltimer ns), kernel
+// kind, SM id, aux (tiles processed / streams), block id}: which SM ran what, when -- the only way to see how kernels of
+// different streams share the machine.  Off (null sink): one predictable branch per CTA.
+struct TraceRec {
+    unsigned long long t0, t1;
+    int kind, smid, aux, bid;
+};
+struct TraceSink {
+    TraceRec *buf;
+    unsigned *count;
+    unsigned cap;
+};
+TraceSink trace_sink();  // host side: the installed sink ({nullptr, nullptr, 0} when tracing is off)
+enum TraceKind { TRACE_CONV_TC = 1, TRACE_CONV_SPLIT = 2, TRACE_CONV_FIRST = 3, TRACE_RANS_ENCODE = 4, TRACE_RANS_DECODE = 5 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_emit(const TraceSink &ts, int kind, unsigned long long t0, int aux) {
+    if (ts.buf == nullptr) return;
+    const unsigned i = atomicAdd(ts.count, 1u);
+    if (i >= ts.cap) return;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    TraceRec r;
+    r.t0 = t0;
+    r.t1 = trace_now();
+    r.kind = kind;
+    r.smid = static_cast<int>(smid);
+    r.aux = aux;
+    r.bid = static_cast<int>(blockIdx.x);
+    ts.buf[i] = r;
+}
+#endif
+
 // ---- coder table blob (built on the host by sc2_rans_build_tables) ------------------------------
 struct RansTableHeader {
     int32_t magic;       // 'S2RT'
@@ -57,5 +96,14 @@ int launch_rans_encode_fast(const int32_t *symbols, int batch, int64_t n, int64_
 int launch_rans_decode_fast(const uint8_t *packed, const int64_t *offsets, int batch, int64_t n, int64_t spatial,
                             const void *tables, int n_rows, int cdf_stride, int32_t *out_symbols, float *out_values,
                             const float *means, int32_t *status, cudaStream_t st);
+
+// channel-mode, one lane per stream (rans_lanes.cu): the default; SC2_CODER=warp selects rans_fast.cu
+bool rans_use_lanes();
+int launch_rans_encode_lanes(const int32_t *symbols, int batch, int64_t n, int64_t spatial, const void *tables, int n_rows,
+                             int cdf_stride, uint8_t *arena, int64_t slot_bytes, int32_t *lengths, int32_t *status,
+                             cudaStream_t st);
+int launch_rans_decode_lanes(const uint8_t *packed, const int64_t *offsets, int batch, int64_t n, int64_t spatial,
+                             const void *tables, int32_t *out_symbols, float *out_values, const float *means,
+                             int32_t *status, cudaStream_t st);
 
 }  // namespace sc2

@@ -39,6 +39,8 @@ struct Params {
     const float *beta;     // GDN modes: effective beta [n_total]
     const __half *gdn_x;   // GDN modes: x itself, NHWC [batch, h_out, w_out, n_total]
     void *out;             // NHWC [batch, h_out, w_out, n_total], fp16 or fp32
+    int *tile_counter;     // zeroed by the caller: dynamic tile schedule; nullptr: static
+    TraceSink trace;       // diagnostics (common.cuh)
 };
 
 template <int N_TILE, int STAGES>
@@ -47,7 +49,8 @@ struct Smem {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kRingBytes = STAGES * kStageBytes;
     // full[STAGES], empty[STAGES], xform[STAGES], acc_full[2], acc_empty[2] : 8 bytes each; then the TMEM base address
-    static constexpr int kTotal = kRingBytes + (3 * STAGES + 4) * 8 + 16;
+    static constexpr int kSchedOffset = kRingBytes + (3 * STAGES + 4) * 8 + 16;
+    static constexpr int kTotal = kSchedOffset + kTileSchedBytes;
 };
 
 template <int N_TILE, int STAGES, int MODE>
@@ -73,8 +76,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int k_iters = p.taps_x * p.taps_y * p.k_chunks;
     const int tiles_xy = p.tiles_x * p.tiles_y;
     const int total_tiles = tiles_xy * p.n_tiles * p.batch;
+    const unsigned long long trace_t0 = p.trace.buf ? trace_now() : 0ull;
+    int trace_tiles = 0;
+    TileSched sched;
+    sched.bind(smem + L::kSchedOffset, p.tile_counter, total_tiles);
 
     if (threadIdx.x == 0) {
+        sched.init(kGdn ? 13 : 9);  // consumers: MMA warp, 8 epilogue warps (, 4 transform warps)
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < STAGES; ++s) {
@@ -99,7 +107,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (elect_one()) {
             const uint32_t stage_tx = static_cast<uint32_t>(rows * 128 + L::kBBytes);
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int tile = sched.claim(0);
+            for (uint32_t qn = 0;; ++qn) {
+                sched.publish(qn, tile);
+                if (tile < 0) break;
+                const int next_tile = sched.claim(qn + 1);  // claimed early: the atomic's latency hides behind this tile's loads
                 const int sp = tile % tiles_xy, rest = tile / tiles_xy;
                 const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
                 const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
@@ -113,13 +125,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             tma_load_4d(&map_a, &full[s], dst, kc * kBlockK, x0 + tx - p.pad, y0 + ty - p.pad, img);
                             tma_load_2d(&map_b, &full[s], dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
                         }
+                tile = next_tile;
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         constexpr uint32_t idesc = make_idesc(N_TILE);
-        uint32_t it = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        uint32_t it = 0;
+        for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
             const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
             mbar_wait(&acc_empty[as], aph ^ 1u);  // the epilogue has drained this accumulator stage
             tcgen05_fence_after();
@@ -146,8 +159,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int quarter = warp & 3;         // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;  // tile row = TMEM lane = pixel index inside the tile
         const int ty = row / p.tw, tx = row - ty * p.tw;
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (uint32_t lt = 0;; ++lt) {
+            const int tile = sched.next(lt, lane);
+            if (tile < 0) break;
+            ++trace_tiles;
             const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
             const int sp = tile % tiles_xy, rest = tile / tiles_xy;
             const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
@@ -225,7 +240,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // =============================== |x| transform warps (10..13, GDN modes) ===============================
         const int row = (warp - 10) * 32 + lane;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
             for (int k_it = 0; k_it < k_iters; ++k_it, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&full[s], ph);
@@ -250,20 +265,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+    if (threadIdx.x == 64) trace_emit(p.trace, TRACE_CONV_TC, trace_t0, trace_tiles);
 }
 
 template <int N_TILE, int STAGES, int MODE>
 static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const Params &p, cudaStream_t st) {
     using L = Smem<N_TILE, STAGES>;
     constexpr bool kGdn = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
-    const int smem = L::kTotal + 1024;  // slack for the manual 1024-byte alignment
+    const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
     static bool configured = false;
     if (!configured) {
         SC2_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<N_TILE, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     const int total = p.tiles_x * p.tiles_y * p.n_tiles * p.batch;
-    const int grid = total < kNumSMs ? total : kNumSMs;
+    const int grid = total < persistent_grid() ? total : persistent_grid();
     tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kGdn ? 448 : 320, smem, st>>>(ma, mb, p);
     SC2_LAUNCH_CHECK("tc_conv_kernel");
     return SC2_OK;
@@ -304,7 +320,7 @@ int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, i
 }
 
 int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta, const void *gdn_x,
-                     void *out, sc2_stream_t stream) {
+                     void *out, int32_t *tile_counter, sc2_stream_t stream) {
     using namespace sc2::tc;
     if (!d || !x || !w_packed || !out) return SC2_ERR_INVALID_ARG;
     if (d->batch < 1 || d->c_in_pad % kBlockK || d->c_in_pad < kBlockK) return SC2_ERR_INVALID_ARG;
@@ -339,7 +355,9 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
     p.beta = beta;
     p.gdn_x = static_cast<const __half *>(gdn_x);
     p.out = out;
-    if (static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.n_tiles * p.batch > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
+    p.tile_counter = tile_counter;
+    p.trace = sc2::trace_sink();
+    if (static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.n_tiles * p.batch > 0x7fffffff - 1024) return SC2_ERR_UNSUPPORTED;
     CUtensorMap ma, mb;
     int rc = make_nhwc_map(&ma, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in_pad, d->w_in, d->h_in, d->batch, kBlockK, tw, th);
     if (rc) return rc;

@@ -29,6 +29,8 @@ struct Params {
     int k_steps;         // ceil(K / 16)
     int c_out, out_c;    // valid channels, channel pitch of the output planes
     int tiles_x, tiles_y, tw, th;
+    int *tile_counter;   // zeroed by the caller: dynamic tile schedule; nullptr: static
+    TraceSink trace;     // diagnostics (common.cuh)
 };
 
 template <int N_TILE>
@@ -40,7 +42,8 @@ struct Smem {
     static constexpr int kStagePlane = kTileM * N_TILE * 2;
     static constexpr int kStagingOffset = kResBytes + kRingBytes;
     static constexpr int kBarOffset = kStagingOffset + 2 * kStagePlane;
-    static constexpr int kTotal = kBarOffset + (2 * kAStages + 5) * 8 + 16;
+    static constexpr int kSchedOffset = kBarOffset + (2 * kAStages + 5) * 8 + 16;
+    static constexpr int kTotal = kSchedOffset + kTileSchedBytes;
     static_assert(kTotal + 1024 <= 227 * 1024, "shared memory budget");
 };
 
@@ -104,8 +107,13 @@ tc_first_layer_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid
     const int rows = p.tw * p.th;
     const int tiles_xy = p.tiles_x * p.tiles_y;
     const int total_tiles = tiles_xy * p.batch * 4;
+    const unsigned long long trace_t0 = p.trace.buf ? trace_now() : 0ull;
+    int trace_tiles = 0;
+    TileSched sched;
+    sched.bind(smem_res + L::kSchedOffset, p.tile_counter, total_tiles);
 
     if (threadIdx.x == 0) {
+        sched.init(13);  // consumers: MMA warp, 8 epilogue warps, 4 im2col producer warps
         tma_prefetch_desc(&map_b_hi);
         tma_prefetch_desc(&map_b_lo);
         tma_prefetch_desc(&map_o_hi);
@@ -135,13 +143,18 @@ tc_first_layer_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid
             tma_load_2d(&map_b_lo, b_full, smem_res + 1 * L::kBBytes, 0, 0);
             tma_load_2d(&map_b_hi, b_full, smem_res + 2 * L::kBBytes, kBlockK, 0);
             tma_load_2d(&map_b_lo, b_full, smem_res + 3 * L::kBBytes, kBlockK, 0);
+            // ... and the tile scheduler: claim tiles and hand them to the other warps
+            for (uint32_t qn = 0;; ++qn) {
+                const int tile = sched.claim(qn);
+                sched.publish(qn, tile);
+                if (tile < 0 || p.tile_counter == nullptr) break;
+            }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         constexpr uint32_t idesc = make_idesc(N_TILE);
         mbar_wait(b_full, 0);
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
             const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
             const uint32_t s = lt % kAStages, ph = (lt / kAStages) & 1u;
             mbar_wait(&acc_empty[as], aph ^ 1u);
@@ -172,8 +185,10 @@ tc_first_layer_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid
         const int row = quarter * 32 + lane;
         const bool issuer = threadIdx.x == 64;
         __half *st_hi = reinterpret_cast<__half *>(staging), *st_lo = reinterpret_cast<__half *>(staging + L::kStagePlane);
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (uint32_t lt = 0;; ++lt) {
+            const int tile = sched.next(lt, lane);
+            if (tile < 0) break;
+            ++trace_tiles;
             const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
             const int sp = tile % tiles_xy, img = tile / tiles_xy;  // img = b * 4 + parity
             const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
@@ -219,8 +234,9 @@ tc_first_layer_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid
         const int row = (warp - 10) * 32 + lane;
         const int ty = row / p.tw, tx = row - ty * p.tw;
         const int KK = p.kh * p.kw;
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (uint32_t lt = 0;; ++lt) {
+            const int tile = sched.next(lt, lane);
+            if (tile < 0) break;
             const uint32_t s = lt % kAStages, ph = (lt / kAStages) & 1u;
             const int sp = tile % tiles_xy, img = tile / tiles_xy;
             const int b = img >> 2, py = (img >> 1) & 1, px = img & 1;
@@ -289,12 +305,13 @@ tc_first_layer_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (threadIdx.x == 64) trace_emit(p.trace, TRACE_CONV_FIRST, trace_t0, trace_tiles);
 }
 
 template <int N_TILE>
 static int launch(const CUtensorMap *maps, const Params &p, cudaStream_t st) {
     using L = Smem<N_TILE>;
-    const int smem = L::kTotal + 1024;
+    const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
     static bool configured = false;
     if (!configured) {
         SC2_CUDA_TRY(cudaFuncSetAttribute(tc_first_layer_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -302,7 +319,7 @@ static int launch(const CUtensorMap *maps, const Params &p, cudaStream_t st) {
     }
     const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.batch * 4;
     if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
-    const int grid = total < kNumSMs ? static_cast<int>(total) : kNumSMs;
+    const int grid = total < persistent_grid() ? static_cast<int>(total) : persistent_grid();
     tc_first_layer_kernel<N_TILE><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
     SC2_LAUNCH_CHECK("tc_first_layer_kernel");
     return SC2_OK;
@@ -314,7 +331,8 @@ static int launch(const CUtensorMap *maps, const Params &p, cudaStream_t st) {
 extern "C" {
 
 int sc2_tc_first_layer(const float *image, int batch, int c_in, int h_in, int w_in, int kh, int kw, int pad, int c_out,
-                       const void *w_hi, const void *w_lo, void *out_hi, void *out_lo, int out_c, sc2_stream_t stream) {
+                       const void *w_hi, const void *w_lo, void *out_hi, void *out_lo, int out_c, int32_t *tile_counter,
+                       sc2_stream_t stream) {
     using namespace sc2::tcf;
     if (!image || !w_hi || !w_lo || !out_hi || !out_lo || batch < 1) return SC2_ERR_INVALID_ARG;
     const int K = c_in * kh * kw;
@@ -333,6 +351,8 @@ int sc2_tc_first_layer(const float *image, int batch, int c_in, int h_in, int w_
     p.hp = h_out / 2; p.wp = w_out / 2;
     p.K = K; p.k_steps = (K + 15) / 16;
     p.c_out = c_out; p.out_c = out_c;
+    p.tile_counter = tile_counter;
+    p.trace = sc2::trace_sink();
     int n_col_tiles = (p.wp + 127) / 128;
     int tw = (p.wp + n_col_tiles - 1) / n_col_tiles;
     tw = (tw + 7) / 8 * 8;

@@ -53,6 +53,8 @@ struct Params {
     int out_c;         // channel pitch of the output planes
     int32_t *out_sym;
     const __half *x_hi, *x_lo;
+    int *tile_counter;  // zeroed by the caller: dynamic tile schedule; nullptr: static
+    TraceSink trace;    // diagnostics (common.cuh)
 };
 
 // B_RES: 1x1 convolutions (one tap, <= 2 K chunks) keep the whole weight matrix resident in shared memory for the life of
@@ -69,7 +71,8 @@ struct Smem {
     static constexpr int kStagingBytes = 2 * kStagePlane;
     static constexpr int kStagingOffset = kResBytes + kRingBytes;
     static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
-    static constexpr int kTotal = kBarOffset + (3 * STAGES + 6) * 8 + 16;
+    static constexpr int kSchedOffset = kBarOffset + (3 * STAGES + 6) * 8 + 16;
+    static constexpr int kTotal = kSchedOffset + kTileSchedBytes;
     static_assert(kTotal + 1024 <= 227 * 1024, "shared memory budget");
 };
 
@@ -121,8 +124,13 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     const int tiles_xy = p.tiles_x * p.tiles_y;
     const int total_tiles = tiles_xy * p.images;
     const uint32_t acc_stages = p.groups == 1 ? 2u : 1u;
+    const unsigned long long trace_t0 = p.trace.buf ? trace_now() : 0ull;
+    int trace_tiles = 0;
+    TileSched sched;
+    sched.bind(smem_res + L::kSchedOffset, p.tile_counter, total_tiles);
 
     if (threadIdx.x == 0) {
+        sched.init(kGdn ? 13 : 9);  // consumers: MMA warp, 8 epilogue warps (, 4 transform warps)
         tma_prefetch_desc(&map_a_hi);
         tma_prefetch_desc(&map_a_lo);
         tma_prefetch_desc(&map_b_hi);
@@ -162,7 +170,11 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 }
             }
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int tile = sched.claim(0);
+            for (uint32_t qn = 0;; ++qn) {
+                sched.publish(qn, tile);
+                if (tile < 0) break;
+                const int next_tile = sched.claim(qn + 1);  // claimed early: the atomic's latency hides behind this tile's loads
                 const int sp = tile % tiles_xy, img = tile / tiles_xy;
                 const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
                 for (int t = 0; t < p.n_taps; ++t) {
@@ -181,14 +193,15 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         }
                     }
                 }
+                tile = next_tile;
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         constexpr uint32_t idesc = make_idesc(N_TILE);
-        uint32_t it = 0, lt = 0;
+        uint32_t it = 0;
         if (B_RES) mbar_wait(b_full, 0);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
             const uint32_t as = lt % acc_stages, aph = (lt / acc_stages) & 1u;
             mbar_wait(&acc_empty[as], aph ^ 1u);
             tcgen05_fence_after();
@@ -228,8 +241,10 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const int ty = row / p.tw, tx = row - ty * p.tw;
         const bool issuer = threadIdx.x == 64;  // first epilogue thread: owns the bulk-store group and the x-tile loads
         __half *st_hi = reinterpret_cast<__half *>(staging), *st_lo = reinterpret_cast<__half *>(staging + L::kStagePlane);
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (uint32_t lt = 0;; ++lt) {
+            const int tile = sched.next(lt, lane);
+            if (tile < 0) break;
+            ++trace_tiles;
             const uint32_t as = lt % acc_stages, aph = (lt / acc_stages) & 1u;
             const int sp = tile % tiles_xy, img = tile / tiles_xy;
             const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
@@ -322,7 +337,7 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         // |a| = |hi| + sign(hi) * lo / 2048: clear hi's sign bits, flip lo's where hi was negative
         const int row = (warp - 10) * 32 + lane;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+        for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt)
             for (int k_it = 0; k_it < k_iters; ++k_it, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&full[s], ph);
@@ -349,6 +364,7 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+    if (threadIdx.x == 64) trace_emit(p.trace, TRACE_CONV_SPLIT, trace_t0, trace_tiles);
 }
 
 // ---- im2col for the first layer (c_in = 3): fp32 NCHW image -> split fp16 patches in parity-plane pixel order -------
@@ -392,7 +408,7 @@ template <int N_TILE, int STAGES, int MODE, bool B_RES>
 static int launch(const CUtensorMap *maps, const Params &p, int images, cudaStream_t st) {
     const CUtensorMap &mah = maps[0], &mal = maps[1], &mbh = maps[2], &mbl = maps[3];
     using L = Smem<N_TILE, STAGES, B_RES>;
-    const int smem = L::kTotal + 1024;
+    const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
     static bool configured = false;
     if (!configured) {
         SC2_CUDA_TRY(cudaFuncSetAttribute(tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -400,7 +416,7 @@ static int launch(const CUtensorMap *maps, const Params &p, int images, cudaStre
     }
     const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * images;
     if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
-    const int grid = total < kNumSMs ? static_cast<int>(total) : kNumSMs;
+    const int grid = total < persistent_grid() ? static_cast<int>(total) : persistent_grid();
     tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES><<<grid, MODE == MODE_GDN1_SPLIT ? 448 : 320, smem, st>>>(mah, mal, mbh, mbl, maps[4], maps[5], maps[6], maps[7], p);
     SC2_LAUNCH_CHECK("tc_split_conv_kernel");
     return SC2_OK;
@@ -436,7 +452,7 @@ int sc2_tc_split_n_tile(int c_out) {
 
 int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo,
                       const float *beta, const float *medians, const void *gdn_x_hi, const void *gdn_x_lo, void *out_hi,
-                      void *out_lo, int32_t *out_sym, sc2_stream_t stream) {
+                      void *out_lo, int32_t *out_sym, int32_t *tile_counter, sc2_stream_t stream) {
     using namespace sc2::tcs;
     if (!d || !x_hi || !x_lo || !w_hi || !w_lo) return SC2_ERR_INVALID_ARG;
     if (d->images < 1 || d->c_in < 16 || d->c_in % 16 || d->c_out < 1) return SC2_ERR_INVALID_ARG;
@@ -498,6 +514,8 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     p.out_c = d->out_c;
     p.out_sym = out_sym;
     p.x_hi = static_cast<const __half *>(gdn_x_hi); p.x_lo = static_cast<const __half *>(gdn_x_lo);
+    p.tile_counter = tile_counter;
+    p.trace = sc2::trace_sink();
     CUtensorMap maps[8];
     CUtensorMap &mah = maps[0], &mal = maps[1], &mbh = maps[2], &mbl = maps[3];
     // input planes: [images * planes, h_in, w_in, c_in] (h_in, w_in = plane geometry)
@@ -532,7 +550,7 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     cudaStream_t st = sc2::as_stream(stream);
     switch (n_tile) {
         case 32: return dispatch_mode<32, 4, 5>(d->mode, maps, p, d->images, st);
-        case 48: return dispatch_mode<48, 4, 5>(d->mode, maps, p, d->images, st);
+        case 48: return dispatch_mode<48, 4, 4>(d->mode, maps, p, d->images, st);
         case 64: return dispatch_mode<64, 3, 4>(d->mode, maps, p, d->images, st);
         case 96: return dispatch_mode<96, 2, 3>(d->mode, maps, p, d->images, st);
         default: return dispatch_mode<128, 2, 2>(d->mode, maps, p, d->images, st);

@@ -18,9 +18,27 @@ int cuda_fail(cudaError_t e, const char *where) {
 
 }  // namespace sc2
 
+namespace sc2 {
+static TraceSink g_trace = {nullptr, nullptr, 0};
+TraceSink trace_sink() { return g_trace; }
+}  // namespace sc2
+
 extern "C" {
 
 int sc2_abi_version(void) { return SC2_ABI_VERSION; }
+
+int sc2_trace_start(void *device_buffer, int64_t bytes) {
+    if (!device_buffer || bytes < 16 + static_cast<int64_t>(sizeof(sc2::TraceRec))) return SC2_ERR_INVALID_ARG;
+    sc2::g_trace.count = static_cast<unsigned *>(device_buffer);
+    sc2::g_trace.buf = reinterpret_cast<sc2::TraceRec *>(static_cast<uint8_t *>(device_buffer) + 16);
+    sc2::g_trace.cap = static_cast<unsigned>((bytes - 16) / static_cast<int64_t>(sizeof(sc2::TraceRec)));
+    return SC2_OK;
+}
+
+int sc2_trace_stop(void) {
+    sc2::g_trace = sc2::TraceSink{nullptr, nullptr, 0};
+    return SC2_OK;
+}
 
 const char *sc2_error_string(int code) {
     switch (code) {

@@ -439,6 +439,9 @@ int sc2_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int ba
     cudaStream_t st = sc2::as_stream(stream);
     if (n_rows < 1 || cdf_stride < 2) return SC2_ERR_INVALID_ARG;
     if (!indexes && (n_per_stream + spatial - 1) / spatial > n_rows) return SC2_ERR_INVALID_ARG;
+    if (!indexes && spatial <= 0x7fffffff && sc2::rans_use_lanes())
+        return sc2::launch_rans_encode_lanes(symbols, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, arena, slot_bytes,
+                                             lengths, status, st);
     if (!indexes && spatial <= 0x7fffffff)
         return sc2::launch_rans_encode_fast(symbols, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, arena, slot_bytes,
                                             lengths, status, st);
@@ -487,6 +490,9 @@ int sc2_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, int bat
     cudaStream_t st = sc2::as_stream(stream);
     if (n_rows < 1 || cdf_stride < 2) return SC2_ERR_INVALID_ARG;
     if (!indexes && (n_per_stream + spatial - 1) / spatial > n_rows) return SC2_ERR_INVALID_ARG;
+    if (!indexes && spatial <= 0x7fffffff && sc2::rans_use_lanes())
+        return sc2::launch_rans_decode_lanes(packed, offsets, batch, n_per_stream, spatial, tables, out_symbols, out_values, means,
+                                             status, st);
     if (!indexes && spatial <= 0x7fffffff)
         return sc2::launch_rans_decode_fast(packed, offsets, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, out_symbols,
                                             out_values, means, status, st);

@@ -1,5 +1,6 @@
 // tc_common.cuh -- PTX wrappers shared by the tcgen05 kernels (mbarrier, TMA, TMEM, UMMA descriptors).
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -50,6 +51,62 @@ __device__ __forceinline__ bool elect_one() {
         "}" : "=r"(pred));
     return pred != 0;
 }
+
+// ---- tile scheduler of the persistent kernels -----------------------------------------------------------------------
+// Static: CTA b walks tiles b, b + gridDim.x, ...  A persistent kernel scheduled that way takes TWICE as long as soon as
+// one of its CTAs cannot be placed next to blocks of another stream (the coder kernels run for milliseconds), because the
+// late CTA still owns 1/gridDim of the tiles.  Dynamic (counter != nullptr): one thread of the CTA claims tiles from a
+// global counter (zero at launch) and publishes them to the other warps through a small shared-memory queue; a CTA that
+// starts late simply finds no work.
+constexpr int kTileQ = 4;
+constexpr int kTileSchedBytes = 2 * kTileQ * 8 + kTileQ * 4;  // full[], empty[] mbarriers + tile ids
+
+struct TileSched {
+    uint64_t *qfull, *qempty;
+    int *qtile;
+    int *counter;
+    int total;
+
+    __device__ __forceinline__ void bind(uint8_t *smem_at, int *ctr, int total_tiles) {  // smem_at: 8-byte aligned
+        qfull = reinterpret_cast<uint64_t *>(smem_at);
+        qempty = qfull + kTileQ;
+        qtile = reinterpret_cast<int *>(qempty + kTileQ);
+        counter = ctr;
+        total = total_tiles;
+    }
+    __device__ __forceinline__ void init(uint32_t consumer_warps) const {  // one thread, before fence_barrier_init
+        for (int i = 0; i < kTileQ; ++i) {
+            mbar_init(&qfull[i], 1);
+            mbar_init(&qempty[i], consumer_warps);
+        }
+    }
+    // producer (ONE thread): the n-th tile of this CTA, -1 when there is none
+    __device__ __forceinline__ int claim(uint32_t n) const {
+        if (counter == nullptr) {
+            const int64_t t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(n) * gridDim.x;
+            return t < total ? static_cast<int>(t) : -1;
+        }
+        const int t = atomicAdd(counter, 1);
+        return t < total ? t : -1;
+    }
+    __device__ __forceinline__ void publish(uint32_t n, int tile) const {
+        if (counter == nullptr) return;
+        const uint32_t slot = n % kTileQ, ph = (n / kTileQ) & 1u;
+        mbar_wait(&qempty[slot], ph ^ 1u);
+        *reinterpret_cast<volatile int *>(qtile + slot) = tile;
+        mbar_arrive(&qfull[slot]);
+    }
+    // consumer: every lane of a consumer warp calls it (converged); -1 ends the CTA's tile loop
+    __device__ __forceinline__ int next(uint32_t n, int lane) const {
+        if (counter == nullptr) return claim(n);
+        const uint32_t slot = n % kTileQ, ph = (n / kTileQ) & 1u;
+        mbar_wait(&qfull[slot], ph);
+        const int t = *reinterpret_cast<volatile int *>(qtile + slot);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&qempty[slot]);
+        return t;
+    }
+};
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -174,4 +231,21 @@ inline int make_weight_map(CUtensorMap *m, const void *base, int c_in_pad, int r
 }
 
 }  // namespace tc
+// Every persistent tensor-core kernel asks for the SAME amount of dynamic shared memory (when it needs no more than that).
+// Shared memory is handed out as contiguous ranges: while a long-running coder block of another stream sits on the SM, the
+// range a finished convolution CTA leaves behind can only be reused by a CTA that is not larger -- with kernels of
+// different sizes following each other, the SM stays closed to them until the coder block is gone.
+constexpr int kUniformSmem = 202 * 1024;
+inline int uniform_smem(int needed) { return needed <= kUniformSmem ? kUniformSmem : needed; }
+
+// CTAs of a persistent kernel: one per SM, or fewer when SC2_TC_GRID is set (experiments: leave SMs to co-running kernels)
+inline int persistent_grid() {
+    static const int g = [] {
+        const char *e = std::getenv("SC2_TC_GRID");
+        const int v = e ? std::atoi(e) : 0;
+        return (v > 0 && v < kNumSMs) ? v : kNumSMs;
+    }();
+    return g;
+}
+
 }  // namespace sc2

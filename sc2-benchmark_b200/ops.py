@@ -62,6 +62,39 @@ def _stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _TileCounters:
+    """Zeroed int32 slots for the dynamic tile schedule of the persistent tensor-core kernels (include/sc2b200.h,
+    `tile_counter`): one slot per launch, handed out from a per-stream block that is re-zeroed (stream-ordered, so after
+    every kernel that used it) when it runs out.  SC2_TC_STATIC=1 selects the static schedule (NULL counters)."""
+    SLOTS = 4096
+
+    def __init__(self):
+        self._blocks = {}
+        self._lock = threading.Lock()
+        self.static = bool(int(__import__('os').environ.get('SC2_TC_STATIC', '0')))
+
+    def next(self):
+        if self.static:
+            return ctypes.c_void_p(0)
+        stream = torch.cuda.current_stream()
+        key = (stream.device.index, stream.cuda_stream)
+        with self._lock:
+            blk = self._blocks.get(key)
+            if blk is None:
+                with torch.inference_mode(False):
+                    blk = [torch.zeros(self.SLOTS, dtype=torch.int32, device=stream.device), 0]
+                self._blocks[key] = blk
+            if blk[1] == self.SLOTS:
+                blk[0].zero_()
+                blk[1] = 0
+            i = blk[1]
+            blk[1] += 1
+        return ctypes.c_void_p(blk[0].data_ptr() + 4 * i)
+
+
+_TILE_COUNTERS = _TileCounters()
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -416,8 +449,8 @@ def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None,
     b = beta.detach().contiguous().float() if beta is not None else None
     tag = 'tc_conv[%d->%d,k%d,m%d]' % (Cp, c_out, kh, mode)
     with torch.cuda.device(x_nhwc.device), _launch(tag):
-        check(_lib().sc2_tc_conv_nhwc(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(b), _ptr(gdn_x), _ptr(out), _stream_ptr()),
-              'sc2_tc_conv_nhwc')
+        check(_lib().sc2_tc_conv_nhwc(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(b), _ptr(gdn_x), _ptr(out),
+                                      _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_conv_nhwc')
     return out
 
 
@@ -499,7 +532,7 @@ def tc_split_conv(x_hi, x_lo, w_hi, w_lo, c_out, kh, kw, stride, pad, mode, beta
     with torch.cuda.device(dev), _launch(tag):
         check(_lib().sc2_tc_split_conv(ctypes.byref(d), _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(b), _ptr(m),
                                        _ptr(x_hi) if gdn else None, _ptr(x_lo) if gdn else None, _ptr(out_hi), _ptr(out_lo),
-                                       _ptr(out_sym), _stream_ptr()), 'sc2_tc_split_conv')
+                                       _ptr(out_sym), _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_split_conv')
     return out_sym if mode == _native.TCS_QUANT else (out_hi, out_lo)
 
 
@@ -515,5 +548,5 @@ def tc_first_layer(x, w_hi, w_lo, c_out, kh, kw, pad):
     lo = torch.empty_like(hi)
     with torch.cuda.device(x.device), _launch('tc_first[%d->%d,k%d,s2]' % (C, c_out, kh)):
         check(_lib().sc2_tc_first_layer(_ptr(x), B, C, H, W, kh, kw, pad, c_out, _ptr(w_hi), _ptr(w_lo), _ptr(hi), _ptr(lo), out_c,
-                                        _stream_ptr()), 'sc2_tc_first_layer')
+                                        _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_first_layer')
     return hi, lo
