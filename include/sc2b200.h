@@ -94,10 +94,18 @@ SC2_API int64_t sc2_rans_max_stream_bytes(int64_t n_symbols);
  *   arena     batch slots of slot_bytes (multiple of 4); stream b is written BACKWARDS from the end
  *             of slot b and occupies its last lengths[b] bytes
  *   lengths   [batch] int32 out, bytes
- *   status    [1] int32, OR-ed fault flags (caller zeroes it) */
+ *   status    [1] int32, OR-ed fault flags (caller zeroes it)
+ *   layout    channel mode only (a stream is one serial chain; the layouts produce identical bytes):
+ *             SC2_RANS_WARP_PER_STREAM  lowest latency for ONE batch: a warp per stream, 25 instructions per symbol
+ *             SC2_RANS_LANE_PER_STREAM  32 streams per warp: ~2x the latency of a batch but 1/16 of the issue slots and
+ *                                       one SM per 256 streams -- for batches in flight next to the tensor-core kernels
+ *             SC2_RANS_AUTO             warp per stream (or what the SC2_CODER=warp|lanes environment variable says) */
+#define SC2_RANS_AUTO 0
+#define SC2_RANS_WARP_PER_STREAM 1
+#define SC2_RANS_LANE_PER_STREAM 2
 SC2_API int sc2_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n_per_stream,
                           int64_t spatial, const void *tables, int n_rows, int cdf_stride, uint8_t *arena,
-                          int64_t slot_bytes, int32_t *lengths, int32_t *status, sc2_stream_t stream);
+                          int64_t slot_bytes, int32_t *lengths, int32_t *status, int layout, sc2_stream_t stream);
 
 /* Device: compact the streams to the front of `packed`: offsets[b] = sum(lengths[:b]) (int64, batch+1
  * entries, offsets[batch] = total).  One D2H copy of offsets[batch] bytes then carries all strings. */
@@ -113,7 +121,7 @@ SC2_API int sc2_rans_pack(const uint8_t *arena, int64_t slot_bytes, const int32_
 SC2_API int sc2_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, int batch, int64_t n_per_stream,
                           const int32_t *indexes, int64_t spatial, const void *tables, int n_rows, int cdf_stride,
                           int32_t *out_symbols, float *out_values, const float *means,
-                          int32_t *status, sc2_stream_t stream);
+                          int32_t *status, int layout, sc2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Device: EntropyModel.quantize(x, "symbols", means): int32(rint(x - mean[c])) over [batch, C, spatial].

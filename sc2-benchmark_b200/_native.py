@@ -40,7 +40,7 @@ SIGNATURES = {
     'sc2_rans_table_bytes': (_c.c_size_t, [i32, i32]),
     'sc2_rans_build_tables': (i32, [vp, vp, vp, i32, i32, vp]),
     'sc2_rans_max_stream_bytes': (i64, [i64]),
-    'sc2_rans_encode_batch': (i32, [vp, vp, i32, i64, i64, vp, i32, i32, vp, i64, vp, vp, vp]),
+    'sc2_rans_encode_batch': (i32, [vp, vp, i32, i64, i64, vp, i32, i32, vp, i64, vp, vp, i32, vp]),
     'sc2_rans_pack': (i32, [vp, i64, vp, i32, vp, vp, vp]),
     'sc2_rans_decode_batch': (i32, [vp, vp, i32, i64, vp, i64, vp, i32, i32, vp, vp, vp, vp, vp]),
     'sc2_quantize_symbols': (i32, [vp, vp, vp, i32, i32, i64, vp]),
@@ -63,6 +63,7 @@ EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2
 IN_NONE, IN_ABS = 0, 1
 TC_STORE_F16, TC_STORE_F32, TC_IGDN1_F16, TC_GDN1_F16 = 0, 1, 2, 3
 TCS_STORE, TCS_GDN1, TCS_QUANT = 0, 1, 2
+RANS_LAYOUTS = {None: 0, 'auto': 0, 'warp': 1, 'lanes': 2}
 
 _lib = None
 

@@ -269,14 +269,18 @@ class FPBasedResNetBottleneck(BaseBottleneck):
         if stream is True:
             stream = torch.cuda.Stream(device=self.entropy_bottleneck._quantized_cdf.device)
         self._transform_stream = stream or None
+        # batches in flight: the coder layout that leaves the SMs to the transforms (sc2_rans_encode_batch, `layout`)
+        self.entropy_bottleneck.coder_layout = 'lanes' if self._transform_stream is not None else None
         return self._transform_stream
 
     def _on_transform_stream(self, fn, *tensors):
         """Runs fn() on the transform stream, ordered after the current stream's work on `tensors` and before whatever the
         current stream does next with the result."""
         ts = self._transform_stream
+        if ts is None:
+            return fn()
         cur = torch.cuda.current_stream()
-        if ts is None or ts == cur:
+        if ts == cur:
             return fn()
         if getattr(self, '_transform_host_wait', False):
             cur.synchronize()

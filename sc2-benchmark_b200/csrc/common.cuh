@@ -98,7 +98,7 @@ int launch_rans_decode_fast(const uint8_t *packed, const int64_t *offsets, int b
                             const float *means, int32_t *status, cudaStream_t st);
 
 // channel-mode, one lane per stream (rans_lanes.cu): the default; SC2_CODER=warp selects rans_fast.cu
-bool rans_use_lanes();
+bool rans_use_lanes(int layout);
 int launch_rans_encode_lanes(const int32_t *symbols, int batch, int64_t n, int64_t spatial, const void *tables, int n_rows,
                              int cdf_stride, uint8_t *arena, int64_t slot_bytes, int32_t *lengths, int32_t *status,
                              cudaStream_t st);

@@ -430,7 +430,7 @@ extern "C" {
 
 int sc2_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n_per_stream,
                           int64_t spatial, const void *tables, int n_rows, int cdf_stride, uint8_t *arena,
-                          int64_t slot_bytes, int32_t *lengths, int32_t *status, sc2_stream_t stream) {
+                          int64_t slot_bytes, int32_t *lengths, int32_t *status, int layout, sc2_stream_t stream) {
     if (batch == 0) return SC2_OK;
     if ((!symbols && n_per_stream > 0) || !tables || !arena || !lengths || !status) return SC2_ERR_INVALID_ARG;
     if (batch < 0 || n_per_stream < 0 || n_per_stream > 0x7fffffff || slot_bytes < 8 || (slot_bytes & 3)) return SC2_ERR_INVALID_ARG;
@@ -439,7 +439,8 @@ int sc2_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int ba
     cudaStream_t st = sc2::as_stream(stream);
     if (n_rows < 1 || cdf_stride < 2) return SC2_ERR_INVALID_ARG;
     if (!indexes && (n_per_stream + spatial - 1) / spatial > n_rows) return SC2_ERR_INVALID_ARG;
-    if (!indexes && spatial <= 0x7fffffff && sc2::rans_use_lanes())
+    if (layout < SC2_RANS_AUTO || layout > SC2_RANS_LANE_PER_STREAM) return SC2_ERR_INVALID_ARG;
+    if (!indexes && spatial <= 0x7fffffff && sc2::rans_use_lanes(layout))
         return sc2::launch_rans_encode_lanes(symbols, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, arena, slot_bytes,
                                              lengths, status, st);
     if (!indexes && spatial <= 0x7fffffff)
@@ -481,7 +482,7 @@ int sc2_rans_pack(const uint8_t *arena, int64_t slot_bytes, const int32_t *lengt
 
 int sc2_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, int batch, int64_t n_per_stream,
                           const int32_t *indexes, int64_t spatial, const void *tables, int n_rows, int cdf_stride,
-                          int32_t *out_symbols, float *out_values, const float *means, int32_t *status,
+                          int32_t *out_symbols, float *out_values, const float *means, int32_t *status, int layout,
                           sc2_stream_t stream) {
     if (!packed || !offsets || !tables || !status || (!out_symbols && !out_values)) return SC2_ERR_INVALID_ARG;
     if (batch < 0 || n_per_stream < 0 || n_per_stream > 0x7fffffff) return SC2_ERR_INVALID_ARG;
@@ -490,7 +491,8 @@ int sc2_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, int bat
     cudaStream_t st = sc2::as_stream(stream);
     if (n_rows < 1 || cdf_stride < 2) return SC2_ERR_INVALID_ARG;
     if (!indexes && (n_per_stream + spatial - 1) / spatial > n_rows) return SC2_ERR_INVALID_ARG;
-    if (!indexes && spatial <= 0x7fffffff && sc2::rans_use_lanes())
+    if (layout < SC2_RANS_AUTO || layout > SC2_RANS_LANE_PER_STREAM) return SC2_ERR_INVALID_ARG;
+    if (!indexes && spatial <= 0x7fffffff && sc2::rans_use_lanes(layout))
         return sc2::launch_rans_decode_lanes(packed, offsets, batch, n_per_stream, spatial, tables, out_symbols, out_values, means,
                                              status, st);
     if (!indexes && spatial <= 0x7fffffff)

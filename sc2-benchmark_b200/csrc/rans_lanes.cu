@@ -29,6 +29,7 @@ namespace {
 constexpr int kMaxWarps = 8;             // warps (x 32 streams) per block, see the launchers
 constexpr uint32_t kLutBuckets = 4096;   // 2^16 / 16
 constexpr uint32_t kLutFlag = 0xffffffffu;
+constexpr int kSymTab = 256;             // symbols per row with a shared-memory (start, freq) entry
 constexpr int kEncStageLimit = 16 * 1024;  // encoder table staged in shared memory up to this size
 
 struct Tables {
@@ -349,7 +350,17 @@ __device__ __noinline__ DecEscape dec_slow_step(DecState s, const uint32_t *word
 // The block rebuilds the LUT of one CDF row: bucket j covers cumulative values [16 j, 16 j + 16).
 //   lut32[j] = start << 16 | (freq - 1) of the symbol holding the whole bucket, kLutFlag when a symbol boundary falls inside
 //   lutv[j]  = index of the symbol holding 16 j (saturated at 255): the decoded value, or where the flagged walk starts
-__device__ __forceinline__ void build_row_lut(const int32_t *__restrict__ crow, uint32_t *lut32, uint8_t *lutv) {
+//   symtab[k] = start << 16 | (freq - 1) of symbol k < 256: resolves a flagged bucket with two shared-memory loads
+__device__ __forceinline__ void build_row_lut(const int32_t *__restrict__ crow, int n_sym, uint32_t *lut32, uint8_t *lutv,
+                                              uint32_t *symtab) {
+    for (int k = threadIdx.x; k < kSymTab; k += blockDim.x) {
+        uint32_t e = kLutFlag;
+        if (k < n_sym) {
+            const int32_t a = __ldg(crow + k), b = __ldg(crow + k + 1);
+            e = (static_cast<uint32_t>(a) << 16) | static_cast<uint32_t>(b - a - 1);
+        }
+        symtab[k] = e;
+    }
     int k = 0;
     int32_t c0 = __ldg(crow), c1 = __ldg(crow + 1);
     for (uint32_t j = threadIdx.x; j < kLutBuckets; j += blockDim.x) {
@@ -382,6 +393,8 @@ rans_decode_lanes_kernel(const uint8_t *__restrict__ packed, const int64_t *__re
     uint32_t lut32_s;
     asm volatile("mov.u32 %0, %1;" : "=r"(lut32_s) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(lut32))));
     const uint32_t lutv_s = lut32_s + kLutBuckets * 4u;
+    uint32_t *symtab = reinterpret_cast<uint32_t *>(lutv + kLutBuckets);
+    const uint32_t symtab_s = lutv_s + kLutBuckets;
 
     bool active = b < batch;
     const uint32_t *words = nullptr;
@@ -414,7 +427,7 @@ rans_decode_lanes_kernel(const uint8_t *__restrict__ packed, const int64_t *__re
         const uint32_t row_n = (n - done) < spatial ? (n - done) : spatial;
         const int32_t *crow = t.dec + static_cast<int64_t>(row) * t.dec_stride;
         __syncthreads();  // every warp has left the previous row's LUT (all streams of a block walk the rows together)
-        build_row_lut(crow, lut32, lutv);
+        build_row_lut(crow, __ldg(t.sizes + row) - 1, lut32, lutv, symtab);
         __syncthreads();
         if (active) {
             const int32_t max_value = __ldg(t.sizes + row) - 2;
@@ -423,8 +436,19 @@ rans_decode_lanes_kernel(const uint8_t *__restrict__ packed, const int64_t *__re
             // one symbol -> its value relative to the row offset
             auto step = [&]() -> int32_t {
                 const uint32_t cum = s.xl & 0xffffu;
-                const uint32_t ent = lds_u32(lut32_s + ((cum >> 4) << 2));
+                uint32_t ent = lds_u32(lut32_s + ((cum >> 4) << 2));
                 int32_t value = static_cast<int32_t>(lds_u8(lutv_s + (cum >> 4)));
+                if (ent == kLutFlag && value < kSymTab - 1) {
+                    // a symbol boundary inside the bucket (some lane of the warp hits one in a quarter of the steps): the
+                    // symbol holding the bucket's first value, or the next one
+                    const uint32_t e0 = lds_u32(symtab_s + 4u * value), e1 = lds_u32(symtab_s + 4u * value + 4u);
+                    const bool up = cum >= (e1 >> 16);
+                    const uint32_t e = up ? e1 : e0;
+                    if (cum - (e >> 16) <= (e & 0xffffu)) {  // (else: two boundaries in one bucket -> the walk below)
+                        ent = e;
+                        value += up ? 1 : 0;
+                    }
+                }
                 if (__builtin_expect(ent == kLutFlag || value == max_value, 0)) {
                     const DecEscape r = dec_slow_step(s, words, n_words, crow, value, max_value);
                     s = r.s;
@@ -459,6 +483,12 @@ rans_decode_lanes_kernel(const uint8_t *__restrict__ packed, const int64_t *__re
             const uint32_t head = vec_out ? min(row_n, (4u - (done & 3u)) & 3u) : row_n;
             for (; i < head; ++i) put(done + i, step());
             for (; i + 4 <= row_n; i += 4) {
+                {   // Touch the stream one 32-byte sector ahead (a load whose result is never read does not stall).  next_w
+                    // shares its register with the other 31 lanes: whenever ANY lane's refill misses L1, the whole warp
+                    // waits for L2 at its next step -- with this the refills hit L1.
+                    uint32_t unused;
+                    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(unused) : "l"(words + min(s.p + 8u, n_words - 1u)));
+                }
                 const int32_t v0 = step(), v1 = step(), v2 = step(), v3 = step();
                 if (SYM) *reinterpret_cast<int4 *>(osym + done + i) = make_int4(v0, v1, v2, v3);
                 if (VAL)
@@ -490,12 +520,14 @@ static int lanes_block_threads(int batch) {
     return 32 * (warps < max_warps ? warps : max_warps);
 }
 
-bool rans_use_lanes() {
-    static const bool use = [] {
+bool rans_use_lanes(int layout) {
+    if (layout == SC2_RANS_LANE_PER_STREAM) return true;
+    if (layout == SC2_RANS_WARP_PER_STREAM) return false;
+    static const bool env_lanes = [] {
         const char *e = std::getenv("SC2_CODER");
-        return !(e && e[0] == 'w');  // SC2_CODER=warp selects the warp-per-stream kernels of rans_fast.cu
+        return e && e[0] == 'l';  // SC2_CODER=lanes; default (and SC2_CODER=warp): warp per stream
     }();
-    return use;
+    return env_lanes;
 }
 
 int launch_rans_encode_lanes(const int32_t *symbols, int batch, int64_t n, int64_t spatial, const void *tables, int n_rows,
@@ -523,7 +555,7 @@ int launch_rans_encode_lanes(const int32_t *symbols, int batch, int64_t n, int64
 int launch_rans_decode_lanes(const uint8_t *packed, const int64_t *offsets, int batch, int64_t n, int64_t spatial,
                              const void *tables, int32_t *out_symbols, float *out_values, const float *means,
                              int32_t *status, cudaStream_t st) {
-    const size_t smem = kLutBuckets * 4 + kLutBuckets;
+    const size_t smem = kLutBuckets * 4 + kLutBuckets + kSymTab * 4;
     const int threads = lanes_block_threads(batch);
     const int grid = (batch + threads - 1) / threads;
     static bool configured = false;

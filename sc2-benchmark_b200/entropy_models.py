@@ -276,7 +276,7 @@ class EntropyBottleneck(EntropyModel):
     # ---- hot path: channel-indexed batched coder ------------------------------------------------
     def compress_symbols(self, symbols, spatial):
         """int32 symbols [B, C, ...] already centred on the medians -> PackedStreams (device resident)."""
-        return ops.rans_encode(symbols, self.coder_tables(), spatial=spatial)
+        return ops.rans_encode(symbols, self.coder_tables(), spatial=spatial, layout=getattr(self, 'coder_layout', None))
 
     def compress_packed(self, x):
         """Like `compress` but leaves the bitstreams on the device (PackedStreams)."""
@@ -289,7 +289,7 @@ class EntropyBottleneck(EntropyModel):
         medians = self._get_medians().detach().reshape(-1)
         symbols = ops.quantize_symbols(x, medians)
         spatial = x[0, 0].numel() if x.dim() > 2 else 1
-        return ops.rans_encode(symbols, tables, spatial=spatial)
+        return ops.rans_encode(symbols, tables, spatial=spatial, layout=getattr(self, 'coder_layout', None))
 
     def compress(self, x):
         return self.compress_packed(x).tolist()
@@ -302,7 +302,8 @@ class EntropyBottleneck(EntropyModel):
         spatial = int(np.prod(size)) if len(size) else 1
         medians = self._get_medians().detach().reshape(-1)
         out, self.last_decode_status = ops.rans_decode(streams, C * spatial, tables, spatial=spatial, means=medians, want=want,
-                                                       check_status=check_status, return_status=True)
+                                                       check_status=check_status, return_status=True,
+                                                       layout=getattr(self, 'coder_layout', None))
         return out.view(streams.batch, C, *size)
 
     def check_faults(self):

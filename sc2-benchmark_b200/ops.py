@@ -266,8 +266,9 @@ def quantize_symbols(x, means=None):
     return out
 
 
-def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None):
-    """symbols: int32 [B, n] (or [B, C, ...]) CUDA tensor -> PackedStreams."""
+def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None, layout=None):
+    """symbols: int32 [B, n] (or [B, C, ...]) CUDA tensor -> PackedStreams.  layout (channel mode): None / 'warp' (a warp per
+    stream, lowest latency) or 'lanes' (32 streams per warp, for batches in flight; include/sc2b200.h)."""
     require_cuda(symbols, 'rans_encode')
     dev = symbols.device
     B = symbols.shape[0]
@@ -297,7 +298,8 @@ def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None):
         st = _stream_ptr()
         with _launch('rans_encode', 1 if B else 0):
             check(lib.sc2_rans_encode_batch(_ptr(sym), _ptr(idx), B, n, int(spatial or 0), _ptr(tab), tables.n_rows,
-                                            tables.cdf_stride, _ptr(arena), slot_bytes, _ptr(lengths), _ptr(status), st),
+                                            tables.cdf_stride, _ptr(arena), slot_bytes, _ptr(lengths), _ptr(status),
+                                            _native.RANS_LAYOUTS[layout], st),
                   'sc2_rans_encode_batch')
         with _launch('rans_pack', 2 if B else 1):
             check(lib.sc2_rans_pack(_ptr(arena), slot_bytes, _ptr(lengths), B, _ptr(packed), _ptr(offsets), st), 'sc2_rans_pack')
@@ -311,7 +313,7 @@ def raise_on_decode_fault(st):
 
 
 def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means=None, want='values', check_status=True,
-                return_status=False):
+                return_status=False, layout=None):
     """PackedStreams -> [B, n] float32 (symbol + means[row]) or int32 symbols."""
     dev = streams.packed.device
     B = streams.batch
@@ -331,7 +333,8 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
     with torch.cuda.device(dev), _launch('rans_decode', 1 if B and n_per_stream else 0):
         check(_lib().sc2_rans_decode_batch(_ptr(streams.packed), _ptr(streams.offsets), B, n_per_stream, _ptr(idx),
                                            int(spatial or 0), _ptr(tab), tables.n_rows, tables.cdf_stride, _ptr(out_sym),
-                                           _ptr(out_val), _ptr(m), _ptr(status), _stream_ptr()), 'sc2_rans_decode_batch')
+                                           _ptr(out_val), _ptr(m), _ptr(status), _native.RANS_LAYOUTS[layout], _stream_ptr()),
+              'sc2_rans_decode_batch')
     if check_status:
         raise_on_decode_fault(int(status.item()))
     out = out_sym if want == 'symbols' else out_val

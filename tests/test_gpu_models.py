@@ -225,3 +225,45 @@ def test_entropic_classifier_wrapper(s2, oracle_compressai):
         f_hat = oeb.decompress(want, feats.shape[-2:]).to(dev)
         want_logits = model.classifier(torch.flatten(model.decoder(f_hat), 1))
     assert torch.equal(logits, want_logits)
+
+
+def test_transform_stream_pipeline_matches_serial(s2):
+    """Throughput mode (FPBasedResNetBottleneck.use_transform_stream): several batches in flight, transforms on one stream,
+    lane-per-stream coders on per-batch streams.  Bitstreams and features must equal the serial path's, batch by batch."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    layer = s2.get_layer('FPBasedResNetBottleneck').eval()
+    layer.update()
+    layer.to(dev)
+    torch.manual_seed(1)
+    xs = [torch.randn(8, 3, 224, 224, device=dev) * (1 + i) for i in range(5)]
+    with torch.inference_mode():
+        want = []
+        for x in xs:
+            st, shape = layer.encode_packed(x)
+            want.append((st.tolist(), layer.decode_packed(st, shape).clone()))
+        assert layer.entropy_bottleneck.coder_layout is None if hasattr(layer.entropy_bottleneck, 'coder_layout') else True
+        ts = layer.use_transform_stream(True)
+        assert ts is not None and layer.entropy_bottleneck.coder_layout == 'lanes'
+        side = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        depth, enc, got = 2, {}, {}
+        for i in range(len(xs) + depth):
+            if i < len(xs):
+                with torch.cuda.stream(side[i % 3]):
+                    enc[i] = layer.encode_packed(xs[i])
+            if i >= depth:
+                j = i - depth
+                with torch.cuda.stream(side[j % 3]):
+                    st, shape = enc.pop(j)
+                    got[j] = (st, layer.decode_packed(st, shape))
+        torch.cuda.synchronize()
+        for j, (strings, feat) in enumerate(want):
+            assert got[j][0].tolist() == strings
+            assert torch.equal(got[j][1], feat)
+        # the reference-facing calls work in this mode too (one host thread per batch would use host_wait=True)
+        layer.use_transform_stream(ts, host_wait=True)
+        obj = layer.encode(xs[0])
+        assert obj['strings'][0] == want[0][0]
+        assert torch.equal(layer.decode(**obj), want[0][1])
+        layer.use_transform_stream(None)
+        assert layer.entropy_bottleneck.coder_layout is None

@@ -60,26 +60,29 @@ def test_rans_golden_streams_explicit_indexes(s2, dev, g, name):
     assert torch.equal(back, sym)
 
 
-def test_rans_empty_batch_and_empty_stream(s2, dev, g):
+@pytest.mark.parametrize('layout', ['warp', 'lanes'])
+def test_rans_empty_batch_and_empty_stream(s2, dev, g, layout):
     tables = _tables(s2, g['eb24_cdf'], g['eb24_len'], g['eb24_off'])
     sym = torch.zeros((3, 0), dtype=torch.int32, device=dev)
-    out = s2.ops.rans_encode(sym, tables, spatial=1).tolist()
+    out = s2.ops.rans_encode(sym, tables, spatial=1, layout=layout).tolist()
     assert out == [g['empty_stream'].tobytes()] * 3
     assert s2.ops.rans_encode(torch.zeros((0, 5), dtype=torch.int32, device=dev), tables, spatial=5).tolist() == []
 
 
-def test_rans_config1_golden_channel_mode(s2, dev, g):
+@pytest.mark.parametrize('layout', ['warp', 'lanes'])
+def test_rans_config1_golden_channel_mode(s2, dev, g, layout):
     c1 = load_golden('config1_entropic_student_resnet50.npz')
     tables = _tables(s2, g['eb24_cdf'], g['eb24_len'], g['eb24_off'])
     sym = torch.from_numpy(c1['symbols'].astype(np.int32)).to(dev)
-    streams = s2.ops.rans_encode(sym, tables, spatial=55 * 55)
+    streams = s2.ops.rans_encode(sym, tables, spatial=55 * 55, layout=layout)
     got = streams.tolist()
     assert len(got) == 1 and got[0] == c1['stream'].tobytes()
-    back = s2.ops.rans_decode(streams, 24 * 55 * 55, tables, spatial=55 * 55, want='symbols')
+    back = s2.ops.rans_decode(streams, 24 * 55 * 55, tables, spatial=55 * 55, layout=layout, want='symbols')
     assert torch.equal(back.view_as(sym), sym)
 
 
-def test_rans_full_size_batch_roundtrip_and_oracle_sample(s2, dev, g):
+@pytest.mark.parametrize('layout', ['warp', 'lanes'])
+def test_rans_full_size_batch_roundtrip_and_oracle_sample(s2, dev, g, layout):
     """BASELINE configs[1] size: 256 streams x 72,600 symbols, random symbols including escapes."""
     tables = _tables(s2, g['eb24_cdf'], g['eb24_len'], g['eb24_off'])
     gen = torch.Generator(device='cpu').manual_seed(5)
@@ -88,11 +91,11 @@ def test_rans_full_size_batch_roundtrip_and_oracle_sample(s2, dev, g):
     sym[3, 2, 10, 10] = 100000
     sym[3, 2, 10, 11] = -100000
     sym_d = sym.to(dev)
-    streams = s2.ops.rans_encode(sym_d, tables, spatial=55 * 55)
-    back = s2.ops.rans_decode(streams, 24 * 55 * 55, tables, spatial=55 * 55, want='symbols')
+    streams = s2.ops.rans_encode(sym_d, tables, spatial=55 * 55, layout=layout)
+    back = s2.ops.rans_decode(streams, 24 * 55 * 55, tables, spatial=55 * 55, layout=layout, want='symbols')
     assert torch.equal(back.view_as(sym_d), sym_d)
     med = torch.linspace(-1, 1, 24, device=dev)
-    vals = s2.ops.rans_decode(streams, 24 * 55 * 55, tables, spatial=55 * 55, means=med, want='values')
+    vals = s2.ops.rans_decode(streams, 24 * 55 * 55, tables, spatial=55 * 55, layout=layout, means=med, want='values')
     assert torch.equal(vals.view_as(sym_d), sym_d.float() + med.view(1, 24, 1, 1))
     strings = streams.tolist()
     idx = np.repeat(np.arange(24, dtype=np.int32), 55 * 55)
@@ -100,11 +103,12 @@ def test_rans_full_size_batch_roundtrip_and_oracle_sample(s2, dev, g):
         assert strings[b] == cref.encode_with_indexes(sym[b].reshape(-1).numpy(), idx, g['eb24_cdf'], g['eb24_len'], g['eb24_off'])
     assert all(len(s) % 4 == 0 and len(s) >= 8 for s in strings)
     # host round trip of the contract object: list[bytes] -> device -> symbols
-    again = s2.ops.rans_decode(s2.ops.PackedStreams.from_list(strings, dev), 24 * 55 * 55, tables, spatial=55 * 55, want='symbols')
+    again = s2.ops.rans_decode(s2.ops.PackedStreams.from_list(strings, dev), 24 * 55 * 55, tables, spatial=55 * 55, layout=layout, want='symbols')
     assert torch.equal(again.view_as(sym_d), sym_d)
 
 
-def test_rans_wide_tables_and_ragged_rows(s2, dev, oracle_compressai):
+@pytest.mark.parametrize('layout', ['warp', 'lanes'])
+def test_rans_wide_tables_and_ragged_rows(s2, dev, oracle_compressai, layout):
     """Tables wider than one / two warps (trained-like EntropyBottleneck) and all 64 GaussianConditional rows."""
     from compressai.entropy_models import EntropyBottleneck as OracleEB
     torch.manual_seed(2)
@@ -121,11 +125,11 @@ def test_rans_wide_tables_and_ragged_rows(s2, dev, oracle_compressai):
     rng = np.random.RandomState(9)
     sym = np.round(rng.randn(5, 40, 7, 9) * np.linspace(1, 60, 40).reshape(1, 40, 1, 1)).astype(np.int32)
     sym_d = torch.from_numpy(sym).to(dev)
-    strings = s2.ops.rans_encode(sym_d, tables, spatial=63).tolist()
+    strings = s2.ops.rans_encode(sym_d, tables, spatial=63, layout=layout).tolist()
     idx = np.repeat(np.arange(40, dtype=np.int32), 63)
     for b in range(5):
         assert strings[b] == cref.encode_with_indexes(sym[b].reshape(-1), idx, cdf, ln, off)
-    back = s2.ops.rans_decode(s2.ops.PackedStreams.from_list(strings, dev), 40 * 63, tables, spatial=63, want='symbols')
+    back = s2.ops.rans_decode(s2.ops.PackedStreams.from_list(strings, dev), 40 * 63, tables, spatial=63, layout=layout, want='symbols')
     assert torch.equal(back.view_as(sym_d), sym_d)
     # GaussianConditional: explicit indexes, every row, tables up to 3133 entries (not staged in shared memory)
     gc = s2.GaussianConditional(None)
@@ -405,3 +409,52 @@ def test_conv_leaky_relu_abs_and_dequantize(s2, dev):
     assert torch.equal(s2.ops.dequantize(sym.to(dev)).cpu(), sym.float())
     y = torch.randn(3, 5, 7) * 4
     assert torch.equal(s2.ops.quantize_symbols(y.to(dev), means.to(dev)).cpu(), torch.round(y - means).int())
+
+
+def test_rans_lanes_layout_edge_cases(s2, dev, g, oracle_compressai):
+    """Lane-per-stream layout (rans_lanes.cu): stream counts that are not a multiple of 32 or of the block size, stream
+    lengths that are not a multiple of 4 or 8 (scalar head / tail of the vector stores, partial last block), CDF rows with
+    more than 255 symbols (the decoder LUT's 8-bit symbol index saturates) and rows shorter than one LUT bucket step, and
+    malformed / truncated streams.  Always byte-identical to the warp-per-stream layout and to the oracle."""
+    from compressai.entropy_models import EntropyBottleneck as OracleEB
+    torch.manual_seed(4)
+    eb = OracleEB(6)
+    with torch.no_grad():
+        eb.quantiles[:, 0, 0] = -torch.tensor([2., 40., 160., 300., 5., 900.])
+        eb.quantiles[:, 0, 2] = torch.tensor([3., 50., 170., 280., 4., 800.])
+        for m in eb.matrices:
+            m.sub_(2.0)
+    eb.update(force=True)
+    cdf, ln, off = eb._quantized_cdf.numpy(), eb._cdf_length.numpy(), eb._offset.numpy()
+    assert ln.max() > 600 and ln.min() < 16
+    tables = _tables(s2, cdf, ln, off)
+    rng = np.random.RandomState(11)
+    scale = np.array([1, 15, 60, 110, 2, 300], dtype=np.float64).reshape(1, 6, 1)
+    for B, spatial in ((1, 7), (33, 13), (70, 101), (300, 9)):
+        sym = np.round(rng.randn(B, 6, spatial) * scale).astype(np.int32)
+        sym[0, 0, 0] = 5000       # escapes on both sides
+        sym[B - 1, 5, spatial - 1] = -70000
+        sym_d = torch.from_numpy(sym).to(dev)
+        lanes = s2.ops.rans_encode(sym_d, tables, spatial=spatial, layout='lanes').tolist()
+        warp = s2.ops.rans_encode(sym_d, tables, spatial=spatial, layout='warp').tolist()
+        assert lanes == warp
+        idx = np.repeat(np.arange(6, dtype=np.int32), spatial)
+        for b in sorted({0, B // 2, B - 1}):
+            assert lanes[b] == cref.encode_with_indexes(sym[b].reshape(-1), idx, cdf, ln, off)
+        ps = s2.ops.PackedStreams.from_list(lanes, dev)
+        back = s2.ops.rans_decode(ps, 6 * spatial, tables, spatial=spatial, want='symbols', layout='lanes')
+        assert torch.equal(back.view_as(sym_d), sym_d)
+        med = torch.linspace(-2, 2, 6, device=dev)
+        vals = s2.ops.rans_decode(ps, 6 * spatial, tables, spatial=spatial, means=med, want='values', layout='lanes')
+        assert torch.equal(vals.view_as(sym_d), sym_d.float() + med.view(1, 6, 1))
+    # a truncated stream among good ones is reported, and does not disturb its neighbours' lanes
+    good = lanes[:40]
+    bad = list(good)
+    bad[7] = bad[7][:8]
+    with pytest.raises(ValueError, match='Invalid bitstream'):
+        s2.ops.rans_decode(s2.ops.PackedStreams.from_list(bad, dev), 6 * spatial, tables, spatial=spatial, want='symbols', layout='lanes')
+    out, st = s2.ops.rans_decode(s2.ops.PackedStreams.from_list(bad, dev), 6 * spatial, tables, spatial=spatial, want='symbols',
+                                 layout='lanes', check_status=False, return_status=True)
+    assert int(st.item()) != 0
+    keep = [i for i in range(40) if i != 7]
+    assert torch.equal(out.view(40, 6, spatial)[keep], sym_d[:40][keep])
