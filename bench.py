@@ -180,15 +180,15 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
     ap.add_argument('--cpu-images', type=int, default=8, help='images per step of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-threads', type=int, default=6, help='host threads (one CUDA stream each) driving the e2e steps')
-    ap.add_argument('--inflight', type=int, default=8, help='batches in flight (CUDA streams): the serial rANS chain of one batch overlaps the convolutions of the next')
+    ap.add_argument('--e2e-threads', type=int, default=12, help='host threads (one CUDA stream each) driving the e2e steps')
+    ap.add_argument('--inflight', type=int, default=8, help='depth of the batch pipeline: the serial rANS chains of up to this many batches overlap the convolutions of the others')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -227,10 +227,11 @@ def main():
         streams, shape = layer.encode_packed(dev_inputs[i & 1])
         return streams, layer.decode_packed(streams, shape)
 
-    # Batches are independent, and a stream's rANS chain is latency-bound (2 warps per SM): step i runs on CUDA stream
-    # i % inflight so that the coder of one batch overlaps the tensor-core work of the next.  Every step still does all of
-    # its work inside the timed region; the region ends when every stream has drained.
-    workers = [torch.cuda.Stream(device=device) for _ in range(max(1, args.inflight))]
+    # Batches are independent and a batch's coder is one serial rANS chain per image (milliseconds on a handful of warps),
+    # so steps are software-pipelined (sc2bench_b200/pipeline.py): every g_a / g_s on ONE transform stream in a fixed order,
+    # g_a(i + depth) ahead of g_s(i), and the coder of each batch on its own stream in the layout that occupies one SM.
+    # Every step does all of its work inside the timed region; the region ends when the pipeline has drained.
+    pipe = s2.pipeline.CodecPipeline(layer, depth=max(1, args.inflight))
 
     def run_steps(n, first=0):
         main = torch.cuda.current_stream()
@@ -238,20 +239,19 @@ def main():
         start.record(main)
         last = None
         for i in range(first, first + n):
-            w = workers[i % len(workers)]
-            w.wait_event(start)
-            with torch.cuda.stream(w):
-                last = device_step(i)
-        for w in workers:
-            main.wait_stream(w)
+            last = pipe.submit(dev_inputs[i & 1]) or last
+        for r in pipe.drain():
+            last = r
+        main.wait_stream(pipe.transform_stream)  # the last g_s, hence every batch, has finished
+        last.wait(main)
         stop = torch.cuda.Event(enable_timing=True)
         stop.record(main)
-        return start, stop, last
+        return start, stop, (last.streams, last.features)
 
     # ---- device-resident throughput ("value") -------------------------------------------------
     with torch.inference_mode():
-        # warm-up: at least W steps and at least one step per worker stream (each stream has its own allocator pool)
-        n_warm = max(args.warmup, len(workers))
+        # warm-up: at least W steps and at least one step per batch stream (each stream has its own allocator pool)
+        n_warm = max(args.warmup, len(pipe.batch_streams))
         run_steps(n_warm)
         barrier()
         sampler = ClockSampler(local_rank)
@@ -263,6 +263,7 @@ def main():
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
         total_bytes = streams.total_bytes()
+        pipe.close()  # back to one batch at a time (warp-per-stream coder: the low-latency layout)
         # per-kernel accounting: a second, SERIAL timed pass (one batch in flight, CUDA events around every launch on the
         # launching stream) -- with batches overlapping, a kernel's event time would include waiting for SMs held by others
         n_prof = max(1, min(args.steps, 5))
@@ -302,11 +303,16 @@ def main():
                 x = host_inputs[i & 1].to(device, non_blocking=True)
                 obj = layer.encode(x)                       # {'strings': [list[bytes]], 'shape'}: bitstreams land on the host
                 feat = layer.decode(**obj)                  # list[bytes] -> device -> features
-                res = feat.mean(dim=(1, 2, 3)).cpu()        # per-image result read back (synchronises this stream)
+                res = feat.mean(dim=(1, 2, 3))
+                torch.cuda.current_stream().synchronize()   # (a blocking .cpu() would hold a driver lock while it waits)
+                res = res.cpu()                             # per-image result read back
             return obj, res
 
         n_thr = max(1, args.e2e_threads)
         e2e_streams = [torch.cuda.Stream(device=device) for _ in range(n_thr)]
+        # the threads' transforms share one stream (in arrival order); a thread queues a transform only once its own stream
+        # has produced the input, so a batch that is still copying or coding never holds up the others
+        layer.use_transform_stream(True, host_wait=True)
         with concurrent.futures.ThreadPoolExecutor(max_workers=n_thr) as pool:
             list(pool.map(e2e_step, range(max(args.warmup, 2 * n_thr))))
             barrier()
@@ -315,6 +321,7 @@ def main():
             torch.cuda.synchronize()
             e2e_ms = (time.perf_counter() - t0) * 1e3  # host wall clock: host work is part of this contract
             barrier()
+        layer.use_transform_stream(None)
         obj, res = results[-1]
         te = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
         if world > 1:
@@ -381,7 +388,8 @@ def main():
                        'images_per_gpu_per_step': B, 'global_images_per_step': B * world, 'symbols_per_image': n_sym,
                        'l2_policy': 'two alternating 154 MB input batches (> 126 MB L2); activations are GBs per step',
                        'parallelism': 'dp%d (batch sharded, one counter all-reduce per evaluation)' % world,
-                       'batches_in_flight': len(workers)},
+                       'batches_in_flight': args.inflight,
+                       'schedule': 'software pipeline: transforms on one stream, g_a(i + depth) ahead of g_s(i); coders on per-batch streams'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
             'serial_ms_per_step': serial_ms, 'kernel_accounting': 'serial pass of %d steps after the timed region (CUDA events per launch)' % n_prof,
             'kernels': kernels,

@@ -19,7 +19,8 @@ from .layers import GDN, GDN1  # noqa: E402,F401
 from .models import (CompressionModel, FactorizedPrior, ScaleHyperprior, bmshj2018_factorized,  # noqa: E402,F401
                      bmshj2018_hyperprior, get_scale_table, update_registered_buffers)
 
-from . import backbone, wrapper  # noqa: E402,F401
+from . import backbone, pipeline, wrapper  # noqa: E402,F401
+from .pipeline import CodecPipeline  # noqa: E402,F401
 from .wrapper import (COMPRESSAI_DICT, WRAPPER_CLASS_DICT, AdaptivePad, EntropicClassifier,  # noqa: E402,F401
                       NeuralInputCompressionClassifier, get_compression_model, redesign_model, register_compressai_model)
 

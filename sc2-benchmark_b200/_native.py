@@ -91,6 +91,25 @@ def load():
     return lib
 
 
+_hostbytes = None
+
+
+def hostbytes():
+    """The CPython helper module (csrc/hostbytes.c): list[bytes] <-> staging buffer with the GIL released."""
+    global _hostbytes
+    if _hostbytes is None:
+        import importlib.util
+        load()  # builds everything if needed
+        path = _build.hostbytes_path()
+        if not os.path.exists(path):
+            _build.build_hostbytes()
+        spec = importlib.util.spec_from_file_location('_sc2_hostbytes', path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _hostbytes = mod
+    return _hostbytes
+
+
 class NativeError(RuntimeError):
     pass
 

@@ -20,14 +20,31 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
 NVCC_FLAGS.remove('--use_fast_math=false')  # never fast-math: bit-exactness matters on this path
 
 
+HOSTBYTES_SRC = os.path.join(CSRC, 'hostbytes.c')
+
+
+def hostbytes_path():
+    import sysconfig
+    return os.path.join(LIB_DIR, '_sc2_hostbytes' + sysconfig.get_config_var('EXT_SUFFIX'))
+
+
 def _sources():
     return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+
+
+def build_hostbytes():
+    """The CPython helper that splits / gathers the contract's list[bytes] with the GIL released (csrc/hostbytes.c)."""
+    import sysconfig
+    out = hostbytes_path()
+    cc = os.environ.get('CC', 'gcc')
+    subprocess.check_call([cc, '-O2', '-shared', '-fPIC', '-I', sysconfig.get_paths()['include'], HOSTBYTES_SRC, '-o', out])
+    return out
 
 
 def _fingerprint():
     h = hashlib.sha256()
     for path in _sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + \
-            [os.path.join(os.path.dirname(HERE), 'include', 'sc2b200.h'), os.path.abspath(__file__)]:
+            [HOSTBYTES_SRC, os.path.join(os.path.dirname(HERE), 'include', 'sc2b200.h'), os.path.abspath(__file__)]:
         h.update(path.encode())
         with open(path, 'rb') as f:
             h.update(f.read())
@@ -38,7 +55,8 @@ def build_native(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     stamp = os.path.join(LIB_DIR, 'build.stamp')
     fp = _fingerprint()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(hostbytes_path()) and os.path.exists(stamp) \
+            and open(stamp).read().strip() == fp:
         return LIB_PATH
     if not os.path.exists(NVCC):
         raise RuntimeError('nvcc not found at %s; libsc2b200.so cannot be built' % NVCC)
@@ -57,6 +75,7 @@ def build_native(force=False, verbose=False):
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
     link = [NVCC, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC']
     subprocess.check_call(link)
+    build_hostbytes()
     with open(stamp, 'w') as f:
         f.write(fp)
     return LIB_PATH

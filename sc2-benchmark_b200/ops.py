@@ -194,7 +194,11 @@ class PackedStreams:
 
     def _to_host(self):
         if self._host is None:
-            offs = self.offsets.cpu()  # sync point
+            # Wait for the coder with a stream synchronise FIRST: a blocking copy to pageable memory (.cpu(), .item()) holds
+            # a driver lock while it waits for the GPU, and every other host thread's event record / stream wait then
+            # blocks behind it for milliseconds (measured: scripts/diag_e2e_calls.py).
+            torch.cuda.current_stream(self.packed.device).synchronize()
+            offs = self.offsets.cpu()
             if self.status is not None and int(self.status.item()) & _native.FAULT_ARENA_OVERFLOW:
                 raise RuntimeError('rANS encoder ran out of arena space (device fault flag)')
             total = int(offs[-1])
@@ -205,8 +209,8 @@ class PackedStreams:
 
     def tolist(self):
         offs, data = self._to_host()
-        view = memoryview(data)  # one copy per stream, straight out of the (per-thread, reused) pinned staging buffer
-        out = [bytes(view[offs[i]:offs[i + 1]]) for i in range(self.batch)]
+        # one copy per stream, straight out of the (per-thread, reused) pinned staging buffer, with the GIL released
+        out = _native.hostbytes().split(data, np.ascontiguousarray(offs, dtype=np.int64))
         self._host = (offs, None)  # the staging buffer is reused by the next call
         return out
 
@@ -222,19 +226,20 @@ class PackedStreams:
     def from_list(strings, device):
         if not isinstance(strings, (tuple, list)):
             raise ValueError('Invalid `strings` parameter type.')
-        lens = np.fromiter((len(s) for s in strings), dtype=np.int64, count=len(strings))
+        if not all(isinstance(b, bytes) for b in strings):
+            strings = [bytes(b) for b in strings]
+        total = sum(map(len, strings))
+        # one pinned staging buffer per thread: [streams ... | pad to 8 | int64 offsets], uploaded with ONE H2D copy;
+        # the gather runs with the GIL released (csrc/hostbytes.c)
+        off_pos = (max(total, 4) + 7) // 8 * 8
+        n_off = 8 * (len(strings) + 1)
+        host = _PINNED.get_h2d(off_pos + n_off)
+        hv = host.numpy()
+        _native.hostbytes().join(strings, hv[:off_pos], hv[off_pos:off_pos + n_off])
+        offs = hv[off_pos:off_pos + n_off].view(np.int64)
+        lens = np.diff(offs)
         if len(strings) and ((lens < 8).any() or (lens & 3).any()):
             raise ValueError('Invalid bitstream: a CompressAI rANS stream is a multiple of 4 bytes and >= 8 bytes long')
-        offs = np.zeros(len(strings) + 1, dtype=np.int64)
-        np.cumsum(lens, out=offs[1:])
-        total = int(offs[-1])
-        # one pinned staging buffer per thread: [streams ... | pad to 8 | int64 offsets], uploaded with ONE H2D copy
-        off_pos = (max(total, 4) + 7) // 8 * 8
-        host = _PINNED.get_h2d(off_pos + offs.nbytes)
-        dst = memoryview(host.numpy())
-        for i, s in enumerate(strings):  # one copy per stream, straight into the pinned staging buffer
-            dst[offs[i]:offs[i + 1]] = s
-        host.numpy()[off_pos:off_pos + offs.nbytes] = offs.view(np.uint8)
         blob = host.to(device, non_blocking=True)
         _PINNED.h2d_event = torch.cuda.Event()
         _PINNED.h2d_event.record()
@@ -336,6 +341,7 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
                                            _ptr(out_val), _ptr(m), _ptr(status), _native.RANS_LAYOUTS[layout], _stream_ptr()),
               'sc2_rans_decode_batch')
     if check_status:
+        torch.cuda.current_stream(dev).synchronize()  # (not a blocking copy: see PackedStreams._to_host)
         raise_on_decode_fault(int(status.item()))
     out = out_sym if want == 'symbols' else out_val
     return (out, status) if return_status else out

@@ -1,0 +1,77 @@
+"""Software pipeline over batches for the bottleneck path (throughput mode).
+
+`FPBasedResNetBottleneck.encode` / `.decode` (sc2bench/models/layer.py:496-521) are one batch at a time: g_a, coder, g_s in
+sequence, and the coder -- one serial rANS chain per image -- leaves the tensor cores idle for most of the step.  Batches are
+independent, so a caller with a queue of batches can overlap them.  Doing that with one CUDA stream per batch is not enough:
+the batches drift into lock-step (all in their transforms, then all in their coders; scripts/diag_trace.py).  CodecPipeline
+fixes the order instead:
+
+    transform stream:  g_a(0) g_a(1) ... g_a(d)  g_s(0) g_a(d+1)  g_s(1) g_a(d+2) ...
+    batch streams:           coder(0) coder(1) ...          (lane-per-stream layout: a batch's coder is one block)
+
+Results come back in submission order, `depth` submissions late.  Nothing here synchronises the host.
+"""
+import collections
+
+import torch
+
+
+class PipelineResult:
+    """One batch out of the pipeline: device-resident bitstreams and decoder features, valid once `ready` has happened."""
+
+    def __init__(self, streams, shape, features, ready):
+        self.streams, self.shape, self.features, self.ready = streams, shape, features, ready
+
+    def wait(self, stream=None):
+        """Orders `stream` (default: the current stream) after this batch; no host synchronisation."""
+        stream = stream or torch.cuda.current_stream()
+        stream.wait_event(self.ready)
+        self.features.record_stream(stream)
+        return self
+
+
+class CodecPipeline:
+    def __init__(self, layer, depth=8):
+        if depth < 1:
+            raise ValueError('depth must be >= 1')
+        self.layer, self.depth = layer, depth
+        device = layer.entropy_bottleneck._quantized_cdf.device
+        if device.type != 'cuda':
+            raise RuntimeError('CodecPipeline: the sc2bench_b200 hot path runs on CUDA only; move the layer to a GPU')
+        self.transform_stream = layer.use_transform_stream(True)
+        self.batch_streams = [torch.cuda.Stream(device=device) for _ in range(depth + 1)]
+        self._pending = collections.deque()
+        self._submitted = 0
+
+    @torch.no_grad()
+    def submit(self, x):
+        """Queues g_a + coder of batch x (a CUDA tensor produced on the current stream).  Returns the PipelineResult of the
+        batch submitted `depth` calls earlier, or None while the pipeline fills."""
+        s = self.batch_streams[self._submitted % len(self.batch_streams)]
+        self._submitted += 1
+        s.wait_stream(torch.cuda.current_stream())
+        x.record_stream(s)
+        with torch.cuda.stream(s):
+            encoded = self.layer.encode_packed(x)
+        self._pending.append((s, encoded))
+        return self._retire() if len(self._pending) > self.depth else None
+
+    @torch.no_grad()
+    def _retire(self):
+        s, (streams, shape) = self._pending.popleft()
+        with torch.cuda.stream(s):
+            features = self.layer.decode_packed(streams, shape)
+            ready = torch.cuda.Event()
+            ready.record(s)
+        return PipelineResult(streams, shape, features, ready)
+
+    def drain(self):
+        """Retires every batch still in flight, in order."""
+        out = []
+        while self._pending:
+            out.append(self._retire())
+        return out
+
+    def close(self):
+        self.drain()
+        self.layer.use_transform_stream(None)
