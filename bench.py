@@ -263,10 +263,14 @@ def main():
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
         total_bytes = streams.total_bytes()
-        pipe.close()  # back to one batch at a time (warp-per-stream coder: the low-latency layout)
-        # per-kernel accounting: a second, SERIAL timed pass (one batch in flight, CUDA events around every launch on the
-        # launching stream) -- with batches overlapping, a kernel's event time would include waiting for SMs held by others
+        pipe.close()  # back to one batch at a time
+        # per-kernel accounting: a second, SERIAL timed pass over the SAME kernels (one batch in flight, CUDA events around
+        # every launch on the launching stream) -- with batches overlapping, a kernel's event time would include waiting for
+        # SMs held by others.  The coder keeps the layout of the timed region (lane per stream).
+        layer.entropy_bottleneck.coder_layout = 'lanes'
         n_prof = max(1, min(args.steps, 5))
+        device_step(0)
+        torch.cuda.synchronize()
         s2.ops.profile_kernels('all')
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
@@ -277,6 +281,16 @@ def main():
         serial_ms = p0.elapsed_time(p1) / n_prof
         prof = s2.ops.profile_results()
         s2.ops.profile_kernels(None)
+        # ... and the latency of ONE batch with the low-latency coder layout (a warp per stream), for reference
+        layer.entropy_bottleneck.coder_layout = None
+        device_step(0)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for i in range(n_prof):
+            device_step(i)
+        l1.record()
+        torch.cuda.synchronize()
+        latency_ms = l0.elapsed_time(l1) / n_prof
 
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     counters = parallel.EvalCounters(device)
@@ -353,10 +367,15 @@ def main():
             k['frac'] = k['achieved'] / k['peak']
         if tag in traffic:  # measured DRAM bytes of one launch (ncu), scaled to this batch size
             k['traffic'] = traffic[tag]['dram_bytes_per_launch'] * B / traffic[tag].get('batch', 256)
+        k['stream'] = 'batch' if tag.startswith('rans_') else 'transform'
         if tag in ('rans_encode', 'rans_decode'):
             k['symbols_per_s_per_stream'] = n_sym / (avg / 1e3)
             k['symbols_per_s_aggregate'] = n_sym * B / (avg / 1e3)
-            k['note'] = 'serial rANS state chain per stream: latency-bound, neither roofline applies (SURVEY.md H1)'
+            k['note'] = ('serial rANS state chain per stream (SURVEY.md H1): latency-bound, neither roofline applies.  Lane-per-stream '
+                         'layout: the %d streams of a batch are ONE block of %d warps on one SM, running next to the transforms of '
+                         'the other batches in flight -- off the critical path of the pipelined step' % (B, (B + 31) // 32))
+        else:
+            k['share_of_pipelined_step'] = per_step / (ms / args.steps)
         kernels.append(k)
     kernels.sort(key=lambda k: -k['share_of_step'])
     roofline = None
@@ -366,9 +385,13 @@ def main():
                     'unit': top.get('unit'), 'frac': top.get('frac'), 'traffic': top.get('traffic'), 'traffic_source': traffic_src,
                     'peak_source': peaks['source'] + (', bf16 sustained' if top.get('bound') == 'tensor' else ', copy bandwidth'),
                     'avg_launch_ms': top['avg_launch_ms'], 'share_of_step': top['share_of_step'], 'note': top.get('note')}
+        keys = ('kernel', 'bound', 'achieved', 'unit', 'peak', 'frac', 'traffic', 'avg_launch_ms', 'share_of_step', 'share_of_pipelined_step')
+        crit = [k for k in kernels if k['stream'] == 'transform']
+        if crit and crit[0] is not top:  # the kernel that bounds the pipelined step: largest on the transform stream
+            roofline['critical_path_kernel'] = {kk: crit[0].get(kk) for kk in keys}
         gemm = [k for k in kernels if k.get('bound') == 'tensor']
         if gemm and gemm[0] is not top:
-            roofline['dominant_gemm'] = {kk: gemm[0].get(kk) for kk in ('kernel', 'bound', 'achieved', 'unit', 'peak', 'frac', 'traffic', 'avg_launch_ms', 'share_of_step')}
+            roofline['dominant_gemm'] = {kk: gemm[0].get(kk) for kk in keys}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -391,7 +414,9 @@ def main():
                        'batches_in_flight': args.inflight,
                        'schedule': 'software pipeline: transforms on one stream, g_a(i + depth) ahead of g_s(i); coders on per-batch streams'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
-            'serial_ms_per_step': serial_ms, 'kernel_accounting': 'serial pass of %d steps after the timed region (CUDA events per launch)' % n_prof,
+            'serial_ms_per_step': serial_ms, 'one_batch_latency_ms': latency_ms,
+            'kernel_accounting': 'serial pass of %d steps after the timed region, same kernels (CUDA events per launch); shares are of '
+                                 'that serial step, as in the ncu launch list; one_batch_latency_ms uses the warp-per-stream coder' % n_prof,
             'kernels': kernels,
             'bytes_per_image': c['bytes_per_image'], 'bits_per_symbol': c['bits_per_symbol'],
             'path_tflops': value * PATH_FLOPS_PER_IMAGE / 1e12, 'path_hbm_gbs_algorithmic': value * PATH_BYTES_PER_IMAGE / 1e9}

@@ -1,2 +1,4 @@
-for t in 6 8 10 12; do python bench.py --no-cpu-baseline --e2e-threads $t 2>&1 | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],3), d['e2e'])"; done
+python scripts/diag_trace.py 8 48 streams > gpurun_out/r1e_trace_streams.log 2>&1
+python scripts/diag_trace.py 8 48 pipeline > gpurun_out/r1e_trace_pipeline.log 2>&1
+python bench.py --no-cpu-baseline > gpurun_out/r1e_bench2.json 2> gpurun_out/r1e_bench2.err
+tail -c 300 gpurun_out/r1e_bench2.err; head -12 gpurun_out/r1e_trace_streams.log; head -12 gpurun_out/r1e_trace_pipeline.log

@@ -1,5 +1,7 @@
-"""Per-CTA trace of the pipelined step (sc2_trace_start): do convolution CTAs run on SMs that host coder blocks?
-python scripts/diag_trace.py [streams] [steps]"""
+"""Per-CTA trace of batches in flight (sc2_trace_start): which SM runs what, when.
+python scripts/diag_trace.py [streams] [steps] [streams|pipeline]
+  streams   one CUDA stream per batch, everything of a batch on its stream (lane-per-stream coder)
+  pipeline  CodecPipeline: transforms on one stream in a fixed order, coders on per-batch streams"""
 import ctypes
 import os
 import sys
@@ -13,6 +15,7 @@ import sc2bench_b200 as s2  # noqa: E402
 
 n_streams = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 48
+mode = sys.argv[3] if len(sys.argv) > 3 else 'streams'
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 layer = s2.get_layer('FPBasedResNetBottleneck').eval()
@@ -26,8 +29,25 @@ with torch.inference_mode():
         return layer.decode_packed(st, sh)
 
     workers = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    layer.entropy_bottleneck.coder_layout = 'lanes'
+    pipe = s2.CodecPipeline(layer, depth=n_streams) if mode == 'pipeline' else None
+
+    def go_pipeline(k):
+        main = torch.cuda.current_stream()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for i in range(k):
+            pipe.submit(xs[i & 1])
+        pipe.drain()
+        main.wait_stream(pipe.transform_stream)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(main)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
 
     def go(k):
+        if pipe is not None:
+            return go_pipeline(k)
         main = torch.cuda.current_stream()
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record(main)
@@ -53,7 +73,7 @@ with torch.inference_mode():
     raw = buf.cpu().numpy()
 n = int(raw[:4].view(np.uint32)[0])
 rec = raw[16:16 + 32 * min(n, cap)].view(np.dtype([('t0', '<u8'), ('t1', '<u8'), ('kind', '<i4'), ('sm', '<i4'), ('aux', '<i4'), ('bid', '<i4')]))
-print('%.3f ms/step, %d trace records' % (ms, n))
+print('mode %s, %d batches in flight: %.3f ms/step, %d trace records' % (mode, n_streams, ms, n))
 t_begin, t_end = rec['t0'].min(), rec['t1'].max()
 lo = t_begin + (t_end - t_begin) // 4
 hi = t_end - (t_end - t_begin) // 4
