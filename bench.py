@@ -187,7 +187,7 @@ def main():
     ap.add_argument('--cpu-images', type=int, default=8, help='images per step of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-threads', type=int, default=12, help='host threads (one CUDA stream each) driving the e2e steps')
+    ap.add_argument('--e2e-threads', type=int, default=0, help='host threads (one CUDA stream each) driving the e2e steps')
     ap.add_argument('--inflight', type=int, default=8, help='depth of the batch pipeline: the serial rANS chains of up to this many batches overlap the convolutions of the others')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
@@ -322,7 +322,8 @@ def main():
                 res = res.cpu()                             # per-image result read back
             return obj, res
 
-        n_thr = max(1, args.e2e_threads)
+        # default: 12 host threads per GPU (they mostly wait on the GPU with the GIL released), fewer when ranks share few cores
+        n_thr = args.e2e_threads if args.e2e_threads > 0 else min(12, max(6, 2 * (os.cpu_count() or 8) // max(world, 1)))
         e2e_streams = [torch.cuda.Stream(device=device) for _ in range(n_thr)]
         # the threads' transforms share one stream (in arrival order); a thread queues a transform only once its own stream
         # has produced the input, so a batch that is still copying or coding never holds up the others
