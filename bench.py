@@ -31,6 +31,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # keep stdout clean for the single JSON line: NCCL's version / debug banner goes to a file
 os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/sc2b200_nccl.%h.%p.log')
+# One hardware queue per CUDA stream for the 10-20 streams of the batch pipeline: with the default 8, streams share queues and
+# a coder kernel waiting for its batch's g_a blocks the transforms queued behind it (measured: 21-41 k images/s from run to
+# run with 8 connections, 43 k every run with 32).  Read by the driver when the context is created, i.e. before torch starts.
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 
 METRIC = 'images/s encode+rANS+decode @224^2 (FPBasedResNetBottleneck, Entropic Student ResNet-50)'
 UNIT = 'images/s'

@@ -4,7 +4,14 @@ The directory is called `sc2-benchmark_b200/` (repo layout contract); it is impo
 thin alias package next to it.  Importing the package loads (and, if needed, builds) libsc2b200.so: the CUDA
 library is the product, there is no CPU fallback for the hot path.
 """
-from . import _native
+import os as _os
+
+# Throughput mode keeps 10-20 CUDA streams busy (pipeline.py).  With the default of 8 hardware queues, streams share queues and a
+# coder kernel that waits for its batch's g_a blocks the transforms queued behind it (21-41 k images/s from run to run; 43 k
+# every run with 32).  The driver reads this when it creates the context; a value the user has set is left alone.
+_os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
+from . import _native  # noqa: E402
 
 _native.load()  # fail loudly right here if the native library is missing and cannot be built
 

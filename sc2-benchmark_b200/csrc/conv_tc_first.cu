@@ -28,6 +28,7 @@ struct Params {
     int K;               // c_in * kh * kw (<= 128)
     int k_steps;         // ceil(K / 16)
     int c_out, out_c;    // valid channels, channel pitch of the output planes
+    int stage_c;         // channel pitch of the staging tile (out_c padded to an odd number of 16-byte units: no bank conflicts)
     int tiles_x, tiles_y, tw, th;
     int *tile_counter;   // zeroed by the caller: dynamic tile schedule; nullptr: static
     TraceSink trace;     // diagnostics (common.cuh)
@@ -39,7 +40,9 @@ struct Smem {
     static constexpr int kResBytes = 4 * kBBytes;          // [chunk 0 hi][chunk 0 lo][chunk 1 hi][chunk 1 lo]
     static constexpr int kStageBytes = 4 * kABytes;        // same order for A
     static constexpr int kRingBytes = kAStages * kStageBytes;
-    static constexpr int kStagePlane = kTileM * N_TILE * 2;
+    // staging rows padded by 16 bytes against bank conflicts (see conv_tc_split.cu) where the budget allows: not for N_TILE = 96
+    static constexpr int kPadC = (kResBytes + kRingBytes + 2 * kTileM * (N_TILE + 8) * 2 + 2048 <= 227 * 1024) ? 8 : 0;
+    static constexpr int kStagePlane = kTileM * (N_TILE + kPadC) * 2;
     static constexpr int kStagingOffset = kResBytes + kRingBytes;
     static constexpr int kBarOffset = kStagingOffset + 2 * kStagePlane;
     static constexpr int kSchedOffset = kBarOffset + (2 * kAStages + 5) * 8 + 16;
@@ -213,8 +216,8 @@ tc_first_layer_kernel(const __grid_constant__ CUtensorMap map_b_hi, const __grid
                             f[e] = (c + e < p.c_out) ? __uint_as_float(d0[8 * g + e]) + __uint_as_float(d1[8 * g + e]) * kLoInv : 0.0f;
                         uint4 h, l;
                         split8(f, h, l);
-                        *reinterpret_cast<uint4 *>(st_hi + row * p.out_c + c) = h;
-                        *reinterpret_cast<uint4 *>(st_lo + row * p.out_c + c) = l;
+                        *reinterpret_cast<uint4 *>(st_hi + row * p.stage_c + c) = h;
+                        *reinterpret_cast<uint4 *>(st_lo + row * p.stage_c + c) = l;
                     }
                 }
             }
@@ -351,6 +354,10 @@ int sc2_tc_first_layer(const float *image, int batch, int c_in, int h_in, int w_
     p.hp = h_out / 2; p.wp = w_out / 2;
     p.K = K; p.k_steps = (K + 15) / 16;
     p.c_out = c_out; p.out_c = out_c;
+    {   // staging pitch: padded to an odd number of 16-byte units where the kernel for this n_tile has the room
+        const int pad_c = n_tile == 32 ? Smem<32>::kPadC : n_tile == 48 ? Smem<48>::kPadC : n_tile == 64 ? Smem<64>::kPadC : Smem<96>::kPadC;
+        p.stage_c = (pad_c && (out_c / 8) % 2 == 0) ? out_c + 8 : out_c;
+    }
     p.tile_counter = tile_counter;
     p.trace = sc2::trace_sink();
     int n_col_tiles = (p.wp + 127) / 128;
@@ -369,9 +376,9 @@ int sc2_tc_first_layer(const float *image, int batch, int c_in, int h_in, int w_
     if (rc) return rc;
     rc = make_weight_map(&maps[1], w_lo, k_pad, n_tile, n_tile);
     if (rc) return rc;
-    rc = make_nhwc_map(&maps[2], out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_c, p.wp, p.hp, batch * 4, out_c, tw, th, CU_TENSOR_MAP_SWIZZLE_NONE);
+    rc = make_nhwc_map(&maps[2], out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_c, p.wp, p.hp, batch * 4, p.stage_c, tw, th, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
-    rc = make_nhwc_map(&maps[3], out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_c, p.wp, p.hp, batch * 4, out_c, tw, th, CU_TENSOR_MAP_SWIZZLE_NONE);
+    rc = make_nhwc_map(&maps[3], out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_c, p.wp, p.hp, batch * 4, p.stage_c, tw, th, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     cudaStream_t st = sc2::as_stream(stream);
     switch (n_tile) {

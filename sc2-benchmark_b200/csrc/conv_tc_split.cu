@@ -51,6 +51,7 @@ struct Params {
     const float *medians;
     __half *out_hi, *out_lo;
     int out_c;         // channel pitch of the output planes
+    int stage_c;       // channel pitch of the staging tile: out_c padded to an ODD number of 16-byte units per row
     int32_t *out_sym;
     const __half *x_hi, *x_lo;
     int *tile_counter;  // zeroed by the caller: dynamic tile schedule; nullptr: static
@@ -67,14 +68,24 @@ struct Smem {
     static constexpr int kRingBytes = STAGES * kStageBytes;
     // output staging: dense [128 rows][N_TILE channels] fp16 for the hi and the lo plane (TMA store source; in the GDN
     // mode the x tile is TMA-loaded into it first and y overwrites x in place)
-    static constexpr int kStagePlane = kTileM * N_TILE * 2;
+    // (rows are padded by 16 bytes: with a pitch of 192 bytes the 16-byte accesses of 8 consecutive rows fall on two bank
+    // groups -- 60 M conflict cycles per launch in GDN1(96); the padding channels lie outside the tensor, so the bulk stores
+    // skip them and the x-tile loads zero-fill them)
+    static constexpr int kStagePlane = kTileM * (N_TILE + 8) * 2;
     static constexpr int kStagingBytes = 2 * kStagePlane;
     static constexpr int kStagingOffset = kResBytes + kRingBytes;
     static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
     static constexpr int kSchedOffset = kBarOffset + (3 * STAGES + 6) * 8 + 16;
-    static constexpr int kTotal = kSchedOffset + kTileSchedBytes;
+    static constexpr int kBetaOffset = kSchedOffset + kTileSchedBytes;  // float[N_TILE]: beta, 1.0 beyond c_out
+    static constexpr int kTotal = kBetaOffset + N_TILE * 4;
     static_assert(kTotal + 1024 <= 227 * 1024, "shared memory budget");
 };
+
+__device__ __forceinline__ float fast_rcp(float v) {  // v > 0 (a GDN norm): reciprocal to within 1 ulp in 3 instructions
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return fmaf(r, fmaf(-v, r, 1.0f), r);
+}
 
 __device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr, __half *lo_ptr) {
     uint4 h, l;
@@ -128,6 +139,9 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     int trace_tiles = 0;
     TileSched sched;
     sched.bind(smem_res + L::kSchedOffset, p.tile_counter, total_tiles);
+
+    float *s_beta = reinterpret_cast<float *>(smem_res + L::kBetaOffset);
+    if (kGdn && threadIdx.x < N_TILE) s_beta[threadIdx.x] = static_cast<int>(threadIdx.x) < p.c_out ? __ldg(p.beta + threadIdx.x) : 1.0f;
 
     if (threadIdx.x == 0) {
         sched.init(kGdn ? 13 : 9);  // consumers: MMA warp, 8 epilogue warps (, 4 transform warps)
@@ -255,7 +269,7 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 if (issuer) {
                     tma_store_wait_read();
                     if (kGdn) {  // x tile (hi, lo) -> staging; y will overwrite it in place
-                        mbar_expect_tx(x_full, static_cast<uint32_t>(2 * rows * p.out_c * 2));
+                        mbar_expect_tx(x_full, static_cast<uint32_t>(2 * rows * p.stage_c * 2));
                         tma_load_4d(&map_x_hi, x_full, st_hi, 0, x0, y0, img);
                         tma_load_4d(&map_x_lo, x_full, st_lo, 0, x0, y0, img);
                     }
@@ -297,10 +311,13 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         const int c = c0 + 8 * g;
                         if (c >= p.out_c) continue;
                         float f[8];
+                        const bool whole = c + 8 <= p.c_out;  // (uniform) every channel of the group is real
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            f[e] = (c + e < p.c_out) ? __uint_as_float(d0[8 * g + e]) + __uint_as_float(d1[8 * g + e]) * kLoInv : 0.0f;
-                        __half *ph = st_hi + row * p.out_c + c, *pl = st_lo + row * p.out_c + c;
+                        for (int e = 0; e < 8; ++e) {
+                            const float v = fmaf(__uint_as_float(d1[8 * g + e]), kLoInv, __uint_as_float(d0[8 * g + e]));
+                            f[e] = (whole || c + e < p.c_out) ? v : 0.0f;
+                        }
+                        __half *ph = st_hi + row * p.stage_c + c, *pl = st_lo + row * p.stage_c + c;
                         if (kGdn) {
                             const uint4 xh = *reinterpret_cast<const uint4 *>(ph);
                             const uint4 xl = *reinterpret_cast<const uint4 *>(pl);
@@ -308,11 +325,10 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 a = __half22float2(xhh[e]), b = __half22float2(xlh[e]);
-                                const float x0f = a.x + b.x * kLoInv, x1f = a.y + b.y * kLoInv;
-                                const float b0 = (c + 2 * e < p.c_out) ? __ldg(p.beta + c + 2 * e) : 1.0f;
-                                const float b1 = (c + 2 * e + 1 < p.c_out) ? __ldg(p.beta + c + 2 * e + 1) : 1.0f;
-                                f[2 * e] = x0f * __fdiv_rn(1.0f, f[2 * e] + b0);      // x * (1 / norm), like the reference
-                                f[2 * e + 1] = x1f * __fdiv_rn(1.0f, f[2 * e + 1] + b1);
+                                const float x0f = fmaf(b.x, kLoInv, a.x), x1f = fmaf(b.y, kLoInv, a.y);
+                                // x * (1 / norm), like the reference; 1 / norm = MUFU.RCP + one Newton step (< 1 ulp)
+                                f[2 * e] = x0f * fast_rcp(f[2 * e] + s_beta[c + 2 * e]);
+                                f[2 * e + 1] = x1f * fast_rcp(f[2 * e + 1] + s_beta[c + 2 * e + 1]);
                             }
                         }
                         split_store8(f, ph, pl);
@@ -512,6 +528,7 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     p.beta = beta; p.medians = medians;
     p.out_hi = static_cast<__half *>(out_hi); p.out_lo = static_cast<__half *>(out_lo);
     p.out_c = d->out_c;
+    p.stage_c = (d->out_c / 8) % 2 == 0 ? d->out_c + 8 : d->out_c;  // odd number of 16-byte units per staging row
     p.out_sym = out_sym;
     p.x_hi = static_cast<const __half *>(gdn_x_hi); p.x_lo = static_cast<const __half *>(gdn_x_lo);
     p.tile_counter = tile_counter;
@@ -530,19 +547,20 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     if (rc) return rc;
     maps[4] = maps[5] = maps[6] = maps[7] = mah;
     if (d->mode != MODE_QUANT) {
-        // dense (unswizzled) boxes {out_c, tw, th, 1}: bulk-store sources / x-tile destinations in the staging buffer
+        // dense (unswizzled) boxes {stage_c, tw, th, 1}: bulk-store sources / x-tile destinations in the staging buffer; the
+        // box is wider than the tensor when the row pitch is padded (out-of-bounds channels: skipped / zero-filled)
         if (d->out_c > n_tile) return SC2_ERR_INVALID_ARG;
-        rc = make_nhwc_map(&maps[4], out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, d->out_c, tw, th,
+        rc = make_nhwc_map(&maps[4], out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
                            CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
-        rc = make_nhwc_map(&maps[5], out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, d->out_c, tw, th,
+        rc = make_nhwc_map(&maps[5], out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
                            CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
         if (d->mode == MODE_GDN1_SPLIT) {
-            rc = make_nhwc_map(&maps[6], gdn_x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, d->out_c, tw,
+            rc = make_nhwc_map(&maps[6], gdn_x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, tw,
                                th, CU_TENSOR_MAP_SWIZZLE_NONE);
             if (rc) return rc;
-            rc = make_nhwc_map(&maps[7], gdn_x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, d->out_c, tw,
+            rc = make_nhwc_map(&maps[7], gdn_x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, tw,
                                th, CU_TENSOR_MAP_SWIZZLE_NONE);
             if (rc) return rc;
         }

@@ -10,6 +10,8 @@ fixes the order instead:
     batch streams:           coder(0) coder(1) ...          (lane-per-stream layout: a batch's coder is one block)
 
 Results come back in submission order, `depth` submissions late.  Nothing here synchronises the host.
+Needs one hardware queue per stream: CUDA_DEVICE_MAX_CONNECTIONS >= depth + 3 (the package sets 32 at import unless the
+variable is already set); with streams sharing queues a waiting coder kernel blocks the transforms queued behind it.
 """
 import collections
 

@@ -1,4 +1,2 @@
-python scripts/diag_trace.py 8 48 streams > gpurun_out/r1e_trace_streams.log 2>&1
-python scripts/diag_trace.py 8 48 pipeline > gpurun_out/r1e_trace_pipeline.log 2>&1
-python bench.py --no-cpu-baseline > gpurun_out/r1e_bench2.json 2> gpurun_out/r1e_bench2.err
-tail -c 300 gpurun_out/r1e_bench2.err; head -12 gpurun_out/r1e_trace_streams.log; head -12 gpurun_out/r1e_trace_pipeline.log
+for c in 8 32; do for i in 1 2 3 4 5; do CUDA_DEVICE_MAX_CONNECTIONS=$c python bench.py --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "
+import json,sys,os; d=json.loads(sys.stdin.read()); print('conn', os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS'), round(d['value']), round(d['ms_per_step'],3))"; done; done
