@@ -42,7 +42,7 @@ class TensorCoreTransform:
                         or k[0] != k[1] or m.padding[0] != m.padding[1] or isinstance(m.padding, str) or m.out_channels % 64):
                     return False
             elif type(m) is GDN1:
-                if m.beta.numel() % 64:
+                if m.beta.numel() % 64 or m.beta.numel() > 512:  # (the kernel keeps beta in shared memory: <= 512 channels)
                     return False
             else:
                 return False

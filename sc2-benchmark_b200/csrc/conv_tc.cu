@@ -43,6 +43,8 @@ struct Params {
     TraceSink trace;       // diagnostics (common.cuh)
 };
 
+constexpr int kMaxBeta = 512;  // channels of a GDN layer held in shared memory
+
 template <int N_TILE, int STAGES>
 struct Smem {
     static constexpr int kBBytes = N_TILE * 128;
@@ -50,7 +52,8 @@ struct Smem {
     static constexpr int kRingBytes = STAGES * kStageBytes;
     // full[STAGES], empty[STAGES], xform[STAGES], acc_full[2], acc_empty[2] : 8 bytes each; then the TMEM base address
     static constexpr int kSchedOffset = kRingBytes + (3 * STAGES + 4) * 8 + 16;
-    static constexpr int kTotal = kSchedOffset + kTileSchedBytes;
+    static constexpr int kBetaOffset = (kSchedOffset + kTileSchedBytes + 15) / 16 * 16;  // float[kMaxBeta] (GDN modes)
+    static constexpr int kTotal = kBetaOffset + kMaxBeta * 4;
 };
 
 template <int N_TILE, int STAGES, int MODE>
@@ -80,6 +83,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int trace_tiles = 0;
     TileSched sched;
     sched.bind(smem + L::kSchedOffset, p.tile_counter, total_tiles);
+
+    // GDN modes: beta in shared memory (the epilogue read it with one LDG per element: a third of its instructions)
+    const float *s_beta = reinterpret_cast<const float *>(smem + L::kBetaOffset);
+    if (kGdn)
+        for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) reinterpret_cast<float *>(smem + L::kBetaOffset)[i] = __ldg(p.beta + i);
 
     if (threadIdx.x == 0) {
         sched.init(kGdn ? 13 : 9);  // consumers: MMA warp, 8 epilogue warps (, 4 transform warps)
@@ -209,11 +217,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (kGdn) {
                             const uint4 xv = xpre[kGdn ? ci : 0][c];
                             const __half2 *xh = reinterpret_cast<const __half2 *>(&xv);
+                            const float4 ba = *reinterpret_cast<const float4 *>(s_beta + n0 + c0 + 8 * c);
+                            const float4 bb = *reinterpret_cast<const float4 *>(s_beta + n0 + c0 + 8 * c + 4);
+                            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 xf = __half22float2(xh[e]);
-                                const float b0 = __ldg(p.beta + n0 + c0 + 8 * c + 2 * e);
-                                const float b1 = __ldg(p.beta + n0 + c0 + 8 * c + 2 * e + 1);
+                                const float b0 = bv[2 * e], b1 = bv[2 * e + 1];
                                 if (MODE == MODE_IGDN1_F16) {
                                     f[2 * e] = xf.x * (f[2 * e] + b0);
                                     f[2 * e + 1] = xf.y * (f[2 * e + 1] + b1);
@@ -327,6 +337,7 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
     if (d->mode < 0 || d->mode > 3) return SC2_ERR_INVALID_ARG;
     const bool gdn = d->mode == MODE_IGDN1_F16 || d->mode == MODE_GDN1_F16;
     if (gdn && (!beta || !gdn_x || d->kh != 1 || d->kw != 1 || d->pad != 0 || d->c_in_pad != d->c_out)) return SC2_ERR_INVALID_ARG;
+    if (gdn && d->c_out > kMaxBeta) return SC2_ERR_UNSUPPORTED;
     const int h_out = d->h_in + 2 * d->pad - d->kh + 1, w_out = d->w_in + 2 * d->pad - d->kw + 1;
     if (h_out < 1 || w_out < 1) return SC2_ERR_INVALID_ARG;
     // tile shape: tw columns x th rows, tw * th <= 128

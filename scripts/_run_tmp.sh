@@ -1,2 +1,5 @@
-for c in 8 32; do for i in 1 2 3 4 5; do CUDA_DEVICE_MAX_CONNECTIONS=$c python bench.py --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "
-import json,sys,os; d=json.loads(sys.stdin.read()); print('conn', os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS'), round(d['value']), round(d['ms_per_step'],3))"; done; done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','one_batch_latency_ms')}); print(d['e2e'])
+for k in d['kernels']:
+    if k['stream']=='transform': print(k['kernel'], round(k['avg_launch_ms'],3))"
