@@ -192,6 +192,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-threads', type=int, default=0, help='host threads (one CUDA stream each) driving the e2e steps')
+    ap.add_argument('--max-ahead', type=int, default=4, help='batches the host may run ahead of the GPU beyond the pipeline depth')
     ap.add_argument('--inflight', type=int, default=8, help='depth of the batch pipeline: the serial rANS chains of up to this many batches overlap the convolutions of the others')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
@@ -235,7 +236,7 @@ def main():
     # so steps are software-pipelined (sc2bench_b200/pipeline.py): every g_a / g_s on ONE transform stream in a fixed order,
     # g_a(i + depth) ahead of g_s(i), and the coder of each batch on its own stream in the layout that occupies one SM.
     # Every step does all of its work inside the timed region; the region ends when the pipeline has drained.
-    pipe = s2.pipeline.CodecPipeline(layer, depth=max(1, args.inflight))
+    pipe = s2.pipeline.CodecPipeline(layer, depth=max(1, args.inflight), max_ahead=args.max_ahead)
 
     def run_steps(n, first=0):
         main = torch.cuda.current_stream()
@@ -255,15 +256,19 @@ def main():
     # ---- device-resident throughput ("value") -------------------------------------------------
     with torch.inference_mode():
         # warm-up: at least W steps and at least one step per batch stream (each stream has its own allocator pool)
-        n_warm = max(args.warmup, len(pipe.batch_streams))
+        n_warm = max(args.warmup, 2 * len(pipe.batch_streams) + args.max_ahead)
         run_steps(n_warm)
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
         launches0 = s2.ops.STATS['launches']
+        allocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
+        t_issue = time.perf_counter()
         e0, e1, (streams, out) = run_steps(args.steps, first=n_warm)
+        t_issue = (time.perf_counter() - t_issue) * 1e3
         barrier()
         launches = s2.ops.STATS['launches'] - launches0
+        allocs = torch.cuda.memory_stats(device).get('num_device_alloc', 0) - allocs0
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
         total_bytes = streams.total_bytes()
@@ -420,6 +425,7 @@ def main():
                        'schedule': 'software pipeline: transforms on one stream, g_a(i + depth) ahead of g_s(i); coders on per-batch streams'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
             'serial_ms_per_step': serial_ms, 'one_batch_latency_ms': latency_ms,
+            'host_issue_ms_per_step': t_issue / args.steps, 'cudaMalloc_calls_in_timed_region': allocs,
             'kernel_accounting': 'serial pass of %d steps after the timed region, same kernels (CUDA events per launch); shares are of '
                                  'that serial step, as in the ncu launch list; one_batch_latency_ms uses the warp-per-stream coder' % n_prof,
             'kernels': kernels,

@@ -9,7 +9,10 @@ fixes the order instead:
     transform stream:  g_a(0) g_a(1) ... g_a(d)  g_s(0) g_a(d+1)  g_s(1) g_a(d+2) ...
     batch streams:           coder(0) coder(1) ...          (lane-per-stream layout: a batch's coder is one block)
 
-Results come back in submission order, `depth` submissions late.  Nothing here synchronises the host.
+Results come back in submission order, `depth` submissions late.  The host is held back only so that it stays at most
+`depth + max_ahead` batches ahead of the GPU: left alone it queues the whole run at once, the caching allocator then has to
+cudaMalloc fresh blocks for every batch in flight, and those calls stall the host until the GPU starves (measured: the same
+command ran at 12 k or 43 k images/s depending on who won).
 Needs one hardware queue per stream: CUDA_DEVICE_MAX_CONNECTIONS >= depth + 3 (the package sets 32 at import unless the
 variable is already set); with streams sharing queues a waiting coder kernel blocks the transforms queued behind it.
 """
@@ -33,10 +36,11 @@ class PipelineResult:
 
 
 class CodecPipeline:
-    def __init__(self, layer, depth=8):
+    def __init__(self, layer, depth=8, max_ahead=4):
         if depth < 1:
             raise ValueError('depth must be >= 1')
-        self.layer, self.depth = layer, depth
+        self.layer, self.depth, self.max_ahead = layer, depth, max(0, max_ahead)
+        self._retired = collections.deque()  # ready events of retired batches the GPU may not have finished yet
         device = layer.entropy_bottleneck._quantized_cdf.device
         if device.type != 'cuda':
             raise RuntimeError('CodecPipeline: the sc2bench_b200 hot path runs on CUDA only; move the layer to a GPU')
@@ -49,6 +53,8 @@ class CodecPipeline:
     def submit(self, x):
         """Queues g_a + coder of batch x (a CUDA tensor produced on the current stream).  Returns the PipelineResult of the
         batch submitted `depth` calls earlier, or None while the pipeline fills."""
+        while len(self._retired) > self.max_ahead:  # back-pressure: bounded work (and memory) in flight
+            self._retired.popleft().synchronize()
         s = self.batch_streams[self._submitted % len(self.batch_streams)]
         self._submitted += 1
         s.wait_stream(torch.cuda.current_stream())
@@ -65,6 +71,7 @@ class CodecPipeline:
             features = self.layer.decode_packed(streams, shape)
             ready = torch.cuda.Event()
             ready.record(s)
+        self._retired.append(ready)
         return PipelineResult(streams, shape, features, ready)
 
     def drain(self):
