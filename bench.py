@@ -340,6 +340,7 @@ def main():
         with concurrent.futures.ThreadPoolExecutor(max_workers=n_thr) as pool:
             list(pool.map(e2e_step, range(max(args.warmup, 2 * n_thr))))
             barrier()
+            e2e_allocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
             t0 = time.perf_counter()
             results = list(pool.map(e2e_step, range(2 * n_thr, 2 * n_thr + args.steps)))
             torch.cuda.synchronize()
@@ -354,6 +355,7 @@ def main():
         e2e = {'value': world * B * args.steps / (float(te.item()) / 1e3), 'unit': UNIT,
                'h2d_bytes_per_step': B * IMG[0] * IMG[1] * IMG[2] * 4 + stream_bytes + 8 * (B + 1),
                'd2h_bytes_per_step': stream_bytes + 8 * (B + 1) + 4 + B * 4, 'host_threads': n_thr,
+               'cudaMalloc_calls_in_timed_region': torch.cuda.memory_stats(device).get('num_device_alloc', 0) - e2e_allocs0,
                'ms_per_step': float(te.item()) / args.steps}
 
     if rank != 0:

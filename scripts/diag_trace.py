@@ -116,6 +116,14 @@ for kind, name in ((4, 'encode'), (5, 'decode')):
     cc = c[c['kind'] == kind]
     if len(cc):
         print('%s blocks: %d, mean duration %.2f ms' % (name, len(cc), ((cc['t1'] - cc['t0']).astype(np.float64) / 1e6).mean()))
+# per kernel kind: CTA lifetimes (a persistent CTA lives as long as its kernel)
+for kind, name in ((1, 'conv_tc'), (2, 'conv_split'), (3, 'conv_first')):
+    kk = k[k['kind'] == kind]
+    if len(kk):
+        d = (kk['t1'] - kk['t0']).astype(np.float64) / 1e3
+        live = d[kk['aux'] > 0]
+        print('%-10s CTAs %6d  mean lifetime of working CTAs %7.1f us (p10 %7.1f, p90 %7.1f)  tiles %8d  sum of lifetimes %8.1f ms'
+              % (name, len(kk), live.mean(), np.percentile(live, 10), np.percentile(live, 90), kk['aux'].sum(), d.sum() / 1e3))
 # coarse timeline: per 0.5 ms, mean number of SMs with a conv CTA and number of resident coder blocks
 step = 250  # bins of `res` ns -> 0.5 ms
 print('t(ms)  conv-SMs  coder-blocks  enc dec   (first 40 rows of the steady window)')
