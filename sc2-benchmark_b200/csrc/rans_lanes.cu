@@ -535,15 +535,6 @@ int launch_rans_encode_lanes(const int32_t *symbols, int batch, int64_t n, int64
                              cudaStream_t st) {
     const size_t table_bytes = static_cast<size_t>(n_rows) * cdf_stride * 16;
     const size_t smem = table_bytes <= static_cast<size_t>(kEncStageLimit) ? table_bytes : 0;
-    // The coder runs for milliseconds next to the persistent tensor-core kernels of other batches.  An SM's shared-memory
-    // carve-out cannot change while blocks are resident, so ask for the maximum: a convolution CTA (~200 KB) can then
-    // join an SM on which a coder block already lives.
-    static bool configured = false;
-    if (!configured && std::getenv("SC2_CODER_CARVEOUT")) {
-        SC2_CUDA_TRY(cudaFuncSetAttribute(rans_encode_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
     const int threads = lanes_block_threads(batch);
     rans_encode_lanes_kernel<<<(batch + threads - 1) / threads, threads, smem, st>>>(symbols, batch, static_cast<uint32_t>(n),
                                                                   static_cast<uint32_t>(spatial), tables, arena, slot_bytes,
@@ -558,13 +549,6 @@ int launch_rans_decode_lanes(const uint8_t *packed, const int64_t *offsets, int 
     const size_t smem = kLutBuckets * 4 + kLutBuckets + kSymTab * 4;
     const int threads = lanes_block_threads(batch);
     const int grid = (batch + threads - 1) / threads;
-    static bool configured = false;
-    if (!configured && std::getenv("SC2_CODER_CARVEOUT")) {  // see launch_rans_encode_lanes
-        SC2_CUDA_TRY(cudaFuncSetAttribute(rans_decode_lanes_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        SC2_CUDA_TRY(cudaFuncSetAttribute(rans_decode_lanes_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        SC2_CUDA_TRY(cudaFuncSetAttribute(rans_decode_lanes_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
     const uint32_t un = static_cast<uint32_t>(n), us = static_cast<uint32_t>(spatial);
     if (out_symbols && out_values)
         rans_decode_lanes_kernel<true, true><<<grid, threads, smem, st>>>(packed, offsets, batch, un, us, tables, out_symbols, out_values, means, status, trace_sink());

@@ -216,3 +216,43 @@ def test_forward_matches_oracle_in_training_mode(s2, oracle_compressai):
     ya, la = eb_a(x)
     yb, lb = eb_b(x)
     assert torch.equal(ya, yb) and torch.allclose(la, lb, rtol=0, atol=0)
+
+
+def test_hostbytes_split_and_join_roundtrip(s2):
+    """csrc/hostbytes.c: the contract's list[bytes] <-> one staging buffer (copies run with the GIL released)."""
+    hb = s2._native.hostbytes()
+    rng = np.random.RandomState(3)
+    lens = [8, 12, 0, 49240, 8, 4096]
+    buf = rng.randint(0, 256, size=sum(lens), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    parts = hb.split(buf, offs)
+    assert [len(p) for p in parts] == lens and all(isinstance(p, bytes) for p in parts)
+    assert b''.join(parts) == buf.tobytes()
+    dst = np.zeros(buf.size + 7, dtype=np.uint8)
+    offs2 = np.zeros(len(lens) + 1, dtype=np.int64)
+    assert hb.join(parts, dst, offs2) == buf.size
+    assert (offs2 == offs).all() and (dst[:buf.size] == buf).all() and not dst[buf.size:].any()
+    assert hb.join(tuple(parts), dst[:10], offs2) == -1           # destination too small: nothing is written past it
+    assert hb.split(buf[:0], np.zeros(1, dtype=np.int64)) == []
+    with pytest.raises(TypeError):
+        hb.join([b'12345678', 'not bytes'], dst, offs2)
+    with pytest.raises(ValueError):
+        hb.split(buf, np.array([0, buf.size + 1], dtype=np.int64))  # offsets beyond the buffer
+    with pytest.raises(ValueError):
+        hb.join(parts, dst, np.zeros(2, dtype=np.int64))            # offsets buffer too small
+
+
+def test_coder_layouts_and_throughput_mode_surface(s2):
+    """The coder layout constants of the header match the Python table; the throughput-mode entry points refuse a CPU layer."""
+    header = open(os.path.join(ROOT, 'include', 'sc2b200.h')).read()
+    consts = dict(re.findall(r'#define (SC2_RANS_\w+) (\d+)', header))
+    assert consts == {'SC2_RANS_AUTO': '0', 'SC2_RANS_WARP_PER_STREAM': '1', 'SC2_RANS_LANE_PER_STREAM': '2'}
+    assert s2._native.RANS_LAYOUTS == {None: 0, 'auto': 0, 'warp': 1, 'lanes': 2}
+    assert os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')  # set at import (one hardware queue per stream), unless the user chose
+    layer = s2.get_layer('FPBasedResNetBottleneck', num_bottleneck_channels=8, num_target_channels=64).eval()
+    layer.update()
+    with pytest.raises(RuntimeError, match='CUDA only'):
+        s2.CodecPipeline(layer, depth=2)
+    with pytest.raises(ValueError):
+        s2.CodecPipeline(layer, depth=0)
+    assert layer.use_transform_stream(None) is None and layer.entropy_bottleneck.coder_layout is None
