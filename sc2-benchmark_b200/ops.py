@@ -5,6 +5,7 @@ computation below is a call into libsc2b200.so on the current CUDA stream.  Ther
 a non-CUDA tensor on the hot path raises.
 """
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -71,7 +72,7 @@ class _TileCounters:
     def __init__(self):
         self._blocks = {}
         self._lock = threading.Lock()
-        self.static = bool(int(__import__('os').environ.get('SC2_TC_STATIC', '0')))
+        self.static = bool(int(os.environ.get('SC2_TC_STATIC', '0')))
 
     def next(self):
         if self.static:
