@@ -256,3 +256,29 @@ def test_coder_layouts_and_throughput_mode_surface(s2):
     with pytest.raises(ValueError):
         s2.CodecPipeline(layer, depth=0)
     assert layer.use_transform_stream(None) is None and layer.entropy_bottleneck.coder_layout is None
+
+
+def test_header_is_valid_c_and_struct_layouts_match_ctypes(s2, tmp_path):
+    """include/sc2b200.h compiles as plain C (gcc) and its descriptor structs have the size / field offsets the ctypes mirror
+    in _native.py assumes (the descriptors are passed by pointer across the ABI)."""
+    import subprocess
+    src = tmp_path / 'abi.c'
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "sc2b200.h"
+int main(void) {
+    printf("%zu %zu %zu\\n", sizeof(sc2_conv_desc), offsetof(sc2_conv_desc, in_transform), offsetof(sc2_conv_desc, epi_param));
+    printf("%zu %zu\\n", sizeof(sc2_tc_conv_desc), offsetof(sc2_tc_conv_desc, mode));
+    printf("%zu %zu\\n", sizeof(sc2_tc_split_desc), offsetof(sc2_tc_split_desc, out_c));
+    printf("%d\\n", SC2_ABI_VERSION);
+    return 0;
+}
+''')
+    exe = tmp_path / 'abi'
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    lines = subprocess.check_output([str(exe)]).decode().split('\n')
+    n = s2._native
+    assert lines[0].split() == [str(ctypes.sizeof(n.ConvDesc)), str(n.ConvDesc.in_transform.offset), str(n.ConvDesc.epi_param.offset)]
+    assert lines[1].split() == [str(ctypes.sizeof(n.TcConvDesc)), str(n.TcConvDesc.mode.offset)]
+    assert lines[2].split() == [str(ctypes.sizeof(n.TcSplitDesc)), str(n.TcSplitDesc.out_c.offset)]
+    assert int(lines[3]) == n.load().sc2_abi_version()
