@@ -416,7 +416,7 @@ def main():
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': n_warm,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32 (g_a, exact) / f16 operands with f32 accumulate (g_s) / u64 (coder)',
+            'dtype': 'f32-grade (g_a: split-f16 operands, 3 tensor-core passes, f32 accumulate) / f16 operands with f32 accumulate (g_s) / u64 (coder)',
             'data': 'synthetic',
             'config': {'workload': 'configs[1]: entropic-student-resnet50 FPBasedResNetBottleneck(24,256) encode+rANS+decode, '
                                    '3x224x224, random init, batch %d per GPU' % B,
