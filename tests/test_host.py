@@ -282,3 +282,43 @@ int main(void) {
     assert lines[1].split() == [str(ctypes.sizeof(n.TcConvDesc)), str(n.TcConvDesc.mode.offset)]
     assert lines[2].split() == [str(ctypes.sizeof(n.TcSplitDesc)), str(n.TcSplitDesc.out_c.offset)]
     assert int(lines[3]) == n.load().sc2_abi_version()
+
+
+def test_c_program_links_the_library_and_builds_tables(s2, tmp_path):
+    """A plain C caller (gcc, no Python in between) links libsc2b200.so and runs the host-side entry points the reference's
+    update() needs: sc2_pmf_to_quantized_cdf (vs the oracle) and sc2_rans_build_tables on the result."""
+    import subprocess
+    pmf = np.array([0.02, 0.08, 0.2, 0.4, 0.2, 0.08, 0.02], dtype=np.float32)
+    want = cref.pmf_to_quantized_cdf(pmf, 16)
+    src = tmp_path / 'caller.c'
+    src.write_text('''#include <stdio.h>
+#include <stdlib.h>
+#include "sc2b200.h"
+int main(void) {
+    const float pmf[7] = {0.02f, 0.08f, 0.2f, 0.4f, 0.2f, 0.08f, 0.02f};
+    uint32_t cdf[8];
+    int rc = sc2_pmf_to_quantized_cdf(pmf, 7, 16, cdf);
+    if (rc != SC2_OK) { printf("error %s\\n", sc2_error_string(rc)); return 1; }
+    for (int i = 0; i < 8; ++i) printf("%u ", cdf[i]);
+    printf("\\n");
+    int32_t row[8], size = 8, offset = -3;
+    for (int i = 0; i < 8; ++i) row[i] = (int32_t)cdf[i];
+    size_t bytes = sc2_rans_table_bytes(1, 8);
+    void *blob = malloc(bytes);
+    rc = sc2_rans_build_tables(row, &size, &offset, 1, 8, blob);
+    printf("%d %zu %d\\n", rc, bytes, sc2_abi_version());
+    row[3] = row[2];  /* not strictly increasing: must be refused, not crash */
+    printf("%d\\n", sc2_rans_build_tables(row, &size, &offset, 1, 8, blob));
+    free(blob);
+    return 0;
+}
+''')
+    exe = tmp_path / 'caller'
+    lib_dir = os.path.dirname(s2._native.lib_path())
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                           '-L', lib_dir, '-lsc2b200', '-Wl,-rpath,' + lib_dir])
+    lines = subprocess.check_output([str(exe)]).decode().strip().split('\n')
+    assert [int(v) for v in lines[0].split()] == want.tolist()
+    rc, nbytes, abi = lines[1].split()
+    assert int(rc) == 0 and int(nbytes) >= 8 * 16 and int(abi) == s2._native.load().sc2_abi_version()
+    assert int(lines[2]) < 0
