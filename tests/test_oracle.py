@@ -121,3 +121,34 @@ def test_config1_golden_stream_decodes(g):
     assert len(stream) == 49240
     assert (cref.decode_with_indexes(stream, idx, g['eb24_cdf'], g['eb24_len'], g['eb24_off']) == sym.reshape(-1)).all()
     assert cref.encode_with_indexes(sym.reshape(-1), idx, g['eb24_cdf'], g['eb24_len'], g['eb24_off']) == stream
+
+
+def test_property_random_tables_c_vs_python_and_roundtrip():
+    """hypothesis: random probability tables (through the oracle's own pmf_to_quantized_cdf), random offsets, symbols far
+    into both escape tails -- the two independent restatements produce the same bytes and decode them back."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 4), st.integers(2, 40), st.integers(0, 2 ** 31 - 1), st.integers(1, 200))
+    def check(n_rows, n_sym, seed, n):
+        rng = np.random.RandomState(seed)
+        stride = n_sym + 2
+        cdf = np.zeros((n_rows, stride), dtype=np.int32)
+        ln = np.zeros(n_rows, dtype=np.int32)
+        off = rng.randint(-30, 5, size=n_rows).astype(np.int32)
+        for r in range(n_rows):
+            k = rng.randint(1, n_sym + 1)                    # symbols of this row (ragged rows)
+            pmf = rng.rand(k + 1).astype(np.float32) ** 3     # + the tail-mass entry CompressAI appends; skewed
+            row = cref.pmf_to_quantized_cdf(pmf / pmf.sum(), 16)
+            cdf[r, :row.size] = row
+            ln[r] = row.size
+        scale = float(rng.choice([0.5, 3.0, 50.0, 5000.0]))
+        sym = np.round(rng.randn(n) * scale).astype(np.int32)
+        idx = rng.randint(0, n_rows, size=n).astype(np.int32)
+        s = cref.encode_with_indexes(sym, idx, cdf, ln, off)
+        assert len(s) % 4 == 0 and len(s) >= 8
+        assert s == pyrans.encode_with_indexes(sym.tolist(), idx.tolist(), cdf.tolist(), ln.tolist(), off.tolist())
+        assert (cref.decode_with_indexes(s, idx, cdf, ln, off) == sym).all()
+        assert pyrans.decode_with_indexes(s, idx.tolist(), cdf.tolist(), ln.tolist(), off.tolist()) == sym.tolist()
+
+    check()
