@@ -60,6 +60,7 @@ extern "C" {
 #define SC2_FAULT_ARENA_OVERFLOW 1   /* encoder ran out of its output slot */
 #define SC2_FAULT_STREAM_TRUNCATED 2 /* decoder would read past the end of a stream */
 #define SC2_FAULT_BAD_STREAM 4       /* stream shorter than 8 bytes or not a multiple of 4 */
+#define SC2_FAULT_BAD_INDEX 8        /* a caller-supplied CDF index is outside [0, n_rows): that symbol was coded with row 0 */
 
 typedef void *sc2_stream_t; /* cudaStream_t */
 

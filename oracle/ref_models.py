@@ -3,7 +3,7 @@
 does not exist (the GPU box): bench.py's cpu_baseline / --impl reference legs, __graft_entry__.smoke(),
 GPU parity tests at sizes other than the golden fixtures.
 
-TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see oracle/README.md).  tests/test_oracle_models.py checks, in the
+TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see oracle/README.md).  tests/test_oracle.py checks, in the
 build container, that this restatement equals the reference's real class output for output.
 """
 import os

@@ -42,7 +42,7 @@ SIGNATURES = {
     'sc2_rans_max_stream_bytes': (i64, [i64]),
     'sc2_rans_encode_batch': (i32, [vp, vp, i32, i64, i64, vp, i32, i32, vp, i64, vp, vp, i32, vp]),
     'sc2_rans_pack': (i32, [vp, i64, vp, i32, vp, vp, vp]),
-    'sc2_rans_decode_batch': (i32, [vp, vp, i32, i64, vp, i64, vp, i32, i32, vp, vp, vp, vp, vp]),
+    'sc2_rans_decode_batch': (i32, [vp, vp, i32, i64, vp, i64, vp, i32, i32, vp, vp, vp, vp, i32, vp]),
     'sc2_quantize_symbols': (i32, [vp, vp, vp, i32, i32, i64, vp]),
     'sc2_dequantize': (i32, [vp, vp, vp, i64, vp]),
     'sc2_gc_build_indexes': (i32, [vp, i64, vp, i32, f32, vp, vp]),
@@ -58,7 +58,7 @@ SIGNATURES = {
 }
 
 SC2_OK = 0
-FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM = 1, 2, 4
+FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM, FAULT_BAD_INDEX = 1, 2, 4, 8
 EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 IN_NONE, IN_ABS = 0, 1
 TC_STORE_F16, TC_STORE_F32, TC_IGDN1_F16, TC_GDN1_F16 = 0, 1, 2, 3

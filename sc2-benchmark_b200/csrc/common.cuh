@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/sc2b200.h"
 
 namespace sc2 {
@@ -23,6 +25,20 @@ int cuda_fail(cudaError_t e, const char *where);
     } while (0)
 
 static inline cudaStream_t as_stream(sc2_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: a process that drives several GPUs
+// (nn.DataParallel replicas, a model moved from cuda:0 to cuda:1) must raise it on each of them.  `done` (one static per
+// call site) remembers the device ordinals already configured; safe to call from several host threads.
+template <typename Kernel>
+static inline int ensure_dyn_smem(Kernel *kernel, int bytes, std::atomic<uint64_t> &done) {
+    int dev = 0;
+    SC2_CUDA_TRY(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (dev < 64 && (done.load(std::memory_order_acquire) & bit)) return SC2_OK;
+    SC2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (dev < 64) done.fetch_or(bit, std::memory_order_release);
+    return SC2_OK;
+}
 
 constexpr int kNumSMs = 148;  // B200
 

@@ -283,11 +283,8 @@ static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const Params &p,
     using L = Smem<N_TILE, STAGES>;
     constexpr bool kGdn = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
     const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
-    static bool configured = false;
-    if (!configured) {
-        SC2_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<N_TILE, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};  // per device ordinal
+    if (int rc = ensure_dyn_smem(tc_conv_kernel<N_TILE, STAGES, MODE>, smem, configured)) return rc;
     const int total = p.tiles_x * p.tiles_y * p.n_tiles * p.batch;
     const int grid = total < persistent_grid() ? total : persistent_grid();
     tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kGdn ? 448 : 320, smem, st>>>(ma, mb, p);

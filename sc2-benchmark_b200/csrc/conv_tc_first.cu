@@ -315,11 +315,8 @@ template <int N_TILE>
 static int launch(const CUtensorMap *maps, const Params &p, cudaStream_t st) {
     using L = Smem<N_TILE>;
     const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
-    static bool configured = false;
-    if (!configured) {
-        SC2_CUDA_TRY(cudaFuncSetAttribute(tc_first_layer_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};  // per device ordinal
+    if (int rc = ensure_dyn_smem(tc_first_layer_kernel<N_TILE>, smem, configured)) return rc;
     const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.batch * 4;
     if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
     const int grid = total < persistent_grid() ? static_cast<int>(total) : persistent_grid();

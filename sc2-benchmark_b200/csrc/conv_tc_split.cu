@@ -425,11 +425,8 @@ static int launch(const CUtensorMap *maps, const Params &p, int images, cudaStre
     const CUtensorMap &mah = maps[0], &mal = maps[1], &mbh = maps[2], &mbl = maps[3];
     using L = Smem<N_TILE, STAGES, B_RES>;
     const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
-    static bool configured = false;
-    if (!configured) {
-        SC2_CUDA_TRY(cudaFuncSetAttribute(tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};  // per device ordinal
+    if (int rc = ensure_dyn_smem(tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES>, smem, configured)) return rc;
     const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * images;
     if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
     const int grid = total < persistent_grid() ? static_cast<int>(total) : persistent_grid();

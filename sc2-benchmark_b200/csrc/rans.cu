@@ -120,7 +120,13 @@ rans_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restric
         if (lane < cnt) {
             const int64_t i = hi - 1 - lane;
             const int32_t v_in = __ldg(sym + i);
-            const int row = kExplicitIndex ? __ldg(idx + i) : static_cast<int>(i / spatial);
+            int row = kExplicitIndex ? __ldg(idx + i) : static_cast<int>(i / spatial);
+            if (kExplicitIndex && static_cast<uint32_t>(row) >= static_cast<uint32_t>(t.n_rows)) {
+                // caller-supplied CDF index out of range (EntropyModel.compress(inputs, indexes) forwards arbitrary tensors):
+                // flag it and code the symbol with row 0 instead of reading outside the tables
+                atomicOr(status, SC2_FAULT_BAD_INDEX);
+                row = 0;
+            }
             const int32_t max_value = __ldg(t.sizes + row) - 2;
             int32_t value = v_in - __ldg(t.offsets + row);
             uint32_t raw = 0;
@@ -315,7 +321,11 @@ rans_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restrict
         int32_t my_value = 0;
         float my_mean = 0.0f;
         for (int j = 0; j < cnt; ++j) {
-            const int r = kExplicitIndex ? __shfl_sync(0xffffffffu, my_row, j) : static_cast<int>((base + j) / spatial);
+            int r = kExplicitIndex ? __shfl_sync(0xffffffffu, my_row, j) : static_cast<int>((base + j) / spatial);
+            if (kExplicitIndex && static_cast<uint32_t>(r) >= static_cast<uint32_t>(t.n_rows)) {  // (uniform) see the encoder
+                if (lane == 0) atomicOr(status, SC2_FAULT_BAD_INDEX);
+                r = 0;
+            }
             if (r != row) {  // uniform branch: (re)load this lane's slice of the row
                 row = r;
                 drow = dec + static_cast<int64_t>(row) * t.dec_stride;

@@ -455,11 +455,8 @@ int launch_rans_encode_fast(const int32_t *symbols, int batch, int64_t n, int64_
     size_t smem = 64 * 16;
     const size_t table_bytes = static_cast<size_t>(n_rows) * cdf_stride * 16;
     if (table_bytes + smem <= 96 * 1024) smem += table_bytes;
-    static bool configured = false;
-    if (!configured) {
-        SC2_CUDA_TRY(cudaFuncSetAttribute(rans_encode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};  // per device ordinal
+    if (int rc = ensure_dyn_smem(rans_encode_fast_kernel, 100 * 1024, configured)) return rc;
     rans_encode_fast_kernel<<<batch, 32, smem, st>>>(symbols, batch, static_cast<uint32_t>(n), static_cast<uint32_t>(spatial),
                                                       tables, arena, slot_bytes, lengths, status);
     SC2_LAUNCH_CHECK("rans_encode_fast_kernel");
@@ -472,11 +469,8 @@ int launch_rans_decode_fast(const uint8_t *packed, const int64_t *offsets, int b
     size_t smem = (kRingWords + 32) * 4;
     const size_t table_bytes = static_cast<size_t>(n_rows) * ((cdf_stride + 31) / 32 * 32) * 4;
     if (table_bytes + smem <= 96 * 1024) smem += table_bytes;
-    static bool configured = false;
-    if (!configured) {
-        SC2_CUDA_TRY(cudaFuncSetAttribute(rans_decode_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};  // per device ordinal
+    if (int rc = ensure_dyn_smem(rans_decode_fast_kernel, 100 * 1024, configured)) return rc;
     rans_decode_fast_kernel<<<batch, 32, smem, st>>>(packed, offsets, batch, static_cast<uint32_t>(n),
                                                       static_cast<uint32_t>(spatial), tables, out_symbols, out_values, means, status);
     SC2_LAUNCH_CHECK("rans_decode_fast_kernel");

@@ -12,6 +12,7 @@ off the hot path and stay plain torch ops.  Tables are always built on the host 
 bit-reproducible (checkpoints carry them as buffers anyway).
 """
 import math
+import threading
 
 import numpy as np
 import torch
@@ -19,6 +20,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+
+_FAULT_LOCK = threading.Lock()
 
 
 class _LowerBoundFn(torch.autograd.Function):
@@ -294,23 +297,40 @@ class EntropyBottleneck(EntropyModel):
     def compress(self, x):
         return self.compress_packed(x).tolist()
 
+    def _fault_word(self, device):
+        """One persistent int32 per device that every unchecked decode of this module ORs its fault flags into: batches in
+        flight (several streams / host threads) share it, so no fault is overwritten by a later batch."""
+        words = self.__dict__.setdefault('_fault_words', {})
+        w = words.get(device)
+        if w is None:
+            with _FAULT_LOCK:
+                w = words.get(device)
+                if w is None:
+                    with torch.inference_mode(False):
+                        w = torch.zeros(1, dtype=torch.int32, device=device)
+                    words[device] = w
+        return w
+
     def decompress_packed(self, streams, size, want='values', check_status=False):
         """Device-resident decode.  With check_status=False (default) nothing synchronises: device fault flags
-        (truncated / malformed stream) stay in `self.last_decode_status` and are raised by `check_faults()`."""
+        (truncated / malformed stream) accumulate in a per-device fault word and are raised by `check_faults()`."""
         tables = self.coder_tables()
         C = self._quantized_cdf.size(0)
         spatial = int(np.prod(size)) if len(size) else 1
         medians = self._get_medians().detach().reshape(-1)
-        out, self.last_decode_status = ops.rans_decode(streams, C * spatial, tables, spatial=spatial, means=medians, want=want,
-                                                       check_status=check_status, return_status=True,
-                                                       layout=getattr(self, 'coder_layout', None))
+        status = None if check_status else self._fault_word(streams.packed.device)
+        out = ops.rans_decode(streams, C * spatial, tables, spatial=spatial, means=medians, want=want, check_status=check_status,
+                              layout=getattr(self, 'coder_layout', None), status=status)
         return out.view(streams.batch, C, *size)
 
     def check_faults(self):
-        """Synchronises and raises if the last device-resident decode flagged a truncated or malformed stream."""
-        st = getattr(self, 'last_decode_status', None)
-        if st is not None:
-            ops.raise_on_decode_fault(int(st.item()))
+        """Synchronises and raises if any device-resident decode since the last call flagged a truncated or malformed stream."""
+        for dev, w in list(self.__dict__.get('_fault_words', {}).items()):
+            torch.cuda.synchronize(dev)
+            st = int(w.item())
+            if st:
+                w.zero_()
+                ops.raise_on_decode_fault(st)
 
     def decompress(self, strings, size):
         if not isinstance(strings, (tuple, list)):

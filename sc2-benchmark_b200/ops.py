@@ -191,37 +191,41 @@ class PackedStreams:
 
     def __init__(self, packed, offsets, batch, status=None, capacity=None):
         self.packed, self.offsets, self.batch, self.status = packed, offsets, batch, status
-        self._host = None
+        self._offs = None
+        # The streams are complete once the PRODUCING stream reaches this point (the coder / the upload may run on a batch
+        # stream of CodecPipeline while the consumer reads them from another stream): host-side readers wait on this event.
+        self.ready = torch.cuda.Event()
+        self.ready.record(torch.cuda.current_stream(packed.device))
 
-    def _to_host(self):
-        if self._host is None:
-            # Wait for the coder with a stream synchronise FIRST: a blocking copy to pageable memory (.cpu(), .item()) holds
-            # a driver lock while it waits for the GPU, and every other host thread's event record / stream wait then
-            # blocks behind it for milliseconds (measured: scripts/diag_e2e_calls.py).
-            torch.cuda.current_stream(self.packed.device).synchronize()
+    def _host_offsets(self):
+        if self._offs is None:
+            # Wait with an event synchronise FIRST: a blocking copy to pageable memory (.cpu(), .item()) holds a driver lock
+            # while it waits for the GPU, and every other host thread's event record / stream wait then blocks behind it for
+            # milliseconds (measured: scripts/diag_e2e_calls.py).
+            self.ready.synchronize()
             offs = self.offsets.cpu()
-            if self.status is not None and int(self.status.item()) & _native.FAULT_ARENA_OVERFLOW:
-                raise RuntimeError('rANS encoder ran out of arena space (device fault flag)')
-            total = int(offs[-1])
-            host = _PINNED.get_d2h(total)
-            host.copy_(self.packed[:total], non_blocking=False)
-            self._host = (offs.numpy(), host.numpy())
-        return self._host
+            if self.status is not None:
+                st = int(self.status.item())
+                if st & _native.FAULT_ARENA_OVERFLOW:
+                    raise RuntimeError('rANS encoder ran out of arena space (device fault flag)')
+                if st & _native.FAULT_BAD_INDEX:
+                    raise ValueError('Invalid `indexes`: a CDF index is outside [0, number of CDF rows)')
+            self._offs = np.ascontiguousarray(offs.numpy(), dtype=np.int64)
+        return self._offs
 
     def tolist(self):
-        offs, data = self._to_host()
-        # one copy per stream, straight out of the (per-thread, reused) pinned staging buffer, with the GIL released
-        out = _native.hostbytes().split(data, np.ascontiguousarray(offs, dtype=np.int64))
-        self._host = (offs, None)  # the staging buffer is reused by the next call
-        return out
+        offs = self._host_offsets()
+        total = int(offs[-1])
+        host = _PINNED.get_d2h(total)  # per-thread staging buffer, reused by the next call: nothing of it is cached here
+        host.copy_(self.packed[:total], non_blocking=False)  # (the producing stream has finished: _host_offsets waited)
+        # one copy per stream, straight out of the pinned staging buffer, with the GIL released
+        return _native.hostbytes().split(host.numpy(), offs)
 
     def lengths(self):
-        offs = self._host[0] if self._host is not None else self.offsets.cpu().numpy()
-        return np.diff(offs)
+        return np.diff(self._host_offsets())
 
     def total_bytes(self):
-        offs = self._host[0] if self._host is not None else self.offsets.cpu().numpy()
-        return int(offs[-1])
+        return int(self._host_offsets()[-1])
 
     @staticmethod
     def from_list(strings, device):
@@ -314,13 +318,16 @@ def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None, la
 
 def raise_on_decode_fault(st):
     if st:
+        if st & _native.FAULT_BAD_INDEX:
+            raise ValueError('Invalid `indexes`: a CDF index is outside [0, number of CDF rows) (device fault flags 0x%x)' % st)
         raise ValueError('Invalid bitstream (device fault flags 0x%x: %s)' % (st, ', '.join(
             name for bit, name in ((2, 'stream truncated'), (4, 'bad stream length')) if st & bit)))
 
 
 def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means=None, want='values', check_status=True,
-                return_status=False, layout=None):
-    """PackedStreams -> [B, n] float32 (symbol + means[row]) or int32 symbols."""
+                return_status=False, layout=None, status=None):
+    """PackedStreams -> [B, n] float32 (symbol + means[row]) or int32 symbols.  `status`: a caller-owned int32 fault word the
+    kernel ORs its flags into (several decodes may share one); default: a fresh zeroed word."""
     dev = streams.packed.device
     B = streams.batch
     idx = None
@@ -334,7 +341,8 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
     out_sym = torch.empty((B, n_per_stream), dtype=torch.int32, device=dev) if want == 'symbols' else None
     out_val = torch.empty((B, n_per_stream), dtype=torch.float32, device=dev) if want == 'values' else None
     m = means.contiguous().float() if means is not None else None
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
     tab = tables.on(dev)
     with torch.cuda.device(dev), _launch('rans_decode', 1 if B and n_per_stream else 0):
         check(_lib().sc2_rans_decode_batch(_ptr(streams.packed), _ptr(streams.offsets), B, n_per_stream, _ptr(idx),
@@ -342,7 +350,7 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
                                            _ptr(out_val), _ptr(m), _ptr(status), _native.RANS_LAYOUTS[layout], _stream_ptr()),
               'sc2_rans_decode_batch')
     if check_status:
-        torch.cuda.current_stream(dev).synchronize()  # (not a blocking copy: see PackedStreams._to_host)
+        torch.cuda.current_stream(dev).synchronize()  # (not a blocking copy: see PackedStreams._host_offsets)
         raise_on_decode_fault(int(status.item()))
     out = out_sym if want == 'symbols' else out_val
     return (out, status) if return_status else out

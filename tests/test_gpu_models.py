@@ -11,7 +11,29 @@ import cref
 from helpers import rel_err
 
 pytestmark = pytest.mark.gpu
-FEATURE_TOL = 1e-3
+FEATURE_TOL = 1e-3   # decoded features / x_hat, max-abs over max-abs (north_star)
+LATENT_TOL = 1e-4    # analysis-transform latents, max-abs over max-abs (north_star)
+
+
+def symbol_budget(n_symbols):
+    """north_star: symbol mismatches from fp32 rounding ties must stay below 1e-6 of the symbols.  For samples smaller than
+    10^6 symbols that is a budget of less than one symbol; one is allowed (a tie is a property of the input, not of the size)."""
+    return max(1, int(np.ceil(1e-6 * n_symbols)))
+
+
+def _torch_seq(seq, x):
+    """Runs an nn.Sequential of this package layer by layer with plain torch CPU ops (the product's GDN modules compute with
+    the differentiable torch branch when gradients are enabled; here the formula is applied directly)."""
+    import torch.nn.functional as F
+    for m in seq:
+        if hasattr(m, 'effective_params'):
+            gamma, beta = m.effective_params()
+            C = beta.numel()
+            norm = F.conv2d(m._norm_input(x), gamma.reshape(C, C, 1, 1), beta)
+            x = m._apply_norm(x, norm)
+        else:
+            x = m(x)
+    return x
 
 
 @pytest.fixture(scope='module')
@@ -54,7 +76,13 @@ def test_neural_input_compression_classifier_q8(s2, oracle_compressai, arch):
         logits = model(x.to(dev))
     assert logits.shape == (2, 10) and len(model.analyzers[0].file_size_list) == 1
     assert len(got_obj['strings']) == len(want_obj['strings']) and tuple(got_obj['shape']) == tuple(want_obj['shape'])
-    # the last string list is the EntropyBottleneck stream (y for factorized, z for the hyperprior): decode both sides' bytes
+    # (1) analysis-transform latents: 1e-4 relative (north_star), whatever the symbols do
+    with torch.inference_mode():
+        y_got = s2.models.run_transform(codec.g_a, xp.to(dev)).cpu()
+        y_want = ref.g_a(xp)
+    assert rel_err(y_got, y_want) < LATENT_TOL
+    # (2) the last string list is the EntropyBottleneck stream (y for factorized, z for the hyperprior): decode both sides'
+    # bytes with the oracle coder; symbol mismatches (fp32 rounding ties) have a budget of 1e-6 of the symbols, at least one
     eb = ref.entropy_bottleneck
     cdf, ln, off = eb._quantized_cdf.numpy(), eb._cdf_length.numpy(), eb._offset.numpy()
     C = cdf.shape[0]
@@ -63,20 +91,19 @@ def test_neural_input_compression_classifier_q8(s2, oracle_compressai, arch):
     s_want = _decode_symbols(want_obj['strings'][-1], cdf, ln, off, idx)
     s_got = _decode_symbols(got_obj['strings'][-1], cdf, ln, off, idx)
     mism = int((s_want != s_got).sum())
-    assert mism <= max(2, s_want.size // 100000), 'symbol mismatches vs oracle: %d of %d' % (mism, s_want.size)
-    if mism == 0:
-        assert got_obj['strings'][-1] == want_obj['strings'][-1]  # identical symbols -> identical bytes
-    if arch.endswith('factorized'):
-        assert rel_err(got.cpu(), want) < FEATURE_TOL
-    else:
-        # a flipped z symbol changes the scales of a whole neighbourhood: compare only when z agrees exactly
-        if mism == 0:
-            assert rel_err(got.cpu(), want) < 5e-3
-        assert float(got.min()) >= 0 and float(got.max()) <= 1
-    # the decoder side accepts the ORACLE's bytes (cross-implementation decode)
+    assert mism <= symbol_budget(s_want.size), 'symbol mismatches vs oracle: %d of %d' % (mism, s_want.size)
+    # (3) the coder is bit-exact on ITS symbols, always: the oracle coder re-encodes the decoded symbols to the same bytes
+    for b, stream in enumerate(got_obj['strings'][-1]):
+        assert stream == cref.encode_with_indexes(s_got[b], idx, cdf, ln, off)
+    # (4) decoder parity on this implementation's own streams: the ORACLE decodes them (for the hyperprior that includes
+    # h_s + build_indexes + the Gaussian-conditional decode of y with the oracle's own indexes) ...
     with torch.inference_mode():
+        oracle_on_got = ref.decompress(**got_obj)['x_hat']
         cross = codec.decompress(**want_obj)['x_hat']
+    assert rel_err(got.cpu(), oracle_on_got) < FEATURE_TOL
+    # (5) ... and this implementation decodes the ORACLE's bytes (cross-implementation decode)
     assert rel_err(cross.cpu(), want) < FEATURE_TOL
+    assert float(got.min()) >= 0 and float(got.max()) <= 1
 
 
 def test_feature_extraction_backbone_coco_shape(s2):
@@ -111,9 +138,9 @@ def test_feature_extraction_backbone_coco_shape(s2):
     idx = np.repeat(np.arange(24, dtype=np.int32), 199 * 335)
     got_sym = cref.decode_with_indexes(enc['strings'][0][0], idx, cdf, ln, off).reshape(1, 24, 199, 335)
     mism = int((got_sym != want_sym.numpy()).sum())
-    assert mism <= 2, 'symbol mismatches vs oracle at COCO shape: %d of %d' % (mism, got_sym.size)
-    if mism == 0:
-        assert enc['strings'][0][0] == cref.encode_with_indexes(want_sym.numpy().reshape(-1), idx, cdf, ln, off)
+    assert mism <= symbol_budget(got_sym.size), 'symbol mismatches vs oracle at COCO shape: %d of %d' % (mism, got_sym.size)
+    # the coder is bit-exact on its symbols, always (1.6 M-symbol stream)
+    assert enc['strings'][0][0] == cref.encode_with_indexes(got_sym.reshape(-1), idx, cdf, ln, off)
     with torch.inference_mode():
         med = eb._get_medians().detach().reshape(1, -1, 1, 1)
         want_feat = oracle.decoder(torch.from_numpy(got_sym).float() + med)
@@ -155,15 +182,6 @@ def test_shp_bottleneck_and_entropy_bottleneck_layer_vs_reference(s2, oracle_com
     shp.eval()
     shp.update()
     assert shp.updated and tuple(shp.gaussian_conditional._quantized_cdf.shape) == (64, 3133)
-    ref = None
-    if os.path.isdir('/root/reference'):
-        sys.path.insert(0, '/root/reference')
-        sys.path.append(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', 'shim'))
-        from sc2bench.models.layer import get_layer as ref_get_layer
-        ref = ref_get_layer('SHPBasedResNetBottleneck', num_latent_channels=16, num_bottleneck_channels=24, num_target_channels=256)
-        ref.load_state_dict(shp.state_dict())
-        ref.eval()
-        ref.update()
     shp.to(dev)
     torch.manual_seed(4)
     x = torch.randn(2, 3, 224, 224)
@@ -171,14 +189,51 @@ def test_shp_bottleneck_and_entropy_bottleneck_layer_vs_reference(s2, oracle_com
         enc = shp.encode(x.to(dev))
         dec = shp.decode(**enc)
     assert len(enc['strings']) == 2 and all(len(l) == 2 for l in enc['strings']) and dec.shape == (2, 256, 56, 56)
-    if ref is not None:
-        with torch.inference_mode():
-            want = ref.encode(x)
-            want_dec = ref.decode(**want)
-        assert tuple(want['shape']) == tuple(enc['shape'])
-        if want['strings'][1] == enc['strings'][1]:  # identical z -> identical scales -> y must match too
-            assert want['strings'][0] == enc['strings'][0]
-            assert rel_err(dec.cpu(), want_dec) < FEATURE_TOL
+    # Oracle pipeline for SHPBasedResNetBottleneck.encode / decode (sc2bench/models/layer.py:631-666), runnable on the GPU box:
+    # the module's own layers as plain torch CPU ops + the restated CompressAI entropy models + the C coder.
+    import copy
+    from compressai.entropy_models import GaussianConditional as OracleGC
+    cpu = copy.deepcopy(shp).cpu()
+    oeb = OracleEB(16)
+    oeb.load_state_dict({k: v.cpu() for k, v in shp.entropy_bottleneck.state_dict().items() if not k.startswith('_')}, strict=False)
+    oeb.update()
+    ogc = OracleGC(None)
+    ogc.update_scale_table(s2.models.get_scale_table())
+    assert torch.equal(oeb._quantized_cdf, shp.entropy_bottleneck._quantized_cdf.cpu())
+    assert torch.equal(ogc._quantized_cdf, shp.gaussian_conditional._quantized_cdf.cpu())
+    with torch.inference_mode():
+        y = _torch_seq(cpu.g_a, x)
+        z = _torch_seq(cpu.h_a, y.abs())
+        z_want = oeb.compress(z)
+        z_hat = oeb.decompress(z_want, z.shape[-2:])
+        idx_want = ogc.build_indexes(_torch_seq(cpu.h_s, z_hat))
+    # z symbols: decode this implementation's z bytes with the oracle coder
+    zc, zl, zo = oeb._quantized_cdf.numpy(), oeb._cdf_length.numpy(), oeb._offset.numpy()
+    zidx = np.repeat(np.arange(16, dtype=np.int32), int(np.prod(z.shape[-2:])))
+    z_got = _decode_symbols(enc['strings'][1], zc, zl, zo, zidx)
+    z_ref = _decode_symbols(z_want, zc, zl, zo, zidx)
+    mism_z = int((z_got != z_ref).sum())
+    assert mism_z <= symbol_budget(z_ref.size), 'z symbol mismatches: %d of %d' % (mism_z, z_ref.size)
+    for b in range(2):
+        assert enc['strings'][1][b] == cref.encode_with_indexes(z_got[b], zidx, zc, zl, zo)
+    # y symbols: the oracle's indexes (from the ORACLE's z_hat: valid when z agrees, which the budget above allows to fail for
+    # at most one symbol -- then the y comparison is meaningless and the z assertion message says why)
+    assert mism_z == 0, 'a z symbol flipped (fp32 tie, within budget): rerun with another seed to compare y'
+    gc_cdf, gc_len, gc_off = ogc._quantized_cdf.numpy(), ogc._cdf_length.numpy(), ogc._offset.numpy()
+    y_want = torch.round(y).int().numpy()
+    mism_y = 0
+    for b in range(2):
+        yi = idx_want[b].reshape(-1).int().numpy()
+        y_got = cref.decode_with_indexes(enc['strings'][0][b], yi, gc_cdf, gc_len, gc_off)
+        mism_y += int((y_got != y_want[b].reshape(-1)).sum())
+        assert enc['strings'][0][b] == cref.encode_with_indexes(y_got, yi, gc_cdf, gc_len, gc_off)
+    assert mism_y <= symbol_budget(y_want.size), 'y symbol mismatches: %d of %d' % (mism_y, y_want.size)
+    with torch.inference_mode():
+        want_dec = _torch_seq(cpu.g_s, torch.from_numpy(y_want).float())
+    if mism_y == 0:
+        assert rel_err(dec.cpu(), want_dec) < FEATURE_TOL
+    else:  # one flipped y symbol moves a 3x3 neighbourhood of the features: compare everything else
+        assert float(((dec.cpu() - want_dec).abs() > FEATURE_TOL * want_dec.abs().max()).float().mean()) < 1e-4
 
 
 def test_entropic_classifier_wrapper(s2, oracle_compressai):

@@ -322,3 +322,41 @@ int main(void) {
     rc, nbytes, abi = lines[1].split()
     assert int(rc) == 0 and int(nbytes) >= 8 * 16 and int(abi) == s2._native.load().sc2_abi_version()
     assert int(lines[2]) < 0
+
+
+def _header_prototypes():
+    """{name: [parameter type strings]} for every SC2_API function include/sc2b200.h declares."""
+    import re
+    text = open(os.path.join(ROOT, 'include', 'sc2b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'SC2_API\s+[\w\s\*]+?\b(sc2_\w+)\s*\(([^;]*?)\)\s*;', text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace('\n', ' ').split(',')]
+        protos[m.group(1)] = [] if params == ['void'] else params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header(s2):
+    """Every function the header declares is bound in _native.SIGNATURES with the same NUMBER of parameters and the same
+    pointer / integer / float class per parameter (a mismatch works by accident under cdecl until it does not), and the
+    library exports every one of them."""
+    protos = _header_prototypes()
+    sigs = s2._native.SIGNATURES
+    assert set(protos) == set(sigs), set(protos) ^ set(sigs)
+    lib = s2._native.load()
+    for name, params in protos.items():
+        assert hasattr(lib, name), name
+        argtypes = sigs[name][1]
+        assert len(argtypes) == len(params), '%s: header has %d parameters, ctypes %d' % (name, len(params), len(argtypes))
+        for p, a in zip(params, argtypes):
+            is_ptr = '*' in p or 'sc2_stream_t' in p
+            if is_ptr:
+                assert a is ctypes.c_void_p or a is ctypes.c_char_p or hasattr(a, 'contents'), (name, p, a)
+            elif 'float' in p:
+                assert a is ctypes.c_float, (name, p, a)
+            elif 'int64_t' in p:
+                assert a is ctypes.c_int64, (name, p, a)
+            elif 'size_t' in p:
+                assert a is ctypes.c_size_t, (name, p, a)
+            else:
+                assert a is ctypes.c_int, (name, p, a)
