@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 3
+#define SC2_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -223,6 +223,24 @@ SC2_API int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, cons
                               const void *w_lo, const float *beta, const float *medians, const void *gdn_x_hi,
                               const void *gdn_x_lo, void *out_hi, void *out_lo, int32_t *out_sym, int32_t *tile_counter,
                               sc2_stream_t stream);
+
+/* Device: stride-2 convolution + GDN1 back to back in one kernel (conv_ga_halo.cu), fp32-grade split fp16: the middle of g_a
+ * (sc2bench/models/layer.py:479-481, Conv2d(k5, s2, p2) -> GDN1).  The conv accumulators never leave the SM: |x| becomes the
+ * A operand of the 1x1 gamma GEMM in shared memory, y = x / (beta + gamma.|x|) leaves as split planes.
+ *   x_hi/x_lo     PARITY PLANES [images * 4, h_in, w_in, c_in] (as for sc2_tc_split_conv, stride 2)
+ *   w_stack       [kh*kw, 2n, c_in] fp16: per tap, rows [0, n) = hi and rows [n, 2n) = lo of the weights, n = sc2_ga_halo_n(c_out)
+ *   gamma_stack   [2n, n] fp16: the effective gamma [c_out, c_out] packed the same way (zero padded)
+ *   out_hi/out_lo [images, h_out, w_out, out_c] split planes, out_c = c_out rounded up to 8 */
+typedef struct sc2_ga_halo_desc {
+    int images, h_in, w_in, c_in;
+    int c_out, kh, kw, pad;
+    int h_out, w_out, out_c;
+} sc2_ga_halo_desc;
+
+SC2_API int sc2_ga_halo_n(int c_out);
+SC2_API int sc2_ga_halo_conv_gdn(const sc2_ga_halo_desc *d, const void *x_hi, const void *x_lo, const void *w_stack,
+                                 const void *gamma_stack, const float *beta, void *out_hi, void *out_lo, int32_t *tile_counter,
+                                 sc2_stream_t stream);
 
 /* Device: im2col of an fp32 NCHW image for the first (c_in = 3) layer: split fp16 patches, K = (c, dy, dx) zero-padded
  * to k_pad, pixels in parity-plane order [batch * 4, h_out/2, w_out/2, k_pad] (h_out, w_out must be even). */

@@ -29,6 +29,11 @@ class TcSplitDesc(_c.Structure):
                                     'h_out', 'w_out', 'out_c')]
 
 
+class GaHaloDesc(_c.Structure):
+    """struct sc2_ga_halo_desc"""
+    _fields_ = [(n, i32) for n in ('images', 'h_in', 'w_in', 'c_in', 'c_out', 'kh', 'kw', 'pad', 'h_out', 'w_out', 'out_c')]
+
+
 # name -> (restype, argtypes): every symbol include/sc2b200.h declares
 SIGNATURES = {
     'sc2_abi_version': (i32, []),
@@ -53,6 +58,8 @@ SIGNATURES = {
     'sc2_nchw_f32_to_nhwc_f16': (i32, [vp, vp, i32, i32, i64, i32, vp]),
     'sc2_tc_split_n_tile': (i32, [i32]),
     'sc2_tc_split_conv': (i32, [_c.POINTER(TcSplitDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sc2_ga_halo_n': (i32, [i32]),
+    'sc2_ga_halo_conv_gdn': (i32, [_c.POINTER(GaHaloDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'sc2_patchify_split': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'sc2_tc_first_layer': (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
 }
@@ -85,7 +92,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sc2_abi_version() != 3:
+    if lib.sc2_abi_version() != 4:
         raise ImportError('libsc2b200.so ABI version mismatch: rebuild with sc2-benchmark_b200/build.py --force')
     _lib = lib
     return lib

@@ -1,0 +1,537 @@
+// conv_ga_halo.cu -- stride-2 convolution + GDN1, back to back in ONE kernel, fp32-grade on the tcgen05 tensor cores.
+//
+// This is the middle of the analysis transform g_a (sc2bench/models/layer.py:479-481: Conv2d(4b -> 2b, k5, s2, p2) followed by
+// GDN1(2b)), the kernel that bounded the pipelined step in round 1 (K3: 25 shifted TMA boxes per tile re-read every input pixel
+// 4.4x from L2; GDN1 was a second launch that re-read the activation from HBM).  What changed:
+//
+//   HALO TILES   The input is stored as four parity planes (plane py*2+px holds input pixel (2Y+py, 2X+px)), so every tap of the
+//                stride-2 convolution is a unit-stride shift of ONE plane.  Per (plane, 64-channel chunk) the CTA loads ONE halo
+//                tile {64 ch, P px, th+2 rows} with TMA (128-byte pixel rows, SWIZZLE_128B) and forms the A operand of tap
+//                (sy, sx) by shifting the UMMA descriptor's start address by (sy * P + sx) rows: the tile is a flat array of
+//                pixel rows whose pitch P (16 / 32 / 64) equals the GEMM tile's row pitch, so "tile row m -> pixel row m + shift"
+//                holds for all 128 rows (the P - tw rightmost columns of each tile row are junk and are never stored).
+//                Hardware fact behind it (profiles/r2a_umma_shift_experiment.log): the 128-byte swizzle is a function of the
+//                absolute shared-memory address, so a descriptor may start at any multiple of 128 bytes (base_offset = 0).
+//   STACKED B    fp32-grade = split fp16: a = hi + lo / 2048, dot = sum hi.hi + (sum hi.lo + sum lo.hi) / 2048.  An MMA with a
+//                narrow N is bound by reading its A operand from shared memory (measured: cycles ~ (4096 + 32 N) / 128 + 10), so
+//                the weights are packed [hi rows; lo rows] and ONE N = 2n MMA computes hi.hi and hi.lo from a single read of
+//                A_hi; a second N = n MMA adds lo.hi.  150 -> 115 cycles per K step for n = 48.
+//   GDN EPILOGUE The conv accumulators leave TMEM once: x (fp32) stays in registers, |x| is split to (hi, lo) fp16 and written to
+//                shared memory as the A operand of the 1x1 "gamma" GEMM (weights resident), whose accumulator comes back as
+//                norm - beta; y = x / norm is split again and leaves through a staged TMA store.  x never visits HBM.
+//
+// Accumulation: tcgen05 adds into fp32 accumulators with truncation; the hi.hi sum over K = 25 * 96 is dealt round-robin over
+// `groups` accumulators that the epilogue adds in fp32.
+#include "tc_common.cuh"
+
+namespace sc2 {
+namespace gah {
+
+using namespace sc2::tc;
+
+constexpr int kThreads = 384;  // warp 0: A (halo) producer + tile scheduler; 1: MMA issuer; 2: B (weights) producer; 3: idle; 4..11: epilogue
+constexpr int kMaxTaps = 25;
+constexpr int kMaxB = 8;
+constexpr float kLoScale = 2048.0f;
+constexpr float kLoInv = 1.0f / 2048.0f;
+
+struct Tap {
+    int8_t plane, sx, sy, group;  // sx, sy in [0, 2]: halo shift of this tap (pixel offset + 1)
+    int8_t widx, first, pad0_, pad1_;  // widx: tap index in the packed weights; first: first tap of its accumulator group
+};
+
+struct Params {
+    int tiles_x, tiles_y, images;
+    int tw, th, pitch_log2;  // tile = th rows x tw valid columns of output pixels; pitch = 1 << pitch_log2 pixel rows per halo row
+    int n_taps;
+    Tap taps[kMaxTaps];
+    int k_chunks, k_steps_last;  // 64-channel chunks of the input, K steps (of 16) in the last one
+    int groups;
+    int c_out, out_c, stage_c;
+    int stage_plane;  // bytes of one staging plane (hi or lo): th * tw * stage_c * 2 rounded up to 128
+    int h_out, w_out;
+    int halo_bytes;  // (th + 2) * pitch * 128
+    int n_b;         // B ring slots
+    int off_gamma, off_ag, off_b, off_bar;  // shared-memory offsets (from the 1024-aligned base)
+    const float *beta;
+    int *tile_counter;
+    TraceSink trace;
+};
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_rcp(float v) {  // v > 0 (a GDN norm): reciprocal to within 1 ulp in 3 instructions
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return fmaf(r, fmaf(-v, r, 1.0f), r);
+}
+
+// 8 fp32 values -> 8 (hi, lo) fp16 pairs as two 16-byte vectors
+__device__ __forceinline__ void split8(const float *f, uint4 &h, uint4 &l) {
+    uint32_t *hw = reinterpret_cast<uint32_t *>(&h), *lw = reinterpret_cast<uint32_t *>(&l);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn((f[2 * e] - back.x) * kLoScale, (f[2 * e + 1] - back.y) * kLoScale);
+        hw[e] = *reinterpret_cast<const uint32_t *>(&hh);
+        lw[e] = *reinterpret_cast<const uint32_t *>(&ll);
+    }
+}
+
+// N: output channels padded to a multiple of 16 (the GEMM's N; the stacked MMA is 2N wide)
+template <int N>
+__global__ void __launch_bounds__(kThreads, 1)
+ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_g,
+                   const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                   const __grid_constant__ Params p) {
+    constexpr int kBSlot = 2 * N * 128;           // stacked weights of one (tap, 64-channel chunk)
+    constexpr int kGC = (N + 63) / 64;            // K chunks of the gamma GEMM
+    constexpr int kGStepsLast = (N - (kGC - 1) * 64) / 16;
+    constexpr int kUnits = N / 16;                // 16-channel units of the epilogue
+    constexpr int kUnits0 = (kUnits + 1) / 2;     // units of epilogue half 0 (half 1 takes the rest)
+    constexpr uint32_t kTmemCols = 512;
+    static_assert(N % 16 == 0 && N >= 16 && N <= 96, "N");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *s_gamma = smem + p.off_gamma;
+    uint8_t *s_ag = smem + p.off_ag;  // |x| (hi chunks, then lo chunks), K-major SWIZZLE_128B; aliased by the output staging tile
+    uint8_t *s_b = smem + p.off_b;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
+    uint64_t *a_empty = a_full + 2;
+    uint64_t *b_full = a_empty + 2;
+    uint64_t *b_empty = b_full + kMaxB;
+    uint64_t *acc_full = b_empty + kMaxB;
+    uint64_t *acc_empty = acc_full + 1;
+    uint64_t *ag_full = acc_empty + 1;
+    uint64_t *g_full = ag_full + 1;
+    uint64_t *gw_full = g_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gw_full + 1);
+    float *s_beta = reinterpret_cast<float *>(tmem_slot + 4);  // [N]
+    TileSched sched;
+    sched.bind(reinterpret_cast<uint8_t *>(s_beta + N), p.tile_counter, p.tiles_x * p.tiles_y * p.images);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_xy = p.tiles_x * p.tiles_y;
+    const int pitch = 1 << p.pitch_log2;
+    const unsigned long long trace_t0 = p.trace.buf ? trace_now() : 0ull;
+    int trace_tiles = 0;
+
+    if (threadIdx.x < N) s_beta[threadIdx.x] = static_cast<int>(threadIdx.x) < p.c_out ? __ldg(p.beta + threadIdx.x) : 1.0f;
+    if (threadIdx.x == 0) {
+        sched.init(10);  // consumers: MMA warp, B producer warp, 8 epilogue warps
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_g);
+        tma_prefetch_desc(&map_o_hi);
+        tma_prefetch_desc(&map_o_lo);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < kMaxB; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 256);
+        mbar_init(ag_full, 256);
+        mbar_init(g_full, 1);
+        mbar_init(gw_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t gamma_col = static_cast<uint32_t>(p.groups) * 2u * N;  // accumulator of the gamma GEMM
+
+    if (warp == 0) {
+        // =============================== halo producer + tile scheduler ===============================
+        if (elect_one()) {
+            uint32_t unit = 0;
+            int tile = sched.claim(0);
+            for (uint32_t qn = 0;; ++qn) {
+                sched.publish(qn, tile);
+                if (tile < 0) break;
+                const int next_tile = sched.claim(qn + 1);
+                const int sp = tile % tiles_xy, img = tile / tiles_xy;
+                const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
+                for (int t = 0; t < p.n_taps;) {
+                    const int plane = p.taps[t].plane;
+                    while (t < p.n_taps && p.taps[t].plane == plane) ++t;
+                    for (int kc = 0; kc < p.k_chunks; ++kc, ++unit) {
+                        const uint32_t s = unit & 1u, ph = (unit >> 1) & 1u;
+                        mbar_wait(&a_empty[s], ph ^ 1u);
+                        uint8_t *dst = smem + s * 2 * p.halo_bytes;
+                        mbar_expect_tx(&a_full[s], static_cast<uint32_t>(2 * p.halo_bytes));
+                        tma_load_4d(&map_a_hi, &a_full[s], dst, kc * kBlockK, x0 - 1, y0 - 1, img * 4 + plane);
+                        tma_load_4d(&map_a_lo, &a_full[s], dst + p.halo_bytes, kc * kBlockK, x0 - 1, y0 - 1, img * 4 + plane);
+                    }
+                }
+                tile = next_tile;
+            }
+        }
+    } else if (warp == 2) {
+        // =============================== weights producer ===============================
+        if (elect_one()) {
+            mbar_expect_tx(gw_full, static_cast<uint32_t>(kGC * kBSlot));
+            for (int c = 0; c < kGC; ++c) tma_load_2d(&map_g, gw_full, s_gamma + c * kBSlot, c * kBlockK, 0);
+        }
+        __syncwarp();
+        uint32_t bq = 0;
+        for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
+            if (elect_one()) {
+                for (int t0 = 0; t0 < p.n_taps;) {
+                    int t1 = t0;
+                    while (t1 < p.n_taps && p.taps[t1].plane == p.taps[t0].plane) ++t1;
+                    for (int kc = 0; kc < p.k_chunks; ++kc)
+                        for (int t = t0; t < t1; ++t, ++bq) {
+                            const uint32_t s = bq % p.n_b, ph = (bq / p.n_b) & 1u;
+                            mbar_wait(&b_empty[s], ph ^ 1u);
+                            mbar_expect_tx(&b_full[s], static_cast<uint32_t>(kBSlot));
+                            tma_load_2d(&map_w, &b_full[s], s_b + s * kBSlot, kc * kBlockK, p.taps[t].widx * 2 * N);
+                        }
+                    t0 = t1;
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        constexpr uint32_t idesc_stack = make_idesc(2 * N), idesc_n = make_idesc(N);
+        uint32_t unit = 0, bq = 0;
+        mbar_wait(gw_full, 0);
+        for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
+            mbar_wait(acc_empty, (lt & 1u) ^ 1u);  // the epilogue has drained the conv accumulators of the previous tile
+            tcgen05_fence_after();
+            for (int t0 = 0; t0 < p.n_taps;) {
+                int t1 = t0;
+                while (t1 < p.n_taps && p.taps[t1].plane == p.taps[t0].plane) ++t1;
+                for (int kc = 0; kc < p.k_chunks; ++kc, ++unit) {
+                    const uint32_t as = unit & 1u;
+                    mbar_wait(&a_full[as], (unit >> 1) & 1u);
+                    const uint32_t a_hi = smem_u32(smem + as * 2 * p.halo_bytes), a_lo = a_hi + p.halo_bytes;
+                    const int k_steps = kc == p.k_chunks - 1 ? p.k_steps_last : kBlockK / 16;
+                    for (int t = t0; t < t1; ++t, ++bq) {
+                        const uint32_t bs = bq % p.n_b;
+                        mbar_wait(&b_full[bs], (bq / p.n_b) & 1u);
+                        tcgen05_fence_after();
+                        if (elect_one()) {
+                            const Tap tap = p.taps[t];
+                            const uint32_t shift = static_cast<uint32_t>((tap.sy << p.pitch_log2) + tap.sx) * 128u;
+                            const uint64_t da_hi = make_smem_desc(a_hi + shift), da_lo = make_smem_desc(a_lo + shift);
+                            const uint64_t db = make_smem_desc(smem_u32(s_b + bs * kBSlot));
+                            // hi.hi | hi.lo -> group g (2N columns); lo.hi -> the D1 half of the PREVIOUS tap's group, so that
+                            // consecutive MMAs never write the same columns (a dependent MMA costs ~16 cycles more)
+                            const uint32_t g = static_cast<uint32_t>(tap.group);
+                            const uint32_t g1 = t == 0 ? 0u : static_cast<uint32_t>(p.taps[t - 1].group);
+                            const uint32_t d_stack = tmem_base + g * 2u * N, d_lohi = tmem_base + g1 * 2u * N + N;
+                            const bool fresh = tap.first && kc == 0;
+                            for (int k = 0; k < k_steps; ++k) {
+                                umma_f16(d_stack, da_hi + 2 * k, db + 2 * k, idesc_stack, (fresh && k == 0) ? 0u : 1u);
+                                umma_f16(d_lohi, da_lo + 2 * k, db + 2 * k, idesc_n, 1u);
+                            }
+                            umma_commit(&b_empty[bs]);
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) {
+                        umma_commit(&a_empty[as]);
+                        if (t1 == p.n_taps && kc == p.k_chunks - 1) umma_commit(acc_full);
+                    }
+                    __syncwarp();
+                }
+                t0 = t1;
+            }
+            // ---- the gamma GEMM of this tile: |x| (written by the epilogue warps) x gamma^T ----
+            mbar_wait(ag_full, lt & 1u);
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint32_t ag = smem_u32(s_ag), gm = smem_u32(s_gamma);
+#pragma unroll
+                for (int c = 0; c < kGC; ++c) {
+                    const uint64_t da_hi = make_smem_desc(ag + c * kABytes), da_lo = make_smem_desc(ag + (kGC + c) * kABytes);
+                    const uint64_t db = make_smem_desc(gm + c * kBSlot);
+                    const int k_steps = c == kGC - 1 ? kGStepsLast : 4;
+                    for (int k = 0; k < k_steps; ++k) {
+                        umma_f16(tmem_base + gamma_col, da_hi + 2 * k, db + 2 * k, idesc_stack, (c > 0 || k > 0) ? 1u : 0u);
+                        umma_f16(tmem_base + gamma_col + N, da_lo + 2 * k, db + 2 * k, idesc_n, 1u);
+                    }
+                }
+                umma_commit(g_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // =============================== epilogue warps (4..11) ===============================
+        const int half = (warp - 4) >> 2;
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+        const int m = quarter * 32 + lane;     // tile row = TMEM lane
+        const int ty = m >> p.pitch_log2, tx = m & (pitch - 1);
+        const bool issuer = threadIdx.x == 128;
+        const int u_begin = half == 0 ? 0 : kUnits0, u_end = half == 0 ? kUnits0 : kUnits;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        __half *st_hi = reinterpret_cast<__half *>(s_ag);
+        __half *st_lo = reinterpret_cast<__half *>(s_ag + p.stage_plane);
+        for (uint32_t lt = 0;; ++lt) {
+            const int tile = sched.next(lt, lane);
+            if (tile < 0) break;
+            ++trace_tiles;
+            const int sp = tile % tiles_xy, img = tile / tiles_xy;
+            const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
+            float x[kUnits0][16];
+            // ---- A: conv accumulators -> x (registers), |x| split -> the gamma GEMM's A operand ----
+            if (issuer) tma_store_wait_read();  // the previous tile's bulk stores have read the staging tile (same memory)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(acc_full, lt & 1u);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int ui = 0; ui < kUnits0; ++ui) {
+                const int u = u_begin + ui;
+                if (u < u_end) {
+                    uint32_t d0[16], d1[16];
+                    tmem_ld16_nowait(lane_addr + u * 16, d0);
+                    tmem_ld16_nowait(lane_addr + N + u * 16, d1);
+                    tmem_ld_wait();
+                    for (int g = 1; g < p.groups; ++g) {  // chunked summation: fp32 round-to-nearest adds of the partial sums
+                        uint32_t e0[16], e1[16];
+                        tmem_ld16_nowait(lane_addr + g * 2 * N + u * 16, e0);
+                        tmem_ld16_nowait(lane_addr + g * 2 * N + N + u * 16, e1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            d0[e] = __float_as_uint(__uint_as_float(d0[e]) + __uint_as_float(e0[e]));
+                            d1[e] = __float_as_uint(__uint_as_float(d1[e]) + __uint_as_float(e1[e]));
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) x[ui][e] = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e]));
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(acc_empty);  // 256 arrivals: the MMA warp may start the next tile's convolution
+#pragma unroll
+            for (int ui = 0; ui < kUnits0; ++ui) {
+                const int u = u_begin + ui;
+                if (u < u_end) {
+                    float a[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) a[e] = fabsf(x[ui][e]);
+                    const int c = u * 16, kc = c >> 6, j = (c & 63) >> 3;  // 16-byte chunk j (and j + 1) of K chunk kc
+                    uint8_t *row_hi = s_ag + kc * kABytes + m * 128, *row_lo = s_ag + (kGC + kc) * kABytes + m * 128;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint4 h, l;
+                        split8(&a[8 * q], h, l);
+                        const int phys = ((j + q) ^ (m & 7)) << 4;
+                        *reinterpret_cast<uint4 *>(row_hi + phys) = h;
+                        *reinterpret_cast<uint4 *>(row_lo + phys) = l;
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(ag_full);
+            // ---- B: gamma accumulator -> y = x / (beta + gamma.|x|) -> staging -> TMA store ----
+            mbar_wait(g_full, lt & 1u);
+            tcgen05_fence_after();
+            const bool store_row = tx < p.tw;
+            const int srow = ty * p.tw + tx;
+#pragma unroll
+            for (int ui = 0; ui < kUnits0; ++ui) {
+                const int u = u_begin + ui;
+                if (u < u_end) {
+                    uint32_t d0[16], d1[16];
+                    tmem_ld16_nowait(lane_addr + gamma_col + u * 16, d0);
+                    tmem_ld16_nowait(lane_addr + gamma_col + N + u * 16, d1);
+                    tmem_ld_wait();
+                    const int c = u * 16;
+                    if (store_row && c < p.out_c) {
+                        float y[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float norm = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e])) + s_beta[c + e];
+                            // x * (1 / norm), like the reference; 1 / norm = MUFU.RCP + one Newton step (< 1 ulp)
+                            y[e] = (c + e < p.c_out) ? x[ui][e] * fast_rcp(norm) : 0.0f;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            if (c + 8 * q < p.out_c) {
+                                uint4 h, l;
+                                split8(&y[8 * q], h, l);
+                                *reinterpret_cast<uint4 *>(st_hi + srow * p.stage_c + c + 8 * q) = h;
+                                *reinterpret_cast<uint4 *>(st_lo + srow * p.stage_c + c + 8 * q) = l;
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            fence_proxy_async();
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (issuer) {
+                tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
+                tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
+                tma_store_commit();
+            }
+        }
+        if (issuer) tma_store_wait_all();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+    if (threadIdx.x == 128) trace_emit(p.trace, TRACE_CONV_SPLIT, trace_t0, trace_tiles);
+}
+
+template <int N>
+static int launch(const CUtensorMap *maps, const Params &p, int smem, cudaStream_t st) {
+    static std::atomic<uint64_t> configured{0};  // per device ordinal
+    if (int rc = ensure_dyn_smem(ga_halo_gdn_kernel<N>, 227 * 1024, configured)) return rc;
+    const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.images;
+    if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
+    const int grid = total < persistent_grid() ? static_cast<int>(total) : persistent_grid();
+    ga_halo_gdn_kernel<N><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+    SC2_LAUNCH_CHECK("ga_halo_gdn_kernel");
+    return SC2_OK;
+}
+
+}  // namespace gah
+}  // namespace sc2
+
+extern "C" {
+
+int sc2_ga_halo_n(int c_out) {
+    const int n = (c_out + 15) / 16 * 16;
+    return (c_out >= 1 && n <= 96) ? n : 0;
+}
+
+int sc2_ga_halo_conv_gdn(const sc2_ga_halo_desc *d, const void *x_hi, const void *x_lo, const void *w_stack, const void *gamma_stack,
+                         const float *beta, void *out_hi, void *out_lo, int32_t *tile_counter, sc2_stream_t stream) {
+    using namespace sc2::gah;
+    if (!d || !x_hi || !x_lo || !w_stack || !gamma_stack || !beta || !out_hi || !out_lo) return SC2_ERR_INVALID_ARG;
+    if (d->images < 1 || d->c_in < 16 || d->c_in % 16 || d->c_out < 1 || d->h_in < 1 || d->w_in < 1) return SC2_ERR_INVALID_ARG;
+    if (d->kh < 1 || d->kw < 1 || d->kh * d->kw > kMaxTaps) return SC2_ERR_UNSUPPORTED;
+    const int n = sc2_ga_halo_n(d->c_out);
+    if (!n) return SC2_ERR_UNSUPPORTED;
+    if (d->out_c % 8 || d->out_c < d->c_out || d->out_c > n) return SC2_ERR_INVALID_ARG;
+    Params p;
+    p.images = d->images;
+    p.h_out = d->h_out; p.w_out = d->w_out;
+    p.c_out = d->c_out; p.out_c = d->out_c;
+    p.stage_c = (d->out_c / 8) % 2 == 0 ? d->out_c + 8 : d->out_c;  // odd number of 16-byte units per staging row
+    // taps: stride 2 on parity planes; halo shift of a tap = its plane offset + 1, must lie in [0, 2]
+    p.n_taps = 0;
+    Tap by_plane[4][kMaxTaps];
+    int n_plane[4] = {0, 0, 0, 0};
+    for (int dy = 0; dy < d->kh; ++dy)
+        for (int dx = 0; dx < d->kw; ++dx) {
+            const int sy = dy - d->pad, sx = dx - d->pad;
+            const int py = ((sy % 2) + 2) % 2, px = ((sx % 2) + 2) % 2;
+            const int oy = (sy - py) / 2 + 1, ox = (sx - px) / 2 + 1;
+            if (oy < 0 || oy > 2 || ox < 0 || ox > 2) return SC2_ERR_UNSUPPORTED;
+            Tap t;
+            t.plane = static_cast<int8_t>(py * 2 + px);
+            t.sy = static_cast<int8_t>(oy); t.sx = static_cast<int8_t>(ox);
+            t.widx = static_cast<int8_t>(dy * d->kw + dx);
+            t.group = 0; t.first = 0; t.pad0_ = t.pad1_ = 0;
+            by_plane[t.plane][n_plane[t.plane]++] = t;
+        }
+    p.k_chunks = (d->c_in + kBlockK - 1) / kBlockK;
+    p.k_steps_last = (d->c_in - (p.k_chunks - 1) * kBlockK) / 16;
+    {   // accumulator groups: as many as TMEM holds next to the gamma accumulator, at most one per ~24 K steps
+        const int steps = d->kh * d->kw * ((p.k_chunks - 1) * 4 + p.k_steps_last);
+        int groups = (steps + 23) / 24;
+        const int max_groups = 512 / (2 * n) - 1;
+        if (groups > max_groups) groups = max_groups;
+        if (groups > d->kh * d->kw) groups = d->kh * d->kw;
+        if (groups > 4) groups = 4;
+        if (groups < 1) groups = 1;
+        p.groups = groups;
+    }
+    for (int pl = 0; pl < 4; ++pl)
+        for (int i = 0; i < n_plane[pl]; ++i) {
+            Tap t = by_plane[pl][i];
+            t.group = static_cast<int8_t>(p.n_taps % p.groups);  // round-robin: consecutive taps use different accumulators
+            t.first = p.n_taps < p.groups;
+            p.taps[p.n_taps++] = t;
+        }
+    // tile shape: th rows x (pitch - 2) columns with th * pitch = 128; pick the pitch that loads the fewest halo pixels
+    int best_log2 = 4;
+    int64_t best_cost = -1;
+    for (int lg = 4; lg <= 6; ++lg) {
+        const int pitch = 1 << lg, th = 128 / pitch, tw_max = pitch - 2;
+        const int n_col = (d->w_out + tw_max - 1) / tw_max;
+        const int64_t cost = static_cast<int64_t>(n_col) * ((d->h_out + th - 1) / th) * (th + 2) * pitch;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_log2 = lg; }
+    }
+    p.pitch_log2 = best_log2;
+    const int pitch = 1 << best_log2;
+    p.th = 128 / pitch;
+    {
+        const int tw_max = pitch - 2;
+        const int n_col = (d->w_out + tw_max - 1) / tw_max;
+        p.tw = (d->w_out + n_col - 1) / n_col;
+        p.tiles_x = n_col;
+    }
+    p.tiles_y = (d->h_out + p.th - 1) / p.th;
+    p.halo_bytes = (p.th + 2) * pitch * 128;
+    // shared memory: [2 halo units (hi, lo)] [gamma, resident] [|x| operand / output staging] [weights ring] [barriers, beta, scheduler]
+    const int gc = (n + 63) / 64, b_slot = 2 * n * 128;
+    p.stage_plane = (p.th * p.tw * p.stage_c * 2 + 127) / 128 * 128;
+    const int ag_bytes = 2 * gc * kABytes, staging_bytes = 2 * p.stage_plane;
+    p.off_gamma = 4 * p.halo_bytes;
+    p.off_ag = p.off_gamma + gc * b_slot;
+    p.off_b = p.off_ag + ((ag_bytes > staging_bytes ? ag_bytes : staging_bytes) + 1023) / 1024 * 1024;
+    const int tail = 1024 + (4 + 2 * kMaxB + 5) * 8 + 16 + n * 4 + kTileSchedBytes + 64;
+    int n_b = (227 * 1024 - 1024 - p.off_b - tail) / b_slot;
+    if (n_b > kMaxB) n_b = kMaxB;
+    if (n_b < 2) return SC2_ERR_UNSUPPORTED;
+    p.n_b = n_b;
+    p.off_bar = p.off_b + n_b * b_slot;
+    const int smem = p.off_bar + tail;
+    p.beta = beta;
+    p.tile_counter = tile_counter;
+    p.trace = sc2::trace_sink();
+    CUtensorMap maps[6];
+    // input parity planes [images * 4, h_in, w_in, c_in]: halo boxes {64 ch, pitch px, th + 2 rows}
+    int rc = make_nhwc_map(&maps[0], x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * 4, kBlockK, pitch, p.th + 2);
+    if (rc) return rc;
+    rc = make_nhwc_map(&maps[1], x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * 4, kBlockK, pitch, p.th + 2);
+    if (rc) return rc;
+    // stacked weights [taps * 2n, c_in] and gamma [2n, n]: boxes {64, 2n}
+    rc = make_weight_map(&maps[2], w_stack, d->c_in, d->kh * d->kw * 2 * n, 2 * n);
+    if (rc) return rc;
+    rc = make_weight_map(&maps[3], gamma_stack, n, 2 * n, 2 * n);
+    if (rc) return rc;
+    rc = make_nhwc_map(&maps[4], out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, p.tw, p.th,
+                       CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = make_nhwc_map(&maps[5], out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, p.tw, p.th,
+                       CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    cudaStream_t st = sc2::as_stream(stream);
+    switch (n) {
+        case 16: return launch<16>(maps, p, smem, st);
+        case 32: return launch<32>(maps, p, smem, st);
+        case 48: return launch<48>(maps, p, smem, st);
+        case 64: return launch<64>(maps, p, smem, st);
+        case 80: return launch<80>(maps, p, smem, st);
+        default: return launch<96>(maps, p, smem, st);
+    }
+}
+
+}  // extern "C"

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _native
-from ._native import ConvDesc, TcConvDesc, TcSplitDesc, check
+from ._native import ConvDesc, GaHaloDesc, TcConvDesc, TcSplitDesc, check
 
 
 def _lib():
@@ -34,14 +34,24 @@ def profile_kernels(tags):
 def profile_results():
     """{tag: [ms, ...]} -- call after a synchronize."""
     out = {}
-    for tag, e0, e1 in _PROFILE['events']:
+    for tag, e0, e1, _ in _PROFILE['events']:
         out.setdefault(tag, []).append(e0.elapsed_time(e1))
     return out
 
 
+def profile_work():
+    """{tag: (flops, bytes, symbols) of ONE launch} for the launches profiled so far (None where an op does not state it)."""
+    return {tag: work for tag, _, _, work in _PROFILE['events']}
+
+
 class _launch:
-    def __init__(self, tag, kernels=1):
+    """Counts a launch and, when profiling is on, brackets it with CUDA events.  flops / nbytes: the ALGORITHMIC work of the
+    launch (2 x MAC of the reference's layers; bytes = every input read once and every output written once at the reference's
+    4 bytes per activation) -- what bench.py's roofline fractions are computed from."""
+
+    def __init__(self, tag, kernels=1, flops=None, nbytes=None, symbols=None):
         self.tag, self.kernels, self.e0 = tag, kernels, None
+        self.work = (flops, nbytes, symbols)
 
     def __enter__(self):
         STATS['launches'] += self.kernels
@@ -55,7 +65,7 @@ class _launch:
         if self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _PROFILE['events'].append((self.tag, self.e0, e1))
+            _PROFILE['events'].append((self.tag, self.e0, e1, self.work))
         return False
 
 
@@ -568,3 +578,43 @@ def tc_first_layer(x, w_hi, w_lo, c_out, kh, kw, pad):
         check(_lib().sc2_tc_first_layer(_ptr(x), B, C, H, W, kh, kw, pad, c_out, _ptr(w_hi), _ptr(w_lo), _ptr(hi), _ptr(lo), out_c,
                                         _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_first_layer')
     return hi, lo
+
+
+# ----------------------------------------------------------------------------------------------
+# fused g_a kernels (round 2): conv + GDN1 back to back, stacked (hi; lo) weights
+# ----------------------------------------------------------------------------------------------
+def pack_conv_weight_stacked(weight, n=None, c_in_pad=None):
+    """Conv2d weight [c_out, c_in, kh, kw] -> [kh*kw, 2n, c_in_pad] fp16: per tap, rows [0, n) hold the hi halves and rows
+    [n, 2n) the lo halves (value = hi + lo / 2048) of the K-contiguous weights; rows beyond c_out are zero.  One stacked
+    N = 2n MMA then yields hi.hi and hi.lo from a single read of the activations (conv_ga_halo.cu)."""
+    w = weight.detach().float()
+    c_out, c_in, kh, kw = w.shape
+    n = n or _lib().sc2_ga_halo_n(c_out)
+    if not n or n < c_out:
+        raise ValueError('c_out %d is not supported by the fused g_a kernels' % c_out)
+    c_in_pad = c_in_pad or (c_in + 15) // 16 * 16
+    full = torch.zeros((kh * kw, n, c_in_pad), dtype=torch.float32, device=w.device)
+    full[:, :c_out, :c_in] = w.permute(2, 3, 0, 1).reshape(kh * kw, c_out, c_in)
+    hi, lo = split_f16(full)
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+def ga_halo_conv_gdn(x_hi, x_lo, w_stack, gamma_stack, beta, c_out, kh, kw, pad):
+    """sc2_ga_halo_conv_gdn: stride-2 conv on parity planes [images * 4, H, W, C] + GDN1, one kernel.
+    Returns split planes (hi, lo) [images, h_out, w_out, c_out rounded up to 8]."""
+    require_cuda(x_hi, 'ga_halo_conv_gdn')
+    planes, H, W, C = x_hi.shape
+    images = planes // 4
+    ho, wo = (2 * H + 2 * pad - kh) // 2 + 1, (2 * W + 2 * pad - kw) // 2 + 1
+    out_c = (c_out + 7) // 8 * 8
+    dev = x_hi.device
+    out_hi = torch.empty((images, ho, wo, out_c), dtype=torch.float16, device=dev)
+    out_lo = torch.empty_like(out_hi)
+    d = GaHaloDesc(images, H, W, C, c_out, kh, kw, pad, ho, wo, out_c)
+    b = beta.detach().contiguous().float()
+    flops = 2.0 * images * ho * wo * c_out * (C * kh * kw + c_out)
+    nbytes = 4.0 * (x_hi.numel() + images * ho * wo * c_out)
+    with torch.cuda.device(dev), _launch('ga_halo[%d->%d,k%d,s2]+gdn1' % (C, c_out, kh), flops=flops, nbytes=nbytes):
+        check(_lib().sc2_ga_halo_conv_gdn(ctypes.byref(d), _ptr(x_hi), _ptr(x_lo), _ptr(w_stack), _ptr(gamma_stack), _ptr(b),
+                                          _ptr(out_hi), _ptr(out_lo), _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_ga_halo_conv_gdn')
+    return out_hi, out_lo

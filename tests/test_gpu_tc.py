@@ -170,3 +170,36 @@ def test_tc_first_layer_fused_im2col(s2, cout, H, W):
     ph, pl = s2.ops.patchify_split(x.to(dev), 5, 5, 2, 2, 80)
     uh, ul = s2.ops.tc_split_conv(ph, pl, wh, wl, cout, 1, 1, 1, 0, s2._native.TCS_STORE)
     assert torch.equal(uh, oh) and torch.equal(ul, ol)
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: fused conv + GDN1 kernels of g_a (halo tiles, stacked weights, gamma GEMM in the epilogue)
+# ---------------------------------------------------------------------------------------------------
+def _gdn1_ref64(x64, gamma, beta):
+    C = beta.numel()
+    norm = F.conv2d(x64.abs(), gamma.double().view(C, C, 1, 1), beta.double())
+    return x64 / norm
+
+
+@pytest.mark.parametrize('cin,cout,H,W,batch', [(96, 48, 112, 112, 2), (96, 48, 40, 72, 3), (32, 16, 24, 40, 2), (64, 96, 36, 20, 1),
+                                                 (48, 24, 400, 140, 1), (192, 64, 20, 28, 2)])
+def test_ga_halo_conv_gdn_matches_fp64(s2, cin, cout, H, W, batch):
+    """sc2_ga_halo_conv_gdn = Conv2d(k5, s2, p2) + GDN1 (layer.py:479-481) vs an fp64 reference of the same fp32 operands, and
+    vs the round-1 two-kernel route (which it must match to fp32 rounding)."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(cin + cout + H)
+    x = torch.randn(batch, cin, H, W) * 2
+    w = torch.randn(cout, cin, 5, 5) / (cin * 25) ** 0.5
+    gamma = 0.1 * torch.eye(cout) + 0.02 * torch.rand(cout, cout)
+    beta = 0.5 + torch.rand(cout)
+    ref = _gdn1_ref64(F.conv2d(x.double(), w.double(), None, 2, 2), gamma, beta).float()
+    xh, xl = _planes(s2, x, dev, parity=True)
+    ws = s2.ops.pack_conv_weight_stacked(w.to(dev))
+    n = ws.shape[1] // 2
+    gs = s2.ops.pack_conv_weight_stacked(gamma.view(cout, cout, 1, 1).to(dev), n=n, c_in_pad=n)[0]
+    oh, ol = s2.ops.ga_halo_conv_gdn(xh, xl, ws, gs, beta.to(dev), cout, 5, 5, 2)
+    got = _unsplit(oh, ol)
+    assert got.shape[1] == (cout + 7) // 8 * 8 and float(got[:, cout:].abs().max() if got.shape[1] > cout else 0.0) == 0.0
+    got = got[:, :cout]
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < SPLIT_TOL, rel_err(got, ref)
