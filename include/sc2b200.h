@@ -242,6 +242,19 @@ SC2_API int sc2_ga_halo_conv_gdn(const sc2_ga_halo_desc *d, const void *x_hi, co
                                  const void *gamma_stack, const float *beta, void *out_hi, void *out_lo, int32_t *tile_counter,
                                  sc2_stream_t stream);
 
+/* Device: first layer of g_a + its GDN1 in one kernel (conv_ga_first.cu): Conv2d(3 -> c_out, k5, s2, p2) on an NCHW image followed
+ * by GDN1(c_out) (sc2bench/models/layer.py:476-478), fp32-grade split fp16, output as split PARITY PLANES
+ * [batch * 4, h_out/2, w_out/2, out_c] -- the input layout of sc2_ga_halo_conv_gdn.
+ *   image        fp32 [batch, 3, h_in, w_in] (w_in % 4 == 0), or, with image_is_u8, uint8 of the same shape (w_in % 16 == 0)
+ *   lut          uint8 input only: float [3][256], the value of byte v of channel c after the data loader's ToTensor + Normalize
+ *                ((v / 255 - mean[c]) / std[c], computed by the caller with the reference's own ops); the conversion happens on
+ *                the fly inside the im2col (device-side pre-transform, sc2bench/transforms: H2D traffic drops 4x)
+ *   w_stack      [2n, 80] fp16: rows [0, n) hi / [n, 2n) lo of weight.reshape(c_out, 75), zero padded; n = sc2_ga_halo_n(c_out)
+ *   gamma_stack  [2n, n] fp16 as for sc2_ga_halo_conv_gdn */
+SC2_API int sc2_ga_first_conv_gdn(const void *image, int image_is_u8, const float *lut, int batch, int h_in, int w_in, int c_out,
+                                  const void *w_stack, const void *gamma_stack, const float *beta, void *out_hi, void *out_lo,
+                                  int out_c, int32_t *tile_counter, sc2_stream_t stream);
+
 /* Device: im2col of an fp32 NCHW image for the first (c_in = 3) layer: split fp16 patches, K = (c, dy, dx) zero-padded
  * to k_pad, pixels in parity-plane order [batch * 4, h_out/2, w_out/2, k_pad] (h_out, w_out must be even). */
 SC2_API int sc2_patchify_split(const float *x, void *out_hi, void *out_lo, int batch, int c_in, int h_in, int w_in,

@@ -60,6 +60,7 @@ SIGNATURES = {
     'sc2_tc_split_conv': (i32, [_c.POINTER(TcSplitDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'sc2_ga_halo_n': (i32, [i32]),
     'sc2_ga_halo_conv_gdn': (i32, [_c.POINTER(GaHaloDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sc2_ga_first_conv_gdn': (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp]),
     'sc2_patchify_split': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'sc2_tc_first_layer': (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
 }

@@ -618,3 +618,49 @@ def ga_halo_conv_gdn(x_hi, x_lo, w_stack, gamma_stack, beta, c_out, kh, kw, pad)
         check(_lib().sc2_ga_halo_conv_gdn(ctypes.byref(d), _ptr(x_hi), _ptr(x_lo), _ptr(w_stack), _ptr(gamma_stack), _ptr(b),
                                           _ptr(out_hi), _ptr(out_lo), _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_ga_halo_conv_gdn')
     return out_hi, out_lo
+
+
+def pack_first_layer_stacked(weight):
+    """Conv2d(3 -> c_out, k5) weight -> [2n, 80] fp16 stacked (hi; lo) of weight.reshape(c_out, 75) (K order (c, dy, dx))."""
+    w = weight.detach().float()
+    c_out, c_in, kh, kw = w.shape
+    if (c_in, kh, kw) != (3, 5, 5):
+        raise ValueError('the fused first layer is Conv2d(3 -> C, k5, s2, p2)')
+    n = _lib().sc2_ga_halo_n(c_out)
+    if not n:
+        raise ValueError('c_out %d is not supported by the fused g_a kernels' % c_out)
+    full = torch.zeros((n, 80), dtype=torch.float32, device=w.device)
+    full[:c_out, :75] = w.reshape(c_out, 75)
+    hi, lo = split_f16(full)
+    return torch.cat([hi, lo], dim=0).contiguous()
+
+
+def normalize_lut(mean, std, device):
+    """float32 [3, 256]: the value of byte v of channel c after torchvision's ToTensor (v / 255) and Normalize
+    ((x - mean) / std), computed with the same torch ops in the same order so that the table is bit-identical to the loader."""
+    v = torch.arange(256, dtype=torch.float32).div(255)
+    m = torch.as_tensor(mean, dtype=torch.float32).view(-1, 1)
+    s = torch.as_tensor(std, dtype=torch.float32).view(-1, 1)
+    return v.view(1, 256).sub(m).div(s).contiguous().to(device)
+
+
+def ga_first_conv_gdn(x, w_stack, gamma_stack, beta, c_out, lut=None):
+    """sc2_ga_first_conv_gdn: Conv2d(3 -> c_out, k5, s2, p2) + GDN1 on an NCHW image (fp32, or uint8 with `lut`).
+    Returns split parity planes (hi, lo) [B * 4, h_out/2, w_out/2, c_out rounded up to 8]."""
+    require_cuda(x, 'ga_first_conv_gdn')
+    u8 = x.dtype == torch.uint8
+    if u8 and lut is None:
+        raise ValueError('uint8 images need the normalisation look-up table (ops.normalize_lut)')
+    x = x.contiguous() if u8 else x.contiguous().float()
+    B, C, H, W = x.shape
+    ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out_c = (c_out + 7) // 8 * 8
+    hi = torch.empty((B * 4, ho // 2, wo // 2, out_c), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    b = beta.detach().contiguous().float()
+    flops = 2.0 * B * ho * wo * c_out * (75 + c_out)
+    nbytes = 4.0 * (x.numel() + B * ho * wo * c_out)
+    with torch.cuda.device(x.device), _launch('ga_first[3->%d,k5,s2]+gdn1%s' % (c_out, ',u8' if u8 else ''), flops=flops, nbytes=nbytes):
+        check(_lib().sc2_ga_first_conv_gdn(_ptr(x), int(u8), _ptr(lut), B, H, W, c_out, _ptr(w_stack), _ptr(gamma_stack), _ptr(b),
+                                           _ptr(hi), _ptr(lo), out_c, _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_ga_first_conv_gdn')
+    return hi, lo

@@ -181,7 +181,7 @@ def _gdn1_ref64(x64, gamma, beta):
     return x64 / norm
 
 
-@pytest.mark.parametrize('cin,cout,H,W,batch', [(96, 48, 112, 112, 2), (96, 48, 40, 72, 3), (32, 16, 24, 40, 2), (64, 96, 36, 20, 1),
+@pytest.mark.parametrize('cin,cout,H,W,batch', [(96, 48, 112, 112, 2), (96, 48, 40, 72, 3), (32, 16, 24, 40, 2), (64, 80, 36, 20, 1),
                                                  (48, 24, 400, 140, 1), (192, 64, 20, 28, 2)])
 def test_ga_halo_conv_gdn_matches_fp64(s2, cin, cout, H, W, batch):
     """sc2_ga_halo_conv_gdn = Conv2d(k5, s2, p2) + GDN1 (layer.py:479-481) vs an fp64 reference of the same fp32 operands, and
@@ -203,3 +203,52 @@ def test_ga_halo_conv_gdn_matches_fp64(s2, cin, cout, H, W, batch):
     got = got[:, :cout]
     assert got.shape == ref.shape
     assert rel_err(got, ref) < SPLIT_TOL, rel_err(got, ref)
+
+
+def _to_parity_full(got, B, cout):
+    """split parity planes [B*4, hp, wp, C] (already unsplit to NCHW [B*4, C, hp, wp]) -> full-resolution [B, C, 2hp, 2wp]."""
+    hp, wp = got.shape[2], got.shape[3]
+    g = got[:, :cout].view(B, 2, 2, cout, hp, wp)
+    full = torch.zeros(B, cout, 2 * hp, 2 * wp)
+    for py in (0, 1):
+        for px in (0, 1):
+            full[:, :, py::2, px::2] = g[:, py, px]
+    return full
+
+
+@pytest.mark.parametrize('cout,H,W,batch', [(96, 224, 224, 2), (96, 64, 48, 3), (32, 36, 44, 2), (48, 20, 28, 1), (96, 160, 336, 1), (80, 40, 24, 2)])
+def test_ga_first_conv_gdn_matches_fp64(s2, cout, H, W, batch):
+    """sc2_ga_first_conv_gdn = Conv2d(3 -> C, k5, s2, p2) + GDN1 (layer.py:476-478) vs an fp64 reference of the same fp32 operands."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(cout + H)
+    x = torch.randn(batch, 3, H, W) * 1.5
+    w = torch.randn(cout, 3, 5, 5) / 75 ** 0.5
+    gamma = 0.1 * torch.eye(cout) + 0.02 * torch.rand(cout, cout)
+    beta = 0.5 + torch.rand(cout)
+    ref = _gdn1_ref64(F.conv2d(x.double(), w.double(), None, 2, 2), gamma, beta).float()
+    ws = s2.ops.pack_first_layer_stacked(w.to(dev))
+    n = ws.shape[0] // 2
+    gs = s2.ops.pack_conv_weight_stacked(gamma.view(cout, cout, 1, 1).to(dev), n=n, c_in_pad=n)[0]
+    oh, ol = s2.ops.ga_first_conv_gdn(x.to(dev), ws, gs, beta.to(dev), cout)
+    full = _to_parity_full(_unsplit(oh, ol), batch, cout)
+    assert full.shape == ref.shape
+    assert rel_err(full, ref) < SPLIT_TOL, rel_err(full, ref)
+
+
+def test_ga_first_uint8_lut_equals_float_input(s2):
+    """Device-side ToTensor + Normalize: a uint8 image through the look-up table gives BIT-IDENTICAL planes to
+    the fp32 image the data loader would have produced with the same torch ops."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(7)
+    u8 = torch.randint(0, 256, (2, 3, 224, 224), dtype=torch.uint8)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    xf = u8.float().div(255).sub(torch.tensor(mean).view(1, 3, 1, 1)).div(torch.tensor(std).view(1, 3, 1, 1))
+    w = torch.randn(96, 3, 5, 5) / 75 ** 0.5
+    gamma = 0.1 * torch.eye(96) + 0.02 * torch.rand(96, 96)
+    beta = 0.5 + torch.rand(96)
+    ws = s2.ops.pack_first_layer_stacked(w.to(dev))
+    gs = s2.ops.pack_conv_weight_stacked(gamma.view(96, 96, 1, 1).to(dev), n=96, c_in_pad=96)[0]
+    lut = s2.ops.normalize_lut(mean, std, dev)
+    fh, fl = s2.ops.ga_first_conv_gdn(xf.to(dev), ws, gs, beta.to(dev), 96)
+    uh, ul = s2.ops.ga_first_conv_gdn(u8.to(dev), ws, gs, beta.to(dev), 96, lut=lut)
+    assert torch.equal(fh, uh) and torch.equal(fl, ul)
