@@ -66,6 +66,7 @@ SIGNATURES = {
 }
 
 SC2_OK = 0
+ABI_VERSION = 4  # include/sc2b200.h SC2_ABI_VERSION
 FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM, FAULT_BAD_INDEX = 1, 2, 4, 8
 EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 IN_NONE, IN_ABS = 0, 1
@@ -93,7 +94,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sc2_abi_version() != 4:
+    if lib.sc2_abi_version() != ABI_VERSION:
         raise ImportError('libsc2b200.so ABI version mismatch: rebuild with sc2-benchmark_b200/build.py --force')
     _lib = lib
     return lib

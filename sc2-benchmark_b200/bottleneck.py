@@ -10,6 +10,9 @@ contract as the reference, so YAML `bottleneck_config: {key, kwargs}` entries re
 The eval-time branch (`updated and not training`) is the hot path: g_a, quantisation, rANS encode / decode and
 g_s all run in libsc2b200.so.  The two training-time branches stay differentiable torch.
 """
+import logging
+import threading
+
 import torch
 from torch import nn
 
@@ -20,6 +23,24 @@ from .models import CompressionModel, get_scale_table, run_transform, update_reg
 
 
 
+_log = logging.getLogger('sc2bench_b200')
+_warned = set()
+_PLAN_LOCK = threading.Lock()
+
+
+def warn_fallback(what, why):
+    """One log line per (layer, reason) whenever a transform leaves the tensor-core kernels for the exact-fp32 CUDA-core ones
+    (conv2d_f32_kernel: 10-20 TFLOP/s), so that a slow model is visible as such."""
+    key = (what, why)
+    if key not in _warned:
+        _warned.add(key)
+        _log.warning('%s runs on the fp32 CUDA-core kernels (conv2d_f32_kernel), not on the tensor cores: %s', what, why)
+
+
+def _param_key(seq):
+    return tuple((q.data_ptr(), q._version, q.device) for q in seq.parameters())
+
+
 class TensorCoreTransform:
     """Execution plan that runs a stride-1 `Conv2d / GDN1` transform (the bottleneck's synthesis transform g_s) on the
     tcgen05 kernels: activations NHWC fp16 between layers, fp32 accumulation in TMEM, GDN1 fused with its 1x1 gamma
@@ -27,127 +48,216 @@ class TensorCoreTransform:
 
     def __init__(self, seq):
         self.seq = seq
-        self._key = None
-        self._steps = None
+        self._plan = None  # (key, steps, c_in_pad): built into locals and published with ONE assignment (host threads share it)
 
     @staticmethod
-    def supports(seq):
+    def why_not(seq):
+        """None when the plan covers `seq`, else the reason (logged by the caller)."""
         mods = list(seq)
         if not mods or not isinstance(mods[-1], nn.Conv2d):
-            return False
+            return 'the transform does not end in a Conv2d'
         for m in mods:
             if isinstance(m, nn.Conv2d):
                 k = m.kernel_size
-                if (m.bias is not None or m.groups != 1 or tuple(m.stride) != (1, 1) or tuple(m.dilation) != (1, 1)
-                        or k[0] != k[1] or m.padding[0] != m.padding[1] or isinstance(m.padding, str) or m.out_channels % 64):
-                    return False
+                if m.bias is not None or m.groups != 1 or tuple(m.dilation) != (1, 1):
+                    return 'bias / groups / dilation'
+                if tuple(m.stride) != (1, 1):
+                    return 'stride %s' % (tuple(m.stride),)
+                if k[0] != k[1] or isinstance(m.padding, str) or m.padding[0] != m.padding[1]:
+                    return 'non-square kernel or padding'
+                if m.out_channels % 64:
+                    return 'c_out %d is not a multiple of 64' % m.out_channels
             elif type(m) is GDN1:
                 if m.beta.numel() % 64 or m.beta.numel() > 512:  # (the kernel keeps beta in shared memory: <= 512 channels)
-                    return False
+                    return 'GDN1 over %d channels' % m.beta.numel()
             else:
-                return False
-        return True
+                return 'layer type %s' % type(m).__name__
+        return None
+
+    @classmethod
+    def supports(cls, seq):
+        return cls.why_not(seq) is None
 
     def _prepare(self):
-        params = [p for p in self.seq.parameters()]
-        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
-        if key == self._key:
-            return
-        steps, mods = [], list(self.seq)
-        for i, m in enumerate(mods):
-            if isinstance(m, nn.Conv2d):
-                c_in_pad = (m.in_channels + 63) // 64 * 64
-                mode = _native.TC_STORE_F32 if i == len(mods) - 1 else _native.TC_STORE_F16
-                steps.append(('conv', ops.pack_conv_weight_f16(m.weight, c_in_pad), m.kernel_size[0], m.padding[0], mode, None))
-            else:
-                gamma, beta = m.effective_params()
-                C = beta.numel()
-                mode = _native.TC_IGDN1_F16 if m.inverse else _native.TC_GDN1_F16
-                steps.append(('gdn', gamma.detach().reshape(1, C, C).half().contiguous(), 1, 0, mode, beta.detach().float().contiguous()))
-        self._steps, self._key = steps, key
-        self.c_in_pad = (mods[0].in_channels + 63) // 64 * 64
+        key = _param_key(self.seq)
+        plan = self._plan
+        if plan is not None and plan[0] == key:
+            return plan
+        with _PLAN_LOCK:
+            plan = self._plan
+            if plan is not None and plan[0] == key:
+                return plan
+            steps, mods = [], list(self.seq)
+            for i, m in enumerate(mods):
+                if isinstance(m, nn.Conv2d):
+                    c_in_pad = (m.in_channels + 63) // 64 * 64
+                    mode = _native.TC_STORE_F32 if i == len(mods) - 1 else _native.TC_STORE_F16
+                    steps.append(('conv', ops.pack_conv_weight_f16(m.weight, c_in_pad), m.kernel_size[0], m.padding[0], mode, None,
+                                  m.in_channels))
+                else:
+                    gamma, beta = m.effective_params()
+                    C = beta.numel()
+                    mode = _native.TC_IGDN1_F16 if m.inverse else _native.TC_GDN1_F16
+                    steps.append(('gdn', gamma.detach().reshape(1, C, C).half().contiguous(), 1, 0, mode, beta.detach().float().contiguous(), C))
+            plan = (key, steps, (mods[0].in_channels + 63) // 64 * 64)
+            self._plan = plan
+        return plan
 
     @torch.no_grad()
     def __call__(self, x_nchw):
         """fp32 NCHW in -> fp32 output, logically NCHW (physically channels-last: what cuDNN prefers for the tail)."""
-        self._prepare()
-        x = ops.nchw_to_nhwc_f16(x_nchw, self.c_in_pad)
-        for kind, w, k, pad, mode, beta in self._steps:
-            x = ops.tc_conv(x, w, k, k, pad, mode=mode, beta=beta, gdn_x=x if kind == 'gdn' else None)
+        _, steps, c_in_pad = self._prepare()
+        x = ops.nchw_to_nhwc_f16(x_nchw, c_in_pad)
+        for kind, w, k, pad, mode, beta, c_in in steps:
+            x = ops.tc_conv(x, w, k, k, pad, mode=mode, beta=beta, gdn_x=x if kind == 'gdn' else None, c_in=c_in)
         return x.permute(0, 3, 1, 2)
 
 
 class TensorCoreAnalysis:
     """Execution plan for the bottleneck's analysis transform g_a (Conv s2 - GDN1 - Conv s2 - GDN1 - Conv s1) on the
-    fp32-grade "split fp16" tcgen05 kernels, ending in the fused quantise-to-symbols epilogue:
+    fp32-grade "split fp16" tcgen05 kernels, ending in the fused quantise-to-symbols epilogue.  Three launches:
 
-        image (fp32 NCHW) --patchify--> patches (parity-plane order) --1x1 GEMM--> x1 --GDN1--> y1 (parity planes)
-        --5x5 s2 conv as 25 shifted boxes--> x2 --GDN1--> y2 --2x2 conv + round(y - median)--> int32 symbols (NCHW)
+        image (fp32 NCHW, or uint8 + normalisation table)
+          --[conv 5x5 s2 + GDN1, conv_ga_first.cu]--> y1 (parity planes)
+          --[conv 5x5 s2 + GDN1, conv_ga_halo.cu]---> y2
+          --[conv 2x2 + round(y - median), conv_tc_split.cu]--> int32 symbols (NCHW = coder order)
 
-    Every intermediate is a (hi, lo) pair of NHWC fp16 planes.  Weights / gammas are split and packed once."""
+    Every intermediate is a (hi, lo) pair of NHWC fp16 planes.  Weights / gammas are split, stacked and packed once.
+    Shapes the fused kernels do not cover take the round-1 route (separate conv and GDN1 launches on the split kernels)."""
 
     def __init__(self, seq):
         self.seq = seq
-        self._key = None
+        self._plan = None
         self.fuse_first_layer = True
+        self.fused = True        # conv + GDN1 in one kernel where the shapes allow (False: round-1 route, for A/B measurements)
+        self._unfused = set()    # (stage, shape) combinations the fused kernels refused
 
     @staticmethod
-    def supports(seq, x_shape):
+    def why_not(seq, x_shape):
         mods = list(seq)
         if len(mods) != 5 or not all(isinstance(mods[i], nn.Conv2d) for i in (0, 2, 4)) or not all(type(mods[i]) is GDN1 for i in (1, 3)):
-            return False
+            return 'not Conv - GDN1 - Conv - GDN1 - Conv'
         c1, c2, c3 = mods[0], mods[2], mods[4]
         for c in (c1, c2, c3):
             if (c.bias is not None or c.groups != 1 or tuple(c.dilation) != (1, 1) or c.kernel_size[0] != c.kernel_size[1]
                     or isinstance(c.padding, str) or c.padding[0] != c.padding[1] or c.stride[0] != c.stride[1]):
-                return False
+                return 'bias / groups / dilation / non-square kernel'
         if c1.stride[0] != 2 or c2.stride[0] != 2 or c3.stride[0] != 1 or mods[1].inverse or mods[3].inverse:
-            return False
+            return 'strides are not (2, 2, 1) or a GDN1 is inverse'
         if c1.in_channels * c1.kernel_size[0] ** 2 > 128 or c2.kernel_size[0] ** 2 > 25 or c3.kernel_size[0] ** 2 > 25:
-            return False
+            return 'kernel too large'
         if c1.out_channels % 16 or c2.out_channels % 16 or max(c1.out_channels, c2.out_channels, c3.out_channels) > 128:
-            return False
+            return 'channel counts %d / %d / %d' % (c1.out_channels, c2.out_channels, c3.out_channels)
         H, W = x_shape[-2:]
         k, p = c1.kernel_size[0], c1.padding[0]
         h1, w1 = (H + 2 * p - k) // 2 + 1, (W + 2 * p - k) // 2 + 1
-        return h1 >= 2 and w1 >= 2 and h1 % 2 == 0 and w1 % 2 == 0
+        if not (h1 >= 2 and w1 >= 2 and h1 % 2 == 0 and w1 % 2 == 0):
+            return 'first-layer output %d x %d is not even' % (h1, w1)
+        return None
+
+    @classmethod
+    def supports(cls, seq, x_shape):
+        return cls.why_not(seq, x_shape) is None
 
     def _prepare(self):
-        params = list(self.seq.parameters())
-        key = tuple((q.data_ptr(), q._version, q.device) for q in params)
-        if key == self._key:
-            return
-        c1, g1, c2, g2, c3 = list(self.seq)
-        self.k1_pad = (c1.in_channels * c1.kernel_size[0] ** 2 + 15) // 16 * 16
-        self.w1 = ops.pack_conv_weight_split(c1.weight, c_in_pad=self.k1_pad, as_patches=True)
-        self.w2 = ops.pack_conv_weight_split(c2.weight)
-        self.w3 = ops.pack_conv_weight_split(c3.weight)
-        self.gdn = []
-        for g in (g1, g2):
-            gamma, beta = g.effective_params()
-            C = beta.numel()
-            self.gdn.append((ops.pack_conv_weight_split(gamma.detach().reshape(C, C, 1, 1)), beta.detach().float().contiguous()))
-        self._key = key
+        key = _param_key(self.seq)
+        plan = self._plan
+        if plan is not None and plan['key'] == key:
+            return plan
+        with _PLAN_LOCK:
+            plan = self._plan
+            if plan is not None and plan['key'] == key:
+                return plan
+            c1, g1, c2, g2, c3 = list(self.seq)
+            plan = {'key': key}
+            plan['k1_pad'] = (c1.in_channels * c1.kernel_size[0] ** 2 + 15) // 16 * 16
+            plan['w1'] = ops.pack_conv_weight_split(c1.weight, c_in_pad=plan['k1_pad'], as_patches=True)
+            plan['w2'] = ops.pack_conv_weight_split(c2.weight)
+            plan['w3'] = ops.pack_conv_weight_split(c3.weight)
+            plan['gdn'] = []
+            for g in (g1, g2):
+                gamma, beta = g.effective_params()
+                C = beta.numel()
+                plan['gdn'].append((ops.pack_conv_weight_split(gamma.detach().reshape(C, C, 1, 1)), beta.detach().float().contiguous()))
+            # stacked (hi; lo) packs of the fused kernels
+            lib = _native.load()
+            n1, n2 = lib.sc2_ga_halo_n(c1.out_channels), lib.sc2_ga_halo_n(c2.out_channels)
+            first_ok = (c1.in_channels, c1.kernel_size[0], c1.stride[0], c1.padding[0]) == (3, 5, 2, 2) and n1 > 0
+            plan['first'] = None
+            if first_ok:
+                gamma, _ = g1.effective_params()
+                C = c1.out_channels
+                plan['first'] = (ops.pack_first_layer_stacked(c1.weight),
+                                 ops.pack_conv_weight_stacked(gamma.detach().reshape(C, C, 1, 1), n=n1, c_in_pad=n1)[0].contiguous())
+            plan['mid'] = None
+            if n2 > 0 and c2.stride[0] == 2 and c2.in_channels % 16 == 0:
+                gamma, _ = g2.effective_params()
+                C = c2.out_channels
+                plan['mid'] = (ops.pack_conv_weight_stacked(c2.weight),
+                               ops.pack_conv_weight_stacked(gamma.detach().reshape(C, C, 1, 1), n=n2, c_in_pad=n2)[0].contiguous())
+            self._plan = plan
+        return plan
+
+    def _try_fused(self, stage, shape_key, fn):
+        """Runs a fused kernel; a shape it refuses (SC2_ERR_UNSUPPORTED) is remembered and takes the two-kernel route from then on."""
+        if not self.fused or (stage, shape_key) in self._unfused:
+            return None
+        try:
+            return fn()
+        except _native.NativeError as e:
+            if 'unsupported' not in str(e):
+                raise
+            self._unfused.add((stage, shape_key))
+            _log.info('g_a %s stage: fused conv + GDN1 kernel does not cover %s; using separate conv and GDN1 launches', stage, shape_key)
+            return None
 
     @torch.no_grad()
-    def __call__(self, x, medians):
-        self._prepare()
+    def __call__(self, x, medians, lut=None):
+        plan = self._prepare()
         c1, _, c2, _, c3 = list(self.seq)
         T = _native
-        if c1.out_channels <= 96 and self.fuse_first_layer:
-            # im2col fused into the kernel: no patch tensor in HBM
-            h, l = ops.tc_first_layer(x, self.w1[0], self.w1[1], c1.out_channels, c1.kernel_size[0], c1.kernel_size[0], c1.padding[0])
-        else:
-            ph, pl = ops.patchify_split(x, c1.kernel_size[0], c1.kernel_size[0], 2, c1.padding[0], self.k1_pad)
-            h, l = ops.tc_split_conv(ph, pl, self.w1[0], self.w1[1], c1.out_channels, 1, 1, 1, 0, T.TCS_STORE)
-        (gh, gl), beta = self.gdn[0]
-        h, l = ops.tc_split_conv(h, l, gh, gl, c1.out_channels, 1, 1, 1, 0, T.TCS_GDN1, beta=beta, gdn=True)
-        h, l = ops.tc_split_conv(h, l, self.w2[0], self.w2[1], c2.out_channels, c2.kernel_size[0], c2.kernel_size[0], 2,
-                                 c2.padding[0], T.TCS_STORE)
-        (gh, gl), beta = self.gdn[1]
-        h, l = ops.tc_split_conv(h, l, gh, gl, c2.out_channels, 1, 1, 1, 0, T.TCS_GDN1, beta=beta, gdn=True)
-        return ops.tc_split_conv(h, l, self.w3[0], self.w3[1], c3.out_channels, c3.kernel_size[0], c3.kernel_size[0], 1,
+        out = None
+        if plan['first'] is not None:
+            ws, gs = plan['first']
+            out = self._try_fused('first', (tuple(x.shape[1:]), x.dtype), lambda: ops.ga_first_conv_gdn(x, ws, gs, plan['gdn'][0][1], c1.out_channels, lut=lut))
+        if out is None:
+            if x.dtype == torch.uint8:
+                x = ops.normalize_u8(x, lut)
+            if c1.out_channels <= 96 and self.fuse_first_layer:
+                # im2col fused into the kernel: no patch tensor in HBM
+                h, l = ops.tc_first_layer(x, plan['w1'][0], plan['w1'][1], c1.out_channels, c1.kernel_size[0], c1.kernel_size[0], c1.padding[0])
+            else:
+                ph, pl = ops.patchify_split(x, c1.kernel_size[0], c1.kernel_size[0], 2, c1.padding[0], plan['k1_pad'])
+                h, l = ops.tc_split_conv(ph, pl, plan['w1'][0], plan['w1'][1], c1.out_channels, 1, 1, 1, 0, T.TCS_STORE)
+            (gh, gl), beta = plan['gdn'][0]
+            out = ops.tc_split_conv(h, l, gh, gl, c1.out_channels, 1, 1, 1, 0, T.TCS_GDN1, beta=beta, gdn=True)
+        h, l = out
+        out = None
+        if plan['mid'] is not None:
+            ws, gs = plan['mid']
+            out = self._try_fused('mid', tuple(h.shape[1:]), lambda: ops.ga_halo_conv_gdn(h, l, ws, gs, plan['gdn'][1][1], c2.out_channels,
+                                                                                         c2.kernel_size[0], c2.kernel_size[0], c2.padding[0]))
+        if out is None:
+            h, l = ops.tc_split_conv(h, l, plan['w2'][0], plan['w2'][1], c2.out_channels, c2.kernel_size[0], c2.kernel_size[0], 2,
+                                     c2.padding[0], T.TCS_STORE)
+            (gh, gl), beta = plan['gdn'][1]
+            out = ops.tc_split_conv(h, l, gh, gl, c2.out_channels, 1, 1, 1, 0, T.TCS_GDN1, beta=beta, gdn=True)
+        h, l = out
+        return ops.tc_split_conv(h, l, plan['w3'][0], plan['w3'][1], c3.out_channels, c3.kernel_size[0], c3.kernel_size[0], 1,
                                  c3.padding[0], T.TCS_QUANT, medians=medians)
+
+
+def _run_synthesis(layer, seq, latent_hat):
+    """g_s on the tensor-core plan when `layer.decoder_precision` and the shapes allow, else on the fp32 kernels (logged)."""
+    why = 'decoder_precision = %r' % layer.decoder_precision if layer.decoder_precision != 'fp16-tc' else TensorCoreTransform.why_not(seq)
+    if why is None:
+        if layer._tc_decoder is None:
+            with _PLAN_LOCK:
+                if layer._tc_decoder is None:
+                    layer._tc_decoder = TensorCoreTransform(seq)
+        return layer._tc_decoder(latent_hat)
+    warn_fallback('%s synthesis transform (g_s)' % type(layer).__name__, why)
+    return run_transform(seq, latent_hat)
 
 
 LAYER_CLASS_DICT = dict()
@@ -304,25 +414,47 @@ class FPBasedResNetBottleneck(BaseBottleneck):
         symbols = self._on_transform_stream(lambda: self.analyze_to_symbols(x), x)
         return eb.compress_symbols(symbols, spatial=symbols[0, 0].numel()), symbols.size()[-2:]
 
+    def set_input_normalization(self, mean, std):
+        """Device-side ToTensor + Normalize: after this call `encode` also accepts uint8 NCHW images and
+        applies (v / 255 - mean[c]) / std[c] on the fly inside the first layer's im2col (a 3 x 256 table built with the data
+        loader's own torch ops, so the values are bit-identical); host-to-device traffic drops 4x.  fp32 input keeps working."""
+        self._input_norm = (tuple(float(m) for m in mean), tuple(float(v) for v in std))
+        self._input_luts = {}
+
+    def _input_lut(self, device):
+        norm = getattr(self, '_input_norm', None)
+        if norm is None:
+            raise ValueError('uint8 images need set_input_normalization(mean, std) first')
+        lut = self._input_luts.get(device)
+        if lut is None:
+            with torch.inference_mode(False):
+                lut = ops.normalize_lut(norm[0], norm[1], device)
+            self._input_luts[device] = lut
+        return lut
+
     @torch.no_grad()
     def analyze_to_symbols(self, x):
         """g_a + round(y - median) on the device: image batch -> int32 symbols [B, C, H, W] (coder order)."""
         ops.require_cuda(x, 'FPBasedResNetBottleneck.encode')
         medians = self.entropy_bottleneck._get_medians().detach().reshape(-1)
-        if self.encoder_precision == 'split-tc' and TensorCoreAnalysis.supports(self.encoder, x.shape):
+        lut = self._input_lut(x.device) if x.dtype == torch.uint8 else None
+        why = 'encoder_precision = %r' % self.encoder_precision if self.encoder_precision != 'split-tc' else \
+            TensorCoreAnalysis.why_not(self.encoder, x.shape)
+        if why is None:
             if self._tc_encoder is None:
-                self._tc_encoder = TensorCoreAnalysis(self.encoder)
-            return self._tc_encoder(x, medians)
+                with _PLAN_LOCK:
+                    if self._tc_encoder is None:
+                        self._tc_encoder = TensorCoreAnalysis(self.encoder)
+            return self._tc_encoder(x, medians, lut=lut)
+        warn_fallback('%s.encoder (g_a)' % type(self).__name__, why)
+        if lut is not None:
+            x = ops.normalize_u8(x, lut)
         return run_transform(self.encoder, x, final_epilogue=_native.EPI_QUANTIZE, final_aux=medians)
 
     @torch.no_grad()
     def synthesize(self, latent_hat):
         """g_s on the device: dequantised latent (fp32 NCHW) -> decoder features."""
-        if self.decoder_precision == 'fp16-tc' and TensorCoreTransform.supports(self.decoder):
-            if self._tc_decoder is None:
-                self._tc_decoder = TensorCoreTransform(self.decoder)
-            return self._tc_decoder(latent_hat)
-        return run_transform(self.decoder, latent_hat)
+        return _run_synthesis(self, self.decoder, latent_hat)
 
     @torch.no_grad()
     def decode_packed(self, streams, shape, check_status=False):
@@ -433,11 +565,7 @@ class SHPBasedResNetBottleneck(BaseBottleneck):
         indexes = self._scales_to_indexes(z_hat)
         y_hat = ops.rans_decode(ops.PackedStreams.from_list(strings[0], device), indexes[0].numel(), gc.coder_tables(),
                                 indexes=indexes, want='values').view(indexes.size())
-        if self.decoder_precision == 'fp16-tc' and TensorCoreTransform.supports(self.g_s):
-            if self._tc_decoder is None:
-                self._tc_decoder = TensorCoreTransform(self.g_s)
-            return self._tc_decoder(y_hat)
-        return run_transform(self.g_s, y_hat)
+        return _run_synthesis(self, self.g_s, y_hat)
 
     def _get_means(self, x):
         medians = self.entropy_bottleneck._get_medians().detach()
@@ -525,11 +653,7 @@ class MSHPBasedResNetBottleneck(SHPBasedResNetBottleneck):
         y_symbols = ops.rans_decode(ops.PackedStreams.from_list(strings[0], device), indexes[0].numel(), gc.coder_tables(),
                                     indexes=indexes, want='symbols').view(indexes.size())
         y_hat = ops.dequantize(y_symbols, means_hat)
-        if self.decoder_precision == 'fp16-tc' and TensorCoreTransform.supports(self.g_s):
-            if self._tc_decoder is None:
-                self._tc_decoder = TensorCoreTransform(self.g_s)
-            return self._tc_decoder(y_hat)
-        return run_transform(self.g_s, y_hat)
+        return _run_synthesis(self, self.g_s, y_hat)
 
     def _forward2train(self, x):
         y = self.g_a(x)

@@ -171,7 +171,11 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
                 mbar_wait(&patch_empty[s], ph ^ 1u);
                 mbar_expect_tx(&patch_full[s], static_cast<uint32_t>(p.box_w * p.box_h * 3 * (U8 ? 1 : 4)));
-                tma_load_4d(&map_img, &patch_full[s], s_patch + s * p.patch_bytes, 4 * x0 + 2 * px - 2, 4 * y0 + 2 * py - 2, 0, b);
+                // TMA wants the box to start on a 16-byte boundary of the innermost dimension: round the first column down
+                // (the producers add the remainder back, patch_col0 below)
+                const int col = 4 * x0 + 2 * px - 2;
+                tma_load_4d(&map_img, &patch_full[s], s_patch + s * p.patch_bytes, U8 ? ((col >> 4) << 4) : ((col >> 2) << 2),
+                            4 * y0 + 2 * py - 2, 0, b);
                 tile = next_tile;
             }
         }
@@ -334,6 +338,9 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             const int tile = sched.next(lt, lane);
             if (tile < 0) break;
             const uint32_t s = lt & 1u;
+            // first image column this tile needs, relative to the (16-byte aligned) box origin: 0 or 2 floats, 0..14 bytes
+            const int col = 4 * ((tile % tiles_xy) % p.tiles_x) * p.tw + 2 * ((tile / tiles_xy) & 1) - 2;
+            const int patch_col0 = U8 ? (col & 15) : (col & 3);
             mbar_wait(&patch_full[s], (lt >> 1) & 1u);
             mbar_wait(a_empty, (lt & 1u) ^ 1u);  // the previous tile's conv MMAs have read the A tile
             if (m < rows) {
@@ -344,20 +351,26 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int dy = 0; dy < 5; ++dy) {
-                        const int e0 = c * chan_elems + (4 * ty + dy) * row_elems + 4 * tx;
+                        const int e0 = c * chan_elems + (4 * ty + dy) * row_elems + 4 * tx + (patch_col0 & ~3);
                         float *o = &f[(c * 5 + dy) * 5];
-                        if (U8) {
-                            const uint32_t w4 = *reinterpret_cast<const uint32_t *>(patch + e0);
-                            const uint32_t b4 = patch[e0 + 4];
+                        if (U8) {  // 5 bytes starting 0 or 2 bytes into an aligned word
+                            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(patch + e0);
+                            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(patch + e0 + 4);
+                            const uint32_t sh = static_cast<uint32_t>(patch_col0 & 3) * 8u;
+                            const uint32_t w4 = __funnelshift_r(w0, w1, sh), b4 = (w1 >> sh) & 255u;
                             o[0] = s_lut[c * 256 + (w4 & 255u)];
                             o[1] = s_lut[c * 256 + ((w4 >> 8) & 255u)];
                             o[2] = s_lut[c * 256 + ((w4 >> 16) & 255u)];
                             o[3] = s_lut[c * 256 + (w4 >> 24)];
                             o[4] = s_lut[c * 256 + b4];
-                        } else {
-                            const float4 v = *reinterpret_cast<const float4 *>(patch + 4 * e0);
-                            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-                            o[4] = *reinterpret_cast<const float *>(patch + 4 * e0 + 16);
+                        } else {   // 5 floats starting 0 or 2 floats into an aligned float4: two conflict-free 16-byte loads
+                            const float4 v0 = *reinterpret_cast<const float4 *>(patch + 4 * e0);
+                            const float4 v1 = *reinterpret_cast<const float4 *>(patch + 4 * e0 + 16);
+                            if (patch_col0 & 2) {
+                                o[0] = v0.z; o[1] = v0.w; o[2] = v1.x; o[3] = v1.y; o[4] = v1.z;
+                            } else {
+                                o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x;
+                            }
                         }
                     }
 #pragma unroll
@@ -448,8 +461,8 @@ int sc2_ga_first_conv_gdn(const void *image, int image_is_u8, const float *lut, 
         p.th = (p.hp + n_row - 1) / n_row;
         p.tiles_x = n_col; p.tiles_y = n_row;
     }
-    p.box_w = 4 * p.tw + 4;
-    if (image_is_u8) p.box_w = (p.box_w + 15) / 16 * 16;
+    // patch box: the 4 tw + 1 columns a tile reads, plus the columns the 16-byte alignment of the box origin adds on the left
+    p.box_w = image_is_u8 ? (4 * p.tw + 1 + 14 + 4 + 15) / 16 * 16 : 4 * p.tw + 4;
     p.box_h = 4 * p.th + 1;
     p.patch_bytes = (p.box_w * p.box_h * 3 * (image_is_u8 ? 1 : 4) + 64 + 1023) / 1024 * 1024;  // + slack: the last thread's 5th value
     p.c_out = c_out; p.out_c = out_c;

@@ -281,7 +281,7 @@ def quantize_symbols(x, means=None):
             raise ValueError('tensor too large for per-element means')
     out = torch.empty(x.shape, dtype=torch.int32, device=x.device)
     m = means.contiguous().float() if means is not None else None
-    with torch.cuda.device(x.device), _launch('quantize_symbols'):
+    with torch.cuda.device(x.device), _launch('quantize_symbols', nbytes=8.0 * x.numel()):
         check(_lib().sc2_quantize_symbols(_ptr(x), _ptr(m), _ptr(out), B, C, spatial, _stream_ptr()), 'sc2_quantize_symbols')
     return out
 
@@ -316,7 +316,7 @@ def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None, la
     tab = tables.on(dev)
     with torch.cuda.device(dev):
         st = _stream_ptr()
-        with _launch('rans_encode', 1 if B else 0):
+        with _launch('rans_encode', 1 if B else 0, nbytes=4.0 * B * n, symbols=(B, n)):
             check(lib.sc2_rans_encode_batch(_ptr(sym), _ptr(idx), B, n, int(spatial or 0), _ptr(tab), tables.n_rows,
                                             tables.cdf_stride, _ptr(arena), slot_bytes, _ptr(lengths), _ptr(status),
                                             _native.RANS_LAYOUTS[layout], st),
@@ -354,7 +354,8 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
     tab = tables.on(dev)
-    with torch.cuda.device(dev), _launch('rans_decode', 1 if B and n_per_stream else 0):
+    with torch.cuda.device(dev), _launch('rans_decode', 1 if B and n_per_stream else 0, nbytes=4.0 * B * n_per_stream,
+                                         symbols=(B, n_per_stream)):
         check(_lib().sc2_rans_decode_batch(_ptr(streams.packed), _ptr(streams.offsets), B, n_per_stream, _ptr(idx),
                                            int(spatial or 0), _ptr(tab), tables.n_rows, tables.cdf_stride, _ptr(out_sym),
                                            _ptr(out_val), _ptr(m), _ptr(status), _native.RANS_LAYOUTS[layout], _stream_ptr()),
@@ -378,7 +379,7 @@ def dequantize(symbols, means=None):
             raise ValueError('means must have the shape of symbols')
         m = means.contiguous().float()
     out = torch.empty(sym.shape, dtype=torch.float32, device=sym.device)
-    with torch.cuda.device(sym.device), _launch('dequantize', 1 if sym.numel() else 0):
+    with torch.cuda.device(sym.device), _launch('dequantize', 1 if sym.numel() else 0, nbytes=8.0 * sym.numel()):
         check(_lib().sc2_dequantize(_ptr(sym), _ptr(m), _ptr(out), sym.numel(), _stream_ptr()), 'sc2_dequantize')
     return out
 
@@ -388,7 +389,7 @@ def gc_build_indexes(scales, scale_table, scale_bound):
     s = scales.contiguous().float()
     out = torch.empty(s.shape, dtype=torch.int32, device=s.device)
     tab = scale_table.to(s.device).contiguous().float()
-    with torch.cuda.device(s.device), _launch('gc_build_indexes'):
+    with torch.cuda.device(s.device), _launch('gc_build_indexes', nbytes=8.0 * s.numel()):
         check(_lib().sc2_gc_build_indexes(_ptr(s), s.numel(), _ptr(tab), tab.numel(), float(scale_bound), _ptr(out),
                                           _stream_ptr()), 'sc2_gc_build_indexes')
     return out
@@ -418,7 +419,8 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, transposed=False, output_p
     b = bias.detach().contiguous().float() if bias is not None else None
     a = aux.detach().contiguous().float() if aux is not None else None
     tag = 'conv2d_f32[%d->%d,k%d,s%d%s]' % (Cin, Cout, w.shape[2], int(stride), ',T' if transposed else '')
-    with torch.cuda.device(x.device), _launch(tag):
+    macs = (B * Cin * H * W * Cout if transposed else B * Cout * ho.value * wo.value * Cin) * w.shape[2] * w.shape[3]
+    with torch.cuda.device(x.device), _launch(tag, flops=2.0 * macs, nbytes=4.0 * (x.numel() + out.numel())):
         check(_lib().sc2_conv2d_f32(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(a), _ptr(out), _stream_ptr()), 'sc2_conv2d_f32')
     return out
 
@@ -432,7 +434,8 @@ def gdn(x, gamma, beta, kind=0, inverse=False):
     g = gamma.detach().reshape(C, C).contiguous().float()
     b = beta.detach().contiguous().float()
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device), _launch('gdn_f32[%d%s]' % (C, ',inv' if inverse else '')):
+    with torch.cuda.device(x.device), _launch('gdn_f32[%d%s]' % (C, ',inv' if inverse else ''), flops=2.0 * B * C * C * spatial,
+                                              nbytes=8.0 * x.numel()):
         check(_lib().sc2_gdn_f32(_ptr(x), _ptr(g), _ptr(b), _ptr(out), B, C, spatial, int(kind), int(bool(inverse)),
                                  _stream_ptr()), 'sc2_gdn_f32')
     return out
@@ -458,13 +461,14 @@ def nchw_to_nhwc_f16(x, c_pad):
     x = x.contiguous().float()
     B, C, H, W = x.shape
     y = torch.empty((B, H, W, c_pad), dtype=torch.float16, device=x.device)
-    with torch.cuda.device(x.device), _launch('nchw_to_nhwc_f16'):
+    with torch.cuda.device(x.device), _launch('nchw_to_nhwc_f16', nbytes=4.0 * x.numel() + 2.0 * y.numel()):
         check(_lib().sc2_nchw_f32_to_nhwc_f16(_ptr(x), _ptr(y), B, C, H * W, c_pad, _stream_ptr()), 'sc2_nchw_f32_to_nhwc_f16')
     return y
 
 
-def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None, gdn_x=None):
-    """tcgen05 implicit-GEMM conv on NHWC fp16 (sc2_tc_conv_nhwc). Returns NHWC fp16 / fp32."""
+def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None, gdn_x=None, c_in=None):
+    """tcgen05 implicit-GEMM conv on NHWC fp16 (sc2_tc_conv_nhwc). Returns NHWC fp16 / fp32.  c_in: the layer's real input
+    channels (the activation may be zero-padded to a multiple of 64), for the work accounting only."""
     require_cuda(x_nhwc, 'tc_conv')
     assert x_nhwc.dtype == torch.float16 and x_nhwc.is_contiguous() and w_packed.dtype == torch.float16
     B, H, W, Cp = x_nhwc.shape
@@ -476,7 +480,10 @@ def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None,
     out = torch.empty((B, ho, wo, c_out), dtype=torch.float32 if mode == _native.TC_STORE_F32 else torch.float16, device=x_nhwc.device)
     b = beta.detach().contiguous().float() if beta is not None else None
     tag = 'tc_conv[%d->%d,k%d,m%d]' % (Cp, c_out, kh, mode)
-    with torch.cuda.device(x_nhwc.device), _launch(tag):
+    c_real = c_in or Cp
+    flops = 2.0 * B * ho * wo * c_out * c_real * kh * kw
+    nbytes = 4.0 * B * (H * W * c_real + ho * wo * c_out)
+    with torch.cuda.device(x_nhwc.device), _launch(tag, flops=flops, nbytes=nbytes):
         check(_lib().sc2_tc_conv_nhwc(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(b), _ptr(gdn_x), _ptr(out),
                                       _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_conv_nhwc')
     return out
@@ -524,7 +531,7 @@ def patchify_split(x, kh, kw, stride, pad, k_pad):
     ho, wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     hi = torch.empty((B * 4, ho // 2, wo // 2, k_pad), dtype=torch.float16, device=x.device)
     lo = torch.empty_like(hi)
-    with torch.cuda.device(x.device), _launch('patchify_split'):
+    with torch.cuda.device(x.device), _launch('patchify_split', nbytes=4.0 * (x.numel() + hi.numel())):
         check(_lib().sc2_patchify_split(_ptr(x), _ptr(hi), _ptr(lo), B, C, H, W, kh, kw, stride, pad, k_pad, _stream_ptr()),
               'sc2_patchify_split')
     return hi, lo
@@ -557,7 +564,9 @@ def tc_split_conv(x_hi, x_lo, w_hi, w_lo, c_out, kh, kw, stride, pad, mode, beta
     b = beta.detach().contiguous().float() if beta is not None else None
     m = medians.detach().contiguous().float() if medians is not None else None
     tag = 'tc_split[%d->%d,k%d,s%d,m%d]' % (C, c_out, kh, stride, mode)
-    with torch.cuda.device(dev), _launch(tag):
+    flops = 2.0 * images * ho * wo * c_out * C * kh * kw
+    nbytes = 4.0 * (x_hi.numel() + images * ho * wo * c_out)
+    with torch.cuda.device(dev), _launch(tag, flops=flops, nbytes=nbytes):
         check(_lib().sc2_tc_split_conv(ctypes.byref(d), _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(b), _ptr(m),
                                        _ptr(x_hi) if gdn else None, _ptr(x_lo) if gdn else None, _ptr(out_hi), _ptr(out_lo),
                                        _ptr(out_sym), _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_split_conv')
@@ -574,7 +583,8 @@ def tc_first_layer(x, w_hi, w_lo, c_out, kh, kw, pad):
     out_c = (c_out + 7) // 8 * 8
     hi = torch.empty((B * 4, ho // 2, wo // 2, out_c), dtype=torch.float16, device=x.device)
     lo = torch.empty_like(hi)
-    with torch.cuda.device(x.device), _launch('tc_first[%d->%d,k%d,s2]' % (C, c_out, kh)):
+    with torch.cuda.device(x.device), _launch('tc_first[%d->%d,k%d,s2]' % (C, c_out, kh), flops=2.0 * B * ho * wo * c_out * C * kh * kw,
+                                              nbytes=4.0 * (x.numel() + B * ho * wo * c_out)):
         check(_lib().sc2_tc_first_layer(_ptr(x), B, C, H, W, kh, kw, pad, c_out, _ptr(w_hi), _ptr(w_lo), _ptr(hi), _ptr(lo), out_c,
                                         _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_first_layer')
     return hi, lo
@@ -642,6 +652,14 @@ def normalize_lut(mean, std, device):
     m = torch.as_tensor(mean, dtype=torch.float32).view(-1, 1)
     s = torch.as_tensor(std, dtype=torch.float32).view(-1, 1)
     return v.view(1, 256).sub(m).div(s).contiguous().to(device)
+
+
+def normalize_u8(x, lut):
+    """uint8 NCHW image -> fp32 through the look-up table (the route for shapes the fused first layer does not cover)."""
+    require_cuda(x, 'normalize_u8')
+    C = x.shape[1]
+    idx = x.long() + (torch.arange(C, device=x.device) * 256).view(1, C, 1, 1)
+    return lut.reshape(-1)[idx]
 
 
 def ga_first_conv_gdn(x, w_stack, gamma_stack, beta, c_out, lut=None):

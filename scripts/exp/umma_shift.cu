@@ -81,6 +81,67 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(float *out, int shift, in
     }
 }
 
+
+// Q3  SWIZZLE_64B operands written by hand: rows of 64 bytes (32 fp16), 16-byte unit j of row r at ((j ^ ((r >> 1) & 3)) << 4),
+//     descriptor layout type 4, 8-row groups 512 bytes apart.  D[128, 64] = A[128, 32] * B[64, 32]^T (two K steps).
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3ffff) >> 4);
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;
+    return d;
+}
+__global__ void __launch_bounds__(128, 1) sw64_kernel(float *out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *a_buf = smem, *b_buf = smem + 128 * 64;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(b_buf + kN * 64);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) {
+        const int r = i / 32, k = i % 32;
+        const uint32_t off = r * 64 + ((((k / 8) ^ ((r >> 1) & 3)) << 4)) + (k % 8) * 2;
+        *reinterpret_cast<__half *>(a_buf + off) = __float2half(static_cast<float>(((r * 7 + k * 3) % 13) - 6));
+    }
+    for (int i = threadIdx.x; i < kN * 32; i += blockDim.x) {
+        const int n = i / 32, k = i % 32;
+        const uint32_t off = n * 64 + ((((k / 8) ^ ((n >> 1) & 3)) << 4)) + (k % 8) * 2;
+        *reinterpret_cast<__half *>(b_buf + off) = __float2half(static_cast<float>(((n * 5 + k) % 11) - 5));
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    if (threadIdx.x < 32) tmem_alloc(tmem_slot, 64);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            const uint64_t a_desc = make_smem_desc_sw64(smem_u32(a_buf)), b_desc = make_smem_desc_sw64(smem_u32(b_buf));
+            for (int k = 0; k < 2; ++k) umma_f16(tmem, a_desc + 2 * k, b_desc + 2 * k, make_idesc(kN), k > 0 ? 1u : 0u);
+            umma_commit(bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(bar, 0);
+    tcgen05_fence_after();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < kN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+        for (int e = 0; e < 32; ++e) out[(warp * 32 + lane) * kN + c0 + e] = __uint_as_float(v[e]);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem, 64);
+    }
+}
+
 // cycles per MMA: `iters` back-to-back tcgen05.mma (M = 128, N, K = 16) on resident operands; variant 1 alternates three
 // (A, B) pairs like the split-fp16 passes
 template <int N>
@@ -192,6 +253,21 @@ int main() {
                 }
             printf("shift %3d base_offset=%s : %d / %d mismatches\n", s, ubo ? "(addr>>7)&7" : "0", bad, 128 * kN);
         }
+    {
+        CK(cudaFuncSetAttribute(sw64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+        sw64_kernel<<<1, 128, 32768>>>(d_out);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h.data(), d_out, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < kN; ++n) {
+                float want = 0.f;
+                for (int k = 0; k < 32; ++k) want += static_cast<float>(((m * 7 + k * 3) % 13) - 6) * static_cast<float>(((n * 5 + k) % 11) - 5);
+                if (want != h[m * kN + n]) ++bad;
+            }
+        printf("SWIZZLE_64B manual layout : %d / %d mismatches\n", bad, 128 * kN);
+    }
+    if (getenv("SC2_EXP_SKIP_RATE")) return 0;
     cudaFree(d_out);
     for (int grid : {1, 148}) {
         if (run_rate<32>(grid, 0) || run_rate<48>(grid, 0) || run_rate<64>(grid, 0) || run_rate<96>(grid, 0) || run_rate<128>(grid, 0) ||

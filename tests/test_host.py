@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(s2):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(s2._native.SIGNATURES), declared ^ set(s2._native.SIGNATURES)
-    assert lib.sc2_abi_version() == 3
+    assert lib.sc2_abi_version() == int(re.search(r'#define SC2_ABI_VERSION (\d+)', header).group(1))
 
 
 def test_pmf_to_quantized_cdf_matches_oracle(s2):
