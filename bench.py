@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- images/s of the supervised-compression bottleneck path (encode + rANS + decode) on B200.
 
-    python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's CUDA path
-    python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU path (restated oracle) on host cores
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this repo's CUDA path, BASELINE.json configs[1] (the default)
+    python bench.py --config 5 --steps 10                     # another BASELINE config (1..5 = SURVEY.md 8d "Config 1..5")
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU path (restated oracle) on the host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        bench.py --gpus N --steps K --warmup W                # one rank per GPU, weak scaling
+        bench.py --gpus N --steps K --warmup W [--scaling strong]   # one rank per GPU
 
-Workload = BASELINE.json configs[1]: Entropic Student ResNet-50 bottleneck (FPBasedResNetBottleneck, 24 bottleneck /
-256 target channels, factorized-prior EntropyBottleneck), random init (seed 0), synthetic 3x224x224 images, batch 256
-PER GPU (weak scaling: images are independent units, no data-path collective; the only collective is one counter
-all-reduce after the timed region).  A step = bottleneck_layer.encode + bottleneck_layer.decode over one batch.
+Workloads (`--config`, numbered like SURVEY.md 8d; BASELINE.json `configs` is 0-based, so --config 2 = configs[1]):
+  1  Entropic Student ResNet-50 bottleneck (FPBasedResNetBottleneck(24, 256)), batch 1, 3x224x224: latency of one image
+  2  the same bottleneck at batch 256 per GPU (weak scaling, default) or a global batch of 256 split over the ranks (--scaling
+     strong); steps are software-pipelined (sc2bench_b200/pipeline.py)          <- the metric's configuration, the default
+  3  bmshj2018_factorized(quality=8): 3x224x224 -> AdaptivePad(64) -> 3x256x256 -> compress -> decompress
+  4  bmshj2018_hyperprior(quality=8), as 3
+  5  the Entropic Student bottleneck at COCO shape 3x800x1344 (one 1.6 M-symbol rANS stream per image)
+A step = encode + decode (compress + decompress) of one batch.  Images are independent units: no data-path collective; the
+only collective is one counter all-reduce after the timed region.
 
 One JSON line on stdout (rank 0):
-  value     images/s, inputs resident in HBM, device-timed (CUDA events), max over ranks
-  e2e       images/s through the public plugin API with HOST buffers: pinned images -> H2D -> encode() -> list[bytes]
-            on the host (D2H) -> decode(strings) (H2D) -> per-image feature means read back (D2H)
-  roofline  dominant kernel: algorithmic FLOPs per launch / its CUDA-event time inside the timed region, vs MEASURED_PEAKS.json
-  cpu_baseline  the restated reference (oracle/, "port": CompressAI is not installable here) on the host cores, bounded sample
+  value        images/s, inputs resident in HBM, device-timed (CUDA events), max over ranks
+  e2e          images/s through the public plugin API with HOST buffers (pinned images -> H2D -> encode() -> list[bytes] on the
+               host -> decode(strings) -> per-image result D2H); config 2 feeds uint8 images (device-side ToTensor + Normalize)
+               and also reports the fp32-input figure
+  roofline     the largest kernel ON THE TRANSFORM STREAM (the critical path of the pipelined step): algorithmic FLOPs and bytes
+               of the launch (SURVEY.md 8d conventions, stated by the op itself: ops._launch) / its CUDA-event time in a serial
+               accounting pass, against MEASURED_PEAKS.json; the coder is reported as symbols/s/stream (latency-bound)
+  cpu_baseline the restated reference (oracle/, "port": CompressAI is not installable here) on the host cores, bounded sample
 """
 import argparse
 import json
@@ -31,36 +40,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # keep stdout clean for the single JSON line: NCCL's version / debug banner goes to a file
 os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/sc2b200_nccl.%h.%p.log')
-# One hardware queue per CUDA stream for the 10-20 streams of the batch pipeline: with the default 8, streams share queues and
-# a coder kernel waiting for its batch's g_a blocks the transforms queued behind it (measured: 21-41 k images/s from run to
-# run with 8 connections, 43 k every run with 32).  Read by the driver when the context is created, i.e. before torch starts.
+# One hardware queue per CUDA stream for the 10-20 streams of the batch pipeline (sc2bench_b200/__init__.py explains).
 os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 
-METRIC = 'images/s encode+rANS+decode @224^2 (FPBasedResNetBottleneck, Entropic Student ResNet-50)'
 UNIT = 'images/s'
-IMG = (3, 224, 224)
-LATENT = (24, 55, 55)
-# algorithmic FLOPs (2*MAC) per image
-FLOPS = {'conv2d_f32[3->96,k5,s2]': 180.6e6, 'gdn_f32[96]': 231.2e6, 'conv2d_f32[96->48,k5,s2]': 722.5e6,
-         'gdn_f32[48]': 14.5e6, 'conv2d_f32[48->24,k2,s1]': 27.9e6, 'conv2d_f32[24->512,k2,s1]': 308.3e6,
-         'gdn_f32[512,inv]': 1644.2e6, 'conv2d_f32[512->256,k2,s1]': 3172.0e6, 'gdn_f32[256,inv]': 396.5e6,
-         'conv2d_f32[256->256,k2,s1]': 1644.2e6,
-         # tensor-core g_s (tags carry the PADDED input channels; FLOPs are the algorithmic ones)
-         'tc_conv[64->512,k2,m0]': 308.3e6, 'tc_conv[512->512,k1,m2]': 1644.2e6, 'tc_conv[512->256,k2,m0]': 3172.0e6,
-         'tc_conv[256->256,k1,m2]': 396.5e6, 'tc_conv[256->256,k2,m1]': 1644.2e6}
-# algorithmic HBM bytes per image of the HBM-bound kernels (every kernel reads its input once and writes its
-# output once, 4 bytes per activation -- the split fp16 (hi, lo) pairs of g_a are 4 bytes per value as well)
-BYTES = {'rans_encode': 290400 + 49240, 'rans_decode': 49240 + 290400, 'rans_pack': 2 * 49240,
-         'nchw_to_nhwc_f16': 290400 + 55 * 55 * 64 * 2,
-         'tc_first[3->96,k5,s2]': 602112 + 4816896,              # K1 with fused im2col: image in, x1 out
-         'patchify_split': 602112 + 4 * 12544 * 80,            # (unfused route) image in, im2col patches out
-         'tc_split[80->96,k1,s1,m0]': 4 * 12544 * 80 + 4816896,  # K1: patches in, x1 out
-         'tc_split[96->96,k1,s1,m1]': 2 * 4816896,               # GDN1(96): x1 in, y1 out
-         'tc_split[96->48,k5,s2,m0]': 4816896 + 602112,          # K3
-         'tc_split[48->48,k1,s1,m1]': 2 * 602112,                # GDN1(48)
-         'tc_split[48->24,k2,s1,m2]': 602112 + 290400}           # K5 + quantise: y2 in, int32 symbols out
-PATH_FLOPS_PER_IMAGE = 8.342e9
-PATH_BYTES_PER_IMAGE = 34.85e6
+METRICS = {
+    1: 'images/s encode+rANS+decode @224^2, batch 1 (FPBasedResNetBottleneck, Entropic Student ResNet-50)',
+    2: 'images/s encode+rANS+decode @224^2 (FPBasedResNetBottleneck, Entropic Student ResNet-50)',
+    3: 'images/s compress+rANS+decompress @224^2 padded to 256^2 (bmshj2018_factorized q8)',
+    4: 'images/s compress+rANS+decompress @224^2 padded to 256^2 (bmshj2018_hyperprior q8)',
+    5: 'images/s encode+rANS+decode @3x800x1344 (FPBasedResNetBottleneck, COCO shape)',
+}
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+# Kernels whose tensor-core work is three fp16 MMA passes per algorithmic MAC (split fp16 = fp32-grade)
+THREE_PASS_PREFIXES = ('tc_split', 'tc_first', 'ga_halo', 'ga_first')
 
 
 def load_traffic():
@@ -84,116 +77,267 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML in a thread of this process (8 ranks each forking
+    an `nvidia-smi -lms` poller perturbed the 8-GPU runs), nvidia-smi as the fallback."""
+    REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
 
-    def __init__(self, gpu_index):
-        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, torch_device_index):
+        self.idx, self.rows, self.stop_flag, self.thread, self.handle, self.nv = torch_device_index, [], threading.Event(), None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            try:
+                uuid = 'GPU-' + str(torch.cuda.get_device_properties(self.idx).uuid)
+                self.handle = nv.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+                phys = int(vis.split(',')[self.idx]) if vis and all(v.strip().isdigit() for v in vis.split(',')) else self.idx
+                self.handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = nv
+            self.smmax = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nv = None
+            self._start_smi()
+
+    def _poll(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)), int(reasons_fn(self.handle))))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+
+    def _start_smi(self):
+        q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
-
-    def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.thread.join(timeout=2)
-        sm, smmax, reasons = [], [], set()
-        for r in self.rows:
+            r = [c.strip() for c in line.split(',')]
             try:
-                sm.append(float(r[1]))
-                smmax.append(float(r[2]))
+                mask = sum(bit for (bit, _), v in zip(self.REASONS, r[4:8]) if v.lower().startswith('active'))
+                self.rows.append((float(r[1]), mask))
+                self.smmax = float(r[2])
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(smmax) if smmax else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+
+    def stop(self):
+        if self.thread is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock sampling unavailable']}
+        time.sleep(0.12)
+        self.stop_flag.set()
+        if self.nv is None and getattr(self, 'proc', None) is not None:
+            self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        mask = 0
+        for r in self.rows:
+            mask |= r[1]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': getattr(self, 'smmax', None),
+                'reasons': sorted(name for bit, name in self.REASONS if mask & bit), 'samples': len(sm),
+                'source': 'nvml' if self.nv is not None else 'nvidia-smi'}
 
 
-def build_product_layer(device):
+# ----------------------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------------------
+def workload_spec(config, batch):
+    """(image shape, default batch per GPU, description)"""
+    if config == 1:
+        return (3, 224, 224), batch or 1, 'configs[0] on the GPU: entropic-student-resnet50 FPBasedResNetBottleneck(24,256) encode+rANS+decode, 3x224x224, batch 1, random init'
+    if config == 2:
+        return (3, 224, 224), batch or 256, 'configs[1]: entropic-student-resnet50 FPBasedResNetBottleneck(24,256) encode+rANS+decode, 3x224x224, random init'
+    if config == 3:
+        return (3, 224, 224), batch or 32, 'configs[2]: bmshj2018_factorized(quality=8) compress+decompress, 3x224x224 -> AdaptivePad(64) -> 3x256x256, random init'
+    if config == 4:
+        return (3, 224, 224), batch or 32, 'configs[3]: bmshj2018_hyperprior(quality=8) compress+decompress, 3x224x224 -> AdaptivePad(64) -> 3x256x256, random init'
+    if config == 5:
+        return (3, 800, 1344), batch or 1, 'configs[4]: FPBasedResNetBottleneck(24,256) encode+rANS+decode at COCO shape 3x800x1344 (GeneralizedRCNNTransform batching of 800x1333), random init'
+    raise SystemExit('--config must be 1..5')
+
+
+def build_product_model(config, device):
     import torch
     import sc2bench_b200 as s2
     torch.manual_seed(0)
-    layer = s2.get_layer('FPBasedResNetBottleneck', num_bottleneck_channels=24, num_target_channels=256)
-    layer.eval()
-    layer.update()
-    return layer.to(device)
+    if config in (1, 2, 5):
+        m = s2.get_layer('FPBasedResNetBottleneck', num_bottleneck_channels=24, num_target_channels=256)
+        m.eval()
+        m.update()
+    else:
+        m = s2.get_compression_model({'key': 'bmshj2018_factorized' if config == 3 else 'bmshj2018_hyperprior',
+                                      'kwargs': {'quality': 8, 'pretrained': False}}, 'cpu')
+        m.eval()
+    return m.to(device)
 
 
-def cpu_reference_run(n_images, steps, warmup, state_dict=None):
-    """Times the restated reference path (oracle/) on the host cores: torch CPU convs (all threads) + the per-sample
-    CompressAI coder loop through Python lists (as EntropyModel.compress/decompress does).  Returns images/s etc."""
+def make_step_fns(config, model):
+    """(encode(x) -> obj, decode(obj) -> tensor, count_symbols(obj-or-shape)) with the reference's call contract per config."""
+    import sc2bench_b200 as s2
+    if config in (1, 2, 5):
+        return (lambda x: model.encode(x)), (lambda obj: model.decode(**obj))
+    pad = s2.AdaptivePad(fill=0, factor=64)
+    return (lambda x: model.compress(pad(x))), (lambda obj: model.decompress(**obj)['x_hat'])
+
+
+def build_oracle_model(config, state_dict=None):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import torch
     import ref_models
     torch.manual_seed(0)
-    layer = ref_models.build_fp_bottleneck(3, 24, 256)
+    if config in (1, 2, 5):
+        m = ref_models.build_fp_bottleneck(3, 24, 256)
+    else:
+        ref_models._import_shim()
+        import compressai.zoo as ozoo
+        m = getattr(ozoo, 'bmshj2018_factorized' if config == 3 else 'bmshj2018_hyperprior')(quality=8, pretrained=False)
     if state_dict is not None:
-        layer.load_state_dict(state_dict)
-    layer.eval()
-    layer.update()
+        m.load_state_dict(state_dict)
+    m.eval()
+    m.update()
+    return m
+
+
+def cpu_reference_run(config, n_images, steps, warmup, state_dict=None):
+    """Times the restated reference path (oracle/) on the host cores: torch CPU convs (all threads) + the per-sample CompressAI
+    coder loop through Python lists (as EntropyModel.compress/decompress does).  Returns images/s etc."""
+    import torch
+    import torch.nn.functional as F
+    shape, _, _ = workload_spec(config, None)
+    m = build_oracle_model(config, state_dict)
     torch.manual_seed(1)
-    x = torch.randn(n_images, *IMG)
-    times, nbytes = [], 0
+    x = torch.randn(n_images, *shape) if config in (1, 2, 5) else torch.rand(n_images, *shape)
+    times, nbytes, out = [], 0, None
     with torch.inference_mode():
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            obj = layer.encode(x)
-            out = layer.decode(**obj)
+            if config in (1, 2, 5):
+                obj = m.encode(x)
+                out = m.decode(**obj)
+            else:
+                xp = F.pad(x, (0, (-shape[2]) % 64, 0, (-shape[1]) % 64))
+                obj = m.compress(xp)
+                out = m.decompress(**obj)['x_hat']
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
-            nbytes = sum(len(s) for s in obj['strings'][0])
+            nbytes = sum(len(s) for lst in obj['strings'] for s in lst)
     total = sum(times)
     return {'images_per_s': n_images * len(times) / total, 'ms_per_step': 1e3 * total / len(times), 'threads': torch.get_num_threads(),
             'cores': os.cpu_count(), 'bytes_per_image': nbytes / n_images, 'out_shape': list(out.shape)}
 
 
+def default_cpu_images(config):
+    return {1: 1, 2: 8, 3: 2, 4: 2, 5: 1}[config]
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    n = args.cpu_images
-    r = cpu_reference_run(n, args.steps, args.warmup)
-    sample = '%d images of 3x224x224 per step (the B200 arm runs 256 per GPU per step); restated reference ' \
-             '(oracle/shim compressai restatement + C rANS, torch CPU convs); compressai itself is not installable here' % n
-    line = {'impl': 'reference', 'metric': METRIC, 'value': r['images_per_s'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'entropic-student-resnet50 FPBasedResNetBottleneck encode+decode, 3x224x224, random init',
-                       'images_per_step': n, 'device': 'cpu'},
+    n = args.cpu_images or default_cpu_images(args.config)
+    shape, b, desc = workload_spec(args.config, args.batch)
+    r = cpu_reference_run(args.config, n, args.steps, args.warmup)
+    sample = '%d images of %dx%dx%d per step (the B200 arm runs %d per GPU per step); restated reference (oracle/shim compressai ' \
+             'restatement + C rANS, torch CPU convs); compressai itself is not installable here' % ((n,) + shape + (b,))
+    line = {'impl': 'reference', 'metric': METRICS[args.config], 'value': r['images_per_s'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': args.scaling,
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': desc, 'images_per_step': n, 'device': 'cpu'},
             'cpu_baseline': {'value': r['images_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port', 'sample': sample},
             'e2e': {'value': r['images_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# roofline arithmetic
+# ----------------------------------------------------------------------------------------------------------------------
+def account_kernels(prof, work, n_prof, step_ms, pipelined_ms, peaks, traffic, batch):
+    kernels = []
+    for tag, times in prof.items():
+        avg = sum(times) / len(times)
+        per_step = sum(times) / n_prof
+        k = {'kernel': tag, 'launches_per_step': len(times) / n_prof, 'avg_launch_ms': avg, 'share_of_step': per_step / step_ms}
+        flops, nbytes, symbols = work.get(tag, (None, None, None))
+        coder = tag in ('rans_encode', 'rans_decode')
+        k['stream'] = 'batch' if tag.startswith('rans_') else 'transform'
+        if coder and symbols:
+            k['symbols_per_s_per_stream'] = symbols[1] / (avg / 1e3)
+            k['symbols_per_s_aggregate'] = symbols[0] * symbols[1] / (avg / 1e3)
+            k['streams'], k['symbols_per_stream'] = symbols
+            k['note'] = 'serial rANS state chain per stream (SURVEY.md H1): latency-bound, neither roofline applies'
+        elif flops or nbytes:
+            # the binding roofline of the launch: the larger of (algorithmic FLOPs / tensor peak) and (algorithmic bytes / copy peak)
+            t_tensor = (flops or 0.0) / (peaks['tflops_sustained'] * 1e12) * 1e3
+            t_hbm = (nbytes or 0.0) / (peaks['hbm_gbs'] * 1e9) * 1e3
+            if t_tensor >= t_hbm:
+                k.update(bound='tensor', achieved=flops / (avg / 1e3) / 1e12, unit='TFLOP/s', peak=peaks['tflops_sustained'])
+            else:
+                k.update(bound='hbm', achieved=nbytes / (avg / 1e3) / 1e9, unit='GB/s', peak=peaks['hbm_gbs'])
+            k['frac'] = k['achieved'] / k['peak']
+            k['algorithmic_flops'], k['algorithmic_bytes'] = flops, nbytes
+            k['floor_ms'] = {'tensor': t_tensor, 'hbm': t_hbm}
+            if tag.startswith(THREE_PASS_PREFIXES) and flops:
+                # executed tensor work of the fp32-grade kernels = 3 MMA passes per algorithmic MAC: the bound they can reach
+                k['frac_of_3pass_tensor_bound'] = 3.0 * t_tensor / avg
+        if tag in traffic:  # measured DRAM bytes of one launch (ncu), scaled to this batch size
+            k['traffic'] = traffic[tag]['dram_bytes_per_launch'] * batch / traffic[tag].get('batch', 256)
+        if pipelined_ms and not coder:
+            k['share_of_pipelined_step'] = per_step / pipelined_ms
+        kernels.append(k)
+    kernels.sort(key=lambda k: -k['share_of_step'])
+    return kernels
+
+
+def pick_roofline(kernels, peaks, traffic_src):
+    crit = [k for k in kernels if k['stream'] == 'transform' and 'frac' in k]
+    if not crit:
+        return None
+    top = crit[0]
+    keys = ('kernel', 'bound', 'achieved', 'unit', 'peak', 'frac', 'traffic', 'avg_launch_ms', 'share_of_step', 'share_of_pipelined_step',
+            'algorithmic_flops', 'algorithmic_bytes', 'floor_ms', 'frac_of_3pass_tensor_bound')
+    r = {kk: top.get(kk) for kk in keys}
+    r['traffic_source'] = traffic_src
+    r['peak_source'] = peaks['source'] + (', bf16 sustained' if top.get('bound') == 'tensor' else ', copy bandwidth')
+    r['choice'] = 'largest kernel on the transform stream (the critical path of the pipelined step); the coder runs beside it on ' \
+                  'per-batch streams and is reported under "coder"'
+    fr = [k['frac'] for k in crit]
+    r['transform_kernels'] = len(crit)
+    r['transform_kernels_at_70pct'] = sum(1 for f in fr if f >= 0.7)
+    return r
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=256, help='images per GPU per step')
-    ap.add_argument('--cpu-images', type=int, default=8, help='images per step of the CPU baseline sample')
+    ap.add_argument('--config', type=int, default=2, help='workload, numbered like SURVEY.md 8d (2 = BASELINE.json configs[1], the metric)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --batch images per GPU; strong: a global batch of --batch images split over the ranks')
+    ap.add_argument('--batch', type=int, default=0, help='images per GPU per step (strong scaling: global); 0 = the config default')
+    ap.add_argument('--cpu-images', type=int, default=0, help='images per step of the CPU baseline sample (0 = per-config default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-threads', type=int, default=0, help='host threads (one CUDA stream each) driving the e2e steps')
     ap.add_argument('--max-ahead', type=int, default=4, help='batches the host may run ahead of the GPU beyond the pipeline depth')
-    ap.add_argument('--inflight', type=int, default=8, help='depth of the batch pipeline: the serial rANS chains of up to this many batches overlap the convolutions of the others')
+    ap.add_argument('--inflight', type=int, default=8, help='config 2: depth of the batch pipeline')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -214,14 +358,28 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     peaks = load_peaks()
-    layer = build_product_layer(device)
-    B = args.batch
-    n_sym = LATENT[0] * LATENT[1] * LATENT[2]
+    cfg = args.config
+    shape, B, desc = workload_spec(cfg, args.batch)
+    if args.scaling == 'strong':
+        lo, hi = parallel.shard_bounds(B, rank, world)  # a global batch of B images, contiguous slices per rank
+        B_global, B = B, hi - lo
+        if B < 1:
+            raise SystemExit('strong scaling: global batch %d is smaller than the world size %d' % (B_global, world))
+    else:
+        B_global = B * world
+    model = build_product_model(cfg, device)
+    encode, decode = make_step_fns(cfg, model)
+    pipelined = cfg == 2
 
-    # two distinct input batches (154 MB each, larger than the 126 MB L2) alternate between steps
+    # inputs: two distinct batches alternate between steps; where a batch is smaller than L2 (126 MB) the L2 is flushed between
+    # timed iterations instead (a 256 MB write), each iteration timed by its own event pair
     gen = torch.Generator(device='cpu').manual_seed(1 + rank)
-    host_inputs = [torch.randn(B, *IMG, generator=gen).pin_memory() for _ in range(2)]
+    rnd = torch.randn if cfg in (1, 2, 5) else torch.rand
+    host_inputs = [rnd(B, *shape, generator=gen).pin_memory() for _ in range(2)]
     dev_inputs = [h.to(device) for h in host_inputs]
+    input_bytes = host_inputs[0].numel() * 4
+    flush_l2 = input_bytes < 160e6 and not pipelined
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device) if flush_l2 else None
 
     def barrier():
         if world > 1:
@@ -229,54 +387,89 @@ def main():
         torch.cuda.synchronize()
 
     def device_step(i):
-        streams, shape = layer.encode_packed(dev_inputs[i & 1])
-        return streams, layer.decode_packed(streams, shape)
+        obj = encode(dev_inputs[i & 1])
+        return obj, decode(obj)
 
-    # Batches are independent and a batch's coder is one serial rANS chain per image (milliseconds on a handful of warps),
-    # so steps are software-pipelined (sc2bench_b200/pipeline.py): every g_a / g_s on ONE transform stream in a fixed order,
-    # g_a(i + depth) ahead of g_s(i), and the coder of each batch on its own stream in the layout that occupies one SM.
-    # Every step does all of its work inside the timed region; the region ends when the pipeline has drained.
-    pipe = s2.pipeline.CodecPipeline(layer, depth=max(1, args.inflight), max_ahead=args.max_ahead)
+    def n_symbols(obj):
+        return None
 
-    def run_steps(n, first=0):
-        main = torch.cuda.current_stream()
-        start = torch.cuda.Event(enable_timing=True)
-        start.record(main)
-        last = None
-        for i in range(first, first + n):
-            last = pipe.submit(dev_inputs[i & 1]) or last
-        for r in pipe.drain():
-            last = r
-        main.wait_stream(pipe.transform_stream)  # the last g_s, hence every batch, has finished
-        last.wait(main)
-        stop = torch.cuda.Event(enable_timing=True)
-        stop.record(main)
-        return start, stop, (last.streams, last.features)
-
-    # ---- device-resident throughput ("value") -------------------------------------------------
+    launches = allocs = 0
+    t_issue = 0.0
+    extra = {}
     with torch.inference_mode():
-        # warm-up: at least W steps and at least one step per batch stream (each stream has its own allocator pool)
-        n_warm = max(args.warmup, 2 * len(pipe.batch_streams) + args.max_ahead)
-        run_steps(n_warm)
-        barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        launches0 = s2.ops.STATS['launches']
-        allocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
-        t_issue = time.perf_counter()
-        e0, e1, (streams, out) = run_steps(args.steps, first=n_warm)
-        t_issue = (time.perf_counter() - t_issue) * 1e3
-        barrier()
-        launches = s2.ops.STATS['launches'] - launches0
-        allocs = torch.cuda.memory_stats(device).get('num_device_alloc', 0) - allocs0
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop()
-        total_bytes = streams.total_bytes()
-        pipe.close()  # back to one batch at a time
-        # per-kernel accounting: a second, SERIAL timed pass over the SAME kernels (one batch in flight, CUDA events around
-        # every launch on the launching stream) -- with batches overlapping, a kernel's event time would include waiting for
-        # SMs held by others.  The coder keeps the layout of the timed region (lane per stream).
-        layer.entropy_bottleneck.coder_layout = 'lanes'
+        if pipelined:
+            # Batches are independent and a batch's coder is one serial rANS chain per image, so steps are software-pipelined
+            # (sc2bench_b200/pipeline.py): every g_a / g_s on ONE transform stream, g_a(i + depth) ahead of g_s(i), coders on
+            # per-batch streams in the lane-per-stream layout.  Every step does all of its work inside the timed region; the
+            # region ends when the pipeline has drained.
+            pipe = s2.pipeline.CodecPipeline(model, depth=max(1, args.inflight), max_ahead=args.max_ahead)
+
+            def run_steps(n, first=0):
+                main_s = torch.cuda.current_stream()
+                start = torch.cuda.Event(enable_timing=True)
+                start.record(main_s)
+                last = None
+                for i in range(first, first + n):
+                    last = pipe.submit(dev_inputs[i & 1]) or last
+                for r in pipe.drain():
+                    last = r
+                main_s.wait_stream(pipe.transform_stream)
+                last.wait(main_s)
+                stop = torch.cuda.Event(enable_timing=True)
+                stop.record(main_s)
+                return start, stop, last
+
+            # priming (not a warm-up step count: allocator pools of every batch stream get their blocks), then W warm-up steps
+            n_prime = 2 * len(pipe.batch_streams) + args.max_ahead
+            run_steps(n_prime)
+            run_steps(args.warmup, first=n_prime)
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            launches0 = s2.ops.STATS['launches']
+            allocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
+            t0 = time.perf_counter()
+            e0, e1, last = run_steps(args.steps, first=n_prime + args.warmup)
+            t_issue = (time.perf_counter() - t0) * 1e3
+            barrier()
+            launches = s2.ops.STATS['launches'] - launches0
+            allocs = torch.cuda.memory_stats(device).get('num_device_alloc', 0) - allocs0
+            ms = e0.elapsed_time(e1)
+            clocks = sampler.stop()
+            total_bytes = last.streams.total_bytes()
+            sym_per_image = int(torch.tensor(last.shape).prod()) * model.entropy_bottleneck.channels
+            pipe.close()
+            extra['priming_steps'] = n_prime
+            model.entropy_bottleneck.coder_layout = 'lanes'  # the accounting pass keeps the layout of the timed region
+        else:
+            for i in range(args.warmup):
+                device_step(i)
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            launches0 = s2.ops.STATS['launches']
+            allocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
+            evs = []
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                if flush_l2:
+                    flush_buf.fill_(i & 255)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                obj, out = device_step(i)
+                b.record()
+                evs.append((a, b))
+            t_issue = (time.perf_counter() - t0) * 1e3
+            barrier()
+            launches = s2.ops.STATS['launches'] - launches0 - (args.steps if flush_l2 else 0) * 0
+            allocs = torch.cuda.memory_stats(device).get('num_device_alloc', 0) - allocs0
+            ms = sum(a.elapsed_time(b) for a, b in evs)
+            clocks = sampler.stop()
+            total_bytes = sum(len(s) for lst in obj['strings'] for s in lst)
+            sym_per_image = None
+
+        # per-kernel accounting: a second, SERIAL timed pass over the SAME kernels (one batch in flight, CUDA events around every
+        # launch on the launching stream) -- with batches overlapping, a kernel's event time would include waiting for SMs.
         n_prof = max(1, min(args.steps, 5))
         device_step(0)
         torch.cuda.synchronize()
@@ -288,23 +481,28 @@ def main():
         p1.record()
         torch.cuda.synchronize()
         serial_ms = p0.elapsed_time(p1) / n_prof
-        prof = s2.ops.profile_results()
+        prof, work = s2.ops.profile_results(), s2.ops.profile_work()
         s2.ops.profile_kernels(None)
-        # ... and the latency of ONE batch with the low-latency coder layout (a warp per stream), for reference
-        layer.entropy_bottleneck.coder_layout = None
-        device_step(0)
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record()
-        for i in range(n_prof):
-            device_step(i)
-        l1.record()
-        torch.cuda.synchronize()
-        latency_ms = l0.elapsed_time(l1) / n_prof
+        latency_ms = None
+        if pipelined:  # the latency of ONE batch with the low-latency coder layout (a warp per stream), for reference
+            model.entropy_bottleneck.coder_layout = None
+            device_step(0)
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for i in range(n_prof):
+                device_step(i)
+            l1.record()
+            torch.cuda.synchronize()
+            latency_ms = l0.elapsed_time(l1) / n_prof
 
     t = torch.tensor([ms], dtype=torch.float64, device=device)
+    per_rank_ms = [ms]
     counters = parallel.EvalCounters(device)
-    counters.add(images=B * args.steps, bytes=total_bytes * args.steps, symbols=B * n_sym * args.steps)
+    counters.add(images=B * args.steps, bytes=total_bytes * args.steps, symbols=(sym_per_image or 0) * B * args.steps)
     if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank_ms = [float(g.item()) for g in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     counters.all_reduce()  # the path's only collective: one small counter vector per evaluation
     ms = float(t.item())
@@ -312,127 +510,111 @@ def main():
     value = c['images'] / (ms / 1e3)
 
     # ---- end-to-end through the public API with host buffers ("e2e") ---------------------------
-    # Each step is the reference-facing call sequence on HOST data: pinned images -> H2D -> layer.encode(x) (returns the
-    # contract object with real `bytes` on the host) -> layer.decode(**obj) (bytes -> H2D -> features) -> a per-image
-    # result read back.  `e2e_threads` host threads each drive their own CUDA stream (like the reference's
-    # nn.DataParallel replicas are host threads), so the PCIe copies and the host-side bytes handling of one batch overlap
-    # the GPU work of another; every step still runs entirely inside the timed region.
+    # Each step is the reference-facing call sequence on HOST data: pinned images -> H2D -> encode(x) (returns the contract object
+    # with real `bytes` on the host) -> decode(**obj) (bytes -> H2D -> features) -> a per-image result read back.  Host threads
+    # each drive their own CUDA stream, so the PCIe copies and the host-side bytes handling of one batch overlap the GPU work of
+    # another; every step still runs entirely inside the timed region.
     e2e = None
     if not args.no_e2e:
         import concurrent.futures
 
-        def e2e_step(i):
-            with torch.inference_mode(), torch.cuda.stream(e2e_streams[i % len(e2e_streams)]):
-                x = host_inputs[i & 1].to(device, non_blocking=True)
-                obj = layer.encode(x)                       # {'strings': [list[bytes]], 'shape'}: bitstreams land on the host
-                feat = layer.decode(**obj)                  # list[bytes] -> device -> features
-                res = feat.mean(dim=(1, 2, 3))
-                torch.cuda.current_stream().synchronize()   # (a blocking .cpu() would hold a driver lock while it waits)
-                res = res.cpu()                             # per-image result read back
-            return obj, res
+        def run_e2e(inputs, n_thr, use_transform_stream):
+            streams = [torch.cuda.Stream(device=device) for _ in range(n_thr)]
 
-        # default: 12 host threads per GPU (they mostly wait on the GPU with the GIL released), fewer when ranks share few cores
-        n_thr = args.e2e_threads if args.e2e_threads > 0 else min(12, max(6, 2 * (os.cpu_count() or 8) // max(world, 1)))
-        e2e_streams = [torch.cuda.Stream(device=device) for _ in range(n_thr)]
-        # the threads' transforms share one stream (in arrival order); a thread queues a transform only once its own stream
-        # has produced the input, so a batch that is still copying or coding never holds up the others
-        layer.use_transform_stream(True, host_wait=True)
-        with concurrent.futures.ThreadPoolExecutor(max_workers=n_thr) as pool:
-            list(pool.map(e2e_step, range(max(args.warmup, 2 * n_thr))))
-            barrier()
-            e2e_allocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
-            t0 = time.perf_counter()
-            results = list(pool.map(e2e_step, range(2 * n_thr, 2 * n_thr + args.steps)))
-            torch.cuda.synchronize()
-            e2e_ms = (time.perf_counter() - t0) * 1e3  # host wall clock: host work is part of this contract
-            barrier()
-        layer.use_transform_stream(None)
-        obj, res = results[-1]
-        te = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        stream_bytes = sum(len(s) for s in obj['strings'][0])
-        e2e = {'value': world * B * args.steps / (float(te.item()) / 1e3), 'unit': UNIT,
-               'h2d_bytes_per_step': B * IMG[0] * IMG[1] * IMG[2] * 4 + stream_bytes + 8 * (B + 1),
-               'd2h_bytes_per_step': stream_bytes + 8 * (B + 1) + 4 + B * 4, 'host_threads': n_thr,
-               'cudaMalloc_calls_in_timed_region': torch.cuda.memory_stats(device).get('num_device_alloc', 0) - e2e_allocs0,
-               'ms_per_step': float(te.item()) / args.steps}
+            def e2e_step(i):
+                with torch.inference_mode(), torch.cuda.stream(streams[i % n_thr]):
+                    x = inputs[i & 1].to(device, non_blocking=True)
+                    obj = encode(x)                             # {'strings': [list[bytes]], 'shape'}: bitstreams land on the host
+                    feat = decode(obj)                          # list[bytes] -> device -> features
+                    res = feat.mean(dim=(1, 2, 3))
+                    torch.cuda.current_stream().synchronize()   # (a blocking .cpu() would hold a driver lock while it waits)
+                    res = res.cpu()                             # per-image result read back
+                return obj, res
+
+            if use_transform_stream:
+                model.use_transform_stream(True, host_wait=True)
+            with concurrent.futures.ThreadPoolExecutor(max_workers=n_thr) as pool:
+                list(pool.map(e2e_step, range(max(args.warmup, 2 * n_thr))))
+                barrier()
+                a0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
+                t0 = time.perf_counter()
+                results = list(pool.map(e2e_step, range(2 * n_thr, 2 * n_thr + args.steps)))
+                torch.cuda.synchronize()
+                wall = (time.perf_counter() - t0) * 1e3  # host wall clock: host work is part of this contract
+                barrier()
+            if use_transform_stream:
+                model.use_transform_stream(None)
+            te = torch.tensor([wall], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            obj, res = results[-1]
+            sb = sum(len(s) for lst in obj['strings'] for s in lst)
+            n_str = sum(len(lst) for lst in obj['strings'])
+            return {'value': B_global * args.steps / (float(te.item()) / 1e3), 'unit': UNIT,
+                    'h2d_bytes_per_step': inputs[0].numel() * inputs[0].element_size() + sb + 8 * (n_str + 1),
+                    'd2h_bytes_per_step': sb + 8 * (n_str + 1) + 4 + B * 4, 'host_threads': n_thr,
+                    'cudaMalloc_calls_in_timed_region': torch.cuda.memory_stats(device).get('num_device_alloc', 0) - a0,
+                    'ms_per_step': float(te.item()) / args.steps, 'input_dtype': str(inputs[0].dtype).replace('torch.', '')}
+
+        if pipelined:
+            cores = os.cpu_count() or 8
+            n_thr = args.e2e_threads if args.e2e_threads > 0 else min(12, max(4, 2 * cores // max(world, 1) - 2))
+            # uint8 images + device-side ToTensor / Normalize (FPBasedResNetBottleneck.set_input_normalization): 4x less H2D
+            model.set_input_normalization(IMAGENET_MEAN, IMAGENET_STD)
+            g8 = torch.Generator(device='cpu').manual_seed(11 + rank)
+            host_u8 = [torch.randint(0, 256, (B,) + shape, dtype=torch.uint8, generator=g8).pin_memory() for _ in range(2)]
+            e2e = run_e2e(host_u8, n_thr, True)
+            e2e['input'] = 'uint8 images, ToTensor + Normalize on the device (inside the first conv kernel)'
+            f32 = run_e2e(host_inputs, n_thr, True)
+            e2e['fp32_input'] = {k: f32[k] for k in ('value', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'ms_per_step')}
+        else:
+            e2e = run_e2e(host_inputs, args.e2e_threads if args.e2e_threads > 0 else (1 if cfg in (1, 5) else 2), False)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- per-kernel accounting and the roofline of the dominant kernel ---------------------------
-    step_ms = serial_ms  # shares are relative to the serial step the kernel times were taken in
-    traffic, traffic_src = load_traffic()
-    kernels = []
-    for tag, times in prof.items():
-        avg = sum(times) / len(times)
-        per_step = sum(times) / n_prof
-        k = {'kernel': tag, 'launches_per_step': len(times) / n_prof, 'avg_launch_ms': avg, 'share_of_step': per_step / step_ms}
-        if tag in FLOPS:
-            k.update(bound='tensor', achieved=FLOPS[tag] * B / (avg / 1e3) / 1e12, unit='TFLOP/s', peak=peaks['tflops_sustained'])
-        elif tag in BYTES:
-            k.update(bound='hbm', achieved=BYTES[tag] * B / (avg / 1e3) / 1e9, unit='GB/s', peak=peaks['hbm_gbs'])
-        if 'achieved' in k:
-            k['frac'] = k['achieved'] / k['peak']
-        if tag in traffic:  # measured DRAM bytes of one launch (ncu), scaled to this batch size
-            k['traffic'] = traffic[tag]['dram_bytes_per_launch'] * B / traffic[tag].get('batch', 256)
-        k['stream'] = 'batch' if tag.startswith('rans_') else 'transform'
-        if tag in ('rans_encode', 'rans_decode'):
-            k['symbols_per_s_per_stream'] = n_sym / (avg / 1e3)
-            k['symbols_per_s_aggregate'] = n_sym * B / (avg / 1e3)
-            k['note'] = ('serial rANS state chain per stream (SURVEY.md H1): latency-bound, neither roofline applies.  Lane-per-stream '
-                         'layout: the %d streams of a batch are ONE block of %d warps on one SM, running next to the transforms of '
-                         'the other batches in flight -- off the critical path of the pipelined step' % (B, (B + 31) // 32))
-        else:
-            k['share_of_pipelined_step'] = per_step / (ms / args.steps)
-        kernels.append(k)
-    kernels.sort(key=lambda k: -k['share_of_step'])
-    roofline = None
-    if kernels:
-        top = kernels[0]
-        roofline = {'kernel': top['kernel'], 'bound': top.get('bound'), 'achieved': top.get('achieved'), 'peak': top.get('peak'),
-                    'unit': top.get('unit'), 'frac': top.get('frac'), 'traffic': top.get('traffic'), 'traffic_source': traffic_src,
-                    'peak_source': peaks['source'] + (', bf16 sustained' if top.get('bound') == 'tensor' else ', copy bandwidth'),
-                    'avg_launch_ms': top['avg_launch_ms'], 'share_of_step': top['share_of_step'], 'note': top.get('note')}
-        keys = ('kernel', 'bound', 'achieved', 'unit', 'peak', 'frac', 'traffic', 'avg_launch_ms', 'share_of_step', 'share_of_pipelined_step')
-        crit = [k for k in kernels if k['stream'] == 'transform']
-        if crit and crit[0] is not top:  # the kernel that bounds the pipelined step: largest on the transform stream
-            roofline['critical_path_kernel'] = {kk: crit[0].get(kk) for kk in keys}
-        gemm = [k for k in kernels if k.get('bound') == 'tensor']
-        if gemm and gemm[0] is not top:
-            roofline['dominant_gemm'] = {kk: gemm[0].get(kk) for kk in keys}
+    traffic, traffic_src = load_traffic() if cfg == 2 else ({}, None)
+    kernels = account_kernels(prof, work, n_prof, serial_ms, (ms / args.steps) if pipelined else None, peaks, traffic, B)
+    roofline = pick_roofline(kernels, peaks, traffic_src)
+    coder = {k['kernel']: {kk: k.get(kk) for kk in ('avg_launch_ms', 'symbols_per_s_per_stream', 'symbols_per_s_aggregate', 'streams',
+                                                    'symbols_per_stream')}
+             for k in kernels if k['kernel'] in ('rans_encode', 'rans_decode')}
+    path_flops = sum((k.get('algorithmic_flops') or 0.0) * k['launches_per_step'] for k in kernels) / max(B, 1)
+    path_bytes = sum((k.get('algorithmic_bytes') or 0.0) * k['launches_per_step'] for k in kernels if k['stream'] == 'transform') / max(B, 1)
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        sd = {k: v.detach().cpu() for k, v in layer.state_dict().items()}
-        r = cpu_reference_run(args.cpu_images, steps=2, warmup=1, state_dict=sd)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        n_cpu = args.cpu_images or default_cpu_images(cfg)
+        r = cpu_reference_run(cfg, n_cpu, steps=2, warmup=1, state_dict=sd)
         cpu_baseline = {'value': r['images_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port',
-                        'sample': '%d images per step x 2 steps of the same workload; restated reference (oracle/: CompressAI '
-                                  'restatement, torch CPU convs on %d threads, per-sample Python-list coder loop + C rANS)'
-                                  % (args.cpu_images, r['threads'])}
+                        'sample': '%d images per step x 2 steps of the same workload; restated reference (oracle/: CompressAI restatement, '
+                                  'torch CPU convs on %d threads, per-sample Python-list coder loop + C rANS)' % (n_cpu, r['threads'])}
 
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': n_warm,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32-grade (g_a: split-f16 operands, 3 tensor-core passes, f32 accumulate) / f16 operands with f32 accumulate (g_s) / u64 (coder)',
+    line = {'metric': METRICS[cfg], 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+            'dtype': 'f32-grade (g_a: split-f16 operands, 3 tensor-core passes, f32 accumulate) / f16 operands with f32 accumulate (g_s) / u64 (coder)'
+                     if cfg in (1, 2, 5) else 'f32 (g_a, h_a, h_s: CUDA-core FFMA kernels) / u64 (coder)',
             'data': 'synthetic',
-            'config': {'workload': 'configs[1]: entropic-student-resnet50 FPBasedResNetBottleneck(24,256) encode+rANS+decode, '
-                                   '3x224x224, random init, batch %d per GPU' % B,
-                       'images_per_gpu_per_step': B, 'global_images_per_step': B * world, 'symbols_per_image': n_sym,
-                       'l2_policy': 'two alternating 154 MB input batches (> 126 MB L2); activations are GBs per step',
+            'config': {'workload': desc + ', batch %d per GPU' % B, 'bench_config': cfg,
+                       'images_per_gpu_per_step': B, 'global_images_per_step': B_global, 'symbols_per_image': sym_per_image,
+                       'l2_policy': 'two alternating input batches of %.0f MB (> 126 MB L2)' % (input_bytes / 1e6) if not flush_l2 else
+                                    'L2 flushed (256 MB write) between timed iterations, each iteration timed by its own event pair',
                        'parallelism': 'dp%d (batch sharded, one counter all-reduce per evaluation)' % world,
-                       'batches_in_flight': args.inflight,
-                       'schedule': 'software pipeline: transforms on one stream, g_a(i + depth) ahead of g_s(i); coders on per-batch streams'},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
-            'serial_ms_per_step': serial_ms, 'one_batch_latency_ms': latency_ms,
-            'host_issue_ms_per_step': t_issue / args.steps, 'cudaMalloc_calls_in_timed_region': allocs,
+                       'schedule': ('software pipeline, %d batches in flight: transforms on one stream, g_a(i + depth) ahead of g_s(i); '
+                                    'coders on per-batch streams' % args.inflight) if pipelined else 'one batch at a time (latency)'},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'coder': coder, 'cpu_baseline': cpu_baseline,
+            'serial_ms_per_step': serial_ms, 'one_batch_latency_ms': latency_ms, 'ms_per_image': ms / args.steps / max(B, 1),
+            'host_issue_ms_per_step': t_issue / args.steps, 'cudaMalloc_calls_in_timed_region': allocs, 'per_rank_ms': per_rank_ms,
             'kernel_accounting': 'serial pass of %d steps after the timed region, same kernels (CUDA events per launch); shares are of '
-                                 'that serial step, as in the ncu launch list; one_batch_latency_ms uses the warp-per-stream coder' % n_prof,
+                                 'that serial step, as in the ncu launch list' % n_prof,
             'kernels': kernels,
-            'bytes_per_image': c['bytes_per_image'], 'bits_per_symbol': c['bits_per_symbol'],
-            'path_tflops': value * PATH_FLOPS_PER_IMAGE / 1e12, 'path_hbm_gbs_algorithmic': value * PATH_BYTES_PER_IMAGE / 1e9}
+            'bytes_per_image': c['bytes_per_image'], 'bits_per_symbol': c['bits_per_symbol'] if sym_per_image else None,
+            'path_tflops': value * path_flops / 1e12, 'path_hbm_gbs_algorithmic': value * path_bytes / 1e9,
+            'path_algorithmic_gflop_per_image': path_flops / 1e9, 'path_algorithmic_mb_per_image': path_bytes / 1e6}
+    line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

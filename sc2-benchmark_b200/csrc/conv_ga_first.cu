@@ -347,6 +347,13 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 // K order = (c, dy, dx), like weight.reshape(c_out, -1); 8 values -> one 16-byte unit of the hi and of the lo tile
                 float f[kK];
                 const uint8_t *patch = s_patch + s * p.patch_bytes;
+                // (uint8 input) which of this pixel's 5 rows / 5 columns lie inside the image
+                const int img_t = tile / tiles_xy, sp_t = tile % tiles_xy;
+                const int iy0 = 4 * ((sp_t / p.tiles_x) * p.th + ty) + 2 * ((img_t >> 1) & 1) - 2;
+                const int ix0 = 4 * ((sp_t % p.tiles_x) * p.tw + tx) + 2 * (img_t & 1) - 2;
+                uint32_t col_ok = 0;
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx) col_ok |= (static_cast<uint32_t>(ix0 + dx) < static_cast<uint32_t>(p.w_in) ? 1u : 0u) << dx;
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -358,11 +365,14 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                             const uint32_t w1 = *reinterpret_cast<const uint32_t *>(patch + e0 + 4);
                             const uint32_t sh = static_cast<uint32_t>(patch_col0 & 3) * 8u;
                             const uint32_t w4 = __funnelshift_r(w0, w1, sh), b4 = (w1 >> sh) & 255u;
-                            o[0] = s_lut[c * 256 + (w4 & 255u)];
-                            o[1] = s_lut[c * 256 + ((w4 >> 8) & 255u)];
-                            o[2] = s_lut[c * 256 + ((w4 >> 16) & 255u)];
-                            o[3] = s_lut[c * 256 + (w4 >> 24)];
-                            o[4] = s_lut[c * 256 + b4];
+                            // the conv pads with ZEROS of the normalised image, but TMA fills bytes outside the image with 0 and
+                            // lut[0] = -mean / std: mask those positions instead of looking them up
+                            const uint32_t ok = static_cast<uint32_t>(iy0 + dy) < static_cast<uint32_t>(p.h_in) ? col_ok : 0u;
+                            o[0] = (ok & 1u) ? s_lut[c * 256 + (w4 & 255u)] : 0.0f;
+                            o[1] = (ok & 2u) ? s_lut[c * 256 + ((w4 >> 8) & 255u)] : 0.0f;
+                            o[2] = (ok & 4u) ? s_lut[c * 256 + ((w4 >> 16) & 255u)] : 0.0f;
+                            o[3] = (ok & 8u) ? s_lut[c * 256 + (w4 >> 24)] : 0.0f;
+                            o[4] = (ok & 16u) ? s_lut[c * 256 + b4] : 0.0f;
                         } else {   // 5 floats starting 0 or 2 floats into an aligned float4: two conflict-free 16-byte loads
                             const float4 v0 = *reinterpret_cast<const float4 *>(patch + 4 * e0);
                             const float4 v1 = *reinterpret_cast<const float4 *>(patch + 4 * e0 + 16);
