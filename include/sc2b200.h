@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 4
+#define SC2_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -180,11 +180,17 @@ SC2_API int sc2_gdn_f32(const float *x, const float *gamma, const float *beta, f
  *   w_packed  [kh*kw, c_out, c_in_pad] fp16  (tap-major repack of the Conv2d weight; for the GDN modes: gamma [c, c])
  *   out       [batch, h_out, w_out, c_out]  fp16 or fp32 (mode), h_out = h_in + 2*pad - kh + 1
  *   modes     0 store fp16 | 1 store fp32 | 2 IGDN1: out = gdn_x * (beta + acc) | 3 GDN1: out = gdn_x / (beta + acc)
- *             (GDN modes: 1x1 "gamma" GEMM over |x|, gdn_x = x itself, c_in_pad == c_out) */
+ *             (GDN modes: 1x1 "gamma" GEMM over |x|, gdn_x = x itself, c_in_pad == c_out)
+ *             4 store |acc| as fp16 + one sign bit per value in `signs` (the conv in front of an IGDN1)
+ *             5 IGDN1 on such a pair: x = |x| tensor (also the A operand, no in-kernel |.| pass), gdn_x = the same |x|,
+ *               signs = the sign words; out = sign * |x| * (beta + acc)
+ *   signs     modes 4 (out) / 5 (in): uint32 [batch * h_out * w_out, c_out / 32]; word layout: conv_tc.cu; else NULL */
 #define SC2_TC_STORE_F16 0
 #define SC2_TC_STORE_F32 1
 #define SC2_TC_IGDN1_F16 2
 #define SC2_TC_GDN1_F16 3
+#define SC2_TC_STORE_ABS_F16 4
+#define SC2_TC_IGDN1_ABS_F16 5
 
 typedef struct sc2_tc_conv_desc {
     int batch, h_in, w_in, c_in_pad;
@@ -196,7 +202,7 @@ typedef struct sc2_tc_conv_desc {
  * ZERO at launch (one per launch; stream-ordered reuse is fine) the CTAs claim tiles dynamically, so a CTA that is placed
  * late -- its SM busy with another stream's blocks -- does not delay the kernel; NULL selects the static schedule. */
 SC2_API int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta,
-                             const void *gdn_x, void *out, int32_t *tile_counter, sc2_stream_t stream);
+                             const void *gdn_x, void *out, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Device: fp32-grade tensor-core convolution ("split fp16", three tcgen05 passes; conv_tc_split.cu) for g_a

@@ -49,6 +49,7 @@ class TensorCoreTransform:
     def __init__(self, seq):
         self.seq = seq
         self._plan = None  # (key, steps, c_in_pad): built into locals and published with ONE assignment (host threads share it)
+        self.split_signs = True  # conv -> IGDN1 pairs exchange (|x|, sign words); False: round-1 route (x, |.| pass in the kernel)
 
     @staticmethod
     def why_not(seq):
@@ -92,12 +93,19 @@ class TensorCoreTransform:
                 if isinstance(m, nn.Conv2d):
                     c_in_pad = (m.in_channels + 63) // 64 * 64
                     mode = _native.TC_STORE_F32 if i == len(mods) - 1 else _native.TC_STORE_F16
+                    # a conv in front of an IGDN1 stores |x| + packed signs: the IGDN1's gamma GEMM then reads |x| straight from
+                    # its TMA tiles (conv_tc.cu, modes 4 / 5)
+                    nxt = mods[i + 1] if i + 1 < len(mods) else None
+                    if self.split_signs and type(nxt) is GDN1 and nxt.inverse and m.out_channels % 32 == 0:
+                        mode = _native.TC_STORE_ABS_F16
                     steps.append(('conv', ops.pack_conv_weight_f16(m.weight, c_in_pad), m.kernel_size[0], m.padding[0], mode, None,
                                   m.in_channels))
                 else:
                     gamma, beta = m.effective_params()
                     C = beta.numel()
                     mode = _native.TC_IGDN1_F16 if m.inverse else _native.TC_GDN1_F16
+                    if steps and steps[-1][4] == _native.TC_STORE_ABS_F16:
+                        mode = _native.TC_IGDN1_ABS_F16
                     steps.append(('gdn', gamma.detach().reshape(1, C, C).half().contiguous(), 1, 0, mode, beta.detach().float().contiguous(), C))
             plan = (key, steps, (mods[0].in_channels + 63) // 64 * 64)
             self._plan = plan
@@ -108,8 +116,12 @@ class TensorCoreTransform:
         """fp32 NCHW in -> fp32 output, logically NCHW (physically channels-last: what cuDNN prefers for the tail)."""
         _, steps, c_in_pad = self._prepare()
         x = ops.nchw_to_nhwc_f16(x_nchw, c_in_pad)
+        signs = None
         for kind, w, k, pad, mode, beta, c_in in steps:
-            x = ops.tc_conv(x, w, k, k, pad, mode=mode, beta=beta, gdn_x=x if kind == 'gdn' else None, c_in=c_in)
+            x = ops.tc_conv(x, w, k, k, pad, mode=mode, beta=beta, gdn_x=x if kind == 'gdn' else None, c_in=c_in, signs=signs)
+            signs = None
+            if mode == _native.TC_STORE_ABS_F16:
+                x, signs = x
         return x.permute(0, 3, 1, 2)
 
 

@@ -25,7 +25,13 @@
 namespace sc2 {
 namespace tc {
 
-enum Mode { MODE_STORE_F16 = 0, MODE_STORE_F32 = 1, MODE_IGDN1_F16 = 2, MODE_GDN1_F16 = 3 };
+enum Mode { MODE_STORE_F16 = 0, MODE_STORE_F32 = 1, MODE_IGDN1_F16 = 2, MODE_GDN1_F16 = 3, MODE_STORE_ABS_F16 = 4, MODE_IGDN1_ABS_F16 = 5 };
+// Modes 4 / 5 (round 2) split "x" into |x| (fp16) and one sign bit per value: the conv in front of an IGDN1 stores |x| and the
+// packed signs, and the IGDN1's 1x1 gamma GEMM reads |x| straight from the TMA-loaded tile -- no in-smem |.| pass between the
+// TMA and the MMA (that extra hop is what kept IGDN1(512) at 25 % tensor-pipe utilisation with a 4-stage ring while the plain
+// conv with the same tiles reached 80 %), and the epilogue rebuilds x = sign * |x| from the sign words.
+// Sign word of 32 consecutive channels (16 half2 words h_0..h_15): S = OR_k ((h_k & 0x80008000) >> k), so bit 15-k is the sign
+// of channel 2k and bit 31-k of channel 2k+1; the reader recovers word k's signs as (S << k) & 0x80008000.
 
 struct Params {
     int tiles_x, tiles_y;  // output tile grid per image
@@ -37,7 +43,8 @@ struct Params {
     int batch;
     int h_out, w_out;
     const float *beta;     // GDN modes: effective beta [n_total]
-    const __half *gdn_x;   // GDN modes: x itself, NHWC [batch, h_out, w_out, n_total]
+    const __half *gdn_x;   // GDN modes: x itself (mode 5: |x|), NHWC [batch, h_out, w_out, n_total]
+    uint32_t *signs;       // mode 4: out, mode 5: in -- packed sign words [batch * h_out * w_out, n_total / 32]
     void *out;             // NHWC [batch, h_out, w_out, n_total], fp16 or fp32
     int *tile_counter;     // zeroed by the caller: dynamic tile schedule; nullptr: static
     TraceSink trace;       // diagnostics (common.cuh)
@@ -57,10 +64,12 @@ struct Smem {
 };
 
 template <int N_TILE, int STAGES, int MODE>
-__global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16) ? 448 : 320, 1)
+__global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16) ? 448 : 320, 1)  // + 4 |x| transform warps
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params p) {
     using L = Smem<N_TILE, STAGES>;
-    constexpr bool kGdn = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
+    constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;  // |x| formed in shared memory by 4 extra warps
+    constexpr bool kGdn = kXform || MODE == MODE_IGDN1_ABS_F16;               // GDN epilogue
+    constexpr bool kSigned = MODE == MODE_IGDN1_ABS_F16;                      // x = sign word * |x|
     constexpr bool kOutF32 = MODE == MODE_STORE_F32;
     constexpr uint32_t kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "two accumulator stages must fit TMEM");
@@ -90,7 +99,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) reinterpret_cast<float *>(smem + L::kBetaOffset)[i] = __ldg(p.beta + i);
 
     if (threadIdx.x == 0) {
-        sched.init(kGdn ? 13 : 9);  // consumers: MMA warp, 8 epilogue warps (, 4 transform warps)
+        sched.init(kXform ? 13 : 9);  // consumers: MMA warp, 8 epilogue warps (, 4 transform warps)
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < STAGES; ++s) {
@@ -146,7 +155,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tcgen05_fence_after();
             for (int k_it = 0; k_it < k_iters; ++k_it, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-                mbar_wait(kGdn ? &xform[s] : &full[s], ph);
+                mbar_wait(kXform ? &xform[s] : &full[s], ph);
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
@@ -180,6 +189,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // GDN modes: request this thread's x values BEFORE waiting for the accumulator (their latency hides behind the MMAs)
             constexpr int kMaxChunks = (N_TILE + 63) / 64;
             uint4 xpre[kGdn ? kMaxChunks : 1][4];
+            uint32_t spre[kSigned ? kMaxChunks : 1];
             if (kGdn && valid) {
 #pragma unroll
                 for (int ci = 0; ci < kMaxChunks; ++ci) {
@@ -187,6 +197,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (c0 < N_TILE) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) xpre[ci][c] = __ldg(reinterpret_cast<const uint4 *>(p.gdn_x + pix * p.n_total + n0 + c0) + c);
+                        if (kSigned) spre[ci] = __ldg(p.signs + pix * (p.n_total >> 5) + ((n0 + c0) >> 5));
                     }
                 }
             }
@@ -209,13 +220,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                              __uint_as_float(v[4 * c + 3]));
                 } else {
                     uint4 *dst = reinterpret_cast<uint4 *>(static_cast<__half *>(p.out) + o);
+                    uint32_t sign_word = 0;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * c + e]);
                         if (kGdn) {
-                            const uint4 xv = xpre[kGdn ? ci : 0][c];
+                            uint4 xv = xpre[kGdn ? ci : 0][c];
+                            if (kSigned) {  // x = sign * |x|: half2 word k = 4c + e of the chunk takes (S << k) & 0x80008000
+                                const uint32_t sw = spre[kSigned ? ci : 0];
+                                xv.x |= (sw << (4 * c)) & 0x80008000u;
+                                xv.y |= (sw << (4 * c + 1)) & 0x80008000u;
+                                xv.z |= (sw << (4 * c + 2)) & 0x80008000u;
+                                xv.w |= (sw << (4 * c + 3)) & 0x80008000u;
+                            }
                             const __half2 *xh = reinterpret_cast<const __half2 *>(&xv);
                             const float4 ba = *reinterpret_cast<const float4 *>(s_beta + n0 + c0 + 8 * c);
                             const float4 bb = *reinterpret_cast<const float4 *>(s_beta + n0 + c0 + 8 * c + 4);
@@ -239,15 +258,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         h = __floats2half2_rn(f[2], f[3]); ov.y = *reinterpret_cast<uint32_t *>(&h);
                         h = __floats2half2_rn(f[4], f[5]); ov.z = *reinterpret_cast<uint32_t *>(&h);
                         h = __floats2half2_rn(f[6], f[7]); ov.w = *reinterpret_cast<uint32_t *>(&h);
+                        if (MODE == MODE_STORE_ABS_F16) {
+                            sign_word |= ((ov.x & 0x80008000u) >> (4 * c)) | ((ov.y & 0x80008000u) >> (4 * c + 1)) |
+                                         ((ov.z & 0x80008000u) >> (4 * c + 2)) | ((ov.w & 0x80008000u) >> (4 * c + 3));
+                            ov.x &= 0x7fff7fffu; ov.y &= 0x7fff7fffu; ov.z &= 0x7fff7fffu; ov.w &= 0x7fff7fffu;
+                        }
                         dst[c] = ov;
                     }
+                    if (MODE == MODE_STORE_ABS_F16) p.signs[pix * (p.n_total >> 5) + ((n0 + c0) >> 5)] = sign_word;
                 }
             }
             tcgen05_fence_before();
             mbar_arrive(&acc_empty[as]);  // 256 arrivals release the accumulator stage to the MMA warp
         }
-    } else if (kGdn) {
-        // =============================== |x| transform warps (10..13, GDN modes) ===============================
+    } else if (kXform) {
+        // =============================== |x| transform warps (10..13, GDN modes 2 / 3) ===============================
         const int row = (warp - 10) * 32 + lane;
         uint32_t it = 0;
         for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
@@ -281,13 +306,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 template <int N_TILE, int STAGES, int MODE>
 static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const Params &p, cudaStream_t st) {
     using L = Smem<N_TILE, STAGES>;
-    constexpr bool kGdn = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
+    constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
     const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
     static std::atomic<uint64_t> configured{0};  // per device ordinal
     if (int rc = ensure_dyn_smem(tc_conv_kernel<N_TILE, STAGES, MODE>, smem, configured)) return rc;
     const int total = p.tiles_x * p.tiles_y * p.n_tiles * p.batch;
     const int grid = total < persistent_grid() ? total : persistent_grid();
-    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kGdn ? 448 : 320, smem, st>>>(ma, mb, p);
+    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kXform ? 448 : 320, smem, st>>>(ma, mb, p);
     SC2_LAUNCH_CHECK("tc_conv_kernel");
     return SC2_OK;
 }
@@ -327,12 +352,13 @@ int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, i
 }
 
 int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta, const void *gdn_x,
-                     void *out, int32_t *tile_counter, sc2_stream_t stream) {
+                     void *out, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream) {
     using namespace sc2::tc;
     if (!d || !x || !w_packed || !out) return SC2_ERR_INVALID_ARG;
     if (d->batch < 1 || d->c_in_pad % kBlockK || d->c_in_pad < kBlockK) return SC2_ERR_INVALID_ARG;
-    if (d->mode < 0 || d->mode > 3) return SC2_ERR_INVALID_ARG;
-    const bool gdn = d->mode == MODE_IGDN1_F16 || d->mode == MODE_GDN1_F16;
+    if (d->mode < 0 || d->mode > 5) return SC2_ERR_INVALID_ARG;
+    const bool gdn = d->mode == MODE_IGDN1_F16 || d->mode == MODE_GDN1_F16 || d->mode == MODE_IGDN1_ABS_F16;
+    if ((d->mode == MODE_STORE_ABS_F16 || d->mode == MODE_IGDN1_ABS_F16) && (!signs || d->c_out % 32)) return SC2_ERR_INVALID_ARG;
     if (gdn && (!beta || !gdn_x || d->kh != 1 || d->kw != 1 || d->pad != 0 || d->c_in_pad != d->c_out)) return SC2_ERR_INVALID_ARG;
     if (gdn && d->c_out > kMaxBeta) return SC2_ERR_UNSUPPORTED;
     const int h_out = d->h_in + 2 * d->pad - d->kh + 1, w_out = d->w_in + 2 * d->pad - d->kw + 1;
@@ -362,6 +388,7 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
     p.h_out = h_out; p.w_out = w_out;
     p.beta = beta;
     p.gdn_x = static_cast<const __half *>(gdn_x);
+    p.signs = signs;
     p.out = out;
     p.tile_counter = tile_counter;
     p.trace = sc2::trace_sink();
@@ -377,6 +404,8 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
         case MODE_STORE_F16: return launch<NT, STG, MODE_STORE_F16>(ma, mb, p, st);  \
         case MODE_STORE_F32: return launch<NT, STG, MODE_STORE_F32>(ma, mb, p, st);  \
         case MODE_IGDN1_F16: return launch<NT, STG, MODE_IGDN1_F16>(ma, mb, p, st);  \
+        case MODE_STORE_ABS_F16: return launch<NT, STG, MODE_STORE_ABS_F16>(ma, mb, p, st);  \
+        case MODE_IGDN1_ABS_F16: return launch<NT, STG, MODE_IGDN1_ABS_F16>(ma, mb, p, st);  \
         default: return launch<NT, STG, MODE_GDN1_F16>(ma, mb, p, st);             \
     }
     if (n_tile == 256) { SC2_TC_DISPATCH(256, 4) }

@@ -466,7 +466,7 @@ def nchw_to_nhwc_f16(x, c_pad):
     return y
 
 
-def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None, gdn_x=None, c_in=None):
+def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None, gdn_x=None, c_in=None, signs=None):
     """tcgen05 implicit-GEMM conv on NHWC fp16 (sc2_tc_conv_nhwc). Returns NHWC fp16 / fp32.  c_in: the layer's real input
     channels (the activation may be zero-padded to a multiple of 64), for the work accounting only."""
     require_cuda(x_nhwc, 'tc_conv')
@@ -479,14 +479,16 @@ def tc_conv(x_nhwc, w_packed, kh, kw, pad, mode=_native.TC_STORE_F16, beta=None,
     ho, wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
     out = torch.empty((B, ho, wo, c_out), dtype=torch.float32 if mode == _native.TC_STORE_F32 else torch.float16, device=x_nhwc.device)
     b = beta.detach().contiguous().float() if beta is not None else None
+    if mode == _native.TC_STORE_ABS_F16:  # |x| + packed signs out (the pair an IGDN1 in mode TC_IGDN1_ABS_F16 reads)
+        signs = torch.empty((B, ho, wo, c_out // 32), dtype=torch.int32, device=x_nhwc.device)
     tag = 'tc_conv[%d->%d,k%d,m%d]' % (Cp, c_out, kh, mode)
     c_real = c_in or Cp
     flops = 2.0 * B * ho * wo * c_out * c_real * kh * kw
     nbytes = 4.0 * B * (H * W * c_real + ho * wo * c_out)
     with torch.cuda.device(x_nhwc.device), _launch(tag, flops=flops, nbytes=nbytes):
-        check(_lib().sc2_tc_conv_nhwc(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(b), _ptr(gdn_x), _ptr(out),
+        check(_lib().sc2_tc_conv_nhwc(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(b), _ptr(gdn_x), _ptr(out), _ptr(signs),
                                       _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_conv_nhwc')
-    return out
+    return (out, signs) if mode == _native.TC_STORE_ABS_F16 else out
 
 
 # ----------------------------------------------------------------------------------------------
