@@ -32,6 +32,7 @@ using namespace sc2::tc;
 constexpr int kThreads = 384;  // warp 0: A (halo) producer + tile scheduler; 1: MMA issuer; 2: B (weights) producer; 3: idle; 4..11: epilogue
 constexpr int kMaxTaps = 25;
 constexpr int kMaxB = 8;
+constexpr int kMaxA = 4;
 constexpr float kLoScale = 2048.0f;
 constexpr float kLoInv = 1.0f / 2048.0f;
 
@@ -51,6 +52,7 @@ struct Params {
     int stage_plane;  // bytes of one staging plane (hi or lo): th * tw * stage_c * 2 rounded up to 128
     int h_out, w_out;
     int halo_bytes;  // (th + 2) * pitch * 128
+    int n_a;         // halo ring units (each: hi + lo)
     int n_b;         // B ring slots
     int off_gamma, off_ag, off_b, off_bar;  // shared-memory offsets (from the 1024-aligned base)
     const float *beta;
@@ -103,19 +105,17 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     static_assert(N % 16 == 0 && N >= 16 && N <= 96, "N");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t *s_gamma = smem + p.off_gamma;
     uint8_t *s_ag = smem + p.off_ag;  // |x| (hi chunks, then lo chunks), K-major SWIZZLE_128B; aliased by the output staging tile
     uint8_t *s_b = smem + p.off_b;
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
-    uint64_t *a_empty = a_full + 2;
-    uint64_t *b_full = a_empty + 2;
+    uint64_t *a_empty = a_full + kMaxA;
+    uint64_t *b_full = a_empty + kMaxA;
     uint64_t *b_empty = b_full + kMaxB;
     uint64_t *acc_full = b_empty + kMaxB;
     uint64_t *acc_empty = acc_full + 1;
     uint64_t *ag_full = acc_empty + 1;
     uint64_t *g_full = ag_full + 1;
-    uint64_t *gw_full = g_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gw_full + 1);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(g_full + 1);
     float *s_beta = reinterpret_cast<float *>(tmem_slot + 4);  // [N]
     TileSched sched;
     sched.bind(reinterpret_cast<uint8_t *>(s_beta + N), p.tile_counter, p.tiles_x * p.tiles_y * p.images);
@@ -136,7 +136,7 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         tma_prefetch_desc(&map_g);
         tma_prefetch_desc(&map_o_hi);
         tma_prefetch_desc(&map_o_lo);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kMaxA; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
         }
@@ -148,7 +148,6 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         mbar_init(acc_empty, 256);
         mbar_init(ag_full, 256);
         mbar_init(g_full, 1);
-        mbar_init(gw_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -173,7 +172,7 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const int plane = p.taps[t].plane;
                     while (t < p.n_taps && p.taps[t].plane == plane) ++t;
                     for (int kc = 0; kc < p.k_chunks; ++kc, ++unit) {
-                        const uint32_t s = unit & 1u, ph = (unit >> 1) & 1u;
+                        const uint32_t s = unit % p.n_a, ph = (unit / p.n_a) & 1u;
                         mbar_wait(&a_empty[s], ph ^ 1u);
                         uint8_t *dst = smem + s * 2 * p.halo_bytes;
                         mbar_expect_tx(&a_full[s], static_cast<uint32_t>(2 * p.halo_bytes));
@@ -186,11 +185,6 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
     } else if (warp == 2) {
         // =============================== weights producer ===============================
-        if (elect_one()) {
-            mbar_expect_tx(gw_full, static_cast<uint32_t>(kGC * kBSlot));
-            for (int c = 0; c < kGC; ++c) tma_load_2d(&map_g, gw_full, s_gamma + c * kBSlot, c * kBlockK, 0);
-        }
-        __syncwarp();
         uint32_t bq = 0;
         for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
             if (elect_one()) {
@@ -206,6 +200,14 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         }
                     t0 = t1;
                 }
+                // ... and the gamma matrix of this tile's GDN1 rides through the same ring (kGC more slots): 2 % more L2 traffic
+                // buys a whole slot of shared memory for the rings
+                for (int c = 0; c < kGC; ++c, ++bq) {
+                    const uint32_t s = bq % p.n_b, ph = (bq / p.n_b) & 1u;
+                    mbar_wait(&b_empty[s], ph ^ 1u);
+                    mbar_expect_tx(&b_full[s], static_cast<uint32_t>(kBSlot));
+                    tma_load_2d(&map_g, &b_full[s], s_b + s * kBSlot, c * kBlockK, 0);
+                }
             }
             __syncwarp();
         }
@@ -213,7 +215,6 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         // =============================== MMA issuer ===============================
         constexpr uint32_t idesc_stack = make_idesc(2 * N), idesc_n = make_idesc(N);
         uint32_t unit = 0, bq = 0;
-        mbar_wait(gw_full, 0);
         for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
             mbar_wait(acc_empty, (lt & 1u) ^ 1u);  // the epilogue has drained the conv accumulators of the previous tile
             tcgen05_fence_after();
@@ -221,8 +222,8 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 int t1 = t0;
                 while (t1 < p.n_taps && p.taps[t1].plane == p.taps[t0].plane) ++t1;
                 for (int kc = 0; kc < p.k_chunks; ++kc, ++unit) {
-                    const uint32_t as = unit & 1u;
-                    mbar_wait(&a_full[as], (unit >> 1) & 1u);
+                    const uint32_t as = unit % p.n_a;
+                    mbar_wait(&a_full[as], (unit / p.n_a) & 1u);
                     const uint32_t a_hi = smem_u32(smem + as * 2 * p.halo_bytes), a_lo = a_hi + p.halo_bytes;
                     const int k_steps = kc == p.k_chunks - 1 ? p.k_steps_last : kBlockK / 16;
                     for (int t = t0; t < t1; ++t, ++bq) {
@@ -259,21 +260,25 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             // ---- the gamma GEMM of this tile: |x| (written by the epilogue warps) x gamma^T ----
             mbar_wait(ag_full, lt & 1u);
             tcgen05_fence_after();
-            if (elect_one()) {
-                const uint32_t ag = smem_u32(s_ag), gm = smem_u32(s_gamma);
 #pragma unroll
-                for (int c = 0; c < kGC; ++c) {
+            for (int c = 0; c < kGC; ++c, ++bq) {
+                const uint32_t bs = bq % p.n_b;
+                mbar_wait(&b_full[bs], (bq / p.n_b) & 1u);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t ag = smem_u32(s_ag);
                     const uint64_t da_hi = make_smem_desc(ag + c * kABytes), da_lo = make_smem_desc(ag + (kGC + c) * kABytes);
-                    const uint64_t db = make_smem_desc(gm + c * kBSlot);
+                    const uint64_t db = make_smem_desc(smem_u32(s_b + bs * kBSlot));
                     const int k_steps = c == kGC - 1 ? kGStepsLast : 4;
                     for (int k = 0; k < k_steps; ++k) {
                         umma_f16(tmem_base + gamma_col, da_hi + 2 * k, db + 2 * k, idesc_stack, (c > 0 || k > 0) ? 1u : 0u);
                         umma_f16(tmem_base + gamma_col + N, da_lo + 2 * k, db + 2 * k, idesc_n, 1u);
                     }
+                    umma_commit(&b_empty[bs]);
+                    if (c == kGC - 1) umma_commit(g_full);
                 }
-                umma_commit(g_full);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // =============================== epilogue warps (4..11) ===============================
@@ -305,18 +310,18 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     uint32_t d0[16], d1[16];
                     tmem_ld16_nowait(lane_addr + u * 16, d0);
                     tmem_ld16_nowait(lane_addr + N + u * 16, d1);
-                    tmem_ld_wait();
                     for (int g = 1; g < p.groups; ++g) {  // chunked summation: fp32 round-to-nearest adds of the partial sums
                         uint32_t e0[16], e1[16];
                         tmem_ld16_nowait(lane_addr + g * 2 * N + u * 16, e0);
                         tmem_ld16_nowait(lane_addr + g * 2 * N + N + u * 16, e1);
-                        tmem_ld_wait();
+                        tmem_ld_wait();  // (also covers the loads of d0 / d1 issued before)
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             d0[e] = __float_as_uint(__uint_as_float(d0[e]) + __uint_as_float(e0[e]));
                             d1[e] = __float_as_uint(__uint_as_float(d1[e]) + __uint_as_float(e1[e]));
                         }
                     }
+                    tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 16; ++e) x[ui][e] = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e]));
                 }
@@ -489,20 +494,29 @@ int sc2_ga_halo_conv_gdn(const sc2_ga_halo_desc *d, const void *x_hi, const void
     }
     p.tiles_y = (d->h_out + p.th - 1) / p.th;
     p.halo_bytes = (p.th + 2) * pitch * 128;
-    // shared memory: [2 halo units (hi, lo)] [gamma, resident] [|x| operand / output staging] [weights ring] [barriers, beta, scheduler]
+    // shared memory: [halo ring: n_a units of (hi, lo)] [|x| operand / output staging] [weights ring: n_b slots] [barriers, beta,
+    // scheduler].  A halo unit takes ~1.5 us to arrive and a short unit (4 taps x 32 channels) is consumed in 0.5 us: with two
+    // units the MMAs waited for the halo loads most of the time, so the ring gets 3 units when 4 weight slots still fit.
     const int gc = (n + 63) / 64, b_slot = 2 * n * 128;
     p.stage_plane = (p.th * p.tw * p.stage_c * 2 + 127) / 128 * 128;
     const int ag_bytes = 2 * gc * kABytes, staging_bytes = 2 * p.stage_plane;
-    p.off_gamma = 4 * p.halo_bytes;
-    p.off_ag = p.off_gamma + gc * b_slot;
-    p.off_b = p.off_ag + ((ag_bytes > staging_bytes ? ag_bytes : staging_bytes) + 1023) / 1024 * 1024;
-    const int tail = 1024 + (4 + 2 * kMaxB + 5) * 8 + 16 + n * 4 + kTileSchedBytes + 64;
-    int n_b = (227 * 1024 - 1024 - p.off_b - tail) / b_slot;
+    const int ag_region = ((ag_bytes > staging_bytes ? ag_bytes : staging_bytes) + 1023) / 1024 * 1024;
+    const int tail = (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + n * 4 + kTileSchedBytes + 64;
+    const int budget = 227 * 1024 - 1024 - tail;  // (1024: slack for the manual alignment of the dynamic shared memory base)
+    int n_a = kMaxA, n_b = 0;
+    for (; n_a >= 2; --n_a) {
+        n_b = (budget - n_a * 2 * p.halo_bytes - ag_region) / b_slot;
+        if (n_b >= (n_a > 2 ? 4 : 2)) break;
+    }
+    if (n_a < 2) return SC2_ERR_UNSUPPORTED;
+    if (n_a > 3 && n_b < 6) { n_a = 3; n_b = (budget - n_a * 2 * p.halo_bytes - ag_region) / b_slot; }
     if (n_b > kMaxB) n_b = kMaxB;
-    if (n_b < 2) return SC2_ERR_UNSUPPORTED;
-    p.n_b = n_b;
+    p.n_a = n_a; p.n_b = n_b;
+    p.off_gamma = 0;
+    p.off_ag = n_a * 2 * p.halo_bytes;
+    p.off_b = p.off_ag + ag_region;
     p.off_bar = p.off_b + n_b * b_slot;
-    const int smem = p.off_bar + tail;
+    const int smem = p.off_bar + tail + 1024;
     p.beta = beta;
     p.tile_counter = tile_counter;
     p.trace = sc2::trace_sink();
