@@ -92,7 +92,8 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     constexpr int kUnits0 = (kUnits + 1) / 2;
     static_assert(N % 16 == 0 && N >= 16 && N <= 96, "N");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // (aligned by OFFSET, not through an integer cast: the compiler keeps the shared address space -> LDS / STS, not generic LD / ST)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *s_w = smem;                    // [W chunk 0][W chunk 1]
     uint8_t *s_gamma = smem + p.off_gamma;  // [gamma chunk 0][gamma chunk 1]
     uint8_t *s_a = smem + p.off_a;          // A tile: [hi 0 (16 KB)][lo 0][hi 1 (8 KB)][lo 1]
@@ -108,7 +109,7 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     uint64_t *g_full = ag_full + 1;
     uint64_t *w_full = g_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
-    float *s_beta = reinterpret_cast<float *>(tmem_slot + 4);
+    float *s_beta = reinterpret_cast<float *>(tmem_slot + 6);  // 16-byte aligned (11 barriers = 88 bytes, + 24)
     const float *s_lut = reinterpret_cast<const float *>(smem + p.off_lut);
     TileSched sched;
     sched.bind(reinterpret_cast<uint8_t *>(s_beta + N), p.tile_counter, p.tiles_x * p.tiles_y * p.batch * 4);
@@ -301,11 +302,14 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                     tmem_ld_wait();
                     const int c = u * 16;
                     if (m < rows && c < p.out_c) {
-                        float y[16];
+                        float y[16], bt[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(&bt[4 * q]) = *reinterpret_cast<const float4 *>(s_beta + c + 4 * q);
+                        const bool whole = c + 16 <= p.c_out;  // (uniform) every channel of the unit is real
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
-                            const float norm = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e])) + s_beta[c + e];
-                            y[e] = (c + e < p.c_out) ? x[ui][e] * fast_rcp(norm) : 0.0f;
+                            const float norm = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e])) + bt[e];
+                            y[e] = (whole || c + e < p.c_out) ? x[ui][e] * fast_rcp(norm) : 0.0f;
                         }
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
@@ -461,35 +465,38 @@ int sc2_ga_first_conv_gdn(const void *image, int image_is_u8, const float *lut, 
     Params p;
     p.batch = batch; p.h_in = h_in; p.w_in = w_in;
     p.hp = h_out / 2; p.wp = w_out / 2;
-    {   // tile: tw <= 16 columns x th rows, th * tw <= 128, rows balanced over the plane
-        const int n_col = (p.wp + 15) / 16;
-        p.tw = (p.wp + n_col - 1) / n_col;
-        int th = 128 / p.tw;
-        if (th > p.hp) th = p.hp;
-        if (th > 16) th = 16;  // patch rows 4 th + 1 <= 65 keeps the patch buffers small
-        const int n_row = (p.hp + th - 1) / th;
-        p.th = (p.hp + n_row - 1) / n_row;
-        p.tiles_x = n_col; p.tiles_y = n_row;
-    }
-    // patch box: the 4 tw + 1 columns a tile reads, plus the columns the 16-byte alignment of the box origin adds on the left
-    p.box_w = image_is_u8 ? (4 * p.tw + 1 + 14 + 4 + 15) / 16 * 16 : 4 * p.tw + 4;
-    p.box_h = 4 * p.th + 1;
-    p.patch_bytes = (p.box_w * p.box_h * 3 * (image_is_u8 ? 1 : 4) + 64 + 1023) / 1024 * 1024;  // + slack: the last thread's 5th value
-    p.c_out = c_out; p.out_c = out_c;
-    p.stage_c = (out_c / 8) % 2 == 0 ? out_c + 8 : out_c;
-    p.stage_plane = (p.th * p.tw * p.stage_c * 2 + 127) / 128 * 128;
     const int w0 = 2 * n * 128, w1 = 2 * n * 64;
     const int a_bytes = 2 * kABytes + 2 * kA1Bytes;
-    const int ag_region = ((a_bytes > 2 * p.stage_plane ? a_bytes : 2 * p.stage_plane) + 1023) / 1024 * 1024;
-    p.off_gamma = w0 + w1;
-    p.off_a = p.off_gamma + w0 + w1;
-    p.off_ag = p.off_a + a_bytes;
-    p.off_patch = p.off_ag + ag_region;
-    p.off_bar = p.off_patch + 2 * p.patch_bytes;
-    p.off_lut = p.off_bar + 13 * 8 + 16 + n * 4 + kTileSchedBytes + 16;
-    p.off_lut = (p.off_lut + 15) / 16 * 16;
-    const int smem = p.off_lut + (image_is_u8 ? 3 * 256 * 4 : 0) + 1024;
-    if (smem > 227 * 1024) return SC2_ERR_UNSUPPORTED;
+    int smem = 0;
+    // tile: tw <= 16 columns x th rows, th * tw <= 128, rows balanced over the plane; th shrinks until the patch buffers fit
+    const int n_col = (p.wp + 15) / 16;
+    p.tw = (p.wp + n_col - 1) / n_col;
+    p.tiles_x = n_col;
+    int th_max = 128 / p.tw;
+    if (th_max > p.hp) th_max = p.hp;
+    if (th_max > 16) th_max = 16;
+    for (;; --th_max) {
+        if (th_max < 1) return SC2_ERR_UNSUPPORTED;
+        const int n_row = (p.hp + th_max - 1) / th_max;
+        p.th = (p.hp + n_row - 1) / n_row;
+        p.tiles_y = n_row;
+        // patch box: the 4 tw + 1 columns a tile reads, plus the columns the 16-byte alignment of the box origin adds on the left
+        p.box_w = image_is_u8 ? (4 * p.tw + 1 + 14 + 4 + 15) / 16 * 16 : 4 * p.tw + 4;
+        p.box_h = 4 * p.th + 1;
+        p.patch_bytes = (p.box_w * p.box_h * 3 * (image_is_u8 ? 1 : 4) + 64 + 1023) / 1024 * 1024;  // + slack: the last thread's extra word
+        p.stage_c = (out_c / 8) % 2 == 0 ? out_c + 8 : out_c;
+        p.stage_plane = (p.th * p.tw * p.stage_c * 2 + 127) / 128 * 128;
+        const int ag_region = ((a_bytes > 2 * p.stage_plane ? a_bytes : 2 * p.stage_plane) + 1023) / 1024 * 1024;
+        p.off_gamma = w0 + w1;
+        p.off_a = p.off_gamma + w0 + w1;
+        p.off_ag = p.off_a + a_bytes;
+        p.off_patch = p.off_ag + ag_region;
+        p.off_bar = p.off_patch + 2 * p.patch_bytes;
+        p.off_lut = (p.off_bar + 13 * 8 + 24 + n * 4 + kTileSchedBytes + 16 + 15) / 16 * 16;
+        smem = p.off_lut + (image_is_u8 ? 3 * 256 * 4 : 0) + 1024;
+        if (smem <= 227 * 1024) break;
+    }
+    p.c_out = c_out; p.out_c = out_c;
     p.beta = beta; p.lut = lut;
     p.tile_counter = tile_counter;
     p.trace = sc2::trace_sink();

@@ -46,6 +46,8 @@ struct Params {
     int tw, th, pitch_log2;  // tile = th rows x tw valid columns of output pixels; pitch = 1 << pitch_log2 pixel rows per halo row
     int n_taps;
     Tap taps[kMaxTaps];
+    uint32_t tap_word[kMaxTaps];  // sx | sy << 2 | group << 4 | first << 7 | widx << 8 (what the MMA issuer reads: one constant load)
+    uint8_t run_len[kMaxTaps + 3];  // run_len[t]: taps of the plane run that starts at tap t
     int k_chunks, k_steps_last;  // 64-channel chunks of the input, K steps (of 16) in the last one
     int groups;
     int c_out, out_c, stage_c;
@@ -104,7 +106,8 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     constexpr uint32_t kTmemCols = 512;
     static_assert(N % 16 == 0 && N >= 16 && N <= 96, "N");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // (aligned by OFFSET, not through an integer cast: the compiler keeps the shared address space -> LDS / STS, not generic LD / ST)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *s_ag = smem + p.off_ag;  // |x| (hi chunks, then lo chunks), K-major SWIZZLE_128B; aliased by the output staging tile
     uint8_t *s_b = smem + p.off_b;
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + p.off_bar);
@@ -160,7 +163,7 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (warp == 0) {
         // =============================== halo producer + tile scheduler ===============================
         if (elect_one()) {
-            uint32_t unit = 0;
+            uint32_t as = 0, a_ph = 0;
             int tile = sched.claim(0);
             for (uint32_t qn = 0;; ++qn) {
                 sched.publish(qn, tile);
@@ -171,13 +174,13 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 for (int t = 0; t < p.n_taps;) {
                     const int plane = p.taps[t].plane;
                     while (t < p.n_taps && p.taps[t].plane == plane) ++t;
-                    for (int kc = 0; kc < p.k_chunks; ++kc, ++unit) {
-                        const uint32_t s = unit % p.n_a, ph = (unit / p.n_a) & 1u;
-                        mbar_wait(&a_empty[s], ph ^ 1u);
-                        uint8_t *dst = smem + s * 2 * p.halo_bytes;
-                        mbar_expect_tx(&a_full[s], static_cast<uint32_t>(2 * p.halo_bytes));
-                        tma_load_4d(&map_a_hi, &a_full[s], dst, kc * kBlockK, x0 - 1, y0 - 1, img * 4 + plane);
-                        tma_load_4d(&map_a_lo, &a_full[s], dst + p.halo_bytes, kc * kBlockK, x0 - 1, y0 - 1, img * 4 + plane);
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&a_empty[as], a_ph ^ 1u);
+                        uint8_t *dst = smem + as * 2 * p.halo_bytes;
+                        mbar_expect_tx(&a_full[as], static_cast<uint32_t>(2 * p.halo_bytes));
+                        tma_load_4d(&map_a_hi, &a_full[as], dst, kc * kBlockK, x0 - 1, y0 - 1, img * 4 + plane);
+                        tma_load_4d(&map_a_lo, &a_full[as], dst + p.halo_bytes, kc * kBlockK, x0 - 1, y0 - 1, img * 4 + plane);
+                        if (++as == static_cast<uint32_t>(p.n_a)) { as = 0; a_ph ^= 1u; }
                     }
                 }
                 tile = next_tile;
@@ -185,75 +188,85 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
     } else if (warp == 2) {
         // =============================== weights producer ===============================
-        uint32_t bq = 0;
+        uint32_t bs = 0, b_ph = 0;
         for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
             if (elect_one()) {
                 for (int t0 = 0; t0 < p.n_taps;) {
                     int t1 = t0;
                     while (t1 < p.n_taps && p.taps[t1].plane == p.taps[t0].plane) ++t1;
                     for (int kc = 0; kc < p.k_chunks; ++kc)
-                        for (int t = t0; t < t1; ++t, ++bq) {
-                            const uint32_t s = bq % p.n_b, ph = (bq / p.n_b) & 1u;
-                            mbar_wait(&b_empty[s], ph ^ 1u);
-                            mbar_expect_tx(&b_full[s], static_cast<uint32_t>(kBSlot));
-                            tma_load_2d(&map_w, &b_full[s], s_b + s * kBSlot, kc * kBlockK, p.taps[t].widx * 2 * N);
+                        for (int t = t0; t < t1; ++t) {
+                            mbar_wait(&b_empty[bs], b_ph ^ 1u);
+                            mbar_expect_tx(&b_full[bs], static_cast<uint32_t>(kBSlot));
+                            tma_load_2d(&map_w, &b_full[bs], s_b + bs * kBSlot, kc * kBlockK, p.taps[t].widx * 2 * N);
+                            if (++bs == static_cast<uint32_t>(p.n_b)) { bs = 0; b_ph ^= 1u; }
                         }
                     t0 = t1;
                 }
                 // ... and the gamma matrix of this tile's GDN1 rides through the same ring (kGC more slots): 2 % more L2 traffic
                 // buys a whole slot of shared memory for the rings
-                for (int c = 0; c < kGC; ++c, ++bq) {
-                    const uint32_t s = bq % p.n_b, ph = (bq / p.n_b) & 1u;
-                    mbar_wait(&b_empty[s], ph ^ 1u);
-                    mbar_expect_tx(&b_full[s], static_cast<uint32_t>(kBSlot));
-                    tma_load_2d(&map_g, &b_full[s], s_b + s * kBSlot, c * kBlockK, 0);
+                for (int c = 0; c < kGC; ++c) {
+                    mbar_wait(&b_empty[bs], b_ph ^ 1u);
+                    mbar_expect_tx(&b_full[bs], static_cast<uint32_t>(kBSlot));
+                    tma_load_2d(&map_g, &b_full[bs], s_b + bs * kBSlot, c * kBlockK, 0);
+                    if (++bs == static_cast<uint32_t>(p.n_b)) { bs = 0; b_ph ^= 1u; }
                 }
             }
             __syncwarp();
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
+        // Convergent: all 32 lanes run this code with uniform values; only the tcgen05 instructions are predicated on `lead`.
         constexpr uint32_t idesc_stack = make_idesc(2 * N), idesc_n = make_idesc(N);
-        uint32_t unit = 0, bq = 0;
+        const bool lead = elect_one();
+        const uint32_t a_base16 = smem_u32(smem) >> 4, halo16 = static_cast<uint32_t>(p.halo_bytes) >> 4;
+        const uint32_t b_base16 = smem_u32(s_b) >> 4, ag16 = smem_u32(s_ag) >> 4;
+        uint32_t as = 0, a_ph = 0, bs = 0, b_ph = 0;  // ring positions and phase bits
         for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
             mbar_wait(acc_empty, (lt & 1u) ^ 1u);  // the epilogue has drained the conv accumulators of the previous tile
             tcgen05_fence_after();
+            uint32_t prev_group = 0;
             for (int t0 = 0; t0 < p.n_taps;) {
-                int t1 = t0;
-                while (t1 < p.n_taps && p.taps[t1].plane == p.taps[t0].plane) ++t1;
-                for (int kc = 0; kc < p.k_chunks; ++kc, ++unit) {
-                    const uint32_t as = unit % p.n_a;
-                    mbar_wait(&a_full[as], (unit / p.n_a) & 1u);
-                    const uint32_t a_hi = smem_u32(smem + as * 2 * p.halo_bytes), a_lo = a_hi + p.halo_bytes;
-                    const int k_steps = kc == p.k_chunks - 1 ? p.k_steps_last : kBlockK / 16;
-                    for (int t = t0; t < t1; ++t, ++bq) {
-                        const uint32_t bs = bq % p.n_b;
-                        mbar_wait(&b_full[bs], (bq / p.n_b) & 1u);
+                const int t1 = t0 + p.run_len[t0];
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&a_full[as], a_ph);
+                    const uint32_t a_hi16 = a_base16 + as * 2u * halo16, a_lo16 = a_hi16 + halo16;
+                    const bool last_chunk = kc == p.k_chunks - 1;
+                    const int k_steps = last_chunk ? p.k_steps_last : kBlockK / 16;
+                    uint32_t g1 = t0 == 0 ? 0u : prev_group;
+                    for (int t = t0; t < t1; ++t) {
+                        mbar_wait(&b_full[bs], b_ph);
                         tcgen05_fence_after();
-                        if (elect_one()) {
-                            const Tap tap = p.taps[t];
-                            const uint32_t shift = static_cast<uint32_t>((tap.sy << p.pitch_log2) + tap.sx) * 128u;
-                            const uint64_t da_hi = make_smem_desc(a_hi + shift), da_lo = make_smem_desc(a_lo + shift);
-                            const uint64_t db = make_smem_desc(smem_u32(s_b + bs * kBSlot));
-                            // hi.hi | hi.lo -> group g (2N columns); lo.hi -> the D1 half of the PREVIOUS tap's group, so that
-                            // consecutive MMAs never write the same columns (a dependent MMA costs ~16 cycles more)
-                            const uint32_t g = static_cast<uint32_t>(tap.group);
-                            const uint32_t g1 = t == 0 ? 0u : static_cast<uint32_t>(p.taps[t - 1].group);
-                            const uint32_t d_stack = tmem_base + g * 2u * N, d_lohi = tmem_base + g1 * 2u * N + N;
-                            const bool fresh = tap.first && kc == 0;
-                            for (int k = 0; k < k_steps; ++k) {
-                                umma_f16(d_stack, da_hi + 2 * k, db + 2 * k, idesc_stack, (fresh && k == 0) ? 0u : 1u);
-                                umma_f16(d_lohi, da_lo + 2 * k, db + 2 * k, idesc_n, 1u);
+                        const uint32_t tw = p.tap_word[t];  // sx | sy << 2 | group << 4 | first << 7 | widx << 8
+                        const uint32_t shift16 = ((((tw >> 2) & 3u) << p.pitch_log2) + (tw & 3u)) * 8u;  // rows * 128 bytes >> 4
+                        const uint32_t g = (tw >> 4) & 7u;
+                        // hi.hi | hi.lo -> group g (2N columns); lo.hi -> the D1 half of the PREVIOUS tap's group, so that
+                        // consecutive MMAs never write the same columns (a dependent MMA costs ~16 cycles more)
+                        const uint32_t d_stack = tmem_base + g * 2u * N, d_lohi = tmem_base + g1 * 2u * N + N;
+                        const uint32_t da_hi = a_hi16 + shift16, da_lo = a_lo16 + shift16, db = b_base16 + bs * (kBSlot >> 4);
+                        const uint32_t acc0 = ((tw >> 7) & 1u) && kc == 0 ? 0u : 1u;
+                        if (k_steps == 4) {
+                            umma_f16_lead(lead, d_stack, da_hi, db, kDescHiSw128, idesc_stack, acc0);
+                            umma_f16_lead(lead, d_lohi, da_lo, db, kDescHiSw128, idesc_n, 1u);
+#pragma unroll
+                            for (int k = 1; k < 4; ++k) {
+                                umma_f16_lead(lead, d_stack, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, 1u);
+                                umma_f16_lead(lead, d_lohi, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
                             }
-                            umma_commit(&b_empty[bs]);
+                        } else {
+                            for (int k = 0; k < k_steps; ++k) {
+                                umma_f16_lead(lead, d_stack, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, k == 0 ? acc0 : 1u);
+                                umma_f16_lead(lead, d_lohi, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
+                            }
                         }
-                        __syncwarp();
+                        umma_commit_lead(lead, &b_empty[bs]);
+                        g1 = g;
+                        if (++bs == static_cast<uint32_t>(p.n_b)) { bs = 0; b_ph ^= 1u; }
                     }
-                    if (elect_one()) {
-                        umma_commit(&a_empty[as]);
-                        if (t1 == p.n_taps && kc == p.k_chunks - 1) umma_commit(acc_full);
-                    }
-                    __syncwarp();
+                    if (last_chunk) prev_group = g1;
+                    umma_commit_lead(lead, &a_empty[as]);
+                    if (t1 == p.n_taps && last_chunk) umma_commit_lead(lead, acc_full);
+                    if (++as == static_cast<uint32_t>(p.n_a)) { as = 0; a_ph ^= 1u; }
                 }
                 t0 = t1;
             }
@@ -261,23 +274,21 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             mbar_wait(ag_full, lt & 1u);
             tcgen05_fence_after();
 #pragma unroll
-            for (int c = 0; c < kGC; ++c, ++bq) {
-                const uint32_t bs = bq % p.n_b;
-                mbar_wait(&b_full[bs], (bq / p.n_b) & 1u);
+            for (int c = 0; c < kGC; ++c) {
+                mbar_wait(&b_full[bs], b_ph);
                 tcgen05_fence_after();
-                if (elect_one()) {
-                    const uint32_t ag = smem_u32(s_ag);
-                    const uint64_t da_hi = make_smem_desc(ag + c * kABytes), da_lo = make_smem_desc(ag + (kGC + c) * kABytes);
-                    const uint64_t db = make_smem_desc(smem_u32(s_b + bs * kBSlot));
-                    const int k_steps = c == kGC - 1 ? kGStepsLast : 4;
-                    for (int k = 0; k < k_steps; ++k) {
-                        umma_f16(tmem_base + gamma_col, da_hi + 2 * k, db + 2 * k, idesc_stack, (c > 0 || k > 0) ? 1u : 0u);
-                        umma_f16(tmem_base + gamma_col + N, da_lo + 2 * k, db + 2 * k, idesc_n, 1u);
+                const uint32_t da_hi = ag16 + c * (kABytes >> 4), da_lo = ag16 + (kGC + c) * (kABytes >> 4), db = b_base16 + bs * (kBSlot >> 4);
+                constexpr int k_steps_last = kGStepsLast;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (c < kGC - 1 || k < k_steps_last) {
+                        umma_f16_lead(lead, tmem_base + gamma_col, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, (c > 0 || k > 0) ? 1u : 0u);
+                        umma_f16_lead(lead, tmem_base + gamma_col + N, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
                     }
-                    umma_commit(&b_empty[bs]);
-                    if (c == kGC - 1) umma_commit(g_full);
                 }
-                __syncwarp();
+                umma_commit_lead(lead, &b_empty[bs]);
+                if (c == kGC - 1) umma_commit_lead(lead, g_full);
+                if (++bs == static_cast<uint32_t>(p.n_b)) { bs = 0; b_ph ^= 1u; }
             }
         }
     } else if (warp >= 4) {
@@ -364,12 +375,15 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     tmem_ld_wait();
                     const int c = u * 16;
                     if (store_row && c < p.out_c) {
-                        float y[16];
+                        float y[16], bt[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(&bt[4 * q]) = *reinterpret_cast<const float4 *>(s_beta + c + 4 * q);
+                        const bool whole = c + 16 <= p.c_out;  // (uniform) every channel of the unit is real
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
-                            const float norm = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e])) + s_beta[c + e];
+                            const float norm = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e])) + bt[e];
                             // x * (1 / norm), like the reference; 1 / norm = MUFU.RCP + one Newton step (< 1 ulp)
-                            y[e] = (c + e < p.c_out) ? x[ui][e] * fast_rcp(norm) : 0.0f;
+                            y[e] = (whole || c + e < p.c_out) ? x[ui][e] * fast_rcp(norm) : 0.0f;
                         }
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
@@ -474,6 +488,20 @@ int sc2_ga_halo_conv_gdn(const sc2_ga_halo_desc *d, const void *x_hi, const void
             t.first = p.n_taps < p.groups;
             p.taps[p.n_taps++] = t;
         }
+    for (int t = 0; t < kMaxTaps; ++t) {
+        p.tap_word[t] = 0;
+        p.run_len[t] = 0;
+    }
+    for (int t = 0; t < p.n_taps; ++t) {
+        const Tap &tp = p.taps[t];
+        p.tap_word[t] = static_cast<uint32_t>(tp.sx) | (static_cast<uint32_t>(tp.sy) << 2) | (static_cast<uint32_t>(tp.group) << 4) |
+                        (static_cast<uint32_t>(tp.first) << 7) | (static_cast<uint32_t>(tp.widx) << 8);
+        if (t == 0 || p.taps[t - 1].plane != tp.plane) {
+            int t1 = t;
+            while (t1 < p.n_taps && p.taps[t1].plane == tp.plane) ++t1;
+            p.run_len[t] = static_cast<uint8_t>(t1 - t);
+        }
+    }
     // tile shape: th rows x (pitch - 2) columns with th * pitch = 128; pick the pitch that loads the fewest halo pixels
     int best_log2 = 4;
     int64_t best_cost = -1;

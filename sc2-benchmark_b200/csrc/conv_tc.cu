@@ -243,7 +243,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int e = 0; e < 4; ++e) {
                                 const float2 xf = __half22float2(xh[e]);
                                 const float b0 = bv[2 * e], b1 = bv[2 * e + 1];
-                                if (MODE == MODE_IGDN1_F16) {
+                                if (MODE == MODE_IGDN1_F16 || MODE == MODE_IGDN1_ABS_F16) {
                                     f[2 * e] = xf.x * (f[2 * e] + b0);
                                     f[2 * e + 1] = xf.y * (f[2 * e + 1] + b1);
                                 } else {

@@ -167,6 +167,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- the same two instructions for a CONVERGENT issuer warp (round 2) ------------------------------------------------
+// The MMA-issuing warp of a kernel with many short MMAs (the split-fp16 kernels: 300+ per tile, N = 48..192) is bound by its
+// own instruction stream: `if (elect_one()) { build two 64-bit descriptors; mma }` per tap cost ~950 cycles per (tap, chunk)
+// (ncu source view, profiles/r2g_*).  Here every lane runs the same straight-line code with uniform values, only the
+// tcgen05 instruction is predicated on the leader lane chosen ONCE, and a descriptor is (lo word = address >> 4, constant
+// hi word), so advancing K or shifting rows is one 32-bit add.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);    // SBO 512, version 1, SWIZZLE_64B
+__device__ __forceinline__ void umma_f16_lead(bool lead, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(lead)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_lead(bool lead, uint64_t *bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(static_cast<uint32_t>(lead)) : "memory");
+}
+
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
