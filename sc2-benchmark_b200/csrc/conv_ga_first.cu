@@ -12,7 +12,7 @@
 //   GEMMs     stacked weights [hi; lo] resident in shared memory: one N = 2n MMA gives hi.hi | hi.lo, one N = n MMA adds lo.hi
 //             (see conv_ga_halo.cu).  The conv accumulator is drained once: x stays in registers, |x| (hi, lo) becomes the A
 //             operand of the gamma GEMM (n = 96: 64 + 32 channels), y = x / (beta + gamma.|x|) is split and TMA-stored.
-//   roles     warp 0: patch TMA + tile scheduler; warp 1: MMA issuer; warps 2..9: epilogue; warps 10..13: im2col producers.
+//   roles     warp 0: patch TMA + tile scheduler; warp 1: MMA issuer; warps 2..17: epilogue; warps 18..21: im2col producers.
 #include "tc_common.cuh"
 
 namespace sc2 {
@@ -20,7 +20,10 @@ namespace gaf {
 
 using namespace sc2::tc;
 
-constexpr int kThreads = 448;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kParts = kEpiWarps / 4;  // column parts of the epilogue (x 4 TMEM lane quarters)
+constexpr int kThreads = (2 + kEpiWarps + 4) * 32;  // warp 0 TMA, warp 1 MMA, epilogue warps, 4 im2col producer warps
 constexpr float kLoScale = 2048.0f;
 constexpr float kLoInv = 1.0f / 2048.0f;
 constexpr int kK = 80;            // 3 * 5 * 5 = 75 padded to 5 K steps
@@ -47,6 +50,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -88,8 +96,8 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     constexpr int kW0 = 2 * N * 128, kW1 = 2 * N * 64;  // stacked weights: K chunk 0 (64 wide, SW128), chunk 1 (32 wide, SW64)
     constexpr int kGC0 = N >= 64 ? 64 : N;              // gamma GEMM: channels in chunk 0 / chunk 1
     constexpr int kGC1 = N - kGC0;                      // 0, 16 or 32
-    constexpr int kUnits = N / 16;
-    constexpr int kUnits0 = (kUnits + 1) / 2;
+    constexpr int kSub = N / 8;                               // 8-channel sub-units of the epilogue
+    constexpr int kSubMax = (kSub + kParts - 1) / kParts;      // at most this many per thread
     static_assert(N % 16 == 0 && N >= 16 && N <= 96, "N");
     extern __shared__ uint8_t smem_raw[];
     // (aligned by OFFSET, not through an integer cast: the compiler keeps the shared address space -> LDS / STS, not generic LD / ST)
@@ -128,7 +136,7 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     // 0 * NaN from uninitialised memory would not be) -- written once, the producers only ever touch the first half
     for (int i = threadIdx.x; i < 2 * kA1Bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_a + 2 * kABytes)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
-        sched.init(13);  // consumers: MMA warp, 8 epilogue warps, 4 producer warps
+        sched.init(1 + kEpiWarps + 4);  // consumers: MMA warp, epilogue warps, 4 producer warps
         tma_prefetch_desc(&map_img);
         tma_prefetch_desc(&map_o_hi);
         tma_prefetch_desc(&map_o_lo);
@@ -139,8 +147,8 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         mbar_init(a_full, 128);
         mbar_init(a_empty, 1);
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 256);
-        mbar_init(ag_full, 256);
+        mbar_init(acc_empty, kEpiThreads);
+        mbar_init(ag_full, kEpiThreads);
         mbar_init(g_full, 1);
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -229,13 +237,15 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             }
             __syncwarp();
         }
-    } else if (warp < 10) {
-        // =============================== epilogue warps (2..9) ===============================
-        const int half = (warp - 2) >> 2;
+    } else if (warp < 2 + kEpiWarps) {
+        // =============================== epilogue warps (2..17): 4 column parts x 4 TMEM lane quarters ===============================
+        // The epilogue is this kernel's critical path: ~1300 dependent instructions per warp and tile with 8 warps (ncu:
+        // profiles/r2g_*); sixteen warps of 8-channel sub-units halve the chain.
+        const int part = (warp - 2) >> 2;
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
         const bool issuer = threadIdx.x == 64;
-        const int u_begin = half == 0 ? 0 : kUnits0, u_end = half == 0 ? kUnits0 : kUnits;
+        const int s_begin = part * kSub / kParts, s_end = (part + 1) * kSub / kParts;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         __half *st_hi = reinterpret_cast<__half *>(s_ag);
         __half *st_lo = reinterpret_cast<__half *>(s_ag + p.stage_plane);
@@ -245,46 +255,41 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             ++trace_tiles;
             const int sp = tile % tiles_xy, img = tile / tiles_xy;
             const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
-            float x[kUnits0][16];
+            float x[kSubMax][8];
             if (issuer) tma_store_wait_read();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             mbar_wait(acc_full, lt & 1u);
             tcgen05_fence_after();
 #pragma unroll
-            for (int ui = 0; ui < kUnits0; ++ui) {
-                const int u = u_begin + ui;
-                if (u < u_end) {
-                    uint32_t d0[16], d1[16];
-                    tmem_ld16_nowait(lane_addr + u * 16, d0);
-                    tmem_ld16_nowait(lane_addr + N + u * 16, d1);
+            for (int ui = 0; ui < kSubMax; ++ui) {
+                uint32_t d0[8], d1[8];
+                if (s_begin + ui < s_end) {
+                    tmem_ld8_nowait(lane_addr + (s_begin + ui) * 8, d0);
+                    tmem_ld8_nowait(lane_addr + N + (s_begin + ui) * 8, d1);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) x[ui][e] = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e]));
+                    for (int e = 0; e < 8; ++e) x[ui][e] = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e]));
                 }
             }
             tcgen05_fence_before();
             mbar_arrive(acc_empty);
 #pragma unroll
-            for (int ui = 0; ui < kUnits0; ++ui) {
-                const int u = u_begin + ui;
-                if (u < u_end) {
-                    float a[16];
+            for (int ui = 0; ui < kSubMax; ++ui) {
+                const int su = s_begin + ui;
+                if (su < s_end) {
+                    float a[8];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) a[e] = fabsf(x[ui][e]);
-                    const int c = u * 16;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        uint4 h, l;
-                        split8(&a[8 * q], h, l);
-                        if (c < 64) {  // chunk 0: 128-byte rows, 16-byte unit j XOR (row & 7)
-                            const int phys = (((c >> 3) + q) ^ (m & 7)) << 4;
-                            *reinterpret_cast<uint4 *>(s_ag + m * 128 + phys) = h;
-                            *reinterpret_cast<uint4 *>(s_ag + kABytes + m * 128 + phys) = l;
-                        } else {       // chunk 1: 64-byte rows, unit j XOR ((row >> 1) & 3)
-                            const int phys = ((((c - 64) >> 3) + q) ^ ((m >> 1) & 3)) << 4;
-                            *reinterpret_cast<uint4 *>(s_ag + 2 * kABytes + m * 64 + phys) = h;
-                            *reinterpret_cast<uint4 *>(s_ag + 2 * kABytes + kA1Bytes + m * 64 + phys) = l;
-                        }
+                    for (int e = 0; e < 8; ++e) a[e] = fabsf(x[ui][e]);
+                    uint4 h, l;
+                    split8(a, h, l);
+                    if (su < 8) {  // chunk 0 (channels 0..63): 128-byte rows, 16-byte unit j XOR (row & 7)
+                        const int phys = (su ^ (m & 7)) << 4;
+                        *reinterpret_cast<uint4 *>(s_ag + m * 128 + phys) = h;
+                        *reinterpret_cast<uint4 *>(s_ag + kABytes + m * 128 + phys) = l;
+                    } else {       // chunk 1: 64-byte rows, unit j XOR ((row >> 1) & 3)
+                        const int phys = ((su - 8) ^ ((m >> 1) & 3)) << 4;
+                        *reinterpret_cast<uint4 *>(s_ag + 2 * kABytes + m * 64 + phys) = h;
+                        *reinterpret_cast<uint4 *>(s_ag + 2 * kABytes + kA1Bytes + m * 64 + phys) = l;
                     }
                 }
             }
@@ -293,39 +298,34 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             mbar_wait(g_full, lt & 1u);
             tcgen05_fence_after();
 #pragma unroll
-            for (int ui = 0; ui < kUnits0; ++ui) {
-                const int u = u_begin + ui;
-                if (u < u_end) {
-                    uint32_t d0[16], d1[16];
-                    tmem_ld16_nowait(lane_addr + kGammaCol + u * 16, d0);
-                    tmem_ld16_nowait(lane_addr + kGammaCol + N + u * 16, d1);
+            for (int ui = 0; ui < kSubMax; ++ui) {
+                const int c = (s_begin + ui) * 8;
+                if (s_begin + ui < s_end) {
+                    uint32_t d0[8], d1[8];
+                    tmem_ld8_nowait(lane_addr + kGammaCol + c, d0);
+                    tmem_ld8_nowait(lane_addr + kGammaCol + N + c, d1);
                     tmem_ld_wait();
-                    const int c = u * 16;
                     if (m < rows && c < p.out_c) {
-                        float y[16], bt[16];
+                        float y[8], bt[8];
+                        *reinterpret_cast<float4 *>(&bt[0]) = *reinterpret_cast<const float4 *>(s_beta + c);
+                        *reinterpret_cast<float4 *>(&bt[4]) = *reinterpret_cast<const float4 *>(s_beta + c + 4);
+                        const bool whole = c + 8 <= p.c_out;  // (uniform) every channel of the sub-unit is real
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(&bt[4 * q]) = *reinterpret_cast<const float4 *>(s_beta + c + 4 * q);
-                        const bool whole = c + 16 <= p.c_out;  // (uniform) every channel of the unit is real
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
+                        for (int e = 0; e < 8; ++e) {
                             const float norm = fmaf(__uint_as_float(d1[e]), kLoInv, __uint_as_float(d0[e])) + bt[e];
+                            // x * (1 / norm), like the reference; 1 / norm = MUFU.RCP + one Newton step (< 1 ulp)
                             y[e] = (whole || c + e < p.c_out) ? x[ui][e] * fast_rcp(norm) : 0.0f;
                         }
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            if (c + 8 * q < p.out_c) {
-                                uint4 h, l;
-                                split8(&y[8 * q], h, l);
-                                *reinterpret_cast<uint4 *>(st_hi + m * p.stage_c + c + 8 * q) = h;
-                                *reinterpret_cast<uint4 *>(st_lo + m * p.stage_c + c + 8 * q) = l;
-                            }
-                        }
+                        uint4 h, l;
+                        split8(y, h, l);
+                        *reinterpret_cast<uint4 *>(st_hi + m * p.stage_c + c) = h;
+                        *reinterpret_cast<uint4 *>(st_lo + m * p.stage_c + c) = l;
                     }
                 }
             }
             tcgen05_fence_before();
             fence_proxy_async();
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
             if (issuer) {
                 tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
                 tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
@@ -333,9 +333,9 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             }
         }
         if (issuer) tma_store_wait_all();
-    } else if (warp < 14) {
-        // =============================== im2col producers (warps 10..13): thread = tile row = output pixel ===============================
-        const int m = (warp - 10) * 32 + lane;
+    } else if (warp < 2 + kEpiWarps + 4) {
+        // =============================== im2col producers (4 warps): thread = tile row = output pixel ===============================
+        const int m = (warp - 2 - kEpiWarps) * 32 + lane;
         const int ty = m / p.tw, tx = m - ty * p.tw;
         const int row_elems = p.box_w, chan_elems = p.box_w * p.box_h;
         for (uint32_t lt = 0;; ++lt) {
@@ -349,7 +349,6 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             mbar_wait(a_empty, (lt & 1u) ^ 1u);  // the previous tile's conv MMAs have read the A tile
             if (m < rows) {
                 // K order = (c, dy, dx), like weight.reshape(c_out, -1); 8 values -> one 16-byte unit of the hi and of the lo tile
-                float f[kK];
                 const uint8_t *patch = s_patch + s * p.patch_bytes;
                 // (uint8 input) which of this pixel's 5 rows / 5 columns lie inside the image
                 const int img_t = tile / tiles_xy, sp_t = tile % tiles_xy;
@@ -358,52 +357,59 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
                 uint32_t col_ok = 0;
 #pragma unroll
                 for (int dx = 0; dx < 5; ++dx) col_ok |= (static_cast<uint32_t>(ix0 + dx) < static_cast<uint32_t>(p.w_in) ? 1u : 0u) << dx;
+                // two phases of 8 row segments = 40 K values = 5 sixteen-byte units each (5 * 8 = 8 * 5): half the live registers
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+                for (int phase = 0; phase < 2; ++phase) {
+                    float f[40];
 #pragma unroll
-                    for (int dy = 0; dy < 5; ++dy) {
-                        const int e0 = c * chan_elems + (4 * ty + dy) * row_elems + 4 * tx + (patch_col0 & ~3);
-                        float *o = &f[(c * 5 + dy) * 5];
-                        if (U8) {  // 5 bytes starting 0 or 2 bytes into an aligned word
-                            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(patch + e0);
-                            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(patch + e0 + 4);
-                            const uint32_t sh = static_cast<uint32_t>(patch_col0 & 3) * 8u;
-                            const uint32_t w4 = __funnelshift_r(w0, w1, sh), b4 = (w1 >> sh) & 255u;
-                            // the conv pads with ZEROS of the normalised image, but TMA fills bytes outside the image with 0 and
-                            // lut[0] = -mean / std: mask those positions instead of looking them up
-                            const uint32_t ok = static_cast<uint32_t>(iy0 + dy) < static_cast<uint32_t>(p.h_in) ? col_ok : 0u;
-                            o[0] = (ok & 1u) ? s_lut[c * 256 + (w4 & 255u)] : 0.0f;
-                            o[1] = (ok & 2u) ? s_lut[c * 256 + ((w4 >> 8) & 255u)] : 0.0f;
-                            o[2] = (ok & 4u) ? s_lut[c * 256 + ((w4 >> 16) & 255u)] : 0.0f;
-                            o[3] = (ok & 8u) ? s_lut[c * 256 + (w4 >> 24)] : 0.0f;
-                            o[4] = (ok & 16u) ? s_lut[c * 256 + b4] : 0.0f;
-                        } else {   // 5 floats starting 0 or 2 floats into an aligned float4: two conflict-free 16-byte loads
-                            const float4 v0 = *reinterpret_cast<const float4 *>(patch + 4 * e0);
-                            const float4 v1 = *reinterpret_cast<const float4 *>(patch + 4 * e0 + 16);
-                            if (patch_col0 & 2) {
-                                o[0] = v0.z; o[1] = v0.w; o[2] = v1.x; o[3] = v1.y; o[4] = v1.z;
-                            } else {
-                                o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x;
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int r = phase * 8 + rr;  // row segment (c, dy) = (r / 5, r % 5); r = 15 is the zero padding K 75..79
+                        float *o = &f[rr * 5];
+                        if (r >= 15) {
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) o[i] = 0.0f;
+                        } else {
+                            const int c = r / 5, dy = r % 5;
+                            const int e0 = c * chan_elems + (4 * ty + dy) * row_elems + 4 * tx + (patch_col0 & ~3);
+                            if (U8) {  // 5 bytes starting 0 or 2 bytes into an aligned word
+                                const uint32_t w0 = *reinterpret_cast<const uint32_t *>(patch + e0);
+                                const uint32_t w1 = *reinterpret_cast<const uint32_t *>(patch + e0 + 4);
+                                const uint32_t sh = static_cast<uint32_t>(patch_col0 & 3) * 8u;
+                                const uint32_t w4 = __funnelshift_r(w0, w1, sh), b4 = (w1 >> sh) & 255u;
+                                // the conv pads with ZEROS of the normalised image, but TMA fills bytes outside the image with 0
+                                // and lut[0] = -mean / std: mask those positions instead of looking them up
+                                const uint32_t ok = static_cast<uint32_t>(iy0 + dy) < static_cast<uint32_t>(p.h_in) ? col_ok : 0u;
+                                o[0] = (ok & 1u) ? s_lut[c * 256 + (w4 & 255u)] : 0.0f;
+                                o[1] = (ok & 2u) ? s_lut[c * 256 + ((w4 >> 8) & 255u)] : 0.0f;
+                                o[2] = (ok & 4u) ? s_lut[c * 256 + ((w4 >> 16) & 255u)] : 0.0f;
+                                o[3] = (ok & 8u) ? s_lut[c * 256 + (w4 >> 24)] : 0.0f;
+                                o[4] = (ok & 16u) ? s_lut[c * 256 + b4] : 0.0f;
+                            } else {   // 5 floats starting 0 or 2 floats into an aligned float4: two conflict-free 16-byte loads
+                                const float4 v0 = *reinterpret_cast<const float4 *>(patch + 4 * e0);
+                                const float4 v1 = *reinterpret_cast<const float4 *>(patch + 4 * e0 + 16);
+                                if (patch_col0 & 2) {
+                                    o[0] = v0.z; o[1] = v0.w; o[2] = v1.x; o[3] = v1.y; o[4] = v1.z;
+                                } else {
+                                    o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x;
+                                }
                             }
                         }
                     }
 #pragma unroll
-                for (int k = 75; k < kK; ++k) f[k] = 0.0f;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {  // chunk 0
-                    uint4 h, l;
-                    split8(&f[g * 8], h, l);
-                    const int phys = (g ^ (m & 7)) << 4;
-                    *reinterpret_cast<uint4 *>(s_a + m * 128 + phys) = h;
-                    *reinterpret_cast<uint4 *>(s_a + kABytes + m * 128 + phys) = l;
-                }
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {  // chunk 1 (K 64..79): 64-byte rows
-                    uint4 h, l;
-                    split8(&f[64 + g * 8], h, l);
-                    const int phys = (g ^ ((m >> 1) & 3)) << 4;
-                    *reinterpret_cast<uint4 *>(s_a + 2 * kABytes + m * 64 + phys) = h;
-                    *reinterpret_cast<uint4 *>(s_a + 2 * kABytes + kA1Bytes + m * 64 + phys) = l;
+                    for (int gg = 0; gg < 5; ++gg) {
+                        const int g = phase * 5 + gg;  // 16-byte unit of the K dimension: 0..7 chunk 0, 8..9 chunk 1
+                        uint4 h, l;
+                        split8(&f[gg * 8], h, l);
+                        if (g < 8) {
+                            const int phys = (g ^ (m & 7)) << 4;
+                            *reinterpret_cast<uint4 *>(s_a + m * 128 + phys) = h;
+                            *reinterpret_cast<uint4 *>(s_a + kABytes + m * 128 + phys) = l;
+                        } else {  // K 64..79: 64-byte rows
+                            const int phys = ((g - 8) ^ ((m >> 1) & 3)) << 4;
+                            *reinterpret_cast<uint4 *>(s_a + 2 * kABytes + m * 64 + phys) = h;
+                            *reinterpret_cast<uint4 *>(s_a + 2 * kABytes + kA1Bytes + m * 64 + phys) = l;
+                        }
+                    }
                 }
             }
             fence_proxy_async();
