@@ -72,3 +72,50 @@ def topk_correct(logits, target, ks=(1, 5)):
     pred = logits.topk(maxk, dim=1).indices
     hit = pred.eq(target.view(-1, 1))
     return [hit[:, :k].any(dim=1).sum() for k in ks]
+
+
+def compute_accuracy(outputs, targets, topk=(1,)):
+    """Top-k accuracies in PERCENT of the batch as device tensors (script/task/image_classification.py:91-103: same arithmetic,
+    float32 counts times 100 / batch_size), without leaving the device."""
+    with torch.no_grad():
+        batch_size = targets.size(0)
+        return [c.to(torch.float32) * (100.0 / batch_size) for c in topk_correct(outputs, targets, ks=tuple(topk))]
+
+
+@torch.inference_mode()
+def evaluate(model, data_loader, device, log_freq=1000, title=None, header='Test:', logger=None):
+    """The evaluation loop of script/task/image_classification.py:106-145 for a model built from this package, one process per
+    GPU: images -> model -> top-1 / top-5.  Differences from the reference loop, none of them visible in the result:
+      * no DataParallel / DistributedDataParallel wrapper (inference only: the ranks share nothing but the final counters);
+      * the correct-counts accumulate ON THE DEVICE (EvalCounters) instead of `acc1.item()` per batch, so the host never waits for
+        a batch; ONE all-reduce of [images, correct@1, correct@5] replaces the two float64 all-reduces per meter
+        (SmoothedValue.synchronize_between_processes) -- global_avg = sum(acc_b * n_b) / sum(n_b) = 100 * correct / images.
+    Returns the global top-1 accuracy in percent, like `metric_logger.acc1.global_avg`; `.top5` / `.images` ride on the result."""
+    model = model.to(device)
+    model.eval()
+    counters = EvalCounters(device)
+    if title is not None and logger is not None:
+        logger.info(title)
+    for it, (image, target) in enumerate(data_loader):
+        if isinstance(image, torch.Tensor):
+            image = image.to(device, non_blocking=True)
+        if isinstance(target, torch.Tensor):
+            target = target.to(device, non_blocking=True)
+        output = model(image)
+        c1, c5 = topk_correct(output, target, ks=(1, 5))
+        counters.add(images=len(image), correct_top1=c1, correct_top5=c5)
+        if logger is not None and log_freq and it % log_freq == 0:
+            logger.info('%s [%d]', header, it)
+    counters.all_reduce()  # gather the stats from all processes
+    d = counters.as_dict()
+    result = EvalResult(100.0 * d['top1'])
+    result.top5, result.images = 100.0 * d['top5'], int(d['images'])
+    if logger is not None:
+        logger.info(' * Acc@1 {:.4f}\tAcc@5 {:.4f}\n'.format(float(result), result.top5))
+    if getattr(model, 'activated_analysis', False) and hasattr(model, 'summarize'):
+        model.summarize()
+    return result
+
+
+class EvalResult(float):
+    """top-1 accuracy in percent (what the reference's evaluate returns) carrying .top5 and .images"""

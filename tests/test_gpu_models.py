@@ -322,3 +322,50 @@ def test_transform_stream_pipeline_matches_serial(s2):
         assert torch.equal(layer.decode(**obj), want[0][1])
         layer.use_transform_stream(None)
         assert layer.entropy_bottleneck.coder_layout is None
+
+
+def _ref_compute_accuracy(outputs, targets, topk=(1,)):
+    """script/task/image_classification.py:91-103, restated for the test (the GPU box has no /root/reference)."""
+    maxk = max(topk)
+    batch_size = targets.size(0)
+    _, preds = outputs.topk(maxk, 1, True, True)
+    preds = preds.t()
+    corrects = preds.eq(targets[None])
+    return [corrects[:k].flatten().sum(dtype=torch.float32) * (100.0 / batch_size) for k in topk]
+
+
+def test_evaluate_loop_and_device_counters_vs_reference_meters(s2):
+    """a15: parallel.evaluate / compute_accuracy / EvalCounters on the GPU against the reference's per-batch compute_accuracy +
+    SmoothedValue.global_avg arithmetic (image_classification.py:91-145), on the splittable ResNet-50 with the bottleneck running
+    its compress -> decompress branch, ragged last batch included."""
+    from sc2bench_b200 import parallel
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    model = s2.splittable_resnet(bottleneck_config={'key': 'FPBasedResNetBottleneck', 'kwargs': {'num_bottleneck_channels': 24, 'num_target_channels': 256}},
+                                 resnet_name='resnet50', skips_avgpool=False, skips_fc=False, weights=None,
+                                 analysis_config={'analyzes_after_compress': True, 'analyzer_configs': [{'key': 'FileSizeAnalyzer', 'kwargs': {'unit': 'KB'}}]})
+    model.eval()
+    model.update()
+    model.activate_analysis()
+    torch.manual_seed(1)
+    batches = [(torch.randn(n, 3, 224, 224), torch.randint(0, 1000, (n,))) for n in (4, 4, 3)]
+    # make some predictions right so that the counters are not trivially zero: reuse the model's own top-1 / top-3 as targets
+    model.to(dev)
+    with torch.inference_mode():
+        logits = [model(x.to(dev)).cpu() for x, _ in batches]
+    batches[0] = (batches[0][0], logits[0].argmax(1))
+    batches[1] = (batches[1][0], logits[1].topk(3, 1).indices[:, 2])
+    model.clear_analysis()
+    # reference arithmetic: per-batch accuracies averaged with weights n (SmoothedValue total / count)
+    tot1 = tot5 = cnt = 0.0
+    for (x, t), lg in zip(batches, logits):
+        a1, a5 = _ref_compute_accuracy(lg, t, topk=(1, 5))
+        tot1 += a1.item() * len(x)
+        tot5 += a5.item() * len(x)
+        cnt += len(x)
+        g1, g5 = parallel.compute_accuracy(lg.to(dev), t.to(dev), topk=(1, 5))
+        assert g1.is_cuda and abs(g1.item() - a1.item()) < 1e-4 and abs(g5.item() - a5.item()) < 1e-4
+    got = parallel.evaluate(model, batches, dev)
+    assert abs(float(got) - tot1 / cnt) < 1e-4 and abs(got.top5 - tot5 / cnt) < 1e-4 and got.images == 11
+    assert float(got) > 30.0 and got.top5 > 60.0           # the planted targets were found
+    assert len(model.analyzers[0].file_size_list) == 3      # one analysed object per batch; summarize() ran at the end
