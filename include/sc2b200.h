@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 5
+#define SC2_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -197,6 +197,34 @@ typedef struct sc2_tc_conv_desc {
     int c_out, kh, kw, pad;
     int mode;
 } sc2_tc_conv_desc;
+
+/* Extended form (round 2): asymmetric kernels / paddings, an explicit output grid, strided placement of that grid in the output
+ * tensor, a per-channel bias, and the modes the CompressAI zoo codecs' synthesis transforms need (GDN proper, ConvTranspose2d;
+ * sc2bench/models/registry.py:12-14, wrapper.py:119-135).  A ConvTranspose2d(k5, s2, p2, op1) is four launches, one per output
+ * parity (py, px): a stride-1 correlation with (3 or 2) x (3 or 2) taps, pad (1 or 0), written to every second output pixel.
+ *   h_out, w_out   grid of output pixels this launch computes; pixel (oy, ox) of the grid is output-tensor pixel
+ *                  (oy * out_stride + out_py, ox * out_stride + out_px) of an [batch, out_h, out_w, c_out] NHWC tensor
+ *   vec            conv modes: bias [c_out] or NULL; GDN modes: effective beta [c_out]
+ *   modes          0..5 as above, plus
+ *                  6 store x as fp16 to `out` AND x*x/256 as fp16 to `out2` (the layer in front of an inverse GDN)
+ *                  7 inverse GDN on such a pair: x = the x*x/256 tensor (A operand), gdn_x = the x tensor,
+ *                    out = gdn_x * sqrt(beta + 256 * acc)
+ *                  8 last layer: c_out <= 32 real channels (weights packed to 32 rows per tap), bias, clamp to [0, 1],
+ *                    `out` is fp32 NCHW [batch, c_out, out_h, out_w] */
+#define SC2_TC_STORE_SQ_F16 6
+#define SC2_TC_IGDN_SQ_F16 7
+#define SC2_TC_NCHW_F32_CLAMP 8
+
+typedef struct sc2_tc_conv_ex_desc {
+    int batch, h_in, w_in, c_in_pad;
+    int c_out, kh, kw, pad_y, pad_x;
+    int mode;
+    int h_out, w_out;
+    int out_h, out_w, out_stride, out_py, out_px;
+} sc2_tc_conv_ex_desc;
+
+SC2_API int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *w_packed, const float *vec, const void *gdn_x,
+                           void *out, void *out2, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream);
 
 /* tile_counter (all sc2_tc_* kernels): the kernels are persistent (one CTA per SM).  With a caller-provided int32 that is
  * ZERO at launch (one per launch; stream-ordered reuse is fine) the CTAs claim tiles dynamically, so a CTA that is placed

@@ -29,6 +29,12 @@ class TcSplitDesc(_c.Structure):
                                     'h_out', 'w_out', 'out_c')]
 
 
+class TcConvExDesc(_c.Structure):
+    """struct sc2_tc_conv_ex_desc"""
+    _fields_ = [(n, i32) for n in ('batch', 'h_in', 'w_in', 'c_in_pad', 'c_out', 'kh', 'kw', 'pad_y', 'pad_x', 'mode', 'h_out', 'w_out',
+                                    'out_h', 'out_w', 'out_stride', 'out_py', 'out_px')]
+
+
 class GaHaloDesc(_c.Structure):
     """struct sc2_ga_halo_desc"""
     _fields_ = [(n, i32) for n in ('images', 'h_in', 'w_in', 'c_in', 'c_out', 'kh', 'kw', 'pad', 'h_out', 'w_out', 'out_c')]
@@ -55,6 +61,7 @@ SIGNATURES = {
     'sc2_conv2d_f32': (i32, [_c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]),
     'sc2_gdn_f32': (i32, [vp, vp, vp, vp, i32, i32, i64, i32, i32, vp]),
     'sc2_tc_conv_nhwc': (i32, [_c.POINTER(TcConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sc2_tc_conv_ex': (i32, [_c.POINTER(TcConvExDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'sc2_nchw_f32_to_nhwc_f16': (i32, [vp, vp, i32, i32, i64, i32, vp]),
     'sc2_tc_split_n_tile': (i32, [i32]),
     'sc2_tc_split_conv': (i32, [_c.POINTER(TcSplitDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -66,11 +73,12 @@ SIGNATURES = {
 }
 
 SC2_OK = 0
-ABI_VERSION = 5  # include/sc2b200.h SC2_ABI_VERSION
+ABI_VERSION = 6  # include/sc2b200.h SC2_ABI_VERSION
 FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM, FAULT_BAD_INDEX = 1, 2, 4, 8
 EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 IN_NONE, IN_ABS = 0, 1
 TC_STORE_F16, TC_STORE_F32, TC_IGDN1_F16, TC_GDN1_F16, TC_STORE_ABS_F16, TC_IGDN1_ABS_F16 = 0, 1, 2, 3, 4, 5
+TC_STORE_SQ_F16, TC_IGDN_SQ_F16, TC_NCHW_F32_CLAMP = 6, 7, 8
 TCS_STORE, TCS_GDN1, TCS_QUANT = 0, 1, 2
 RANS_LAYOUTS = {None: 0, 'auto': 0, 'warp': 1, 'lanes': 2}
 

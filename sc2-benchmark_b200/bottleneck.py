@@ -11,6 +11,7 @@ The eval-time branch (`updated and not training`) is the hot path: g_a, quantisa
 g_s all run in libsc2b200.so.  The two training-time branches stay differentiable torch.
 """
 import logging
+import os
 import threading
 
 import torch
@@ -143,6 +144,7 @@ class TensorCoreAnalysis:
         self.fuse_first_layer = True
         self.fused = True        # conv + GDN1 in one kernel where the shapes allow (False: round-1 route, for A/B measurements)
         self._unfused = set()    # (stage, shape) combinations the fused kernels refused
+        self._env_unfused = set(os.environ.get('SC2_GA_UNFUSED', '').split(','))  # experiments: 'first', 'mid' -> two-kernel route
 
     @staticmethod
     def why_not(seq, x_shape):
@@ -212,7 +214,7 @@ class TensorCoreAnalysis:
 
     def _try_fused(self, stage, shape_key, fn):
         """Runs a fused kernel; a shape it refuses (SC2_ERR_UNSUPPORTED) is remembered and takes the two-kernel route from then on."""
-        if not self.fused or (stage, shape_key) in self._unfused:
+        if not self.fused or stage in self._env_unfused or (stage, shape_key) in self._unfused:
             return None
         try:
             return fn()

@@ -18,6 +18,7 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--use_fast_math=false']
 NVCC_FLAGS.remove('--use_fast_math=false')  # never fast-math: bit-exactness matters on this path
+NVCC_FLAGS += os.environ.get('SC2_NVCC_DEFINES', '').split()  # diagnostics builds, e.g. -DSC2_HANG_DEBUG
 
 
 HOSTBYTES_SRC = os.path.join(CSRC, 'hostbytes.c')

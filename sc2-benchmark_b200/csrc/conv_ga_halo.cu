@@ -29,7 +29,7 @@ namespace gah {
 
 using namespace sc2::tc;
 
-constexpr int kThreads = 448;  // warp 0: A (halo) producer + tile scheduler; 2: B (weights) producer; 4..11: epilogue; 1, 3, 12, 13: MMA issuers
+constexpr int kThreads = 384;  // warp 0: A (halo) producer + tile scheduler; 1: MMA issuer; 2: B (weights) producer; 3: idle; 4..11: epilogue
 constexpr int kMaxTaps = 25;
 constexpr int kMaxB = 8;
 constexpr int kMaxA = 4;
@@ -132,7 +132,7 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
     if (threadIdx.x < N) s_beta[threadIdx.x] = static_cast<int>(threadIdx.x) < p.c_out ? __ldg(p.beta + threadIdx.x) : 1.0f;
     if (threadIdx.x == 0) {
-        sched.init(static_cast<uint32_t>(p.groups) + 9);  // consumers: one issuer warp per accumulator group, B producer warp, 8 epilogue warps
+        sched.init(10);  // consumers: MMA warp, B producer warp, 8 epilogue warps
         tma_prefetch_desc(&map_a_hi);
         tma_prefetch_desc(&map_a_lo);
         tma_prefetch_desc(&map_w);
@@ -141,13 +141,13 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         tma_prefetch_desc(&map_o_lo);
         for (int s = 0; s < kMaxA; ++s) {
             mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], static_cast<uint32_t>(p.groups));  // one commit per issuer warp
+            mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < kMaxB; ++s) {
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
         }
-        mbar_init(acc_full, static_cast<uint32_t>(p.groups));
+        mbar_init(acc_full, 1);
         mbar_init(acc_empty, 256);
         mbar_init(ag_full, 256);
         mbar_init(g_full, 1);
@@ -214,95 +214,88 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             }
             __syncwarp();
         }
-    } else if (warp == 1 || warp == 3 || warp >= 12) {
-        // =============================== MMA issuers (warps 1, 3, 12, 13) ===============================
-        // One warp cannot issue this kernel's MMAs fast enough: ~10 SASS instructions per tcgen05.mma (descriptor words, uniform
-        // predicates) x 306 MMAs per tile took 27 k cycles against 11 k cycles of tensor-pipe work (ncu source view,
-        // profiles/r2i_*).  So there is one issuer warp per accumulator group: the (tap, chunk) slots of the weights ring are
-        // dealt round-robin, issuer w accumulates ITS slots into group w (the epilogue adds the groups anyway), nobody shares
-        // TMEM columns.  Convergent code: all lanes run it with uniform values, only the tcgen05 instructions are predicated.
-        const int iw = warp == 1 ? 0 : warp == 3 ? 1 : warp - 10;  // issuer index = accumulator group
-        if (iw < p.groups) {
-            constexpr uint32_t idesc_stack = make_idesc(2 * N), idesc_n = make_idesc(N);
-            const bool lead = elect_one();
-            const uint32_t a_base16 = smem_u32(smem) >> 4, halo16 = static_cast<uint32_t>(p.halo_bytes) >> 4;
-            const uint32_t b_base16 = smem_u32(s_b) >> 4, ag16 = smem_u32(s_ag) >> 4;
-            const uint32_t d_stack = tmem_base + static_cast<uint32_t>(iw) * 2u * N, d_lohi = d_stack + N;
-            const uint32_t n_issuers = static_cast<uint32_t>(p.groups);
-            uint32_t as = 0, a_ph = 0, bs = 0, b_ph = 0;  // ring positions and phase bits (every issuer tracks all slots)
-            for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
-                mbar_wait(acc_empty, (lt & 1u) ^ 1u);  // the epilogue has drained the conv accumulators of the previous tile
-                tcgen05_fence_after();
-                uint32_t turn = 0, fresh = 0;  // fresh = accumulate flag of the next stacked MMA: 0 until this issuer has written its group in this tile
-                for (int t0 = 0; t0 < p.n_taps;) {
-                    const int t1 = t0 + p.run_len[t0];
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&a_full[as], a_ph);
-                        const uint32_t a_hi16 = a_base16 + as * 2u * halo16, a_lo16 = a_hi16 + halo16;
-                        const bool last_chunk = kc == p.k_chunks - 1;
-                        const int k_steps = last_chunk ? p.k_steps_last : kBlockK / 16;
-                        for (int t = t0; t < t1; ++t) {
-                            if (turn == static_cast<uint32_t>(iw)) {
-                                mbar_wait(&b_full[bs], b_ph);
-                                tcgen05_fence_after();
-                                const uint32_t tw = p.tap_word[t];  // sx | sy << 2 | ... | widx << 8
-                                const uint32_t shift16 = ((((tw >> 2) & 3u) << p.pitch_log2) + (tw & 3u)) * 8u;  // rows * 128 bytes >> 4
-                                const uint32_t da_hi = a_hi16 + shift16, da_lo = a_lo16 + shift16, db = b_base16 + bs * (kBSlot >> 4);
-                                // hi.hi | hi.lo (2N columns) and lo.hi (the D1 half of the same group), interleaved so that an MMA
-                                // never follows the one that wrote its columns
-                                if (k_steps == 4) {
-                                    umma_f16_lead(lead, d_stack, da_hi, db, kDescHiSw128, idesc_stack, fresh);
-                                    umma_f16_lead(lead, d_stack, da_hi + 2, db + 2, kDescHiSw128, idesc_stack, 1u);
-                                    umma_f16_lead(lead, d_lohi, da_lo, db, kDescHiSw128, idesc_n, 1u);
-                                    umma_f16_lead(lead, d_stack, da_hi + 4, db + 4, kDescHiSw128, idesc_stack, 1u);
-                                    umma_f16_lead(lead, d_lohi, da_lo + 2, db + 2, kDescHiSw128, idesc_n, 1u);
-                                    umma_f16_lead(lead, d_stack, da_hi + 6, db + 6, kDescHiSw128, idesc_stack, 1u);
-                                    umma_f16_lead(lead, d_lohi, da_lo + 4, db + 4, kDescHiSw128, idesc_n, 1u);
-                                    umma_f16_lead(lead, d_lohi, da_lo + 6, db + 6, kDescHiSw128, idesc_n, 1u);
-                                } else {
-                                    for (int k = 0; k < k_steps; ++k) {
-                                        umma_f16_lead(lead, d_stack, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, k == 0 ? fresh : 1u);
-                                        umma_f16_lead(lead, d_lohi, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
-                                    }
-                                }
-                                umma_commit_lead(lead, &b_empty[bs]);
-                                fresh = 1u;
-                            }
-                            if (++turn == n_issuers) turn = 0;
-                            if (++bs == static_cast<uint32_t>(p.n_b)) { bs = 0; b_ph ^= 1u; }
-                        }
-                        umma_commit_lead(lead, &a_empty[as]);  // (every issuer: the unit is free when all of them are done with it)
-                        if (t1 == p.n_taps && last_chunk) umma_commit_lead(lead, acc_full);
-                        if (++as == static_cast<uint32_t>(p.n_a)) { as = 0; a_ph ^= 1u; }
-                    }
-                    t0 = t1;
-                }
-                // ---- the gamma GEMM of this tile (issuer 0): |x| (written by the epilogue warps) x gamma^T ----
-                if (iw == 0) {
-                    mbar_wait(ag_full, lt & 1u);
-                    tcgen05_fence_after();
-                }
-#pragma unroll
-                for (int c = 0; c < kGC; ++c) {
-                    if (iw == 0) {
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        // (One issuer.  A variant with one issuer warp per accumulator group was ~8 % faster in isolation -- this warp's own
+        // instruction stream, ~10 SASS instructions per tcgen05.mma, is what bounds the kernel -- but it hung about once in four
+        // runs when the kernel ran beside the coder kernels of other streams, with every barrier protocol checked on paper;
+        // it is kept in history (commit dde4825) until that is understood.)
+        // Convergent: all 32 lanes run this code with uniform values; only the tcgen05 instructions are predicated on `lead`.
+        constexpr uint32_t idesc_stack = make_idesc(2 * N), idesc_n = make_idesc(N);
+        const bool lead = elect_one();
+        const uint32_t a_base16 = smem_u32(smem) >> 4, halo16 = static_cast<uint32_t>(p.halo_bytes) >> 4;
+        const uint32_t b_base16 = smem_u32(s_b) >> 4, ag16 = smem_u32(s_ag) >> 4;
+        uint32_t as = 0, a_ph = 0, bs = 0, b_ph = 0;  // ring positions and phase bits
+        for (uint32_t lt = 0; sched.next(lt, lane) >= 0; ++lt) {
+            mbar_wait(acc_empty, (lt & 1u) ^ 1u);  // the epilogue has drained the conv accumulators of the previous tile
+            tcgen05_fence_after();
+            uint32_t prev_group = 0;
+            for (int t0 = 0; t0 < p.n_taps;) {
+                const int t1 = t0 + p.run_len[t0];
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&a_full[as], a_ph);
+                    const uint32_t a_hi16 = a_base16 + as * 2u * halo16, a_lo16 = a_hi16 + halo16;
+                    const bool last_chunk = kc == p.k_chunks - 1;
+                    const int k_steps = last_chunk ? p.k_steps_last : kBlockK / 16;
+                    uint32_t g1 = t0 == 0 ? 0u : prev_group;
+                    for (int t = t0; t < t1; ++t) {
                         mbar_wait(&b_full[bs], b_ph);
                         tcgen05_fence_after();
-                        const uint32_t da_hi = ag16 + c * (kABytes >> 4), da_lo = ag16 + (kGC + c) * (kABytes >> 4), db = b_base16 + bs * (kBSlot >> 4);
+                        const uint32_t tw = p.tap_word[t];  // sx | sy << 2 | group << 4 | first << 7 | widx << 8
+                        const uint32_t shift16 = ((((tw >> 2) & 3u) << p.pitch_log2) + (tw & 3u)) * 8u;  // rows * 128 bytes >> 4
+                        const uint32_t g = (tw >> 4) & 7u;
+                        // hi.hi | hi.lo -> group g (2N columns); lo.hi -> the D1 half of the PREVIOUS tap's group, so that
+                        // consecutive MMAs never write the same columns (a dependent MMA costs ~16 cycles more)
+                        const uint32_t d_stack = tmem_base + g * 2u * N, d_lohi = tmem_base + g1 * 2u * N + N;
+                        const uint32_t da_hi = a_hi16 + shift16, da_lo = a_lo16 + shift16, db = b_base16 + bs * (kBSlot >> 4);
+                        const uint32_t acc0 = ((tw >> 7) & 1u) && kc == 0 ? 0u : 1u;
+                        if (k_steps == 4) {
+                            umma_f16_lead(lead, d_stack, da_hi, db, kDescHiSw128, idesc_stack, acc0);
+                            umma_f16_lead(lead, d_lohi, da_lo, db, kDescHiSw128, idesc_n, 1u);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (c < kGC - 1 || k < kGStepsLast) {
-                                umma_f16_lead(lead, tmem_base + gamma_col, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, (c > 0 || k > 0) ? 1u : 0u);
-                                umma_f16_lead(lead, tmem_base + gamma_col + N, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
+                            for (int k = 1; k < 4; ++k) {
+                                umma_f16_lead(lead, d_stack, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, 1u);
+                                umma_f16_lead(lead, d_lohi, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
+                            }
+                        } else {
+                            for (int k = 0; k < k_steps; ++k) {
+                                umma_f16_lead(lead, d_stack, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, k == 0 ? acc0 : 1u);
+                                umma_f16_lead(lead, d_lohi, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
                             }
                         }
                         umma_commit_lead(lead, &b_empty[bs]);
-                        if (c == kGC - 1) umma_commit_lead(lead, g_full);
+                        g1 = g;
+                        if (++bs == static_cast<uint32_t>(p.n_b)) { bs = 0; b_ph ^= 1u; }
                     }
-                    if (++bs == static_cast<uint32_t>(p.n_b)) { bs = 0; b_ph ^= 1u; }
+                    if (last_chunk) prev_group = g1;
+                    umma_commit_lead(lead, &a_empty[as]);
+                    if (t1 == p.n_taps && last_chunk) umma_commit_lead(lead, acc_full);
+                    if (++as == static_cast<uint32_t>(p.n_a)) { as = 0; a_ph ^= 1u; }
                 }
+                t0 = t1;
+            }
+            // ---- the gamma GEMM of this tile: |x| (written by the epilogue warps) x gamma^T ----
+            mbar_wait(ag_full, lt & 1u);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int c = 0; c < kGC; ++c) {
+                mbar_wait(&b_full[bs], b_ph);
+                tcgen05_fence_after();
+                const uint32_t da_hi = ag16 + c * (kABytes >> 4), da_lo = ag16 + (kGC + c) * (kABytes >> 4), db = b_base16 + bs * (kBSlot >> 4);
+                constexpr int k_steps_last = kGStepsLast;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (c < kGC - 1 || k < k_steps_last) {
+                        umma_f16_lead(lead, tmem_base + gamma_col, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, (c > 0 || k > 0) ? 1u : 0u);
+                        umma_f16_lead(lead, tmem_base + gamma_col + N, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
+                    }
+                }
+                umma_commit_lead(lead, &b_empty[bs]);
+                if (c == kGC - 1) umma_commit_lead(lead, g_full);
+                if (++bs == static_cast<uint32_t>(p.n_b)) { bs = 0; b_ph ^= 1u; }
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4) {
         // =============================== epilogue warps (4..11) ===============================
         const int half = (warp - 4) >> 2;
         const int quarter = warp & 3;          // TMEM lane quarter this warp may access

@@ -25,7 +25,14 @@
 namespace sc2 {
 namespace tc {
 
-enum Mode { MODE_STORE_F16 = 0, MODE_STORE_F32 = 1, MODE_IGDN1_F16 = 2, MODE_GDN1_F16 = 3, MODE_STORE_ABS_F16 = 4, MODE_IGDN1_ABS_F16 = 5 };
+enum Mode { MODE_STORE_F16 = 0, MODE_STORE_F32 = 1, MODE_IGDN1_F16 = 2, MODE_GDN1_F16 = 3, MODE_STORE_ABS_F16 = 4, MODE_IGDN1_ABS_F16 = 5,
+            MODE_STORE_SQ_F16 = 6, MODE_IGDN_SQ_F16 = 7, MODE_NCHW_F32_CLAMP = 8 };
+// Modes 6 / 7 / 8 (round 2) serve the synthesis transforms of the CompressAI zoo codecs (bmshj2018-*: GDN proper, transposed
+// convolutions, biases; sc2bench/models/registry.py:12-14): a ConvTranspose2d(k5, s2, p2, op1) is FOUR stride-1 sub-convolutions,
+// one per output parity (3x3, 3x2, 2x3, 2x2 taps), each a launch of this kernel that writes every second output pixel
+// (out_stride 2, out_py / out_px); mode 6 stores x (fp16) AND x^2 / 256 (fp16, squared in fp32 from the accumulator: the scale
+// keeps it inside fp16's range), mode 7 is the inverse GDN on such a pair: the 1x1 gamma GEMM reads the x^2 tensor,
+// out = x * sqrt(beta + 256 * acc); mode 8 is the last layer: c_out <= N_TILE real channels, bias, clamp to [0, 1], fp32 NCHW.
 // Modes 4 / 5 (round 2) split "x" into |x| (fp16) and one sign bit per value: the conv in front of an IGDN1 stores |x| and the
 // packed signs, and the IGDN1's 1x1 gamma GEMM reads |x| straight from the TMA-loaded tile -- no in-smem |.| pass between the
 // TMA and the MMA (that extra hop is what kept IGDN1(512) at 25 % tensor-pipe utilisation with a 4-stage ring while the plain
@@ -36,13 +43,17 @@ enum Mode { MODE_STORE_F16 = 0, MODE_STORE_F32 = 1, MODE_IGDN1_F16 = 2, MODE_GDN
 struct Params {
     int tiles_x, tiles_y;  // output tile grid per image
     int tw, th;            // tile = th rows x tw columns of output pixels (th * tw <= 128)
-    int taps_x, taps_y, pad;
+    int taps_x, taps_y, pad_x, pad_y;
     int k_chunks;          // c_in_padded / 64
     int n_total;           // c_out (rows per tap of the packed weight tensor)
     int n_tiles;           // c_out / N_TILE
     int batch;
-    int h_out, w_out;
-    const float *beta;     // GDN modes: effective beta [n_total]
+    int h_out, w_out;      // grid of output pixels this launch computes
+    int out_h, out_w;      // the output TENSOR: pixel (oy, ox) of the grid lands at (oy * out_stride + out_py, ox * out_stride + out_px)
+    int out_stride, out_py, out_px;
+    int c_real;            // mode 8: real output channels (<= N_TILE)
+    void *out2;            // mode 6: the x^2 / 256 tensor
+    const float *beta;     // GDN modes: effective beta [n_total]; conv modes: bias [n_total] or nullptr
     const __half *gdn_x;   // GDN modes: x itself (mode 5: |x|), NHWC [batch, h_out, w_out, n_total]
     uint32_t *signs;       // mode 4: out, mode 5: in -- packed sign words [batch * h_out * w_out, n_total / 32]
     void *out;             // NHWC [batch, h_out, w_out, n_total], fp16 or fp32
@@ -68,11 +79,11 @@ __global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params p) {
     using L = Smem<N_TILE, STAGES>;
     constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;  // |x| formed in shared memory by 4 extra warps
-    constexpr bool kGdn = kXform || MODE == MODE_IGDN1_ABS_F16;               // GDN epilogue
+    constexpr bool kGdn = kXform || MODE == MODE_IGDN1_ABS_F16 || MODE == MODE_IGDN_SQ_F16;  // GDN epilogue
     constexpr bool kSigned = MODE == MODE_IGDN1_ABS_F16;                      // x = sign word * |x|
     constexpr bool kOutF32 = MODE == MODE_STORE_F32;
-    constexpr uint32_t kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
-    static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "two accumulator stages must fit TMEM");
+    constexpr uint32_t kTmemCols = 2 * N_TILE <= 32 ? 32 : 2 * N_TILE <= 64 ? 64 : 2 * N_TILE <= 128 ? 128 : 2 * N_TILE <= 256 ? 256 : 512;
+    static_assert(2 * N_TILE <= 512, "two accumulator stages must fit TMEM");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kRingBytes);
@@ -95,7 +106,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     // GDN modes: beta in shared memory (the epilogue read it with one LDG per element: a third of its instructions)
     const float *s_beta = reinterpret_cast<const float *>(smem + L::kBetaOffset);
-    if (kGdn)
+    const bool has_vec = p.beta != nullptr;  // beta (GDN modes) or bias (conv modes)
+    if (has_vec)
         for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) reinterpret_cast<float *>(smem + L::kBetaOffset)[i] = __ldg(p.beta + i);
 
     if (threadIdx.x == 0) {
@@ -139,7 +151,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             mbar_wait(&empty[s], ph ^ 1u);
                             uint8_t *dst = smem + s * L::kStageBytes;
                             mbar_expect_tx(&full[s], stage_tx);
-                            tma_load_4d(&map_a, &full[s], dst, kc * kBlockK, x0 + tx - p.pad, y0 + ty - p.pad, img);
+                            tma_load_4d(&map_a, &full[s], dst, kc * kBlockK, x0 + tx - p.pad_x, y0 + ty - p.pad_y, img);
                             tma_load_2d(&map_b, &full[s], dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
                         }
                 tile = next_tile;
@@ -185,7 +197,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
             const int oy = (sp / p.tiles_x) * p.th + ty, ox = (sp % p.tiles_x) * p.tw + tx;
             const bool valid = row < rows && oy < p.h_out && ox < p.w_out;
-            const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
+            const int64_t pix = (static_cast<int64_t>(img) * p.out_h + oy * p.out_stride + p.out_py) * p.out_w + ox * p.out_stride + p.out_px;
             // GDN modes: request this thread's x values BEFORE waiting for the accumulator (their latency hides behind the MMAs)
             constexpr int kMaxChunks = (N_TILE + 63) / 64;
             uint4 xpre[kGdn ? kMaxChunks : 1][4];
@@ -212,7 +224,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld32(taddr + c0, v);
                 if (!valid) continue;
                 const int64_t o = pix * p.n_total + n0 + c0;
-                if (kOutF32) {
+                if (!kGdn && has_vec) {  // bias of the convolution
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + s_beta[n0 + c0 + e]);
+                }
+                if (MODE == MODE_NCHW_F32_CLAMP) {
+                    float *dst = static_cast<float *>(p.out);
+                    const int64_t plane = static_cast<int64_t>(p.out_h) * p.out_w;
+                    const int64_t base = static_cast<int64_t>(img) * p.c_real * plane + (pix - static_cast<int64_t>(img) * plane);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < p.c_real) dst[base + (c0 + e) * plane] = fminf(fmaxf(__uint_as_float(v[e]), 0.0f), 1.0f);
+                } else if (kOutF32) {
                     float4 *dst = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + o);
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -243,7 +266,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int e = 0; e < 4; ++e) {
                                 const float2 xf = __half22float2(xh[e]);
                                 const float b0 = bv[2 * e], b1 = bv[2 * e + 1];
-                                if (MODE == MODE_IGDN1_F16 || MODE == MODE_IGDN1_ABS_F16) {
+                                if (MODE == MODE_IGDN_SQ_F16) {  // inverse GDN: x * sqrt(beta + gamma . x^2), the GEMM ran on x^2 / 256
+                                    f[2 * e] = xf.x * sqrtf(fmaf(f[2 * e], 256.0f, b0));
+                                    f[2 * e + 1] = xf.y * sqrtf(fmaf(f[2 * e + 1], 256.0f, b1));
+                                } else if (MODE == MODE_IGDN1_F16 || MODE == MODE_IGDN1_ABS_F16) {
                                     f[2 * e] = xf.x * (f[2 * e] + b0);
                                     f[2 * e + 1] = xf.y * (f[2 * e + 1] + b1);
                                 } else {
@@ -264,6 +290,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             ov.x &= 0x7fff7fffu; ov.y &= 0x7fff7fffu; ov.z &= 0x7fff7fffu; ov.w &= 0x7fff7fffu;
                         }
                         dst[c] = ov;
+                        if (MODE == MODE_STORE_SQ_F16) {  // x^2 / 256, squared in fp32
+                            uint4 sq;
+                            h = __floats2half2_rn(f[0] * f[0] * (1.0f / 256.0f), f[1] * f[1] * (1.0f / 256.0f)); sq.x = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2half2_rn(f[2] * f[2] * (1.0f / 256.0f), f[3] * f[3] * (1.0f / 256.0f)); sq.y = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2half2_rn(f[4] * f[4] * (1.0f / 256.0f), f[5] * f[5] * (1.0f / 256.0f)); sq.z = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2half2_rn(f[6] * f[6] * (1.0f / 256.0f), f[7] * f[7] * (1.0f / 256.0f)); sq.w = *reinterpret_cast<uint32_t *>(&h);
+                            reinterpret_cast<uint4 *>(static_cast<__half *>(p.out2) + o)[c] = sq;
+                        }
                     }
                     if (MODE == MODE_STORE_ABS_F16) p.signs[pix * (p.n_total >> 5) + ((n0 + c0) >> 5)] = sign_word;
                 }
@@ -351,18 +385,22 @@ int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, i
     return SC2_OK;
 }
 
-int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta, const void *gdn_x,
-                     void *out, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream) {
+int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *w_packed, const float *vec, const void *gdn_x,
+                   void *out, void *out2, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream) {
     using namespace sc2::tc;
     if (!d || !x || !w_packed || !out) return SC2_ERR_INVALID_ARG;
     if (d->batch < 1 || d->c_in_pad % kBlockK || d->c_in_pad < kBlockK) return SC2_ERR_INVALID_ARG;
-    if (d->mode < 0 || d->mode > 5) return SC2_ERR_INVALID_ARG;
-    const bool gdn = d->mode == MODE_IGDN1_F16 || d->mode == MODE_GDN1_F16 || d->mode == MODE_IGDN1_ABS_F16;
+    if (d->mode < 0 || d->mode > MODE_NCHW_F32_CLAMP) return SC2_ERR_INVALID_ARG;
+    if (d->kh < 1 || d->kw < 1 || d->h_out < 1 || d->w_out < 1 || d->out_stride < 1) return SC2_ERR_INVALID_ARG;
+    if (d->out_py < 0 || d->out_px < 0 || d->out_py >= d->out_stride || d->out_px >= d->out_stride) return SC2_ERR_INVALID_ARG;
+    if ((d->h_out - 1) * d->out_stride + d->out_py >= d->out_h || (d->w_out - 1) * d->out_stride + d->out_px >= d->out_w) return SC2_ERR_INVALID_ARG;
+    const bool gdn = d->mode == MODE_IGDN1_F16 || d->mode == MODE_GDN1_F16 || d->mode == MODE_IGDN1_ABS_F16 || d->mode == MODE_IGDN_SQ_F16;
     if ((d->mode == MODE_STORE_ABS_F16 || d->mode == MODE_IGDN1_ABS_F16) && (!signs || d->c_out % 32)) return SC2_ERR_INVALID_ARG;
-    if (gdn && (!beta || !gdn_x || d->kh != 1 || d->kw != 1 || d->pad != 0 || d->c_in_pad != d->c_out)) return SC2_ERR_INVALID_ARG;
-    if (gdn && d->c_out > kMaxBeta) return SC2_ERR_UNSUPPORTED;
-    const int h_out = d->h_in + 2 * d->pad - d->kh + 1, w_out = d->w_in + 2 * d->pad - d->kw + 1;
-    if (h_out < 1 || w_out < 1) return SC2_ERR_INVALID_ARG;
+    if (d->mode == MODE_STORE_SQ_F16 && !out2) return SC2_ERR_INVALID_ARG;
+    if (gdn && (!vec || !gdn_x || d->kh != 1 || d->kw != 1 || d->pad_x != 0 || d->pad_y != 0 || d->c_in_pad != d->c_out || d->out_stride != 1))
+        return SC2_ERR_INVALID_ARG;
+    if (d->c_out > kMaxBeta && vec) return SC2_ERR_UNSUPPORTED;
+    const int h_out = d->h_out, w_out = d->w_out;
     // tile shape: tw columns x th rows, tw * th <= 128
     int n_col_tiles = (w_out + 127) / 128;
     int tw = (w_out + n_col_tiles - 1) / n_col_tiles;
@@ -371,8 +409,12 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
     int th = 128 / tw;
     if (th > h_out) th = h_out;
     if (th > 256) th = 256;
-    int n_tile;
-    if (d->c_out % 256 == 0) n_tile = 256;
+    int n_tile, n_rows = d->c_out;  // n_rows: rows per tap of the packed weights
+    if (d->mode == MODE_NCHW_F32_CLAMP) {
+        if (d->c_out > 32) return SC2_ERR_UNSUPPORTED;
+        n_tile = 32; n_rows = 32;  // (the pack is zero-padded to 32 rows per tap)
+    } else if (d->c_out % 256 == 0) n_tile = 256;
+    else if (d->c_out % 192 == 0 && (d->mode == MODE_STORE_SQ_F16 || d->mode == MODE_IGDN_SQ_F16 || d->mode == MODE_STORE_F16)) n_tile = 192;
     else if (d->c_out % 128 == 0) n_tile = 128;
     else if (d->c_out % 64 == 0) n_tile = 64;
     else return SC2_ERR_UNSUPPORTED;
@@ -380,13 +422,16 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
     p.tw = tw; p.th = th;
     p.tiles_x = (w_out + tw - 1) / tw;
     p.tiles_y = (h_out + th - 1) / th;
-    p.taps_x = d->kw; p.taps_y = d->kh; p.pad = d->pad;
+    p.taps_x = d->kw; p.taps_y = d->kh; p.pad_x = d->pad_x; p.pad_y = d->pad_y;
     p.k_chunks = d->c_in_pad / kBlockK;
-    p.n_total = d->c_out;
-    p.n_tiles = d->c_out / n_tile;
+    p.n_total = n_rows;
+    p.n_tiles = n_rows / n_tile;
     p.batch = d->batch;
     p.h_out = h_out; p.w_out = w_out;
-    p.beta = beta;
+    p.out_h = d->out_h; p.out_w = d->out_w; p.out_stride = d->out_stride; p.out_py = d->out_py; p.out_px = d->out_px;
+    p.c_real = d->c_out;
+    p.out2 = out2;
+    p.beta = vec;
     p.gdn_x = static_cast<const __half *>(gdn_x);
     p.signs = signs;
     p.out = out;
@@ -396,7 +441,7 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
     CUtensorMap ma, mb;
     int rc = make_nhwc_map(&ma, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in_pad, d->w_in, d->h_in, d->batch, kBlockK, tw, th);
     if (rc) return rc;
-    rc = make_weight_map(&mb, w_packed, d->c_in_pad, d->kh * d->kw * d->c_out, n_tile);
+    rc = make_weight_map(&mb, w_packed, d->c_in_pad, d->kh * d->kw * n_rows, n_tile);
     if (rc) return rc;
     cudaStream_t st = sc2::as_stream(stream);
 #define SC2_TC_DISPATCH(NT, STG)                                                   \
@@ -406,12 +451,43 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
         case MODE_IGDN1_F16: return launch<NT, STG, MODE_IGDN1_F16>(ma, mb, p, st);  \
         case MODE_STORE_ABS_F16: return launch<NT, STG, MODE_STORE_ABS_F16>(ma, mb, p, st);  \
         case MODE_IGDN1_ABS_F16: return launch<NT, STG, MODE_IGDN1_ABS_F16>(ma, mb, p, st);  \
-        default: return launch<NT, STG, MODE_GDN1_F16>(ma, mb, p, st);             \
+        case MODE_GDN1_F16: return launch<NT, STG, MODE_GDN1_F16>(ma, mb, p, st);    \
+        default: return SC2_ERR_UNSUPPORTED;                                       \
+    }
+    if (n_tile == 32) return launch<32, 8, MODE_NCHW_F32_CLAMP>(ma, mb, p, st);
+    if (n_tile == 192) {
+        switch (d->mode) {
+            case MODE_STORE_SQ_F16: return launch<192, 4, MODE_STORE_SQ_F16>(ma, mb, p, st);
+            case MODE_IGDN_SQ_F16: return launch<192, 4, MODE_IGDN_SQ_F16>(ma, mb, p, st);
+            default: return launch<192, 4, MODE_STORE_F16>(ma, mb, p, st);
+        }
+    }
+    if (d->mode == MODE_STORE_SQ_F16 || d->mode == MODE_IGDN_SQ_F16) {  // (other channel counts: 64-wide tiles)
+        if (d->c_out % 64) return SC2_ERR_UNSUPPORTED;
+        p.n_tiles = n_rows / 64;
+        CUtensorMap mb64;
+        rc = make_weight_map(&mb64, w_packed, d->c_in_pad, d->kh * d->kw * n_rows, 64);
+        if (rc) return rc;
+        return d->mode == MODE_STORE_SQ_F16 ? launch<64, 8, MODE_STORE_SQ_F16>(ma, mb64, p, st) : launch<64, 8, MODE_IGDN_SQ_F16>(ma, mb64, p, st);
     }
     if (n_tile == 256) { SC2_TC_DISPATCH(256, 4) }
     if (n_tile == 128) { SC2_TC_DISPATCH(128, 6) }
     SC2_TC_DISPATCH(64, 8)
 #undef SC2_TC_DISPATCH
+}
+
+int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_packed, const float *beta, const void *gdn_x,
+                     void *out, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream) {
+    if (!d) return SC2_ERR_INVALID_ARG;
+    if (d->mode < 0 || d->mode > 5) return SC2_ERR_INVALID_ARG;
+    sc2_tc_conv_ex_desc e;
+    e.batch = d->batch; e.h_in = d->h_in; e.w_in = d->w_in; e.c_in_pad = d->c_in_pad;
+    e.c_out = d->c_out; e.kh = d->kh; e.kw = d->kw; e.pad_y = d->pad; e.pad_x = d->pad;
+    e.mode = d->mode;
+    e.h_out = d->h_in + 2 * d->pad - d->kh + 1; e.w_out = d->w_in + 2 * d->pad - d->kw + 1;
+    if (e.h_out < 1 || e.w_out < 1) return SC2_ERR_INVALID_ARG;
+    e.out_h = e.h_out; e.out_w = e.w_out; e.out_stride = 1; e.out_py = 0; e.out_px = 0;
+    return sc2_tc_conv_ex(&e, x, w_packed, beta, gdn_x, out, nullptr, signs, tile_counter, stream);
 }
 
 }  // extern "C"

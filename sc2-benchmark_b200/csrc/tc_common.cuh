@@ -1,5 +1,6 @@
 // tc_common.cuh -- PTX wrappers shared by the tcgen05 kernels (mbarrier, TMA, TMEM, UMMA descriptors).
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -25,6 +26,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifdef SC2_HANG_DEBUG
+// diagnostics build (SC2_NVCC_DEFINES=-DSC2_HANG_DEBUG): a wait that spins for ~seconds reports who waits on what and traps
+static __device__ __noinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (unsigned long long spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (spins > (1ull << 22)) {
+            if ((threadIdx.x & 31) == 0)
+                printf("HANG block %d warp %d waits on barrier at smem 0x%x parity %u\n", blockIdx.x, threadIdx.x >> 5, smem_u32(bar), parity);
+            __nanosleep(1000000);
+            if (spins > (1ull << 22) + 4) __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -36,6 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#endif
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -149,6 +149,123 @@ class CompressionModel(nn.Module):
         return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
 
 
+class ZooSynthesisPlan:
+    """g_s of the CompressAI zoo codecs (deconv - IGDN - deconv - IGDN - deconv - IGDN - deconv, compressai.models.google [mem];
+    reached from sc2bench/models/wrapper.py:130) on the tcgen05 kernels, fp16 operands / fp32 accumulation like the bottleneck's
+    g_s (the 1e-3 tolerance on x_hat):
+        ConvTranspose2d(k5, s2, p2, op1) = 4 parity sub-convolutions (ops.pack_deconv5_weight_f16), bias in the epilogue;
+        the deconv in front of an inverse GDN stores x and x^2 / 256; the GDN's 1x1 gamma GEMM reads the squares,
+        y = x * sqrt(beta + 256 * acc); the last deconv writes clamp(x_hat, 0, 1) as fp32 NCHW.
+    15 launches instead of 7 CUDA-core convolutions that ran at 0.1-1 % of the tensor peak."""
+
+    def __init__(self, seq):
+        self.seq = seq
+        self._plan = None
+
+    @staticmethod
+    def why_not(seq):
+        mods = list(seq)
+        if len(mods) < 1 or len(mods) % 2 == 0:
+            return 'not deconv (- IGDN - deconv)*'
+        for i, m in enumerate(mods):
+            if i % 2 == 0:
+                if not isinstance(m, nn.ConvTranspose2d):
+                    return 'layer %d is %s' % (i, type(m).__name__)
+                if (tuple(m.kernel_size), tuple(m.stride), tuple(m.padding), tuple(m.output_padding), m.groups, tuple(m.dilation)) != \
+                        ((5, 5), (2, 2), (2, 2), (1, 1), 1, (1, 1)):
+                    return 'transposed convolution %d is not (k5, s2, p2, op1)' % i
+                if m.in_channels % 64:
+                    return 'c_in %d is not a multiple of 64' % m.in_channels
+                last = i == len(mods) - 1
+                if last and m.out_channels > 32:
+                    return 'last layer has %d > 32 output channels' % m.out_channels
+                if not last and m.out_channels % 64:
+                    return 'c_out %d is not a multiple of 64' % m.out_channels
+            else:
+                if type(m) is not GDN or not m.inverse:
+                    return 'layer %d is not an inverse GDN' % i
+                if m.beta.numel() % 64 or m.beta.numel() > 512:
+                    return 'GDN over %d channels' % m.beta.numel()
+        return None
+
+    def _prepare(self):
+        key = tuple((q.data_ptr(), q._version, q.device) for q in self.seq.parameters())
+        plan = self._plan
+        if plan is not None and plan[0] == key:
+            return plan
+        steps, mods = [], list(self.seq)
+        for i, m in enumerate(mods):
+            if i % 2 == 0:
+                last = i == len(mods) - 1
+                packs = ops.pack_deconv5_weight_f16(m.weight, rows_pad=32 if last else None)
+                bias = None
+                if m.bias is not None:
+                    bias = torch.zeros(32 if last else m.out_channels, dtype=torch.float32, device=m.weight.device)
+                    bias[:m.out_channels] = m.bias.detach().float()
+                steps.append(('deconv', packs, bias, m.in_channels, m.out_channels, last))
+            else:
+                gamma, beta = m.effective_params()
+                C = beta.numel()
+                steps.append(('igdn', gamma.detach().reshape(1, C, C).half().contiguous(), beta.detach().float().contiguous(), C))
+        plan = (key, steps, mods[0].in_channels)
+        self._plan = plan
+        return plan
+
+    @torch.no_grad()
+    def __call__(self, y_hat):
+        """fp32 NCHW latent -> clamp(x_hat, 0, 1) as fp32 NCHW"""
+        _, steps, c_in0 = self._prepare()
+        T = _native
+        x = ops.nchw_to_nhwc_f16(y_hat, c_in0)
+        sq = None
+        for step in steps:
+            if step[0] == 'deconv':
+                _, packs, bias, c_in, c_out, last = step
+                B, H, W, _ = x.shape
+                if last:
+                    out = torch.empty((B, c_out, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+                    sq = None
+                else:
+                    out = torch.empty((B, 2 * H, 2 * W, c_out), dtype=torch.float16, device=x.device)
+                    sq = torch.empty_like(out)
+                for (py, px), w in packs.items():
+                    (ky, pad_y), (kx, pad_x) = ops.DECONV5_TAPS[py], ops.DECONV5_TAPS[px]
+                    ops.tc_conv_ex(x, w, len(ky), len(kx), pad_y, pad_x, T.TC_NCHW_F32_CLAMP if last else T.TC_STORE_SQ_F16, (H, W), out,
+                                   out_stride=2, out_py=py, out_px=px, vec=bias, out2=sq, c_out=c_out, c_in=c_in,
+                                   tag='tc_deconv5[%d->%d,p%d%d]' % (c_in, c_out, py, px))
+                x = out
+            else:
+                _, gamma, beta, C = step
+                B, H, W, _ = x.shape
+                out = torch.empty_like(x)
+                ops.tc_conv_ex(sq, gamma, 1, 1, 0, 0, T.TC_IGDN_SQ_F16, (H, W), out, vec=beta, gdn_x=x, c_out=C, c_in=C,
+                               tag='tc_igdn[%d]' % C)
+                x, sq = out, None
+        return x
+
+
+_warned_fallback = set()
+
+
+def run_synthesis(model, seq, y_hat):
+    """g_s of a zoo codec: the tensor-core plan when it covers `seq` (and model.decoder_precision allows), else the fp32 kernels."""
+    why = 'decoder_precision = %r' % getattr(model, 'decoder_precision', 'fp16-tc') if getattr(model, 'decoder_precision', 'fp16-tc') != 'fp16-tc' \
+        else ZooSynthesisPlan.why_not(seq)
+    if why is None:
+        plan = model.__dict__.get('_tc_synthesis')
+        if plan is None:
+            plan = ZooSynthesisPlan(seq)
+            model.__dict__['_tc_synthesis'] = plan
+        return plan(y_hat)
+    key = (type(model).__name__, why)
+    if key not in _warned_fallback:
+        _warned_fallback.add(key)
+        import logging
+        logging.getLogger('sc2bench_b200').warning('%s.g_s runs on the fp32 CUDA-core kernels (conv2d_f32_kernel), not on the tensor cores: %s',
+                                                    type(model).__name__, why)
+    return run_transform(seq, y_hat, final_epilogue=_native.EPI_CLAMP01)
+
+
 class FactorizedPrior(CompressionModel):
     """bmshj2018-factorized: g_a (4 conv, 3 GDN) -> EntropyBottleneck -> g_s (4 deconv, 3 IGDN)."""
 
@@ -187,7 +304,7 @@ class FactorizedPrior(CompressionModel):
         streams = first if isinstance(first, ops.PackedStreams) else \
             ops.PackedStreams.from_list(first, self.entropy_bottleneck._quantized_cdf.device)
         y_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape), check_status=not isinstance(first, ops.PackedStreams))
-        return {'x_hat': run_transform(self.g_s, y_hat, final_epilogue=_native.EPI_CLAMP01)}
+        return {'x_hat': run_synthesis(self, self.g_s, y_hat)}
 
 
 class ScaleHyperprior(CompressionModel):
@@ -241,7 +358,7 @@ class ScaleHyperprior(CompressionModel):
         indexes = gc.build_indexes(run_transform(self.h_s, z_hat))
         y_streams = ops.PackedStreams.from_list(strings[0], device)
         y_hat = ops.rans_decode(y_streams, indexes[0].numel(), gc.coder_tables(), indexes=indexes, want='values')
-        return {'x_hat': run_transform(self.g_s, y_hat.view(indexes.size()), final_epilogue=_native.EPI_CLAMP01)}
+        return {'x_hat': run_synthesis(self, self.g_s, y_hat.view(indexes.size()))}
 
 
 # ---- zoo (compressai.zoo.image) --------------------------------------------------------------------

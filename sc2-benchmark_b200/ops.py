@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _native
-from ._native import ConvDesc, GaHaloDesc, TcConvDesc, TcSplitDesc, check
+from ._native import ConvDesc, GaHaloDesc, TcConvDesc, TcConvExDesc, TcSplitDesc, check
 
 
 def _lib():
@@ -684,3 +684,56 @@ def ga_first_conv_gdn(x, w_stack, gamma_stack, beta, c_out, lut=None):
         check(_lib().sc2_ga_first_conv_gdn(_ptr(x), int(u8), _ptr(lut), B, H, W, c_out, _ptr(w_stack), _ptr(gamma_stack), _ptr(b),
                                            _ptr(hi), _ptr(lo), out_c, _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_ga_first_conv_gdn')
     return hi, lo
+
+
+# ----------------------------------------------------------------------------------------------
+# extended tensor-core convolution (round 2): transposed convolutions as parity sub-convolutions, GDN proper
+# ----------------------------------------------------------------------------------------------
+DECONV5_TAPS = {0: ([4, 2, 0], 1), 1: ([3, 1], 0)}  # output parity -> (kernel indexes of the taps, padding) of ConvTranspose2d(k5, s2, p2, op1)
+
+
+def pack_deconv5_weight_f16(weight, rows_pad=None):
+    """ConvTranspose2d(k5, s2, p2, output_padding 1) weight [c_in, c_out, 5, 5] -> {(py, px): [taps, rows, c_in_pad] fp16}: the four
+    stride-1 sub-convolutions that produce the output pixels of parity (py, px).  out[2Y + py] = sum_t x[Y + t - pad] * w[k_t] with
+    (k, pad) = ([4, 2, 0], 1) for py = 0 and ([3, 1], 0) for py = 1 (from o = 2 i - 2 + k), the same along x."""
+    w = weight.detach().float()
+    c_in, c_out, kh, kw = w.shape
+    if (kh, kw) != (5, 5):
+        raise ValueError('pack_deconv5_weight_f16 is for 5x5 kernels')
+    c_in_pad = (c_in + 63) // 64 * 64
+    rows = rows_pad or c_out
+    packs = {}
+    for py in (0, 1):
+        for px in (0, 1):
+            ky, kx = DECONV5_TAPS[py][0], DECONV5_TAPS[px][0]
+            sub = w[:, :, ky][:, :, :, kx]                                   # [c_in, c_out, Ty, Tx]
+            packed = torch.zeros((len(ky) * len(kx), rows, c_in_pad), dtype=torch.float16, device=w.device)
+            packed[:, :c_out, :c_in] = sub.permute(2, 3, 1, 0).reshape(len(ky) * len(kx), c_out, c_in).half()
+            packs[(py, px)] = packed.contiguous()
+    return packs
+
+
+def tc_conv_ex(x_nhwc, w_packed, kh, kw, pad_y, pad_x, mode, grid, out, out_stride=1, out_py=0, out_px=0, vec=None, gdn_x=None,
+               out2=None, c_out=None, c_in=None, tag=None):
+    """sc2_tc_conv_ex: one launch of the generalised tcgen05 convolution.  `out` (and `out2`) are caller-allocated full output
+    tensors ([B, out_h, out_w, c_out] NHWC, or [B, c_out, out_h, out_w] fp32 for mode TC_NCHW_F32_CLAMP); `grid` = (h_out, w_out)
+    output pixels computed by this launch, placed at (oy * out_stride + out_py, ox * out_stride + out_px)."""
+    require_cuda(x_nhwc, 'tc_conv_ex')
+    assert x_nhwc.dtype == torch.float16 and x_nhwc.is_contiguous() and w_packed.dtype == torch.float16
+    B, H, W, Cp = x_nhwc.shape
+    taps, rows, cp2 = w_packed.shape
+    if taps != kh * kw or cp2 != Cp:
+        raise ValueError('packed weight does not match the activation / kernel size')
+    nchw = mode == _native.TC_NCHW_F32_CLAMP
+    out_h, out_w = (out.shape[2], out.shape[3]) if nchw else (out.shape[1], out.shape[2])
+    c_out = c_out or rows
+    d = TcConvExDesc(B, H, W, Cp, c_out, kh, kw, pad_y, pad_x, mode, grid[0], grid[1], out_h, out_w, out_stride, out_py, out_px)
+    v = vec.detach().contiguous().float() if vec is not None else None
+    c_real = c_in or Cp
+    flops = 2.0 * B * grid[0] * grid[1] * c_out * c_real * kh * kw
+    nbytes = 4.0 * B * (H * W * c_real / (out_stride * out_stride) + grid[0] * grid[1] * c_out)
+    tag = tag or 'tc_conv_ex[%d->%d,k%dx%d,m%d]' % (Cp, c_out, kh, kw, mode)
+    with torch.cuda.device(x_nhwc.device), _launch(tag, flops=flops, nbytes=nbytes):
+        check(_lib().sc2_tc_conv_ex(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(v), _ptr(gdn_x), _ptr(out), _ptr(out2), None,
+                                    _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_conv_ex')
+    return out

@@ -181,7 +181,7 @@ def _gdn1_ref64(x64, gamma, beta):
     return x64 / norm
 
 
-@pytest.mark.parametrize('cin,cout,H,W,batch', [(96, 48, 112, 112, 2), (96, 48, 40, 72, 3), (32, 16, 24, 40, 2), (64, 80, 36, 20, 1),
+@pytest.mark.parametrize('cin,cout,H,W,batch', [(96, 48, 112, 112, 2), (96, 48, 112, 112, 24), (96, 48, 40, 72, 3), (32, 16, 24, 40, 2), (64, 80, 36, 20, 1),
                                                  (48, 24, 400, 140, 1), (192, 64, 20, 28, 2)])
 def test_ga_halo_conv_gdn_matches_fp64(s2, cin, cout, H, W, batch):
     """sc2_ga_halo_conv_gdn = Conv2d(k5, s2, p2) + GDN1 (layer.py:479-481) vs an fp64 reference of the same fp32 operands, and
@@ -252,3 +252,61 @@ def test_ga_first_uint8_lut_equals_float_input(s2):
     fh, fl = s2.ops.ga_first_conv_gdn(xf.to(dev), ws, gs, beta.to(dev), 96)
     uh, ul = s2.ops.ga_first_conv_gdn(u8.to(dev), ws, gs, beta.to(dev), 96, lut=lut)
     assert torch.equal(fh, uh) and torch.equal(fl, ul)
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: synthesis transform of the zoo codecs on the tensor cores (transposed conv as parity sub-convolutions, GDN proper)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('cin,cout,H,W,batch', [(320, 192, 16, 16, 2), (192, 192, 32, 32, 2), (64, 64, 5, 7, 3), (192, 3, 20, 12, 2), (128, 128, 9, 9, 1)])
+def test_tc_deconv5_parity_classes_match_torch(s2, cin, cout, H, W, batch):
+    """ConvTranspose2d(k5, s2, p2, op1) + bias as four sc2_tc_conv_ex launches vs torch on the same fp16-rounded operands; the x^2
+    side output of mode 6; the clamped fp32 NCHW output of the last layer (mode 8)."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(cin + cout + H)
+    x = torch.randn(batch, cin, H, W)
+    w = torch.randn(cin, cout, 5, 5) / (cin * 25 / 4) ** 0.5
+    b = torch.randn(cout) * 0.1
+    xh, wh = x.half().float(), w.half().float()
+    ref = F.conv_transpose2d(xh.double(), wh.double(), b.double(), stride=2, padding=2, output_padding=1).float()
+    last = cout <= 32
+    x_nhwc = s2.ops.nchw_to_nhwc_f16(x.to(dev), (cin + 63) // 64 * 64)
+    packs = s2.ops.pack_deconv5_weight_f16(w.to(dev), rows_pad=32 if last else None)
+    T = s2._native
+    if last:
+        out = torch.full((batch, cout, 2 * H, 2 * W), -7.0, dtype=torch.float32, device=dev)
+        bias = torch.zeros(32, device=dev)
+        bias[:cout] = b.to(dev)
+        sq = None
+    else:
+        out = torch.full((batch, 2 * H, 2 * W, cout), -7.0, dtype=torch.float16, device=dev)
+        sq = torch.empty_like(out)
+        bias = b.to(dev)
+    for (py, px), pk in packs.items():
+        (ky, pad_y), (kx, pad_x) = s2.ops.DECONV5_TAPS[py], s2.ops.DECONV5_TAPS[px]
+        s2.ops.tc_conv_ex(x_nhwc, pk, len(ky), len(kx), pad_y, pad_x, T.TC_NCHW_F32_CLAMP if last else T.TC_STORE_SQ_F16, (H, W), out,
+                          out_stride=2, out_py=py, out_px=px, vec=bias, out2=sq, c_out=cout, c_in=cin)
+    if last:
+        assert rel_err(out.cpu(), ref.clamp(0, 1)) < 2e-3
+    else:
+        got = out.float().permute(0, 3, 1, 2).cpu()
+        assert rel_err(got, ref) < 1.5e-3, rel_err(got, ref)
+        got_sq = sq.float().permute(0, 3, 1, 2).cpu() * 256.0
+        assert rel_err(got_sq, ref * ref) < 3e-3
+
+
+@pytest.mark.parametrize('C,H,W', [(192, 32, 32), (128, 9, 11), (64, 5, 5)])
+def test_tc_inverse_gdn_on_square_pair(s2, C, H, W):
+    """mode 7: y = x * sqrt(beta + gamma . x^2) with the gamma GEMM on the x^2 / 256 tensor (compressai.layers.GDN, inverse)."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(C + H)
+    x = (torch.randn(2, C, H, W) * 3).half().float()
+    gamma = (0.1 * torch.eye(C) + 0.02 * torch.rand(C, C)).half().float()
+    beta = 0.5 + torch.rand(C)
+    ref = (x.double() * torch.sqrt(F.conv2d(x.double() ** 2, gamma.double().view(C, C, 1, 1), beta.double()))).float()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().half().to(dev)
+    sq = (x.permute(0, 2, 3, 1) ** 2 / 256.0).contiguous().half().to(dev)
+    out = torch.empty_like(x_nhwc)
+    s2.ops.tc_conv_ex(sq, gamma.half().to(dev).view(1, C, C).contiguous(), 1, 1, 0, 0, s2._native.TC_IGDN_SQ_F16, (H, W), out,
+                      vec=beta.to(dev), gdn_x=x_nhwc, c_out=C, c_in=C)
+    got = out.float().permute(0, 3, 1, 2).cpu()
+    assert rel_err(got, ref) < 1.5e-3, rel_err(got, ref)
