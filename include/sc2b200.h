@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 6
+#define SC2_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -223,8 +223,14 @@ typedef struct sc2_tc_conv_ex_desc {
     int out_h, out_w, out_stride, out_py, out_px;
 } sc2_tc_conv_ex_desc;
 
-SC2_API int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *w_packed, const float *vec, const void *gdn_x,
-                           void *out, void *out2, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream);
+/* Split activations (optional, all NULL = plain fp16): fp16 activations between the LAST layers of a synthesis transform cost
+ * 1.5e-3 on x_hat (scripts/diag note in DESIGN.md), so that stage can carry x = hi + lo (two fp16 tensors):
+ *   x_lo       second A tensor: the MMA runs over x and x_lo with the same weights (two passes into one accumulator)
+ *   out3       mode 6: also store the lo half of x
+ *   gdn_x_lo   mode 7: lo half of the multiplicand x; the result is then stored as out (hi) + out2 (lo) */
+SC2_API int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *x_lo, const void *w_packed, const float *vec,
+                           const void *gdn_x, const void *gdn_x_lo, void *out, void *out2, void *out3, uint32_t *signs,
+                           int32_t *tile_counter, sc2_stream_t stream);
 
 /* tile_counter (all sc2_tc_* kernels): the kernels are persistent (one CTA per SM).  With a caller-provided int32 that is
  * ZERO at launch (one per launch; stream-ordered reuse is fine) the CTAs claim tiles dynamically, so a CTA that is placed

@@ -61,7 +61,7 @@ SIGNATURES = {
     'sc2_conv2d_f32': (i32, [_c.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]),
     'sc2_gdn_f32': (i32, [vp, vp, vp, vp, i32, i32, i64, i32, i32, vp]),
     'sc2_tc_conv_nhwc': (i32, [_c.POINTER(TcConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
-    'sc2_tc_conv_ex': (i32, [_c.POINTER(TcConvExDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sc2_tc_conv_ex': (i32, [_c.POINTER(TcConvExDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'sc2_nchw_f32_to_nhwc_f16': (i32, [vp, vp, i32, i32, i64, i32, vp]),
     'sc2_tc_split_n_tile': (i32, [i32]),
     'sc2_tc_split_conv': (i32, [_c.POINTER(TcSplitDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -73,7 +73,7 @@ SIGNATURES = {
 }
 
 SC2_OK = 0
-ABI_VERSION = 6  # include/sc2b200.h SC2_ABI_VERSION
+ABI_VERSION = 7  # include/sc2b200.h SC2_ABI_VERSION
 FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM, FAULT_BAD_INDEX = 1, 2, 4, 8
 EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 IN_NONE, IN_ABS = 0, 1

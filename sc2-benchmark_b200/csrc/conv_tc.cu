@@ -52,7 +52,10 @@ struct Params {
     int out_h, out_w;      // the output TENSOR: pixel (oy, ox) of the grid lands at (oy * out_stride + out_py, ox * out_stride + out_px)
     int out_stride, out_py, out_px;
     int c_real;            // mode 8: real output channels (<= N_TILE)
-    void *out2;            // mode 6: the x^2 / 256 tensor
+    void *out2;            // mode 6: the x^2 / 256 tensor; mode 7 with gdn_x_lo: the lo half of y
+    void *out3;            // mode 6, optional: the lo half of x (x = out + out3: activation rounding out of the last stage)
+    const __half *gdn_x_lo;  // mode 7, optional: lo half of x
+    int a_passes;          // 1, or 2: the A operand is the sum of two fp16 tensors (map_a, map_a2), same weights
     const float *beta;     // GDN modes: effective beta [n_total]; conv modes: bias [n_total] or nullptr
     const __half *gdn_x;   // GDN modes: x itself (mode 5: |x|), NHWC [batch, h_out, w_out, n_total]
     uint32_t *signs;       // mode 4: out, mode 5: in -- packed sign words [batch * h_out * w_out, n_total / 32]
@@ -76,7 +79,8 @@ struct Smem {
 
 template <int N_TILE, int STAGES, int MODE>
 __global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16) ? 448 : 320, 1)  // + 4 |x| transform warps
-tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Params p) {
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ Params p) {
     using L = Smem<N_TILE, STAGES>;
     constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;  // |x| formed in shared memory by 4 extra warps
     constexpr bool kGdn = kXform || MODE == MODE_IGDN1_ABS_F16 || MODE == MODE_IGDN_SQ_F16;  // GDN epilogue
@@ -96,7 +100,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int rows = p.tw * p.th;
-    const int k_iters = p.taps_x * p.taps_y * p.k_chunks;
+    const int k_iters = p.a_passes * p.taps_x * p.taps_y * p.k_chunks;
     const int tiles_xy = p.tiles_x * p.tiles_y;
     const int total_tiles = tiles_xy * p.n_tiles * p.batch;
     const unsigned long long trace_t0 = p.trace.buf ? trace_now() : 0ull;
@@ -113,6 +117,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (threadIdx.x == 0) {
         sched.init(kXform ? 13 : 9);  // consumers: MMA warp, 8 epilogue warps (, 4 transform warps)
         tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_a2);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
@@ -144,16 +149,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int sp = tile % tiles_xy, rest = tile / tiles_xy;
                 const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
                 const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
-                for (int ty = 0; ty < p.taps_y; ++ty)
-                    for (int tx = 0; tx < p.taps_x; ++tx)
-                        for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
-                            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-                            mbar_wait(&empty[s], ph ^ 1u);
-                            uint8_t *dst = smem + s * L::kStageBytes;
-                            mbar_expect_tx(&full[s], stage_tx);
-                            tma_load_4d(&map_a, &full[s], dst, kc * kBlockK, x0 + tx - p.pad_x, y0 + ty - p.pad_y, img);
-                            tma_load_2d(&map_b, &full[s], dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
-                        }
+                for (int pass = 0; pass < p.a_passes; ++pass)
+                    for (int ty = 0; ty < p.taps_y; ++ty)
+                        for (int tx = 0; tx < p.taps_x; ++tx)
+                            for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+                                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                                mbar_wait(&empty[s], ph ^ 1u);
+                                uint8_t *dst = smem + s * L::kStageBytes;
+                                mbar_expect_tx(&full[s], stage_tx);
+                                tma_load_4d(pass == 0 ? &map_a : &map_a2, &full[s], dst, kc * kBlockK, x0 + tx - p.pad_x, y0 + ty - p.pad_y, img);
+                                tma_load_2d(&map_b, &full[s], dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
+                            }
                 tile = next_tile;
             }
         }
@@ -202,6 +208,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             constexpr int kMaxChunks = (N_TILE + 63) / 64;
             uint4 xpre[kGdn ? kMaxChunks : 1][4];
             uint32_t spre[kSigned ? kMaxChunks : 1];
+            uint4 xlo[MODE == MODE_IGDN_SQ_F16 ? kMaxChunks : 1][4];  // (split activations: x = hi + lo)
             if (kGdn && valid) {
 #pragma unroll
                 for (int ci = 0; ci < kMaxChunks; ++ci) {
@@ -210,6 +217,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int c = 0; c < 4; ++c) xpre[ci][c] = __ldg(reinterpret_cast<const uint4 *>(p.gdn_x + pix * p.n_total + n0 + c0) + c);
                         if (kSigned) spre[ci] = __ldg(p.signs + pix * (p.n_total >> 5) + ((n0 + c0) >> 5));
+                        if (MODE == MODE_IGDN_SQ_F16 && p.gdn_x_lo) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) xlo[ci][c] = __ldg(reinterpret_cast<const uint4 *>(p.gdn_x_lo + pix * p.n_total + n0 + c0) + c);
+                        }
                     }
                 }
             }
@@ -267,8 +278,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 const float2 xf = __half22float2(xh[e]);
                                 const float b0 = bv[2 * e], b1 = bv[2 * e + 1];
                                 if (MODE == MODE_IGDN_SQ_F16) {  // inverse GDN: x * sqrt(beta + gamma . x^2), the GEMM ran on x^2 / 256
-                                    f[2 * e] = xf.x * sqrtf(fmaf(f[2 * e], 256.0f, b0));
-                                    f[2 * e + 1] = xf.y * sqrtf(fmaf(f[2 * e + 1], 256.0f, b1));
+                                    float x0f = xf.x, x1f = xf.y;
+                                    if (p.gdn_x_lo) {
+                                        const float2 lf = __half22float2(reinterpret_cast<const __half2 *>(&xlo[MODE == MODE_IGDN_SQ_F16 ? ci : 0][c])[e]);
+                                        x0f += lf.x;
+                                        x1f += lf.y;
+                                    }
+                                    f[2 * e] = x0f * sqrtf(fmaf(f[2 * e], 256.0f, b0));
+                                    f[2 * e + 1] = x1f * sqrtf(fmaf(f[2 * e + 1], 256.0f, b1));
                                 } else if (MODE == MODE_IGDN1_F16 || MODE == MODE_IGDN1_ABS_F16) {
                                     f[2 * e] = xf.x * (f[2 * e] + b0);
                                     f[2 * e + 1] = xf.y * (f[2 * e + 1] + b1);
@@ -290,6 +307,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             ov.x &= 0x7fff7fffu; ov.y &= 0x7fff7fffu; ov.z &= 0x7fff7fffu; ov.w &= 0x7fff7fffu;
                         }
                         dst[c] = ov;
+                        if ((MODE == MODE_STORE_SQ_F16 && p.out3) || (MODE == MODE_IGDN_SQ_F16 && p.gdn_x_lo)) {  // lo half: value - fp16(value)
+                            const __half2 *hh = reinterpret_cast<const __half2 *>(&ov);
+                            uint4 lo;
+                            uint32_t *lw = reinterpret_cast<uint32_t *>(&lo);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 back = __half22float2(hh[e]);
+                                const __half2 l2 = __floats2half2_rn(f[2 * e] - back.x, f[2 * e + 1] - back.y);
+                                lw[e] = *reinterpret_cast<const uint32_t *>(&l2);
+                            }
+                            reinterpret_cast<uint4 *>(static_cast<__half *>(MODE == MODE_STORE_SQ_F16 ? p.out3 : p.out2) + o)[c] = lo;
+                        }
                         if (MODE == MODE_STORE_SQ_F16) {  // x^2 / 256, squared in fp32
                             uint4 sq;
                             h = __floats2half2_rn(f[0] * f[0] * (1.0f / 256.0f), f[1] * f[1] * (1.0f / 256.0f)); sq.x = *reinterpret_cast<uint32_t *>(&h);
@@ -338,7 +367,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 template <int N_TILE, int STAGES, int MODE>
-static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const Params &p, cudaStream_t st) {
+static int launch(const CUtensorMap &ma, const CUtensorMap &ma2, const CUtensorMap &mb, const Params &p, cudaStream_t st) {
     using L = Smem<N_TILE, STAGES>;
     constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
     const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
@@ -346,7 +375,7 @@ static int launch(const CUtensorMap &ma, const CUtensorMap &mb, const Params &p,
     if (int rc = ensure_dyn_smem(tc_conv_kernel<N_TILE, STAGES, MODE>, smem, configured)) return rc;
     const int total = p.tiles_x * p.tiles_y * p.n_tiles * p.batch;
     const int grid = total < persistent_grid() ? total : persistent_grid();
-    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kXform ? 448 : 320, smem, st>>>(ma, mb, p);
+    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kXform ? 448 : 320, smem, st>>>(ma, ma2, mb, p);
     SC2_LAUNCH_CHECK("tc_conv_kernel");
     return SC2_OK;
 }
@@ -385,8 +414,8 @@ int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, i
     return SC2_OK;
 }
 
-int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *w_packed, const float *vec, const void *gdn_x,
-                   void *out, void *out2, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream) {
+int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *x_lo, const void *w_packed, const float *vec, const void *gdn_x,
+                   const void *gdn_x_lo, void *out, void *out2, void *out3, uint32_t *signs, int32_t *tile_counter, sc2_stream_t stream) {
     using namespace sc2::tc;
     if (!d || !x || !w_packed || !out) return SC2_ERR_INVALID_ARG;
     if (d->batch < 1 || d->c_in_pad % kBlockK || d->c_in_pad < kBlockK) return SC2_ERR_INVALID_ARG;
@@ -431,6 +460,9 @@ int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *w_pa
     p.out_h = d->out_h; p.out_w = d->out_w; p.out_stride = d->out_stride; p.out_py = d->out_py; p.out_px = d->out_px;
     p.c_real = d->c_out;
     p.out2 = out2;
+    p.out3 = out3;
+    p.gdn_x_lo = static_cast<const __half *>(gdn_x_lo);
+    p.a_passes = x_lo ? 2 : 1;
     p.beta = vec;
     p.gdn_x = static_cast<const __half *>(gdn_x);
     p.signs = signs;
@@ -438,28 +470,34 @@ int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *w_pa
     p.tile_counter = tile_counter;
     p.trace = sc2::trace_sink();
     if (static_cast<int64_t>(p.tiles_x) * p.tiles_y * p.n_tiles * p.batch > 0x7fffffff - 1024) return SC2_ERR_UNSUPPORTED;
-    CUtensorMap ma, mb;
+    if (d->mode == MODE_IGDN_SQ_F16 && gdn_x_lo && !out2) return SC2_ERR_INVALID_ARG;
+    CUtensorMap ma, ma2, mb;
     int rc = make_nhwc_map(&ma, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in_pad, d->w_in, d->h_in, d->batch, kBlockK, tw, th);
     if (rc) return rc;
+    ma2 = ma;
+    if (x_lo) {
+        rc = make_nhwc_map(&ma2, x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in_pad, d->w_in, d->h_in, d->batch, kBlockK, tw, th);
+        if (rc) return rc;
+    }
     rc = make_weight_map(&mb, w_packed, d->c_in_pad, d->kh * d->kw * n_rows, n_tile);
     if (rc) return rc;
     cudaStream_t st = sc2::as_stream(stream);
 #define SC2_TC_DISPATCH(NT, STG)                                                   \
     switch (d->mode) {                                                             \
-        case MODE_STORE_F16: return launch<NT, STG, MODE_STORE_F16>(ma, mb, p, st);  \
-        case MODE_STORE_F32: return launch<NT, STG, MODE_STORE_F32>(ma, mb, p, st);  \
-        case MODE_IGDN1_F16: return launch<NT, STG, MODE_IGDN1_F16>(ma, mb, p, st);  \
-        case MODE_STORE_ABS_F16: return launch<NT, STG, MODE_STORE_ABS_F16>(ma, mb, p, st);  \
-        case MODE_IGDN1_ABS_F16: return launch<NT, STG, MODE_IGDN1_ABS_F16>(ma, mb, p, st);  \
-        case MODE_GDN1_F16: return launch<NT, STG, MODE_GDN1_F16>(ma, mb, p, st);    \
+        case MODE_STORE_F16: return launch<NT, STG, MODE_STORE_F16>(ma, ma2, mb, p, st);  \
+        case MODE_STORE_F32: return launch<NT, STG, MODE_STORE_F32>(ma, ma2, mb, p, st);  \
+        case MODE_IGDN1_F16: return launch<NT, STG, MODE_IGDN1_F16>(ma, ma2, mb, p, st);  \
+        case MODE_STORE_ABS_F16: return launch<NT, STG, MODE_STORE_ABS_F16>(ma, ma2, mb, p, st);  \
+        case MODE_IGDN1_ABS_F16: return launch<NT, STG, MODE_IGDN1_ABS_F16>(ma, ma2, mb, p, st);  \
+        case MODE_GDN1_F16: return launch<NT, STG, MODE_GDN1_F16>(ma, ma2, mb, p, st);    \
         default: return SC2_ERR_UNSUPPORTED;                                       \
     }
-    if (n_tile == 32) return launch<32, 8, MODE_NCHW_F32_CLAMP>(ma, mb, p, st);
+    if (n_tile == 32) return launch<32, 8, MODE_NCHW_F32_CLAMP>(ma, ma2, mb, p, st);
     if (n_tile == 192) {
         switch (d->mode) {
-            case MODE_STORE_SQ_F16: return launch<192, 4, MODE_STORE_SQ_F16>(ma, mb, p, st);
-            case MODE_IGDN_SQ_F16: return launch<192, 4, MODE_IGDN_SQ_F16>(ma, mb, p, st);
-            default: return launch<192, 4, MODE_STORE_F16>(ma, mb, p, st);
+            case MODE_STORE_SQ_F16: return launch<192, 4, MODE_STORE_SQ_F16>(ma, ma2, mb, p, st);
+            case MODE_IGDN_SQ_F16: return launch<192, 4, MODE_IGDN_SQ_F16>(ma, ma2, mb, p, st);
+            default: return launch<192, 4, MODE_STORE_F16>(ma, ma2, mb, p, st);
         }
     }
     if (d->mode == MODE_STORE_SQ_F16 || d->mode == MODE_IGDN_SQ_F16) {  // (other channel counts: 64-wide tiles)
@@ -468,7 +506,7 @@ int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *w_pa
         CUtensorMap mb64;
         rc = make_weight_map(&mb64, w_packed, d->c_in_pad, d->kh * d->kw * n_rows, 64);
         if (rc) return rc;
-        return d->mode == MODE_STORE_SQ_F16 ? launch<64, 8, MODE_STORE_SQ_F16>(ma, mb64, p, st) : launch<64, 8, MODE_IGDN_SQ_F16>(ma, mb64, p, st);
+        return d->mode == MODE_STORE_SQ_F16 ? launch<64, 8, MODE_STORE_SQ_F16>(ma, ma2, mb64, p, st) : launch<64, 8, MODE_IGDN_SQ_F16>(ma, ma2, mb64, p, st);
     }
     if (n_tile == 256) { SC2_TC_DISPATCH(256, 4) }
     if (n_tile == 128) { SC2_TC_DISPATCH(128, 6) }
@@ -487,7 +525,7 @@ int sc2_tc_conv_nhwc(const sc2_tc_conv_desc *d, const void *x, const void *w_pac
     e.h_out = d->h_in + 2 * d->pad - d->kh + 1; e.w_out = d->w_in + 2 * d->pad - d->kw + 1;
     if (e.h_out < 1 || e.w_out < 1) return SC2_ERR_INVALID_ARG;
     e.out_h = e.h_out; e.out_w = e.w_out; e.out_stride = 1; e.out_py = 0; e.out_px = 0;
-    return sc2_tc_conv_ex(&e, x, w_packed, beta, gdn_x, out, nullptr, signs, tile_counter, stream);
+    return sc2_tc_conv_ex(&e, x, nullptr, w_packed, beta, gdn_x, nullptr, out, nullptr, nullptr, signs, tile_counter, stream);
 }
 
 }  // extern "C"

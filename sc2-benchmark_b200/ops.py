@@ -714,7 +714,7 @@ def pack_deconv5_weight_f16(weight, rows_pad=None):
 
 
 def tc_conv_ex(x_nhwc, w_packed, kh, kw, pad_y, pad_x, mode, grid, out, out_stride=1, out_py=0, out_px=0, vec=None, gdn_x=None,
-               out2=None, c_out=None, c_in=None, tag=None):
+               out2=None, c_out=None, c_in=None, tag=None, x_lo=None, gdn_x_lo=None, out3=None):
     """sc2_tc_conv_ex: one launch of the generalised tcgen05 convolution.  `out` (and `out2`) are caller-allocated full output
     tensors ([B, out_h, out_w, c_out] NHWC, or [B, c_out, out_h, out_w] fp32 for mode TC_NCHW_F32_CLAMP); `grid` = (h_out, w_out)
     output pixels computed by this launch, placed at (oy * out_stride + out_py, ox * out_stride + out_px)."""
@@ -730,10 +730,10 @@ def tc_conv_ex(x_nhwc, w_packed, kh, kw, pad_y, pad_x, mode, grid, out, out_stri
     d = TcConvExDesc(B, H, W, Cp, c_out, kh, kw, pad_y, pad_x, mode, grid[0], grid[1], out_h, out_w, out_stride, out_py, out_px)
     v = vec.detach().contiguous().float() if vec is not None else None
     c_real = c_in or Cp
-    flops = 2.0 * B * grid[0] * grid[1] * c_out * c_real * kh * kw
+    flops = 2.0 * B * grid[0] * grid[1] * c_out * c_real * kh * kw  # (algorithmic: the second pass over x_lo is not counted)
     nbytes = 4.0 * B * (H * W * c_real / (out_stride * out_stride) + grid[0] * grid[1] * c_out)
     tag = tag or 'tc_conv_ex[%d->%d,k%dx%d,m%d]' % (Cp, c_out, kh, kw, mode)
     with torch.cuda.device(x_nhwc.device), _launch(tag, flops=flops, nbytes=nbytes):
-        check(_lib().sc2_tc_conv_ex(ctypes.byref(d), _ptr(x_nhwc), _ptr(w_packed), _ptr(v), _ptr(gdn_x), _ptr(out), _ptr(out2), None,
-                                    _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_conv_ex')
+        check(_lib().sc2_tc_conv_ex(ctypes.byref(d), _ptr(x_nhwc), _ptr(x_lo), _ptr(w_packed), _ptr(v), _ptr(gdn_x), _ptr(gdn_x_lo), _ptr(out),
+                                    _ptr(out2), _ptr(out3), None, _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_conv_ex')
     return out
