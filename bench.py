@@ -429,8 +429,10 @@ def main():
             launches0 = s2.ops.STATS['launches']
             allocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
             t0 = time.perf_counter()
+            w0 = pipe.wait_s
             e0, e1, last = run_steps(args.steps, first=n_prime + args.warmup)
-            t_issue = (time.perf_counter() - t0) * 1e3
+            t_issue = (time.perf_counter() - t0 - (pipe.wait_s - w0)) * 1e3  # host time issuing work, back-pressure waits excluded
+            extra['host_backpressure_wait_ms_per_step'] = (pipe.wait_s - w0) * 1e3 / args.steps
             barrier()
             launches = s2.ops.STATS['launches'] - launches0
             allocs = torch.cuda.memory_stats(device).get('num_device_alloc', 0) - allocs0

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 7
+#define SC2_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -65,6 +65,9 @@ extern "C" {
 typedef void *sc2_stream_t; /* cudaStream_t */
 
 SC2_API int sc2_abi_version(void);
+/* Tuning knob (process-wide): CTAs of the persistent tensor-core kernels, 1..148; 0 restores the default (SC2_TC_GRID environment
+ * variable, else one per SM).  Fewer CTAs leave SMs to kernels of other streams (the coders of batches in flight). */
+SC2_API int sc2_set_persistent_ctas(int ctas);
 SC2_API const char *sc2_error_string(int code);
 /* last CUDA error string seen by this thread inside the library (for SC2_ERR_CUDA) */
 SC2_API const char *sc2_last_cuda_error(void);
@@ -310,6 +313,49 @@ SC2_API int sc2_tc_first_layer(const float *image, int batch, int c_in, int h_in
 /* Device: NCHW fp32 -> NHWC fp16 with channels zero-padded to c_pad (even). */
 SC2_API int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, int64_t spatial, int c_pad,
                                      sc2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device: one call per batch for the factorized-prior bottleneck (fp_codec.cu) -- everything FPBasedResNetBottleneck.encode /
+ * .decode do on the device (sc2bench/models/layer.py:496-521), enqueued on the caller's streams into the caller's buffers.
+ * Nothing is allocated; the intermediates live in workspaces sized by sc2_fp_workspace_bytes.  All pointers are device pointers
+ * owned by the caller; the packed weights are the ones the per-layer entry points take (same layouts). */
+typedef struct sc2_fp_plan {
+    int batch, h_in, w_in;               /* image batch [batch, 3, h_in, w_in] */
+    int c1, c2, c3, k1, k2, k3, p3;      /* g_a: Conv(3->c1, k1=5, s2, p2) GDN1 Conv(c1->c2, k2=5, s2, p2) GDN1 Conv(c2->c3, k3, s1, p3) */
+    int d1, d2, d3, kd1, pd1, kd2, pd2, kd3, pd3; /* g_s: Conv(c3->d1, kd1, pd1) IGDN1 Conv(d1->d2, kd2, pd2) IGDN1 Conv(d2->d3, kd3, pd3) */
+    int n_rows, cdf_stride;              /* coder tables */
+    const void *w1_stack, *g1_stack;     /* sc2_ga_first_conv_gdn packs */
+    const float *beta1;
+    const void *w2_stack, *g2_stack;     /* sc2_ga_halo_conv_gdn packs */
+    const float *beta2;
+    const void *w3_hi, *w3_lo;           /* sc2_tc_split_conv packs of the last g_a conv */
+    const float *medians;                /* [c3] EntropyBottleneck medians */
+    const float *lut;                    /* [3][256] normalisation table for uint8 images, or NULL */
+    const void *tables;                  /* sc2_rans_build_tables blob */
+    const void *wd1, *gd1, *wd2, *gd2, *wd3; /* sc2_tc_conv_nhwc packs (fp16) of the g_s convs / gammas */
+    const float *betad1, *betad2;
+} sc2_fp_plan;
+
+/* bytes of the g_a / g_s workspaces (each shared by all batches whose transforms run on ONE stream), symbols per image and
+ * the latent / output geometry; SC2_ERR_UNSUPPORTED when the fused kernels do not cover the shape */
+SC2_API int sc2_fp_workspace_bytes(const sc2_fp_plan *plan, int64_t *ga_bytes, int64_t *gs_bytes, int64_t *symbols_per_image,
+                                   int *latent_h, int *latent_w, int *out_h, int *out_w);
+
+/* encode: image (fp32, or uint8 when image_is_u8 and plan->lut) -> symbols [batch, c3, h3, w3] (int32, coder order) -> streams.
+ *   transform_stream waits for ev_in (may be NULL), runs g_a, records ev_mid; coder_stream waits for ev_mid, zeroes *status, runs
+ *   the encoder and the pack (arena / slot_bytes / lengths / packed / offsets as for sc2_rans_encode_batch + sc2_rans_pack) and
+ *   records ev_out (may be NULL).  tile_counters: 3 int32 (zeroed by the call).  Events are cudaEvent_t passed as void*. */
+SC2_API int sc2_fp_encode_batch(const sc2_fp_plan *plan, const void *image, int image_is_u8, void *ws_ga, int32_t *symbols,
+                                uint8_t *arena, int64_t slot_bytes, int32_t *lengths, uint8_t *packed, int64_t *offsets,
+                                int32_t *status, int32_t *tile_counters, int coder_layout, sc2_stream_t transform_stream,
+                                sc2_stream_t coder_stream, void *ev_in, void *ev_mid, void *ev_out);
+
+/* decode: streams -> latent_hat [batch, c3, h3, w3] fp32 (symbol + median) -> g_s -> out [batch, out_h, out_w, d3] fp32 (NHWC).
+ *   coder_stream waits for ev_in (may be NULL), decodes (fault flags are OR-ed into *status, which the call does not clear),
+ *   records ev_mid; transform_stream waits for it, runs g_s, records ev_out (may be NULL).  tile_counters: 5 int32. */
+SC2_API int sc2_fp_decode_batch(const sc2_fp_plan *plan, const uint8_t *packed, const int64_t *offsets, float *latent_hat,
+                                void *ws_gs, float *out, int32_t *status, int32_t *tile_counters, int coder_layout,
+                                sc2_stream_t coder_stream, sc2_stream_t transform_stream, void *ev_in, void *ev_mid, void *ev_out);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics: per-CTA trace.  While a (caller-allocated, zeroed) device buffer is installed, every CTA of the coder and

@@ -35,6 +35,14 @@ class TcConvExDesc(_c.Structure):
                                     'out_h', 'out_w', 'out_stride', 'out_py', 'out_px')]
 
 
+class FpPlan(_c.Structure):
+    """struct sc2_fp_plan"""
+    _fields_ = [(n, i32) for n in ('batch', 'h_in', 'w_in', 'c1', 'c2', 'c3', 'k1', 'k2', 'k3', 'p3', 'd1', 'd2', 'd3', 'kd1', 'pd1',
+                                    'kd2', 'pd2', 'kd3', 'pd3', 'n_rows', 'cdf_stride')] + \
+               [(n, vp) for n in ('w1_stack', 'g1_stack', 'beta1', 'w2_stack', 'g2_stack', 'beta2', 'w3_hi', 'w3_lo', 'medians', 'lut',
+                                   'tables', 'wd1', 'gd1', 'wd2', 'gd2', 'wd3', 'betad1', 'betad2')]
+
+
 class GaHaloDesc(_c.Structure):
     """struct sc2_ga_halo_desc"""
     _fields_ = [(n, i32) for n in ('images', 'h_in', 'w_in', 'c_in', 'c_out', 'kh', 'kw', 'pad', 'h_out', 'w_out', 'out_c')]
@@ -43,6 +51,7 @@ class GaHaloDesc(_c.Structure):
 # name -> (restype, argtypes): every symbol include/sc2b200.h declares
 SIGNATURES = {
     'sc2_abi_version': (i32, []),
+    'sc2_set_persistent_ctas': (i32, [i32]),
     'sc2_trace_start': (i32, [vp, i64]),
     'sc2_trace_stop': (i32, []),
     'sc2_error_string': (_c.c_char_p, [i32]),
@@ -68,12 +77,16 @@ SIGNATURES = {
     'sc2_ga_halo_n': (i32, [i32]),
     'sc2_ga_halo_conv_gdn': (i32, [_c.POINTER(GaHaloDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'sc2_ga_first_conv_gdn': (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp]),
+    'sc2_fp_workspace_bytes': (i32, [_c.POINTER(FpPlan), _c.POINTER(i64), _c.POINTER(i64), _c.POINTER(i64), _c.POINTER(i32), _c.POINTER(i32),
+                                     _c.POINTER(i32), _c.POINTER(i32)]),
+    'sc2_fp_encode_batch': (i32, [_c.POINTER(FpPlan), vp, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+    'sc2_fp_decode_batch': (i32, [_c.POINTER(FpPlan), vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     'sc2_patchify_split': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'sc2_tc_first_layer': (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
 }
 
 SC2_OK = 0
-ABI_VERSION = 7  # include/sc2b200.h SC2_ABI_VERSION
+ABI_VERSION = 8  # include/sc2b200.h SC2_ABI_VERSION
 FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM, FAULT_BAD_INDEX = 1, 2, 4, 8
 EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 IN_NONE, IN_ABS = 0, 1

@@ -249,19 +249,11 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         const uint32_t d_stack = tmem_base + g * 2u * N, d_lohi = tmem_base + g1 * 2u * N + N;
                         const uint32_t da_hi = a_hi16 + shift16, da_lo = a_lo16 + shift16, db = b_base16 + bs * (kBSlot >> 4);
                         const uint32_t acc0 = ((tw >> 7) & 1u) && kc == 0 ? 0u : 1u;
-                        if (k_steps == 4) {
-                            umma_f16_lead(lead, d_stack, da_hi, db, kDescHiSw128, idesc_stack, acc0);
-                            umma_f16_lead(lead, d_lohi, da_lo, db, kDescHiSw128, idesc_n, 1u);
-#pragma unroll
-                            for (int k = 1; k < 4; ++k) {
-                                umma_f16_lead(lead, d_stack, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, 1u);
-                                umma_f16_lead(lead, d_lohi, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
-                            }
-                        } else {
-                            for (int k = 0; k < k_steps; ++k) {
-                                umma_f16_lead(lead, d_stack, da_hi + 2 * k, db + 2 * k, kDescHiSw128, idesc_stack, k == 0 ? acc0 : 1u);
-                                umma_f16_lead(lead, d_lohi, da_lo + 2 * k, db + 2 * k, kDescHiSw128, idesc_n, 1u);
-                            }
+                        switch (k_steps) {  // (uniform) all MMAs of the tap in one asm block
+                            case 4: umma_split_tap4(lead, d_stack, d_lohi, da_hi, da_lo, db, kDescHiSw128, idesc_stack, idesc_n, acc0); break;
+                            case 3: umma_split_tap3(lead, d_stack, d_lohi, da_hi, da_lo, db, kDescHiSw128, idesc_stack, idesc_n, acc0); break;
+                            case 2: umma_split_tap2(lead, d_stack, d_lohi, da_hi, da_lo, db, kDescHiSw128, idesc_stack, idesc_n, acc0); break;
+                            default: umma_split_tap1(lead, d_stack, d_lohi, da_hi, da_lo, db, kDescHiSw128, idesc_stack, idesc_n, acc0); break;
                         }
                         umma_commit_lead(lead, &b_empty[bs]);
                         g1 = g;

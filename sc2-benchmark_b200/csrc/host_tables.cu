@@ -1,6 +1,8 @@
 // host_tables.cu -- host-side pieces of the C ABI: CDF quantisation and coder-table construction.
 // They run once per update() (sc2bench/models/layer.py:431-441 -> CompressionModel.update), never per image.
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,6 +21,20 @@ int cuda_fail(cudaError_t e, const char *where) {
 }  // namespace sc2
 
 namespace sc2 {
+static std::atomic<int> g_persistent_ctas{0};  // 0: not set (environment variable or one CTA per SM)
+int persistent_grid() {
+    const int set = g_persistent_ctas.load(std::memory_order_relaxed);
+    if (set > 0 && set <= kNumSMs) return set;
+    static const int from_env = [] {
+        const char *e = std::getenv("SC2_TC_GRID");
+        const int v = e ? std::atoi(e) : 0;
+        return (v > 0 && v < kNumSMs) ? v : kNumSMs;
+    }();
+    return from_env;
+}
+}  // namespace sc2
+
+namespace sc2 {
 static TraceSink g_trace = {nullptr, nullptr, 0};
 TraceSink trace_sink() { return g_trace; }
 }  // namespace sc2
@@ -26,6 +42,12 @@ TraceSink trace_sink() { return g_trace; }
 extern "C" {
 
 int sc2_abi_version(void) { return SC2_ABI_VERSION; }
+
+int sc2_set_persistent_ctas(int ctas) {
+    if (ctas < 0 || ctas > sc2::kNumSMs) return SC2_ERR_INVALID_ARG;
+    sc2::g_persistent_ctas.store(ctas, std::memory_order_relaxed);
+    return SC2_OK;
+}
 
 int sc2_trace_start(void *device_buffer, int64_t bytes) {
     if (!device_buffer || bytes < 16 + static_cast<int64_t>(sizeof(sc2::TraceRec))) return SC2_ERR_INVALID_ARG;

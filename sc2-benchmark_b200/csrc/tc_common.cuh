@@ -220,6 +220,99 @@ __device__ __forceinline__ void umma_commit_lead(bool lead, uint64_t *bar) {
         "}" ::"r"(smem_u32(bar)), "r"(static_cast<uint32_t>(lead)) : "memory");
 }
 
+// All MMAs of one (tap, K chunk) of the split-fp16 kernels in ONE asm block: KSTEPS x { D[stack] += A_hi . [B_hi; B_lo],
+// D[lohi] += A_lo . B_hi }.  One predicate set-up and three descriptor registers for the whole block (advancing K by 16 elements
+// is a 64-bit add of 2 = 32 bytes >> 4) instead of two predicate set-ups and two descriptor packs per MMA.
+#define SC2_UMMA_SPLIT_TAP(NAME, BODY)                                                                                              \
+    __device__ __forceinline__ void NAME(bool lead, uint32_t d_stack, uint32_t d_lohi, uint32_t a_hi, uint32_t a_lo, uint32_t b,    \
+                                         uint32_t desc_hi, uint32_t idesc_stack, uint32_t idesc_n, uint32_t acc0) {                 \
+        asm volatile(BODY ::"r"(d_stack), "r"(d_lohi), "r"(a_hi), "r"(a_lo), "r"(b), "r"(desc_hi), "r"(idesc_stack), "r"(idesc_n),   \
+                     "r"(acc0), "r"(static_cast<uint32_t>(lead)) : "memory");                                                        \
+    }
+SC2_UMMA_SPLIT_TAP(umma_split_tap1, \
+        "{\n\t" \
+        ".reg .pred p, q, t;\n\t" \
+        ".reg .b64 dah, dal, db;\n\t" \
+        "setp.ne.b32 p, %8, 0;\n\t" \
+        "setp.ne.b32 q, %9, 0;\n\t" \
+        "setp.eq.b32 t, 0, 0;\n\t" \
+        "mov.b64 dah, {%2, %5};\n\t" \
+        "mov.b64 dal, {%3, %5};\n\t" \
+        "mov.b64 db, {%4, %5};\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, p;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "}")
+SC2_UMMA_SPLIT_TAP(umma_split_tap2, \
+        "{\n\t" \
+        ".reg .pred p, q, t;\n\t" \
+        ".reg .b64 dah, dal, db;\n\t" \
+        "setp.ne.b32 p, %8, 0;\n\t" \
+        "setp.ne.b32 q, %9, 0;\n\t" \
+        "setp.eq.b32 t, 0, 0;\n\t" \
+        "mov.b64 dah, {%2, %5};\n\t" \
+        "mov.b64 dal, {%3, %5};\n\t" \
+        "mov.b64 db, {%4, %5};\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, p;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "add.s64 dah, dah, 2;\n\t" \
+        "add.s64 dal, dal, 2;\n\t" \
+        "add.s64 db, db, 2;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, t;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "}")
+SC2_UMMA_SPLIT_TAP(umma_split_tap3, \
+        "{\n\t" \
+        ".reg .pred p, q, t;\n\t" \
+        ".reg .b64 dah, dal, db;\n\t" \
+        "setp.ne.b32 p, %8, 0;\n\t" \
+        "setp.ne.b32 q, %9, 0;\n\t" \
+        "setp.eq.b32 t, 0, 0;\n\t" \
+        "mov.b64 dah, {%2, %5};\n\t" \
+        "mov.b64 dal, {%3, %5};\n\t" \
+        "mov.b64 db, {%4, %5};\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, p;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "add.s64 dah, dah, 2;\n\t" \
+        "add.s64 dal, dal, 2;\n\t" \
+        "add.s64 db, db, 2;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, t;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "add.s64 dah, dah, 2;\n\t" \
+        "add.s64 dal, dal, 2;\n\t" \
+        "add.s64 db, db, 2;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, t;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "}")
+SC2_UMMA_SPLIT_TAP(umma_split_tap4, \
+        "{\n\t" \
+        ".reg .pred p, q, t;\n\t" \
+        ".reg .b64 dah, dal, db;\n\t" \
+        "setp.ne.b32 p, %8, 0;\n\t" \
+        "setp.ne.b32 q, %9, 0;\n\t" \
+        "setp.eq.b32 t, 0, 0;\n\t" \
+        "mov.b64 dah, {%2, %5};\n\t" \
+        "mov.b64 dal, {%3, %5};\n\t" \
+        "mov.b64 db, {%4, %5};\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, p;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "add.s64 dah, dah, 2;\n\t" \
+        "add.s64 dal, dal, 2;\n\t" \
+        "add.s64 db, db, 2;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, t;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "add.s64 dah, dah, 2;\n\t" \
+        "add.s64 dal, dal, 2;\n\t" \
+        "add.s64 db, db, 2;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, t;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "add.s64 dah, dah, 2;\n\t" \
+        "add.s64 dal, dal, 2;\n\t" \
+        "add.s64 db, db, 2;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, db, %6, t;\n\t" \
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], dal, db, %7, t;\n\t" \
+        "}")
+#undef SC2_UMMA_SPLIT_TAP
+
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -291,14 +384,9 @@ inline int make_weight_map(CUtensorMap *m, const void *base, int c_in_pad, int r
 constexpr int kUniformSmem = 202 * 1024;
 inline int uniform_smem(int needed) { return needed <= kUniformSmem ? kUniformSmem : needed; }
 
-// CTAs of a persistent kernel: one per SM, or fewer when SC2_TC_GRID is set (experiments: leave SMs to co-running kernels)
-inline int persistent_grid() {
-    static const int g = [] {
-        const char *e = std::getenv("SC2_TC_GRID");
-        const int v = e ? std::atoi(e) : 0;
-        return (v > 0 && v < kNumSMs) ? v : kNumSMs;
-    }();
-    return g;
-}
-
+// CTAs of a persistent kernel: one per SM by default.  Fewer leave SMs to co-running kernels: with batches in flight the coder
+// blocks of other streams (one SM each, 8-12 ms long) otherwise start only in the bubbles of the transform stream; with 8 SMs
+// left to them the pipelined step is 4 % faster although every transform kernel is 4 % slower (profiles/r2w_*).
+// sc2_set_persistent_ctas() (process-wide tuning knob, CodecPipeline sets it) or the SC2_TC_GRID environment variable.
+int persistent_grid();
 }  // namespace sc2

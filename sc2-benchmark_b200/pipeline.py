@@ -17,8 +17,15 @@ Needs one hardware queue per stream: CUDA_DEVICE_MAX_CONNECTIONS >= depth + 3 (t
 variable is already set); with streams sharing queues a waiting coder kernel blocks the transforms queued behind it.
 """
 import collections
+import logging
+import time
 
 import torch
+
+from . import _native
+from .native_codec import FpNativeCodec, Slot
+
+_log = logging.getLogger('sc2bench_b200')
 
 
 class PipelineResult:
@@ -36,7 +43,12 @@ class PipelineResult:
 
 
 class CodecPipeline:
-    def __init__(self, layer, depth=8, max_ahead=4):
+    """depth: batches whose coders overlap the transforms of the others; max_ahead: batches the host may additionally run ahead.
+    native (default): a batch is two C calls into preallocated slots (native_codec.FpNativeCodec) -- `streams` / `features` of a
+    result are then VIEWS of ring buffers, valid until `depth + 1` more batches have been submitted (clone to keep them).
+    coder_sms: SMs left to the coder blocks while the pipeline exists (sc2_set_persistent_ctas; 0 = none)."""
+
+    def __init__(self, layer, depth=8, max_ahead=4, native=True, coder_sms=8):
         if depth < 1:
             raise ValueError('depth must be >= 1')
         self.layer, self.depth, self.max_ahead = layer, depth, max(0, max_ahead)
@@ -44,33 +56,76 @@ class CodecPipeline:
         device = layer.entropy_bottleneck._quantized_cdf.device
         if device.type != 'cuda':
             raise RuntimeError('CodecPipeline: the sc2bench_b200 hot path runs on CUDA only; move the layer to a GPU')
+        self.device = device
         self.transform_stream = layer.use_transform_stream(True)
         self.batch_streams = [torch.cuda.Stream(device=device) for _ in range(depth + 1)]
         self._pending = collections.deque()
         self._submitted = 0
+        self.wait_s = 0.0  # host time spent in back-pressure waits (diagnostics: issue time = loop time - wait_s)
+        self._want_native, self._native, self._slots, self._native_shape = bool(native), None, None, None
+        self._coder_sms = int(coder_sms)
+        if self._coder_sms > 0:
+            _native.check(_native.load().sc2_set_persistent_ctas(148 - self._coder_sms), 'sc2_set_persistent_ctas')
+
+    def _native_for(self, x):
+        """The one-call-per-batch codec for batches shaped like x (built at the first batch), or None (per-kernel route)."""
+        if not self._want_native:
+            return None
+        shape = (tuple(x.shape), x.dtype)
+        if self._native is not None and shape == self._native_shape and not self._native.stale():
+            return self._native
+        if self._pending:
+            return None if shape != self._native_shape else self._native  # (never switch routes with batches in flight)
+        try:
+            with torch.cuda.stream(self.transform_stream):
+                self._native = FpNativeCodec(self.layer, x.shape[0], x.shape[2], x.shape[3], self.device)
+                self._slots = [self._native.new_slot(s) for s in self.batch_streams]
+            torch.cuda.current_stream(self.device).wait_stream(self.transform_stream)
+            self._native_shape = shape
+        except (ValueError, _native.NativeError) as e:
+            _log.info('CodecPipeline: per-kernel route (%s)', e)
+            self._want_native, self._native = False, None
+        return self._native
 
     @torch.no_grad()
     def submit(self, x):
         """Queues g_a + coder of batch x (a CUDA tensor produced on the current stream).  Returns the PipelineResult of the
         batch submitted `depth` calls earlier, or None while the pipeline fills."""
-        while len(self._retired) > self.max_ahead:  # back-pressure: bounded work (and memory) in flight
-            self._retired.popleft().synchronize()
-        s = self.batch_streams[self._submitted % len(self.batch_streams)]
+        if len(self._retired) > self.max_ahead:  # back-pressure: bounded work (and memory) in flight
+            t0 = time.perf_counter()
+            while len(self._retired) > self.max_ahead:
+                self._retired.popleft().synchronize()
+            self.wait_s += time.perf_counter() - t0
+        i = self._submitted % len(self.batch_streams)
+        s = self.batch_streams[i]
         self._submitted += 1
-        s.wait_stream(torch.cuda.current_stream())
-        x.record_stream(s)
-        with torch.cuda.stream(s):
-            encoded = self.layer.encode_packed(x)
-        self._pending.append((s, encoded))
+        codec = self._native_for(x)
+        if codec is not None:
+            slot = self._slots[i]
+            cur = torch.cuda.current_stream(self.device)
+            slot.ev_in.record(cur)
+            x.record_stream(self.transform_stream)
+            streams = codec.encode(x, slot, self.transform_stream, s, ev_in=slot.ev_in)
+            self._pending.append((slot, (streams, codec.latent_hw)))
+        else:
+            s.wait_stream(torch.cuda.current_stream())
+            x.record_stream(s)
+            with torch.cuda.stream(s):
+                encoded = self.layer.encode_packed(x)
+            self._pending.append((s, encoded))
         return self._retire() if len(self._pending) > self.depth else None
 
     @torch.no_grad()
     def _retire(self):
         s, (streams, shape) = self._pending.popleft()
-        with torch.cuda.stream(s):
-            features = self.layer.decode_packed(streams, shape)
-            ready = torch.cuda.Event()
-            ready.record(s)
+        if isinstance(s, Slot):
+            features = self._native.decode(s, self.transform_stream, s.stream)
+            ready = s.ev_out
+        else:
+            with torch.cuda.stream(s):
+                features = self.layer.decode_packed(streams, shape)
+                ready = torch.cuda.Event()
+                ready.record(s)
         self._retired.append(ready)
         return PipelineResult(streams, shape, features, ready)
 
@@ -84,3 +139,5 @@ class CodecPipeline:
     def close(self):
         self.drain()
         self.layer.use_transform_stream(None)
+        if self._coder_sms > 0:
+            _native.load().sc2_set_persistent_ctas(0)

@@ -369,3 +369,41 @@ def test_evaluate_loop_and_device_counters_vs_reference_meters(s2):
     assert abs(float(got) - tot1 / cnt) < 1e-4 and abs(got.top5 - tot5 / cnt) < 1e-4 and got.images == 11
     assert float(got) > 30.0 and got.top5 > 60.0           # the planted targets were found
     assert len(model.analyzers[0].file_size_list) == 3      # one analysed object per batch; summarize() ran at the end
+
+
+@pytest.mark.parametrize('dtype', ['f32', 'u8'])
+def test_native_codec_pipeline_matches_per_kernel_route(s2, dtype):
+    """CodecPipeline with the one-call-per-batch codec (csrc/fp_codec.cu: preallocated slots, no allocation per batch) gives the
+    SAME bytes and features as the per-kernel route, batch by batch, for fp32 and for uint8 (device-side normalisation) input."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    layer = s2.get_layer('FPBasedResNetBottleneck').eval()
+    layer.update()
+    layer.set_input_normalization((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    layer.to(dev)
+    torch.manual_seed(1)
+    if dtype == 'u8':
+        xs = [torch.randint(0, 256, (8, 3, 224, 224), dtype=torch.uint8, device=dev) for _ in range(5)]
+    else:
+        xs = [torch.randn(8, 3, 224, 224, device=dev) * (1 + i) for i in range(5)]
+    with torch.inference_mode():
+        want = []
+        for x in xs:
+            st, shape = layer.encode_packed(x)
+            want.append((st.tolist(), layer.decode_packed(st, shape).clone()))
+        pipe = s2.CodecPipeline(layer, depth=2, max_ahead=1)
+        got = []
+        for x in xs:
+            r = pipe.submit(x)
+            if r is not None:
+                r.wait()
+                got.append((r.streams.tolist(), r.features.clone()))
+        for r in pipe.drain():
+            r.wait()
+            got.append((r.streams.tolist(), r.features.clone()))
+        assert pipe._native is not None, 'the native codec was not used'
+        pipe.close()
+    assert len(got) == len(want)
+    for (gs, gf), (ws, wf) in zip(got, want):
+        assert gs == ws
+        assert torch.equal(gf, wf)
