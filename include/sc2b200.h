@@ -352,7 +352,8 @@ SC2_API int sc2_fp_encode_batch(const sc2_fp_plan *plan, const void *image, int 
 
 /* decode: streams -> latent_hat [batch, c3, h3, w3] fp32 (symbol + median) -> g_s -> out [batch, out_h, out_w, d3] fp32 (NHWC).
  *   coder_stream waits for ev_in (may be NULL), decodes (fault flags are OR-ed into *status, which the call does not clear),
- *   records ev_mid; transform_stream waits for it, runs g_s, records ev_out (may be NULL).  tile_counters: 5 int32. */
+ *   records ev_mid; transform_stream waits for it, runs g_s, records ev_out (may be NULL).  tile_counters: 5 int32.
+ *   packed == NULL: the caller has filled latent_hat itself; only g_s runs (transform_stream waits for ev_in if given). */
 SC2_API int sc2_fp_decode_batch(const sc2_fp_plan *plan, const uint8_t *packed, const int64_t *offsets, float *latent_hat,
                                 void *ws_gs, float *out, int32_t *status, int32_t *tile_counters, int coder_layout,
                                 sc2_stream_t coder_stream, sc2_stream_t transform_stream, void *ev_in, void *ev_mid, void *ev_out);

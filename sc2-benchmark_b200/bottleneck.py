@@ -26,7 +26,7 @@ from .models import CompressionModel, get_scale_table, run_transform, update_reg
 
 _log = logging.getLogger('sc2bench_b200')
 _warned = set()
-_PLAN_LOCK = threading.Lock()
+_PLAN_LOCK = threading.RLock()  # re-entrant: building a native codec (under the lock) prepares the per-layer plans (under the lock)
 
 
 def warn_fallback(what, why):
@@ -422,11 +422,74 @@ class FPBasedResNetBottleneck(BaseBottleneck):
         return out
 
     @torch.no_grad()
-    def encode_packed(self, x):
+    def encode_packed(self, x, _slot_buffers=False):
         """g_a + quantise + rANS, bitstreams left on the device: (PackedStreams, latent (H, W))."""
+        nat = self._native_state(x)
+        if nat is not None:
+            codec, slot, ws = nat
+            dev = x.device
+            cur = torch.cuda.current_stream(dev)
+            ts = self._transform_stream or cur
+            if _slot_buffers:
+                # (encode(): the bytes are copied to the host before the call returns, so the calling thread's ring buffers do --
+                # no worst-case-sized device allocation per call)
+                packed = offsets = status = None
+            else:
+                packed = torch.empty(codec.batch * codec.slot_bytes, dtype=torch.uint8, device=dev)
+                offsets = torch.empty(codec.batch + 1, dtype=torch.int64, device=dev)
+                status = torch.empty(1, dtype=torch.int32, device=dev)  # (zeroed by the call, on the coder stream)
+            ev_in = None
+            if ts != cur:
+                if getattr(self, '_transform_host_wait', False):
+                    cur.synchronize()
+                else:
+                    slot.ev_in.record(cur)
+                    ev_in = slot.ev_in
+                x.record_stream(ts)
+            streams = codec.encode(x.contiguous(), slot, ts, cur, ev_in=ev_in, packed=packed, offsets=offsets, status=status,
+                                   ws=ws[0] if ws else None)
+            return streams, torch.Size(codec.latent_hw)
         eb = self.entropy_bottleneck
         symbols = self._on_transform_stream(lambda: self.analyze_to_symbols(x), x)
         return eb.compress_symbols(symbols, spatial=symbols[0, 0].numel()), symbols.size()[-2:]
+
+    def _native_state(self, x, batch_shape=None):
+        """(codec, slot, private workspaces or None) of the calling thread and its current stream for batches shaped like x, or
+        None when the one-call-per-batch route (native_codec.FpNativeCodec) does not apply."""
+        if not getattr(self, 'native_calls', True) or not isinstance(x, torch.Tensor) or not x.is_cuda or x.dim() != 4:
+            return None
+        from .native_codec import FpNativeCodec
+        key = (x.device, tuple(x.shape) if batch_shape is None else tuple(batch_shape), getattr(self, '_input_norm', None) is not None)
+        codecs = self.__dict__.setdefault('_native_codecs', {})
+        codec = codecs.get(key)
+        if codec is None or (codec is not False and codec.stale()):
+            with _PLAN_LOCK:
+                codec = codecs.get(key)
+                if codec is None or (codec is not False and codec.stale()):
+                    try:
+                        with torch.inference_mode(False):
+                            codec = FpNativeCodec(self, key[1][0], key[1][2], key[1][3], x.device,
+                                                  coder_layout=self.entropy_bottleneck.coder_layout if getattr(self.entropy_bottleneck, 'coder_layout', None) else 'auto')
+                    except (ValueError, _native.NativeError) as e:
+                        _log.info('%s: per-kernel route for batches of shape %s (%s)', type(self).__name__, key[1], e)
+                        codec = False
+                    codecs[key] = codec
+        if codec is False:
+            return None
+        wanted = _native.RANS_LAYOUTS[getattr(self.entropy_bottleneck, 'coder_layout', None)]
+        codec.coder_layout = wanted
+        # one slot per CUDA stream (all work on a slot's buffers is ordered by its stream, whichever host thread issues it)
+        slots = codec.__dict__.setdefault('_stream_slots', {})
+        shared_ws = self._transform_stream is not None  # transforms of all callers run on ONE stream: one workspace pair serves all
+        skey = (torch.cuda.current_stream(x.device).cuda_stream, shared_ws)
+        st = slots.get(skey)
+        if st is None:
+            with _PLAN_LOCK:
+                st = slots.get(skey)
+                if st is None:
+                    st = (codec.new_slot(), None if shared_ws else codec.make_workspaces())
+                    slots[skey] = st
+        return codec, st[0], st[1]
 
     def set_input_normalization(self, mean, std):
         """Device-side ToTensor + Normalize: after this call `encode` also accepts uint8 NCHW images and
@@ -472,12 +535,50 @@ class FPBasedResNetBottleneck(BaseBottleneck):
 
     @torch.no_grad()
     def decode_packed(self, streams, shape, check_status=False):
-        latent_hat = self.entropy_bottleneck.decompress_packed(streams, tuple(shape), check_status=check_status)
-        return self._on_transform_stream(lambda: self.synthesize(latent_hat), latent_hat)
+        eb = self.entropy_bottleneck
+        nat = None
+        if getattr(self, 'native_calls', True) and streams.packed.is_cuda:
+            for (dev, bshape, _), codec in self.__dict__.get('_native_codecs', {}).items():
+                if codec is not False and dev == streams.packed.device and bshape[0] == streams.batch and tuple(codec.latent_hw) == tuple(shape) \
+                        and not codec.stale():
+                    nat = self._native_state(streams.packed.new_empty((0, 0, 0, 0)), batch_shape=bshape)
+                    break
+        if nat is None:
+            latent_hat = eb.decompress_packed(streams, tuple(shape), check_status=check_status)
+            return self._on_transform_stream(lambda: self.synthesize(latent_hat), latent_hat)
+        codec, slot, ws = nat
+        dev = streams.packed.device
+        cur = torch.cuda.current_stream(dev)
+        ts = self._transform_stream or cur
+        # (the result is allocated from the TRANSFORM stream's pool, like the per-kernel route does: one pool recycles the blocks of
+        # every caller; per-caller pools of 0.8 GB blocks kept the allocator calling cudaMalloc)
+        with torch.cuda.stream(ts):
+            out = torch.empty((codec.batch, codec.out_hw[0], codec.out_hw[1], codec.d3), dtype=torch.float32, device=dev)
+        if ts != cur and getattr(self, '_transform_host_wait', False):
+            # one host thread per batch: decode on the caller's stream, WAIT for it on the host, then queue g_s -- a transform stream
+            # that waited for this batch's decoder on the device would hold up the transforms of every other thread's batch
+            latent_hat = eb.decompress_packed(streams, tuple(shape), check_status=check_status)
+            if not check_status:
+                cur.synchronize()
+            out.record_stream(cur)
+            latent_hat.record_stream(ts)
+            feats = codec.decode(slot, ts, cur, out=out, ws=ws[1] if ws else None, latent_hat=latent_hat)
+        else:
+            status = torch.zeros(1, dtype=torch.int32, device=dev) if check_status else eb._fault_word(dev)
+            if ts != cur:
+                out.record_stream(cur)
+            feats = codec.decode(slot, ts, cur, packed=streams.packed, offsets=streams.offsets, status=status, out=out,
+                                 ws=ws[1] if ws else None)
+            if check_status:
+                slot.ev_mid2.synchronize() if ts != cur else cur.synchronize()
+                ops.raise_on_decode_fault(int(status.item()))
+        if ts != cur:
+            cur.wait_event(slot.ev_out)
+        return feats
 
     def encode(self, x, **kwargs):
         """-> {'strings': [list of B bytes objects], 'shape': latent (H, W)}  (reference contract, layer.py:496-507)"""
-        streams, shape = self.encode_packed(x)
+        streams, shape = self.encode_packed(x, _slot_buffers=True)
         return {'strings': [streams.tolist()], 'shape': shape}
 
     def decode(self, strings, shape):

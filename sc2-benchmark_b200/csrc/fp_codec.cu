@@ -131,16 +131,21 @@ int sc2_fp_decode_batch(const sc2_fp_plan *p, const uint8_t *packed, const int64
                         sc2_stream_t transform_stream, void *ev_in, void *ev_mid, void *ev_out) {
     FpGeometry g;
     SC2_TRY(fp_geometry(p, &g));
-    if (!packed || !offsets || !latent_hat || !ws_gs || !out || !status || !tile_counters) return SC2_ERR_INVALID_ARG;
+    if (!latent_hat || !ws_gs || !out || !tile_counters) return SC2_ERR_INVALID_ARG;
     cudaStream_t ts = sc2::as_stream(transform_stream), cs = sc2::as_stream(coder_stream);
-    if (ts != cs && !ev_mid) return SC2_ERR_INVALID_ARG;
     uint8_t *ws = static_cast<uint8_t *>(ws_gs);
-    if (ev_in) SC2_CUDA_TRY(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(ev_in), 0));
-    SC2_TRY(sc2_rans_decode_batch(packed, offsets, p->batch, g.n_sym, nullptr, static_cast<int64_t>(g.h3) * g.w3, p->tables, p->n_rows,
-                                  p->cdf_stride, nullptr, latent_hat, p->medians, status, coder_layout, coder_stream));
-    if (ts != cs) {
-        SC2_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(ev_mid), cs));
-        SC2_CUDA_TRY(cudaStreamWaitEvent(ts, static_cast<cudaEvent_t>(ev_mid), 0));
+    if (packed) {
+        if (!offsets || !status) return SC2_ERR_INVALID_ARG;
+        if (ts != cs && !ev_mid) return SC2_ERR_INVALID_ARG;
+        if (ev_in) SC2_CUDA_TRY(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(ev_in), 0));
+        SC2_TRY(sc2_rans_decode_batch(packed, offsets, p->batch, g.n_sym, nullptr, static_cast<int64_t>(g.h3) * g.w3, p->tables, p->n_rows,
+                                      p->cdf_stride, nullptr, latent_hat, p->medians, status, coder_layout, coder_stream));
+        if (ts != cs) {
+            SC2_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(ev_mid), cs));
+            SC2_CUDA_TRY(cudaStreamWaitEvent(ts, static_cast<cudaEvent_t>(ev_mid), 0));
+        }
+    } else if (ev_in) {  // packed == NULL: latent_hat is already there (the caller decoded); only g_s runs, after ev_in
+        SC2_CUDA_TRY(cudaStreamWaitEvent(ts, static_cast<cudaEvent_t>(ev_in), 0));
     }
     SC2_CUDA_TRY(cudaMemsetAsync(tile_counters, 0, 5 * sizeof(int32_t), ts));
     // ---- g_s: layout change + five launches ----

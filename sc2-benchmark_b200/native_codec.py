@@ -24,17 +24,31 @@ class Slot:
         self.symbols = torch.empty((B, codec.c3, codec.latent_hw[0], codec.latent_hw[1]), dtype=torch.int32, device=dev)
         self.slot_bytes = codec.slot_bytes
         self.arena = torch.empty(B * self.slot_bytes, dtype=torch.uint8, device=dev)
-        self.packed = torch.empty(B * self.slot_bytes, dtype=torch.uint8, device=dev)
+        self._packed = self._out = None  # (allocated on first use: callers that bring their own never pay for them)
+        self._codec_shape = (B, codec.out_hw[0], codec.out_hw[1], codec.d3)
         self.lengths = torch.empty(B, dtype=torch.int32, device=dev)
         self.offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.latent_hat = torch.empty((B, codec.c3, codec.latent_hw[0], codec.latent_hw[1]), dtype=torch.float32, device=dev)
-        self.out = torch.empty((B, codec.out_hw[0], codec.out_hw[1], codec.d3), dtype=torch.float32, device=dev)
         self.tile_counters = torch.zeros(8, dtype=torch.int32, device=dev)
         self.ev_in, self.ev_mid, self.ev_enc, self.ev_mid2, self.ev_out = (torch.cuda.Event() for _ in range(5))
         for ev in (self.ev_in, self.ev_mid, self.ev_enc, self.ev_mid2, self.ev_out):
             ev.record(torch.cuda.current_stream(dev))  # (creates the CUDA event: the handle is passed across the C ABI)
         self.n_symbols = n
+
+    @property
+    def packed(self):
+        if self._packed is None:
+            with torch.inference_mode(False):
+                self._packed = torch.empty(self.arena.numel(), dtype=torch.uint8, device=self.arena.device)
+        return self._packed
+
+    @property
+    def out(self):
+        if self._out is None:
+            with torch.inference_mode(False):
+                self._out = torch.empty(self._codec_shape, dtype=torch.float32, device=self.arena.device)
+        return self._out
 
     @property
     def features(self):
@@ -124,8 +138,15 @@ class FpNativeCodec:
         with torch.inference_mode(False), torch.cuda.device(self.device):
             return Slot(self, stream)
 
-    def encode(self, x, slot, transform_stream, coder_stream, ev_in=None):
-        """g_a + coder of batch x into `slot`.  transform_stream waits for ev_in; slot.ev_enc marks the packed streams ready."""
+    def make_workspaces(self):
+        """A private (g_a, g_s) workspace pair, for callers whose transforms do NOT share one stream."""
+        with torch.inference_mode(False), torch.cuda.device(self.device):
+            return (torch.empty(self.ws_ga.numel(), dtype=torch.uint8, device=self.device),
+                    torch.empty(self.ws_gs.numel(), dtype=torch.uint8, device=self.device))
+
+    def encode(self, x, slot, transform_stream, coder_stream, ev_in=None, packed=None, offsets=None, status=None, ws=None):
+        """g_a + coder of batch x into `slot` (or into the caller's packed / offsets / status tensors).  transform_stream waits for
+        ev_in; slot.ev_enc marks the packed streams ready."""
         if tuple(x.shape) != (self.batch, 3, self.plan.h_in, self.plan.w_in) or not x.is_contiguous():
             raise ValueError('batch shape %s does not match the plan' % (tuple(x.shape),))
         u8 = x.dtype == torch.uint8
@@ -134,28 +155,38 @@ class FpNativeCodec:
         if not u8 and x.dtype != torch.float32:
             raise ValueError('images must be float32 or uint8')
         ops.STATS['launches'] += 6
+        packed = slot.packed if packed is None else packed
+        offsets = slot.offsets if offsets is None else offsets
+        status = slot.status if status is None else status
+        ws = self.ws_ga if ws is None else ws
         with torch.cuda.device(self.device):
-            check(self._lib.sc2_fp_encode_batch(ctypes.byref(self.plan), x.data_ptr(), int(u8), self.ws_ga.data_ptr(), slot.symbols.data_ptr(),
-                                                slot.arena.data_ptr(), slot.slot_bytes, slot.lengths.data_ptr(), slot.packed.data_ptr(),
-                                                slot.offsets.data_ptr(), slot.status.data_ptr(), slot.tile_counters.data_ptr(),
+            check(self._lib.sc2_fp_encode_batch(ctypes.byref(self.plan), x.data_ptr(), int(u8), ws.data_ptr(), slot.symbols.data_ptr(),
+                                                slot.arena.data_ptr(), slot.slot_bytes, slot.lengths.data_ptr(), packed.data_ptr(),
+                                                offsets.data_ptr(), status.data_ptr(), slot.tile_counters.data_ptr(),
                                                 self.coder_layout, ctypes.c_void_p(transform_stream.cuda_stream),
                                                 ctypes.c_void_p(coder_stream.cuda_stream), _ev(ev_in), _ev(slot.ev_mid), _ev(slot.ev_enc)),
                   'sc2_fp_encode_batch')
         streams = ops.PackedStreams.__new__(ops.PackedStreams)
         streams.packed, streams.offsets, streams.batch, streams.status, streams._offs, streams.ready = \
-            slot.packed, slot.offsets, self.batch, slot.status, None, slot.ev_enc
+            packed, offsets, self.batch, status, None, slot.ev_enc
         return streams
 
-    def decode(self, slot, transform_stream, coder_stream, ev_in=None, packed=None, offsets=None, status=None):
-        """coder + g_s of the streams in `slot` (or of `packed` / `offsets`); slot.ev_out marks slot.out ready."""
-        ops.STATS['launches'] += 7
+    def decode(self, slot, transform_stream, coder_stream, ev_in=None, packed=None, offsets=None, status=None, out=None, ws=None,
+               latent_hat=None):
+        """coder + g_s of the streams in `slot` (or of `packed` / `offsets`); slot.ev_out marks the output ready.  `out`: the
+        caller's [B, H, W, C] fp32 tensor instead of slot.out.  latent_hat: an already decoded latent -- only g_s runs."""
+        only_gs = latent_hat is not None
+        ops.STATS['launches'] += 6 if only_gs else 7
         packed = slot.packed if packed is None else packed
         offsets = slot.offsets if offsets is None else offsets
         status = slot.status if status is None else status
+        out = slot.out if out is None else out
+        ws = self.ws_gs if ws is None else ws
+        lat = latent_hat if only_gs else slot.latent_hat
         with torch.cuda.device(self.device):
-            check(self._lib.sc2_fp_decode_batch(ctypes.byref(self.plan), packed.data_ptr(), offsets.data_ptr(), slot.latent_hat.data_ptr(),
-                                                self.ws_gs.data_ptr(), slot.out.data_ptr(), status.data_ptr(),
+            check(self._lib.sc2_fp_decode_batch(ctypes.byref(self.plan), None if only_gs else packed.data_ptr(), offsets.data_ptr(),
+                                                lat.data_ptr(), ws.data_ptr(), out.data_ptr(), status.data_ptr(),
                                                 slot.tile_counters.data_ptr() + 12, self.coder_layout, ctypes.c_void_p(coder_stream.cuda_stream),
                                                 ctypes.c_void_p(transform_stream.cuda_stream), _ev(ev_in), _ev(slot.ev_mid2), _ev(slot.ev_out)),
                   'sc2_fp_decode_batch')
-        return slot.features
+        return out.permute(0, 3, 1, 2)
