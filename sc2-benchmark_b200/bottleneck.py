@@ -126,6 +126,9 @@ class TensorCoreTransform:
         return x.permute(0, 3, 1, 2)
 
 
+_NO_QUANT = object()  # TensorCoreAnalysis(x, _NO_QUANT): return the latent y (fp32 NCHW) instead of symbols
+
+
 class TensorCoreAnalysis:
     """Execution plan for the bottleneck's analysis transform g_a (Conv s2 - GDN1 - Conv s2 - GDN1 - Conv s1) on the
     fp32-grade "split fp16" tcgen05 kernels, ending in the fused quantise-to-symbols epilogue.  Three launches:
@@ -257,6 +260,13 @@ class TensorCoreAnalysis:
             (gh, gl), beta = plan['gdn'][1]
             out = ops.tc_split_conv(h, l, gh, gl, c2.out_channels, 1, 1, 1, 0, T.TCS_GDN1, beta=beta, gdn=True)
         h, l = out
+        if medians is _NO_QUANT:
+            # the latent itself (scale-hyperprior bottlenecks need y for h_a and for the Gaussian-conditional coder): split planes
+            # -> fp32 NCHW (value = hi + lo / 2048)
+            oh, ol = ops.tc_split_conv(h, l, plan['w3'][0], plan['w3'][1], c3.out_channels, c3.kernel_size[0], c3.kernel_size[0], 1,
+                                       c3.padding[0], T.TCS_STORE)
+            y = torch.add(oh[..., :c3.out_channels].float(), ol[..., :c3.out_channels].float(), alpha=1.0 / ops.LO_SCALE)
+            return y.permute(0, 3, 1, 2).contiguous()
         return ops.tc_split_conv(h, l, plan['w3'][0], plan['w3'][1], c3.out_channels, c3.kernel_size[0], c3.kernel_size[0], 1,
                                  c3.padding[0], T.TCS_QUANT, medians=medians)
 
@@ -654,13 +664,29 @@ class SHPBasedResNetBottleneck(BaseBottleneck):
         self._tc_decoder = None
 
     @torch.no_grad()
+    def _analysis(self, x):
+        """y = g_a(x) as fp32 NCHW: the fused tensor-core kernels of the factorized-prior bottleneck (same Conv - GDN1 - Conv - GDN1
+        - Conv topology), else the fp32 CUDA-core kernels (logged)."""
+        ops.require_cuda(x, type(self).__name__ + '.encode')
+        why = 'encoder_precision = %r' % self.encoder_precision if getattr(self, 'encoder_precision', 'split-tc') != 'split-tc' else \
+            TensorCoreAnalysis.why_not(self.g_a, x.shape)
+        if why is None:
+            if self.__dict__.get('_tc_encoder') is None:
+                with _PLAN_LOCK:
+                    if self.__dict__.get('_tc_encoder') is None:
+                        self.__dict__['_tc_encoder'] = TensorCoreAnalysis(self.g_a)
+            return self.__dict__['_tc_encoder'](x, _NO_QUANT)
+        warn_fallback('%s.g_a' % type(self).__name__, why)
+        return run_transform(self.g_a, x)
+
+    @torch.no_grad()
     def _scales_to_indexes(self, z_hat):
         return self.gaussian_conditional.build_indexes(run_transform(self.h_s, z_hat))
 
     @torch.no_grad()
     def encode(self, x, **kwargs):
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
-        y = run_transform(self.g_a, x)
+        y = self._analysis(x)
         z_symbols = run_transform(self.h_a, y, final_epilogue=_native.EPI_QUANTIZE,
                                   final_aux=eb._get_medians().detach().reshape(-1), in_abs=True)  # h_a(|y|), |.| on load
         z_shape = z_symbols.size()[-2:]
@@ -747,7 +773,7 @@ class MSHPBasedResNetBottleneck(SHPBasedResNetBottleneck):
     @torch.no_grad()
     def encode(self, x, **kwargs):
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
-        y = run_transform(self.g_a, x)
+        y = self._analysis(x)
         z_symbols = run_transform(self.h_a, y, final_epilogue=_native.EPI_QUANTIZE,
                                   final_aux=eb._get_medians().detach().reshape(-1))
         z_shape = z_symbols.size()[-2:]

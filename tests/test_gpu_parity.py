@@ -373,6 +373,11 @@ def test_shp_bottleneck_small_golden(s2, dev, key, fname):
     x = torch.from_numpy(gs['x']).to(dev)
     y = s2.models.run_transform(layer.g_a, x)
     assert rel_err(y.cpu(), torch.from_numpy(gs['y'])) < LATENT_TOL
+    # the route encode() takes: the fused tensor-core analysis kernels
+    assert s2.bottleneck.TensorCoreAnalysis.why_not(layer.g_a, x.shape) is None
+    y_tc = layer._analysis(x)
+    assert layer.__dict__.get('_tc_encoder') is not None
+    assert rel_err(y_tc.cpu(), torch.from_numpy(gs['y'])) < LATENT_TOL
     enc = layer.encode(x)
     assert tuple(enc['shape']) == tuple(gs['shape']) and len(enc['strings']) == 2
     want_y = unpack_streams(gs['streams0'], gs['stream_offsets0'])
