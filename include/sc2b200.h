@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 8
+#define SC2_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -267,6 +267,37 @@ SC2_API int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, cons
                               const void *gdn_x_lo, void *out_hi, void *out_lo, int32_t *out_sym, int32_t *tile_counter,
                               sc2_stream_t stream);
 
+/* sc2_tc_split_conv for wider layers and the other layer types on the path (analysis / hyper-analysis transforms of the CompressAI
+ * zoo codecs, sc2bench/models/registry.py:12-14 -> compressai.models.google [mem]; g_a of the hyperprior bottlenecks, layer.py:596-603):
+ *   N tiling    one launch computes output channels [n_off, n_off + c_out) (c_out <= 128) of planes whose pixels are out_pitch
+ *               channels apart; w_hi/w_lo hold that tile's rows; vec / medians are the FULL vectors (indexed from n_off);
+ *               mode 2 writes symbols [images, c_total, h_out, w_out].  An inner tile must be full (c_out == n_tile).
+ *   in_nhwc     stride 2 only: x planes are a plain NHWC tensor [images, h_in, w_in, c_in] (h_in, w_in even = FULL resolution),
+ *               read through a 5-D tensor map (pixel parity as a coordinate) -- no parity-plane re-layout between two stride-2 layers
+ *   vec         modes 0 / 2: the convolution's bias (or NULL), added before act / the quantiser; modes 1 / 3: the GDN beta
+ *   act         mode 0: 0 none | 1 ReLU | 2 LeakyReLU(slope)
+ *   mode 3      GDN proper: y = x / sqrt(beta + gamma . x^2) (1x1: w = gamma, the squares are formed in shared memory) */
+#define SC2_TCS_GDN 3
+#define SC2_TCS_ACT_NONE 0
+#define SC2_TCS_ACT_RELU 1
+#define SC2_TCS_ACT_LEAKY 2
+
+typedef struct sc2_tc_split_ex_desc {
+    int images, h_in, w_in, c_in;
+    int c_out, kh, kw, stride, pad;
+    int mode;
+    int h_out, w_out;
+    int out_pitch, n_off, c_total;
+    int in_nhwc;
+    int act;
+    float slope;
+} sc2_tc_split_ex_desc;
+
+SC2_API int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const void *x_lo, const void *w_hi,
+                                 const void *w_lo, const float *vec, const float *medians, const void *gdn_x_hi,
+                                 const void *gdn_x_lo, void *out_hi, void *out_lo, int32_t *out_sym, int32_t *tile_counter,
+                                 sc2_stream_t stream);
+
 /* Device: stride-2 convolution + GDN1 back to back in one kernel (conv_ga_halo.cu), fp32-grade split fp16: the middle of g_a
  * (sc2bench/models/layer.py:479-481, Conv2d(k5, s2, p2) -> GDN1).  The conv accumulators never leave the SM: |x| becomes the
  * A operand of the 1x1 gamma GEMM in shared memory, y = x / (beta + gamma.|x|) leaves as split planes.
@@ -302,6 +333,11 @@ SC2_API int sc2_ga_first_conv_gdn(const void *image, int image_is_u8, const floa
  * to k_pad, pixels in parity-plane order [batch * 4, h_out/2, w_out/2, k_pad] (h_out, w_out must be even). */
 SC2_API int sc2_patchify_split(const float *x, void *out_hi, void *out_lo, int batch, int c_in, int h_in, int w_in,
                                int kh, int kw, int stride, int pad, int k_pad, sc2_stream_t stream);
+
+/* The same im2col with the pixels in plain NHWC order [batch, h_out, w_out, k_pad] (any stride >= 1, any output size): the first
+ * layer of the zoo codecs' g_a, whose next layer reads NHWC through sc2_tc_split_conv_ex(in_nhwc). */
+SC2_API int sc2_patchify_split_nhwc(const float *x, void *out_hi, void *out_lo, int batch, int c_in, int h_in, int w_in,
+                                    int kh, int kw, int stride, int pad, int k_pad, sc2_stream_t stream);
 
 /* Device: first layer of g_a with the im2col fused into the tensor-core kernel (conv_tc_first.cu): stride-2 Conv2d on an fp32
  * NCHW image with c_in*kh*kw <= 128 and c_out <= 96, fp32-grade (split fp16), output as split parity planes

@@ -29,6 +29,12 @@ class TcSplitDesc(_c.Structure):
                                     'h_out', 'w_out', 'out_c')]
 
 
+class TcSplitExDesc(_c.Structure):
+    """struct sc2_tc_split_ex_desc"""
+    _fields_ = [(n, i32) for n in ('images', 'h_in', 'w_in', 'c_in', 'c_out', 'kh', 'kw', 'stride', 'pad', 'mode', 'h_out', 'w_out',
+                                    'out_pitch', 'n_off', 'c_total', 'in_nhwc', 'act')] + [('slope', _c.c_float)]
+
+
 class TcConvExDesc(_c.Structure):
     """struct sc2_tc_conv_ex_desc"""
     _fields_ = [(n, i32) for n in ('batch', 'h_in', 'w_in', 'c_in_pad', 'c_out', 'kh', 'kw', 'pad_y', 'pad_x', 'mode', 'h_out', 'w_out',
@@ -74,6 +80,8 @@ SIGNATURES = {
     'sc2_nchw_f32_to_nhwc_f16': (i32, [vp, vp, i32, i32, i64, i32, vp]),
     'sc2_tc_split_n_tile': (i32, [i32]),
     'sc2_tc_split_conv': (i32, [_c.POINTER(TcSplitDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sc2_tc_split_conv_ex': (i32, [_c.POINTER(TcSplitExDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'sc2_patchify_split_nhwc': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'sc2_ga_halo_n': (i32, [i32]),
     'sc2_ga_halo_conv_gdn': (i32, [_c.POINTER(GaHaloDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'sc2_ga_first_conv_gdn': (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp]),
@@ -86,13 +94,14 @@ SIGNATURES = {
 }
 
 SC2_OK = 0
-ABI_VERSION = 8  # include/sc2b200.h SC2_ABI_VERSION
+ABI_VERSION = 9  # include/sc2b200.h SC2_ABI_VERSION
 FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM, FAULT_BAD_INDEX = 1, 2, 4, 8
 EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 IN_NONE, IN_ABS = 0, 1
 TC_STORE_F16, TC_STORE_F32, TC_IGDN1_F16, TC_GDN1_F16, TC_STORE_ABS_F16, TC_IGDN1_ABS_F16 = 0, 1, 2, 3, 4, 5
 TC_STORE_SQ_F16, TC_IGDN_SQ_F16, TC_NCHW_F32_CLAMP = 6, 7, 8
-TCS_STORE, TCS_GDN1, TCS_QUANT = 0, 1, 2
+TCS_STORE, TCS_GDN1, TCS_QUANT, TCS_GDN = 0, 1, 2, 3
+TCS_ACT_NONE, TCS_ACT_RELU, TCS_ACT_LEAKY = 0, 1, 2
 RANS_LAYOUTS = {None: 0, 'auto': 0, 'warp': 1, 'lanes': 2}
 
 _lib = None

@@ -31,7 +31,10 @@ constexpr float kLoInv = 1.0f / 2048.0f;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kD1Col = 384;
 
-enum Mode { MODE_STORE_SPLIT = 0, MODE_GDN1_SPLIT = 1, MODE_QUANT = 2 };
+// MODE_GDN_SPLIT: the GDN of the CompressAI zoo codecs, y = x / sqrt(beta + gamma . x^2) (compressai.layers.GDN [mem]; the
+// transform warps square the A tile in shared memory instead of taking |.|, the epilogue multiplies by rsqrt).
+enum Mode { MODE_STORE_SPLIT = 0, MODE_GDN1_SPLIT = 1, MODE_QUANT = 2, MODE_GDN_SPLIT = 3 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 
 struct Tap {
     int8_t plane, dx, dy, pad_;
@@ -56,6 +59,13 @@ struct Params {
     const __half *x_hi, *x_lo;
     int *tile_counter;  // zeroed by the caller: dynamic tile schedule; nullptr: static
     TraceSink trace;    // diagnostics (common.cuh)
+    // ---- sc2_tc_split_conv_ex ----
+    int in5d;           // stride-2 taps straight from an NHWC tensor: 5-D map (px * c_in + c, X, py, Y, image), no parity planes
+    int c_in;
+    int sym_c_total;    // MODE_QUANT: channels of the whole symbol tensor; this launch writes [sym_c_off, sym_c_off + c_out)
+    int sym_c_off;
+    int act;            // STORE: activation after the bias (ReLU / LeakyReLU of the hyper-analysis h_a)
+    float slope;
 };
 
 // B_RES: 1x1 convolutions (one tap, <= 2 K chunks) keep the whole weight matrix resident in shared memory for the life of
@@ -87,6 +97,12 @@ __device__ __forceinline__ float fast_rcp(float v) {  // v > 0 (a GDN norm): rec
     return fmaf(r, fmaf(-v, r, 1.0f), r);
 }
 
+__device__ __forceinline__ float fast_rsqrt(float v) {  // v > 0: MUFU.RSQ + one Newton step
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r * fmaf(-0.5f * v * r, r, 1.5f);
+}
+
 __device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr, __half *lo_ptr) {
     uint4 h, l;
     uint32_t *hw = reinterpret_cast<uint32_t *>(&h), *lw = reinterpret_cast<uint32_t *>(&l);
@@ -103,7 +119,7 @@ __device__ __forceinline__ void split_store8(const float (&f)[8], __half *hi_ptr
 }
 
 template <int N_TILE, int STAGES, int MODE, bool B_RES>
-__global__ void __launch_bounds__(MODE == MODE_GDN1_SPLIT ? 448 : 320, 1)
+__global__ void __launch_bounds__((MODE == MODE_GDN1_SPLIT || MODE == MODE_GDN_SPLIT) ? 448 : 320, 1)
 tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                      const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
@@ -113,7 +129,7 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     // halves of TMEM alternate between tiles (epilogue of tile i overlaps the MMAs of tile i + 1); with several D0
     // groups (long K) the whole TMEM belongs to one tile at a time.
     using L = Smem<N_TILE, STAGES, B_RES>;
-    constexpr bool kGdn = MODE == MODE_GDN1_SPLIT;
+    constexpr bool kGdn = MODE == MODE_GDN1_SPLIT || MODE == MODE_GDN_SPLIT;
     constexpr uint32_t kSlot = N_TILE <= 64 ? 64 : 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem_res = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -141,7 +157,9 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     sched.bind(smem_res + L::kSchedOffset, p.tile_counter, total_tiles);
 
     float *s_beta = reinterpret_cast<float *>(smem_res + L::kBetaOffset);
-    if (kGdn && threadIdx.x < N_TILE) s_beta[threadIdx.x] = static_cast<int>(threadIdx.x) < p.c_out ? __ldg(p.beta + threadIdx.x) : 1.0f;
+    // GDN: beta (1.0 beyond c_out keeps the reciprocal finite); otherwise the convolution's bias (0 when there is none)
+    if (threadIdx.x < N_TILE)
+        s_beta[threadIdx.x] = (p.beta && static_cast<int>(threadIdx.x) < p.c_out) ? __ldg(p.beta + threadIdx.x) : (kGdn ? 1.0f : 0.0f);
 
     if (threadIdx.x == 0) {
         sched.init(kGdn ? 13 : 9);  // consumers: MMA warp, 8 epilogue warps (, 4 transform warps)
@@ -199,8 +217,14 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         uint8_t *dst = smem + s * L::kStageBytes;
                         mbar_expect_tx(&full[s], stage_tx);
                         const int cx = x0 + tap.dx, cy = y0 + tap.dy, cz = img * p.planes + tap.plane;
-                        tma_load_4d(&map_a_hi, &full[s], dst, kc * kBlockK, cx, cy, cz);
-                        tma_load_4d(&map_a_lo, &full[s], dst + kABytes, kc * kBlockK, cx, cy, cz);
+                        if (p.in5d) {
+                            const int cc = (tap.plane & 1) * p.c_in + kc * kBlockK;
+                            tma_load_5d(&map_a_hi, &full[s], dst, cc, cx, tap.plane >> 1, cy, img);
+                            tma_load_5d(&map_a_lo, &full[s], dst + kABytes, cc, cx, tap.plane >> 1, cy, img);
+                        } else {
+                            tma_load_4d(&map_a_hi, &full[s], dst, kc * kBlockK, cx, cy, cz);
+                            tma_load_4d(&map_a_lo, &full[s], dst + kABytes, kc * kBlockK, cx, cy, cz);
+                        }
                         if (!B_RES) {
                             tma_load_2d(&map_b_hi, &full[s], dst + 2 * kABytes, kc * kBlockK, t * N_TILE);
                             tma_load_2d(&map_b_lo, &full[s], dst + 2 * kABytes + L::kBBytes, kc * kBlockK, t * N_TILE);
@@ -299,9 +323,9 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     for (int e = 0; e < 32; ++e) {
                         const int c = c0 + e;
                         if (c < p.c_out) {
-                            const float v = __uint_as_float(d0[e]) + __uint_as_float(d1[e]) * kLoInv;
+                            const float v = __uint_as_float(d0[e]) + __uint_as_float(d1[e]) * kLoInv + s_beta[c];
                             const float med = p.medians ? __ldg(p.medians + c) : 0.0f;
-                            p.out_sym[((static_cast<int64_t>(img) * p.c_out + c) * p.h_out + oy) * p.w_out + ox] =
+                            p.out_sym[((static_cast<int64_t>(img) * p.sym_c_total + p.sym_c_off + c) * p.h_out + oy) * p.w_out + ox] =
                                 __float2int_rn(rintf(v - med));
                         }
                     }
@@ -314,7 +338,12 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         const bool whole = c + 8 <= p.c_out;  // (uniform) every channel of the group is real
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float v = fmaf(__uint_as_float(d1[8 * g + e]), kLoInv, __uint_as_float(d0[8 * g + e]));
+                            float v = fmaf(__uint_as_float(d1[8 * g + e]), kLoInv, __uint_as_float(d0[8 * g + e]));
+                            if (!kGdn) {
+                                v += s_beta[c + e];
+                                if (p.act == ACT_RELU) v = fmaxf(v, 0.0f);
+                                else if (p.act == ACT_LEAKY) v = v > 0.0f ? v : v * p.slope;
+                            }
                             f[e] = (whole || c + e < p.c_out) ? v : 0.0f;
                         }
                         __half *ph = st_hi + row * p.stage_c + c, *pl = st_lo + row * p.stage_c + c;
@@ -326,9 +355,14 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                             for (int e = 0; e < 4; ++e) {
                                 const float2 a = __half22float2(xhh[e]), b = __half22float2(xlh[e]);
                                 const float x0f = fmaf(b.x, kLoInv, a.x), x1f = fmaf(b.y, kLoInv, a.y);
-                                // x * (1 / norm), like the reference; 1 / norm = MUFU.RCP + one Newton step (< 1 ulp)
-                                f[2 * e] = x0f * fast_rcp(f[2 * e] + s_beta[c + 2 * e]);
-                                f[2 * e + 1] = x1f * fast_rcp(f[2 * e + 1] + s_beta[c + 2 * e + 1]);
+                                if (MODE == MODE_GDN_SPLIT) {
+                                    f[2 * e] = x0f * fast_rsqrt(f[2 * e] + s_beta[c + 2 * e]);
+                                    f[2 * e + 1] = x1f * fast_rsqrt(f[2 * e + 1] + s_beta[c + 2 * e + 1]);
+                                } else {
+                                    // x * (1 / norm), like the reference; 1 / norm = MUFU.RCP + one Newton step (< 1 ulp)
+                                    f[2 * e] = x0f * fast_rcp(f[2 * e] + s_beta[c + 2 * e]);
+                                    f[2 * e + 1] = x1f * fast_rcp(f[2 * e + 1] + s_beta[c + 2 * e + 1]);
+                                }
                             }
                         }
                         split_store8(f, ph, pl);
@@ -365,8 +399,24 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         // rotate the 16-byte chunk with the row: 8 neighbouring rows hit 8 different bank groups
                         const int cc = (c + row) & 7;
                         uint4 h = rh[cc], l = rl[cc];
-                        l.x ^= h.x & 0x80008000u; l.y ^= h.y & 0x80008000u; l.z ^= h.z & 0x80008000u; l.w ^= h.w & 0x80008000u;
-                        h.x &= 0x7fff7fffu; h.y &= 0x7fff7fffu; h.z &= 0x7fff7fffu; h.w &= 0x7fff7fffu;
+                        if (MODE == MODE_GDN_SPLIT) {  // x^2 in fp32, split again
+                            uint32_t *hw = reinterpret_cast<uint32_t *>(&h), *lw = reinterpret_cast<uint32_t *>(&l);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&hw[e]));
+                                const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&lw[e]));
+                                const float x0f = fmaf(b.x, kLoInv, a.x), x1f = fmaf(b.y, kLoInv, a.y);
+                                const float s0 = x0f * x0f, s1 = x1f * x1f;
+                                const __half2 hh = __floats2half2_rn(s0, s1);
+                                const float2 back = __half22float2(hh);
+                                const __half2 ll = __floats2half2_rn((s0 - back.x) * kLoScale, (s1 - back.y) * kLoScale);
+                                hw[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                                lw[e] = *reinterpret_cast<const uint32_t *>(&ll);
+                            }
+                        } else {
+                            l.x ^= h.x & 0x80008000u; l.y ^= h.y & 0x80008000u; l.z ^= h.z & 0x80008000u; l.w ^= h.w & 0x80008000u;
+                            h.x &= 0x7fff7fffu; h.y &= 0x7fff7fffu; h.z &= 0x7fff7fffu; h.w &= 0x7fff7fffu;
+                        }
                         rh[cc] = h;
                         rl[cc] = l;
                     }
@@ -388,20 +438,20 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 // K index = (c * kh + dy) * kw + dx, zero padded to k_pad.
 __global__ void patchify_split_kernel(const float *__restrict__ x, __half *__restrict__ out_hi, __half *__restrict__ out_lo,
                                       int c_in, int h_in, int w_in, int kh, int kw, int stride, int pad, int hp, int wp,
-                                      int k_pad, int64_t total_groups) {
+                                      int k_pad, int64_t total_groups, int plain) {
     const int groups = k_pad / 8;
     const int K = c_in * kh * kw;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total_groups;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int g = static_cast<int>(i % groups);
-        int64_t pixel = i / groups;  // ((b * 4 + parity) * hp + Y) * wp + X
+        int64_t pixel = i / groups;  // ((b * 4 + parity) * hp + Y) * wp + X;  plain: (b * hp + oy) * wp + ox
         const int X = static_cast<int>(pixel % wp);
         pixel /= wp;
         const int Y = static_cast<int>(pixel % hp);
         pixel /= hp;
-        const int parity = static_cast<int>(pixel & 3);
-        const int64_t b = pixel >> 2;
-        const int oy = 2 * Y + (parity >> 1), ox = 2 * X + (parity & 1);
+        const int parity = plain ? 0 : static_cast<int>(pixel & 3);
+        const int64_t b = plain ? pixel : pixel >> 2;
+        const int oy = plain ? Y : 2 * Y + (parity >> 1), ox = plain ? X : 2 * X + (parity & 1);
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -430,7 +480,7 @@ static int launch(const CUtensorMap *maps, const Params &p, int images, cudaStre
     const int64_t total = static_cast<int64_t>(p.tiles_x) * p.tiles_y * images;
     if (total > 0x7fffffff) return SC2_ERR_UNSUPPORTED;
     const int grid = total < persistent_grid() ? static_cast<int>(total) : persistent_grid();
-    tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES><<<grid, MODE == MODE_GDN1_SPLIT ? 448 : 320, smem, st>>>(mah, mal, mbh, mbl, maps[4], maps[5], maps[6], maps[7], p);
+    tc_split_conv_kernel<N_TILE, STAGES, MODE, B_RES><<<grid, (MODE == MODE_GDN1_SPLIT || MODE == MODE_GDN_SPLIT) ? 448 : 320, smem, st>>>(mah, mal, mbh, mbl, maps[4], maps[5], maps[6], maps[7], p);
     SC2_LAUNCH_CHECK("tc_split_conv_kernel");
     return SC2_OK;
 }
@@ -445,6 +495,9 @@ static int dispatch_mode(int mode, const CUtensorMap *maps, const Params &p, int
         case MODE_GDN1_SPLIT:
             return res ? launch<N_TILE, STAGES_RES, MODE_GDN1_SPLIT, true>(maps, p, images, st)
                        : launch<N_TILE, STAGES, MODE_GDN1_SPLIT, false>(maps, p, images, st);
+        case MODE_GDN_SPLIT:
+            return res ? launch<N_TILE, STAGES_RES, MODE_GDN_SPLIT, true>(maps, p, images, st)
+                       : launch<N_TILE, STAGES, MODE_GDN_SPLIT, false>(maps, p, images, st);
         default:
             return res ? launch<N_TILE, STAGES_RES, MODE_QUANT, true>(maps, p, images, st)
                        : launch<N_TILE, STAGES, MODE_QUANT, false>(maps, p, images, st);
@@ -463,22 +516,33 @@ int sc2_tc_split_n_tile(int c_out) {
     return 0;
 }
 
-int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo,
-                      const float *beta, const float *medians, const void *gdn_x_hi, const void *gdn_x_lo, void *out_hi,
-                      void *out_lo, int32_t *out_sym, int32_t *tile_counter, sc2_stream_t stream) {
+int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo,
+                         const float *vec, const float *medians, const void *gdn_x_hi, const void *gdn_x_lo, void *out_hi,
+                         void *out_lo, int32_t *out_sym, int32_t *tile_counter, sc2_stream_t stream) {
     using namespace sc2::tcs;
     if (!d || !x_hi || !x_lo || !w_hi || !w_lo) return SC2_ERR_INVALID_ARG;
-    if (d->images < 1 || d->c_in < 16 || d->c_in % 16 || d->c_out < 1) return SC2_ERR_INVALID_ARG;
+    if (d->images < 1 || d->c_in < 16 || d->c_in % 16 || d->c_out < 1 || d->n_off < 0 || d->n_off % 8) return SC2_ERR_INVALID_ARG;
     if (d->stride != 1 && d->stride != 2) return SC2_ERR_UNSUPPORTED;
     if (d->kh * d->kw > kMaxTaps || d->kh < 1 || d->kw < 1) return SC2_ERR_UNSUPPORTED;
-    if ((d->c_in * 2) % 16) return SC2_ERR_INVALID_ARG;
     const int n_tile = sc2_tc_split_n_tile(d->c_out);
     if (!n_tile) return SC2_ERR_UNSUPPORTED;
-    if (d->mode == MODE_GDN1_SPLIT && (!beta || !gdn_x_hi || !gdn_x_lo || d->kh != 1 || d->kw != 1 || d->stride != 1)) return SC2_ERR_INVALID_ARG;
+    const bool gdn = d->mode == MODE_GDN1_SPLIT || d->mode == MODE_GDN_SPLIT;
+    if (d->mode < 0 || d->mode > MODE_GDN_SPLIT) return SC2_ERR_INVALID_ARG;
+    if (gdn && (!vec || !gdn_x_hi || !gdn_x_lo || d->kh != 1 || d->kw != 1 || d->stride != 1)) return SC2_ERR_INVALID_ARG;
     if (d->mode == MODE_QUANT ? !out_sym : (!out_hi || !out_lo)) return SC2_ERR_INVALID_ARG;
-    if (d->mode != MODE_QUANT && (d->out_c % 8 || d->out_c < d->c_out)) return SC2_ERR_INVALID_ARG;
+    if (d->mode == MODE_QUANT && (d->c_total < d->n_off + d->c_out)) return SC2_ERR_INVALID_ARG;
+    if (d->in_nhwc && (d->stride != 2 || (d->h_in & 1) || (d->w_in & 1))) return SC2_ERR_UNSUPPORTED;
+    if (d->act < ACT_NONE || d->act > ACT_LEAKY) return SC2_ERR_INVALID_ARG;
+    // channels of the output planes this launch owns: [n_off, n_off + out_ext); a launch that does not reach the end of the
+    // pixel (an inner N tile) must fill its tile completely
+    int out_ext = 0;
+    if (d->mode != MODE_QUANT) {
+        if (d->out_pitch % 8 || d->out_pitch < d->n_off + d->c_out) return SC2_ERR_INVALID_ARG;
+        out_ext = d->out_pitch - d->n_off < n_tile ? d->out_pitch - d->n_off : n_tile;
+        if (d->n_off + out_ext < d->out_pitch && d->c_out != n_tile) return SC2_ERR_INVALID_ARG;
+    }
     Params p;
-    const int planes = d->stride == 2 ? 4 : 1;
+    const int planes = (d->stride == 2 && !d->in_nhwc) ? 4 : 1;
     p.planes = planes;
     p.images = d->images;
     p.h_out = d->h_out; p.w_out = d->w_out;
@@ -522,21 +586,41 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
         p.groups = groups;
     }
     p.c_out = d->c_out;
-    p.beta = beta; p.medians = medians;
-    p.out_hi = static_cast<__half *>(out_hi); p.out_lo = static_cast<__half *>(out_lo);
-    p.out_c = d->out_c;
-    p.stage_c = (d->out_c / 8) % 2 == 0 ? d->out_c + 8 : d->out_c;  // odd number of 16-byte units per staging row
+    p.beta = vec ? vec + d->n_off : nullptr;
+    p.medians = medians ? medians + d->n_off : nullptr;
+    __half *o_hi = static_cast<__half *>(out_hi), *o_lo = static_cast<__half *>(out_lo);
+    if (o_hi) { o_hi += d->n_off; o_lo += d->n_off; }
+    p.out_hi = o_hi; p.out_lo = o_lo;
+    p.out_c = out_ext;
+    p.stage_c = (out_ext / 8) % 2 == 0 ? out_ext + 8 : out_ext;  // odd number of 16-byte units per staging row
     p.out_sym = out_sym;
-    p.x_hi = static_cast<const __half *>(gdn_x_hi); p.x_lo = static_cast<const __half *>(gdn_x_lo);
+    const __half *gx_hi = static_cast<const __half *>(gdn_x_hi), *gx_lo = static_cast<const __half *>(gdn_x_lo);
+    if (gx_hi) { gx_hi += d->n_off; gx_lo += d->n_off; }
+    p.x_hi = gx_hi; p.x_lo = gx_lo;
     p.tile_counter = tile_counter;
     p.trace = sc2::trace_sink();
+    p.in5d = d->in_nhwc ? 1 : 0;
+    p.c_in = d->c_in;
+    p.sym_c_total = d->mode == MODE_QUANT ? d->c_total : 0;
+    p.sym_c_off = d->n_off;
+    p.act = d->act;
+    p.slope = d->slope;
     CUtensorMap maps[8];
     CUtensorMap &mah = maps[0], &mal = maps[1], &mbh = maps[2], &mbl = maps[3];
-    // input planes: [images * planes, h_in, w_in, c_in] (h_in, w_in = plane geometry)
-    int rc = make_nhwc_map(&mah, x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * planes, kBlockK, tw, th);
-    if (rc) return rc;
-    rc = make_nhwc_map(&mal, x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * planes, kBlockK, tw, th);
-    if (rc) return rc;
+    int rc;
+    if (d->in_nhwc) {
+        // input: an NHWC tensor [images, h_in, w_in, c_in] (full resolution) read through the stride-2 view
+        rc = make_nhwc_s2_map(&mah, x_hi, d->c_in, d->w_in, d->h_in, d->images, kBlockK, tw, th);
+        if (rc) return rc;
+        rc = make_nhwc_s2_map(&mal, x_lo, d->c_in, d->w_in, d->h_in, d->images, kBlockK, tw, th);
+        if (rc) return rc;
+    } else {
+        // input planes: [images * planes, h_in, w_in, c_in] (h_in, w_in = plane geometry)
+        rc = make_nhwc_map(&mah, x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * planes, kBlockK, tw, th);
+        if (rc) return rc;
+        rc = make_nhwc_map(&mal, x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->c_in, d->w_in, d->h_in, d->images * planes, kBlockK, tw, th);
+        if (rc) return rc;
+    }
     // packed weights: [taps * n_tile, c_in] (rows beyond c_out are zero)
     rc = make_weight_map(&mbh, w_hi, d->c_in, p.n_taps * n_tile, n_tile);
     if (rc) return rc;
@@ -545,20 +629,20 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     maps[4] = maps[5] = maps[6] = maps[7] = mah;
     if (d->mode != MODE_QUANT) {
         // dense (unswizzled) boxes {stage_c, tw, th, 1}: bulk-store sources / x-tile destinations in the staging buffer; the
-        // box is wider than the tensor when the row pitch is padded (out-of-bounds channels: skipped / zero-filled)
-        if (d->out_c > n_tile) return SC2_ERR_INVALID_ARG;
-        rc = make_nhwc_map(&maps[4], out_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
-                           CU_TENSOR_MAP_SWIZZLE_NONE);
+        // box is wider than the tensor view when the row pitch is padded (channels beyond the view: skipped / zero-filled)
+        const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        rc = make_nhwc_map_pitch(&maps[4], o_hi, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
-        rc = make_nhwc_map(&maps[5], out_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
-                           CU_TENSOR_MAP_SWIZZLE_NONE);
+        rc = make_nhwc_map_pitch(&maps[5], o_lo, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
-        if (d->mode == MODE_GDN1_SPLIT) {
-            rc = make_nhwc_map(&maps[6], gdn_x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, tw,
-                               th, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (gdn) {
+            rc = make_nhwc_map_pitch(&maps[6], gx_hi, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE);
             if (rc) return rc;
-            rc = make_nhwc_map(&maps[7], gdn_x_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->out_c, d->w_out, d->h_out, d->images, p.stage_c, tw,
-                               th, CU_TENSOR_MAP_SWIZZLE_NONE);
+            rc = make_nhwc_map_pitch(&maps[7], gx_lo, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE);
             if (rc) return rc;
         }
     }
@@ -572,6 +656,22 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     }
 }
 
+int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo,
+                      const float *beta, const float *medians, const void *gdn_x_hi, const void *gdn_x_lo, void *out_hi,
+                      void *out_lo, int32_t *out_sym, int32_t *tile_counter, sc2_stream_t stream) {
+    if (!d) return SC2_ERR_INVALID_ARG;
+    if (d->mode < 0 || d->mode > 2) return SC2_ERR_INVALID_ARG;
+    if (d->mode != 2 && d->out_c > sc2_tc_split_n_tile(d->c_out)) return SC2_ERR_INVALID_ARG;
+    sc2_tc_split_ex_desc e;
+    e.images = d->images; e.h_in = d->h_in; e.w_in = d->w_in; e.c_in = d->c_in;
+    e.c_out = d->c_out; e.kh = d->kh; e.kw = d->kw; e.stride = d->stride; e.pad = d->pad;
+    e.mode = d->mode;
+    e.h_out = d->h_out; e.w_out = d->w_out;
+    e.out_pitch = d->out_c; e.n_off = 0; e.c_total = d->c_out; e.in_nhwc = 0; e.act = 0; e.slope = 0.0f;
+    return sc2_tc_split_conv_ex(&e, x_hi, x_lo, w_hi, w_lo, beta, medians, gdn_x_hi, gdn_x_lo, out_hi, out_lo, out_sym, tile_counter,
+                                stream);
+}
+
 int sc2_patchify_split(const float *x, void *out_hi, void *out_lo, int batch, int c_in, int h_in, int w_in, int kh, int kw,
                        int stride, int pad, int k_pad, sc2_stream_t stream) {
     if (!x || !out_hi || !out_lo || batch < 1 || k_pad % 16 || k_pad < c_in * kh * kw) return SC2_ERR_INVALID_ARG;
@@ -582,7 +682,22 @@ int sc2_patchify_split(const float *x, void *out_hi, void *out_lo, int batch, in
     int64_t blocks = (total + 255) / 256;
     if (blocks > sc2::kNumSMs * 32) blocks = sc2::kNumSMs * 32;
     sc2::tcs::patchify_split_kernel<<<static_cast<int>(blocks), 256, 0, sc2::as_stream(stream)>>>(
-        x, static_cast<__half *>(out_hi), static_cast<__half *>(out_lo), c_in, h_in, w_in, kh, kw, stride, pad, hp, wp, k_pad, total);
+        x, static_cast<__half *>(out_hi), static_cast<__half *>(out_lo), c_in, h_in, w_in, kh, kw, stride, pad, hp, wp, k_pad, total, 0);
+    SC2_LAUNCH_CHECK("patchify_split_kernel");
+    return SC2_OK;
+}
+
+int sc2_patchify_split_nhwc(const float *x, void *out_hi, void *out_lo, int batch, int c_in, int h_in, int w_in, int kh, int kw,
+                            int stride, int pad, int k_pad, sc2_stream_t stream) {
+    if (!x || !out_hi || !out_lo || batch < 1 || k_pad % 16 || k_pad < c_in * kh * kw || stride < 1) return SC2_ERR_INVALID_ARG;
+    const int h_out = (h_in + 2 * pad - kh) / stride + 1, w_out = (w_in + 2 * pad - kw) / stride + 1;
+    if (h_out < 1 || w_out < 1) return SC2_ERR_INVALID_ARG;
+    const int64_t total = static_cast<int64_t>(batch) * h_out * w_out * (k_pad / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > sc2::kNumSMs * 32) blocks = sc2::kNumSMs * 32;
+    sc2::tcs::patchify_split_kernel<<<static_cast<int>(blocks), 256, 0, sc2::as_stream(stream)>>>(
+        x, static_cast<__half *>(out_hi), static_cast<__half *>(out_lo), c_in, h_in, w_in, kh, kw, stride, pad, h_out, w_out, k_pad,
+        total, 1);
     SC2_LAUNCH_CHECK("patchify_split_kernel");
     return SC2_OK;
 }

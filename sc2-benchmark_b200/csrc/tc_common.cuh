@@ -140,6 +140,12 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap *m, uint64_t *bar,
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -359,6 +365,39 @@ inline int make_nhwc_map(CUtensorMap *m, const void *base, CUtensorMapDataType d
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SC2_OK : SC2_ERR_INVALID_ARG;
+}
+
+// channels [0, c) of an NHWC tensor whose pixels are `pitch_c` elements apart (one N tile of a wider tensor)
+inline int make_nhwc_map_pitch(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int elem_bytes, int c, int pitch_c, int w, int h,
+                               int batch, int box_c, int box_w, int box_h, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return SC2_ERR_CUDA;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(batch)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch_c) * elem_bytes, static_cast<cuuint64_t>(w) * pitch_c * elem_bytes,
+                             static_cast<cuuint64_t>(h) * w * pitch_c * elem_bytes};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SC2_OK : SC2_ERR_INVALID_ARG;
+}
+
+// An fp16 NHWC tensor [batch, h, w, c] (h, w even) seen by a stride-2 convolution: dims (px * c + channel, X, py, Y, image) with
+// pixel (2Y + py, 2X + px), so that a tap is a unit-stride box {box_c, box_w, 1, box_h, 1} of one pixel parity -- the parity
+// planes of the bottleneck's g_a without the re-layout.
+inline int make_nhwc_s2_map(CUtensorMap *m, const void *base, int c, int w, int h, int batch, int box_c, int box_w, int box_h) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return SC2_ERR_CUDA;
+    const cuuint64_t row = static_cast<cuuint64_t>(w) * c * 2;
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(2 * c), static_cast<cuuint64_t>(w / 2), 2, static_cast<cuuint64_t>(h / 2),
+                          static_cast<cuuint64_t>(batch)};
+    cuuint64_t strides[4] = {static_cast<cuuint64_t>(2 * c) * 2, row, 2 * row, static_cast<cuuint64_t>(h) * row};
+    cuuint32_t box[5] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), 1, static_cast<cuuint32_t>(box_h), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SC2_OK : SC2_ERR_INVALID_ARG;
 }
 

@@ -149,6 +149,161 @@ class CompressionModel(nn.Module):
         return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
 
 
+class SplitAnalysisPlan:
+    """An analysis-side transform (Conv2d / GDN / GDN1 / ReLU / LeakyReLU in sequence: g_a and h_a of the CompressAI zoo codecs,
+    compressai.models.google [mem], reached from sc2bench/models/wrapper.py:108-126) on the tcgen05 tensor cores in fp32-grade
+    split-fp16 arithmetic (conv_tc_split.cu) -- the symbols must match the fp32 reference, so the fp16 route of g_s is not enough.
+        first layer (3 input channels): im2col (sc2_patchify_split_nhwc) + a 1x1 GEMM over K = 75 -> 80
+        Conv2d(k <= 5, stride 1 | 2) with bias, optional ReLU / LeakyReLU in the epilogue; stride-2 layers read the NHWC planes of the
+            layer before through a 5-D tensor map (pixel parity = a coordinate), layers wider than 128 channels run as N tiles
+        GDN / GDN1: a 1x1 gamma GEMM on x^2 / |x| formed in shared memory, y = x * rsqrt(beta + acc) / x / (beta + acc)
+        the last conv can quantise straight to coder symbols (round(y + bias - median), NCHW order)."""
+
+    def __init__(self, seq):
+        self.seq = seq
+        self._plan = None
+
+    @staticmethod
+    def why_not(seq, x_shape, planes_in=False):
+        """None when the plan covers `seq` for an input of shape x_shape (NCHW), else the reason."""
+        mods = list(seq)
+        if not mods or not isinstance(mods[0], nn.Conv2d):
+            return 'does not start with a Conv2d'
+        C, H, W = x_shape[-3:]
+        prev_conv = False
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Conv2d):
+                k, st = m.kernel_size[0], m.stride[0]
+                if (m.groups != 1 or tuple(m.dilation) != (1, 1) or m.kernel_size[0] != m.kernel_size[1] or isinstance(m.padding, str)
+                        or m.padding[0] != m.padding[1] or m.stride[0] != m.stride[1] or st not in (1, 2) or k > 5
+                        or m.padding_mode != 'zeros'):
+                    return 'convolution %d: groups / dilation / kernel / stride outside the kernel' % i
+                if m.in_channels != C:
+                    return 'convolution %d expects %d channels, gets %d' % (i, m.in_channels, C)
+                if i == 0 and not planes_in and C * k * k <= 128:
+                    pass  # im2col + 1x1 GEMM
+                elif C % 16:
+                    return 'convolution %d: c_in %d is not a multiple of 16' % (i, C)
+                elif st == 2 and (H % 2 or W % 2):
+                    return 'convolution %d: stride 2 on an odd %d x %d input' % (i, H, W)
+                H, W = (H + 2 * m.padding[0] - k) // st + 1, (W + 2 * m.padding[0] - k) // st + 1
+                if H < 1 or W < 1:
+                    return 'empty output'
+                C = m.out_channels
+                prev_conv = True
+            elif isinstance(m, GDN):
+                if m.inverse:
+                    return 'layer %d is an inverse GDN' % i
+                if C % 16 or m.beta.numel() != C:
+                    return 'GDN over %d channels' % C
+                prev_conv = False
+            elif isinstance(m, (nn.ReLU, nn.LeakyReLU)):
+                if not prev_conv:
+                    return 'activation %d does not follow a convolution' % i
+                prev_conv = False
+            else:
+                return 'layer %d is %s' % (i, type(m).__name__)
+        return None
+
+    def _prepare(self, planes_in):
+        key = (tuple((q.data_ptr(), q._version, q.device) for q in self.seq.parameters()), planes_in)
+        plan = self._plan
+        if plan is not None and plan[0] == key:
+            return plan
+        steps, mods = [], list(self.seq)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Conv2d):
+                act, slope = _native.TCS_ACT_NONE, 0.0
+                if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                    act = _native.TCS_ACT_RELU
+                elif i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU):
+                    act, slope = _native.TCS_ACT_LEAKY, mods[i + 1].negative_slope
+                patches = i == 0 and not planes_in and m.in_channels * m.kernel_size[0] ** 2 <= 128
+                k_pad = (m.in_channels * m.kernel_size[0] ** 2 + 15) // 16 * 16 if patches else None
+                tiles = ops.pack_conv_weight_split_tiles(m.weight, c_in_pad=k_pad, as_patches=patches)
+                bias = m.bias.detach().float().contiguous() if m.bias is not None else None
+                steps.append(('conv', m, tiles, bias, act, slope, k_pad))
+                i += 2 if act != _native.TCS_ACT_NONE else 1
+            else:
+                gamma, beta = m.effective_params()
+                C = beta.numel()
+                tiles = ops.pack_conv_weight_split_tiles(gamma.detach().reshape(C, C, 1, 1))
+                steps.append(('gdn', m, tiles, beta.detach().float().contiguous(), _native.TCS_GDN1 if m._kind == 0 else _native.TCS_GDN))
+                i += 1
+        plan = (key, steps)
+        self._plan = plan
+        return plan
+
+    @torch.no_grad()
+    def __call__(self, x, medians=None, out='nchw'):
+        """x: fp32 NCHW, or split planes (hi, lo) [B, H, W, C].  out: 'symbols' (the last layer must be a Conv2d; int32 NCHW,
+        round(y - medians)) | 'nchw' (fp32) | 'planes' (hi, lo)."""
+        planes_in = isinstance(x, tuple)
+        _, steps = self._prepare(planes_in)
+        T = _native
+        h = l = None
+        if planes_in:
+            h, l = x
+        elif steps[0][6] is None:  # an fp32 NCHW activation (not an image): split NHWC planes
+            h, l = ops.split_f16(x.permute(0, 2, 3, 1))
+        for si, step in enumerate(steps):
+            last = si == len(steps) - 1
+            if step[0] == 'conv':
+                _, m, tiles, bias, act, slope, k_pad = step
+                k, st, pad = m.kernel_size[0], m.stride[0], m.padding[0]
+                mode = T.TCS_QUANT if (last and out == 'symbols') else T.TCS_STORE
+                med = medians if mode == T.TCS_QUANT else None
+                if k_pad is not None:
+                    ph, pl = ops.patchify_split_nhwc(x, k, k, st, pad, k_pad)
+                    res = ops.tc_split_conv_tiled(ph, pl, tiles, 1, 1, 1, 0, mode, vec=bias, medians=med, act=act, slope=slope,
+                                                  name='tcs_conv_first')
+                else:
+                    res = ops.tc_split_conv_tiled(h, l, tiles, k, k, st, pad, mode, vec=bias, medians=med, act=act, slope=slope,
+                                                  in_nhwc=st == 2, name='tcs_conv')
+                if mode == T.TCS_QUANT:
+                    return res
+                h, l = res
+            else:
+                _, m, tiles, beta, mode = step
+                h, l = ops.tc_split_conv_tiled(h, l, tiles, 1, 1, 1, 0, mode, vec=beta, gdn_x=(h, l), name='tcs_gdn')
+        if out == 'symbols':
+            raise NotImplementedError('the transform does not end with a convolution')
+        if out == 'planes':
+            return h, l
+        c_out = [st for st in steps if st[0] == 'conv'][-1][1].out_channels
+        return ops.unsplit_to_nchw(h, l, c_out)
+
+
+def run_analysis(model, name, seq, x, medians=None, out='nchw', in_abs=False):
+    """g_a / h_a of a zoo codec: the split tensor-core plan when it covers `seq` (and model.encoder_precision allows), else the fp32
+    CUDA-core kernels (logged once).  x: fp32 NCHW, or split planes (hi, lo) [B, H, W, C] from a previous plan."""
+    planes_in = isinstance(x, tuple)
+    shape = (x[0].shape[3], x[0].shape[1], x[0].shape[2]) if planes_in else tuple(x.shape[-3:])
+    prec = getattr(model, 'encoder_precision', 'split-tc')
+    why = 'encoder_precision = %r' % prec if prec != 'split-tc' else SplitAnalysisPlan.why_not(seq, shape, planes_in=planes_in)
+    if why is None:
+        plans = model.__dict__.setdefault('_tc_analysis', {})
+        plan = plans.get(name)
+        if plan is None:
+            plan = plans[name] = SplitAnalysisPlan(seq)
+        if in_abs:
+            x = ops.abs_split(*x) if planes_in else torch.abs(x)
+        return plan(x, medians=medians, out=out)
+    _warn_fp32(model, name, why)
+    if planes_in:
+        c = list(seq)[0].in_channels
+        x = ops.unsplit_to_nchw(x[0], x[1], c)
+    if out == 'symbols':
+        return run_transform(seq, x, final_epilogue=_native.EPI_QUANTIZE, final_aux=medians, in_abs=in_abs)
+    y = run_transform(seq, x, in_abs=in_abs)
+    if out == 'planes':
+        c = y.shape[1]
+        return ops.split_f16(torch.nn.functional.pad(y.permute(0, 2, 3, 1), (0, -c % 8)))
+    return y
+
+
 class ZooSynthesisPlan:
     """g_s of the CompressAI zoo codecs (deconv - IGDN - deconv - IGDN - deconv - IGDN - deconv, compressai.models.google [mem];
     reached from sc2bench/models/wrapper.py:130) on the tcgen05 kernels, fp16 operands / fp32 accumulation like the bottleneck's
@@ -267,13 +422,17 @@ def run_synthesis(model, seq, y_hat):
             plan = ZooSynthesisPlan(seq)
             model.__dict__['_tc_synthesis'] = plan
         return plan(y_hat)
-    key = (type(model).__name__, why)
+    _warn_fp32(model, 'g_s', why)
+    return run_transform(seq, y_hat, final_epilogue=_native.EPI_CLAMP01)
+
+
+def _warn_fp32(model, name, why):
+    key = (type(model).__name__, name, why)
     if key not in _warned_fallback:
         _warned_fallback.add(key)
         import logging
-        logging.getLogger('sc2bench_b200').warning('%s.g_s runs on the fp32 CUDA-core kernels (conv2d_f32_kernel), not on the tensor cores: %s',
-                                                    type(model).__name__, why)
-    return run_transform(seq, y_hat, final_epilogue=_native.EPI_CLAMP01)
+        logging.getLogger('sc2bench_b200').warning('%s.%s runs on the fp32 CUDA-core kernels (conv2d_f32_kernel), not on the tensor cores: %s',
+                                                    type(model).__name__, name, why)
 
 
 class FactorizedPrior(CompressionModel):
@@ -300,7 +459,7 @@ class FactorizedPrior(CompressionModel):
     def compress_packed(self, x):
         eb = self.entropy_bottleneck
         medians = eb._get_medians().detach().reshape(-1)
-        symbols = run_transform(self.g_a, x, final_epilogue=_native.EPI_QUANTIZE, final_aux=medians)
+        symbols = run_analysis(self, 'g_a', self.g_a, x, medians=medians, out='symbols')
         return eb.compress_symbols(symbols, spatial=symbols[0, 0].numel()), symbols.size()[-2:]
 
     def compress(self, x):
@@ -348,9 +507,10 @@ class ScaleHyperprior(CompressionModel):
     @torch.no_grad()
     def compress(self, x):
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
-        y = run_transform(self.g_a, x)
-        z_symbols = run_transform(self.h_a, torch.abs(y), final_epilogue=_native.EPI_QUANTIZE,
-                                  final_aux=eb._get_medians().detach().reshape(-1))
+        y_planes = run_analysis(self, 'g_a', self.g_a, x, out='planes')
+        y = ops.unsplit_to_nchw(y_planes[0], y_planes[1], self.M)
+        z_symbols = run_analysis(self, 'h_a', self.h_a, y_planes, medians=eb._get_medians().detach().reshape(-1), out='symbols',
+                                 in_abs=True)
         z_streams = eb.compress_symbols(z_symbols, spatial=z_symbols[0, 0].numel())
         # the encoder decodes z itself so that both sides derive the scales from identical values
         z_hat = eb.decompress_packed(z_streams, tuple(z_symbols.size()[-2:]))

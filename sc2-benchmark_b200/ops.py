@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _native
-from ._native import ConvDesc, GaHaloDesc, TcConvDesc, TcConvExDesc, TcSplitDesc, check
+from ._native import ConvDesc, GaHaloDesc, TcConvDesc, TcConvExDesc, TcSplitDesc, TcSplitExDesc, check
 
 
 def _lib():
@@ -573,6 +573,94 @@ def tc_split_conv(x_hi, x_lo, w_hi, w_lo, c_out, kh, kw, stride, pad, mode, beta
                                        _ptr(x_hi) if gdn else None, _ptr(x_lo) if gdn else None, _ptr(out_hi), _ptr(out_lo),
                                        _ptr(out_sym), _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_split_conv')
     return out_sym if mode == _native.TCS_QUANT else (out_hi, out_lo)
+
+
+def patchify_split_nhwc(x, kh, kw, stride, pad, k_pad):
+    """fp32 NCHW image -> split fp16 patches [B, h_out, w_out, k_pad], pixels in plain NHWC order (sc2_patchify_split_nhwc)."""
+    require_cuda(x, 'patchify_split_nhwc')
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    ho, wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    hi = torch.empty((B, ho, wo, k_pad), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(x.device), _launch('patchify_split', nbytes=4.0 * (x.numel() + hi.numel())):
+        check(_lib().sc2_patchify_split_nhwc(_ptr(x), _ptr(hi), _ptr(lo), B, C, H, W, kh, kw, stride, pad, k_pad, _stream_ptr()),
+              'sc2_patchify_split_nhwc')
+    return hi, lo
+
+
+def split_n_tiles(c_out):
+    """Output-channel tiles [(first channel, channels)] of a layer wider than one tensor-core tile (sc2_tc_split_conv_ex): equal
+    tiles of the largest size <= 128 that divides c_out into multiples of 16, else 128s and a remainder."""
+    if c_out <= 128:
+        return [(0, c_out)]
+    for n in (128, 96, 64, 48, 32):
+        if c_out % n == 0 and c_out // n <= 3:
+            return [(i * n, n) for i in range(c_out // n)]
+    tiles, c0 = [], 0
+    while c0 < c_out:
+        n = min(128, c_out - c0)
+        tiles.append((c0, n))
+        c0 += n
+    return tiles
+
+
+def pack_conv_weight_split_tiles(weight, c_in_pad=None, as_patches=False):
+    """pack_conv_weight_split per output-channel tile: [(first channel, channels, w_hi, w_lo)]."""
+    return [(c0, n) + pack_conv_weight_split(weight[c0:c0 + n], c_in_pad=c_in_pad, as_patches=as_patches)
+            for c0, n in split_n_tiles(weight.shape[0])]
+
+
+def tc_split_conv_tiled(x_hi, x_lo, tiles, kh, kw, stride, pad, mode, vec=None, medians=None, gdn_x=None, act=_native.TCS_ACT_NONE,
+                        slope=0.0, in_nhwc=False, name='tc_split'):
+    """sc2_tc_split_conv_ex over the output-channel tiles of pack_conv_weight_split_tiles (one launch per tile, all writing the same
+    planes).  x planes: [images, H, W, C] (stride 1, or stride 2 with in_nhwc) or parity planes [images * 4, H/2, W/2, C].
+    vec: bias (STORE / QUANT) or GDN beta, the full vector; gdn_x: (hi, lo) planes of x for the GDN modes.
+    Returns (hi, lo) planes [images, h_out, w_out, ceil8(c_out)], or int32 symbols [images, c_out, h_out, w_out] (TCS_QUANT)."""
+    require_cuda(x_hi, 'tc_split_conv_tiled')
+    n_img_planes, H, W, C = x_hi.shape
+    planes = 4 if (stride == 2 and not in_nhwc) else 1
+    images = n_img_planes // planes
+    if stride == 2 and not in_nhwc:
+        ho, wo = (2 * H + 2 * pad - kh) // 2 + 1, (2 * W + 2 * pad - kw) // 2 + 1
+    else:
+        ho, wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    c_out = tiles[-1][0] + tiles[-1][1]
+    dev = x_hi.device
+    out_hi = out_lo = out_sym = None
+    pitch = (c_out + 7) // 8 * 8
+    if mode == _native.TCS_QUANT:
+        out_sym = torch.empty((images, c_out, ho, wo), dtype=torch.int32, device=dev)
+    else:
+        out_hi = torch.empty((images, ho, wo, pitch), dtype=torch.float16, device=dev)
+        out_lo = torch.empty_like(out_hi)
+    v = vec.detach().contiguous().float() if vec is not None else None
+    m = medians.detach().contiguous().float() if medians is not None else None
+    gx_hi, gx_lo = gdn_x if gdn_x is not None else (None, None)
+    if gx_hi is not None and (gx_hi.shape[-1] != pitch or tuple(gx_hi.shape[:3]) != (images, ho, wo)):
+        raise ValueError('gdn_x planes %s do not match the output planes' % (tuple(gx_hi.shape),))
+    for c0, n, w_hi, w_lo in tiles:
+        d = TcSplitExDesc(images, H, W, C, n, kh, kw, stride, pad, mode, ho, wo, pitch, c0, c_out, 1 if in_nhwc else 0, act, float(slope))
+        tag = '%s[%d->%d/%d,k%d,s%d,m%d]' % (name, C, n, c_out, kh, stride, mode)
+        flops = 2.0 * images * ho * wo * n * C * kh * kw
+        nbytes = 4.0 * (x_hi.numel() + images * ho * wo * n)
+        with torch.cuda.device(dev), _launch(tag, flops=flops, nbytes=nbytes):
+            check(_lib().sc2_tc_split_conv_ex(ctypes.byref(d), _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), _ptr(v), _ptr(m),
+                                              _ptr(gx_hi), _ptr(gx_lo), _ptr(out_hi), _ptr(out_lo), _ptr(out_sym),
+                                              _TILE_COUNTERS.next(), _stream_ptr()), 'sc2_tc_split_conv_ex')
+    return out_sym if mode == _native.TCS_QUANT else (out_hi, out_lo)
+
+
+def unsplit_to_nchw(hi, lo, channels):
+    """split planes [B, H, W, C_pad] -> fp32 NCHW [B, channels, H, W] (value = hi + lo / 2048)"""
+    y = torch.add(hi[..., :channels].float(), lo[..., :channels].float(), alpha=1.0 / LO_SCALE)
+    return y.permute(0, 3, 1, 2).contiguous()
+
+
+def abs_split(hi, lo):
+    """|a| of split planes: |hi|, lo with the sign of hi folded in (a = hi + lo / 2048; hi = 0 leaves |lo|)"""
+    neg = (hi < 0) | ((hi == 0) & (lo < 0))
+    return hi.abs(), torch.where(neg, -lo, lo)
 
 
 def tc_first_layer(x, w_hi, w_lo, c_out, kh, kw, pad):

@@ -310,3 +310,73 @@ def test_tc_inverse_gdn_on_square_pair(s2, C, H, W):
                       vec=beta.to(dev), gdn_x=x_nhwc, c_out=C, c_in=C)
     got = out.float().permute(0, 3, 1, 2).cpu()
     assert rel_err(got, ref) < 1.5e-3, rel_err(got, ref)
+
+
+# ---- sc2_tc_split_conv_ex: N tiles, NHWC stride-2 input, bias / activation, GDN proper (zoo g_a / h_a) ----------------------
+@pytest.mark.parametrize('cin,cout,k,stride,pad,H,W,act', [(192, 192, 5, 2, 2, 32, 32, 0), (192, 320, 5, 2, 2, 16, 24, 0), (320, 192, 3, 1, 1, 16, 16, 1),
+                                                           (32, 200, 5, 2, 2, 10, 14, 2), (64, 48, 3, 2, 1, 12, 20, 0), (16, 144, 1, 1, 0, 7, 9, 1)])
+def test_tc_split_conv_ex_tiles_bias_activation(s2, cin, cout, k, stride, pad, H, W, act):
+    dev = torch.device('cuda:0')
+    torch.manual_seed(cin + cout + H + act)
+    x = torch.randn(2, cin, H, W) * 2
+    w = torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5
+    b = torch.randn(cout)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride, pad)
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = F.leaky_relu(ref, 0.2)
+    xh, xl = _planes(s2, x, dev)  # plain NHWC, also for the stride-2 layers
+    tiles = s2.ops.pack_conv_weight_split_tiles(w.to(dev))
+    assert sum(t[1] for t in tiles) == cout and all(t[1] <= 128 for t in tiles)
+    oh, ol = s2.ops.tc_split_conv_tiled(xh, xl, tiles, k, k, stride, pad, s2._native.TCS_STORE, vec=b.to(dev), act=act, slope=0.2,
+                                        in_nhwc=stride == 2)
+    assert oh.shape[-1] == (cout + 7) // 8 * 8
+    got = _unsplit(oh, ol)[:, :cout]
+    assert got.shape == ref.shape
+    assert rel_err(got, ref.float()) < SPLIT_TOL, rel_err(got, ref.float())
+    if act == 0:
+        med = torch.randn(cout)
+        sym = s2.ops.tc_split_conv_tiled(xh, xl, tiles, k, k, stride, pad, s2._native.TCS_QUANT, vec=b.to(dev), medians=med.to(dev),
+                                         in_nhwc=stride == 2)
+        want = torch.round(ref.float() - med.view(1, -1, 1, 1)).int()
+        assert sym.shape == want.shape
+        assert int((sym.cpu() != want).sum()) <= max(1, want.numel() // 100000)  # ties at fp32 resolution only
+
+
+@pytest.mark.parametrize('C,H,W,kind', [(192, 32, 32, 'gdn'), (192, 9, 11, 'gdn'), (128, 16, 16, 'gdn'), (320, 8, 8, 'gdn'), (192, 12, 12, 'gdn1'),
+                                        (48, 20, 12, 'gdn')])
+def test_tc_split_gdn_proper_and_tiled(s2, C, H, W, kind):
+    """GDN of the zoo codecs: y = x / sqrt(beta + gamma . x^2), squares formed in shared memory; N-tiled over 192 / 320 channels."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(C + H)
+    x = torch.randn(2, C, H, W) * 3
+    x[0, :, 0, 0] = 1e-4 * torch.randn(C)  # tiny activations: x^2 under fp16's normal range
+    gamma = 0.1 * torch.eye(C) + 0.02 * torch.rand(C, C)
+    beta = 0.5 + torch.rand(C)
+    if kind == 'gdn':
+        norm = torch.sqrt(F.conv2d(x.double() ** 2, gamma.double().view(C, C, 1, 1), beta.double()))
+    else:
+        norm = F.conv2d(x.double().abs(), gamma.double().view(C, C, 1, 1), beta.double())
+    ref = (x.double() / norm).float()
+    xh, xl = _planes(s2, x, dev)
+    tiles = s2.ops.pack_conv_weight_split_tiles(gamma.view(C, C, 1, 1).to(dev))
+    mode = s2._native.TCS_GDN if kind == 'gdn' else s2._native.TCS_GDN1
+    oh, ol = s2.ops.tc_split_conv_tiled(xh, xl, tiles, 1, 1, 1, 0, mode, vec=beta.to(dev), gdn_x=(xh, xl))
+    assert rel_err(_unsplit(oh, ol)[:, :C], ref) < SPLIT_TOL
+
+
+def test_patchify_nhwc_and_abs_split(s2):
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 37, 44)
+    hi, lo = s2.ops.patchify_split_nhwc(x.to(dev), 5, 5, 2, 2, 80)
+    got = (hi.float() + lo.float() / 2048.0).cpu()
+    cols = F.unfold(x, 5, padding=2, stride=2).view(2, 75, 19, 22).permute(0, 2, 3, 1)
+    assert got.shape == (2, 19, 22, 80)
+    assert float((got[..., :75] - cols).abs().max()) < 1e-6 and float(got[..., 75:].abs().max()) == 0.0
+    a = torch.randn(4, 5, 6, 16) * torch.tensor([1.0, 1e-9, 1e-3, 50.0]).view(4, 1, 1, 1)
+    h, l = s2.ops.split_f16(a.to(dev))
+    ah, al = s2.ops.abs_split(h, l)
+    assert torch.equal(ah.float() + al.float() / 2048.0, (h.float() + l.float() / 2048.0).abs())
+    assert float(ah.min()) >= 0
