@@ -276,7 +276,11 @@ SC2_API int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, cons
  *               read through a 5-D tensor map (pixel parity as a coordinate) -- no parity-plane re-layout between two stride-2 layers
  *   vec         modes 0 / 2: the convolution's bias (or NULL), added before act / the quantiser; modes 1 / 3: the GDN beta
  *   act         mode 0: 0 none | 1 ReLU | 2 LeakyReLU(slope)
- *   mode 3      GDN proper: y = x / sqrt(beta + gamma . x^2) (1x1: w = gamma, the squares are formed in shared memory) */
+ *   mode 3      GDN proper: y = x / sqrt(beta + gamma . x^2) (1x1: w = gamma, the squares are formed in shared memory)
+ *   pad_x       horizontal padding when it differs from pad (< 0: pad_x = pad)
+ *   out_stride  2 (mode 0, stride 1): the h_out x w_out results are the pixels (2Y + out_py, 2X + out_px) of planes
+ *               [images, 2 h_out, 2 w_out, out_pitch] -- one of the four stride-1 sub-convolutions of a ConvTranspose2d(k5, s2, p2, op1)
+ *               (hyper-synthesis h_s, sc2bench/models/layer.py:611-617; taps as in sc2_tc_conv_ex) */
 #define SC2_TCS_GDN 3
 #define SC2_TCS_ACT_NONE 0
 #define SC2_TCS_ACT_RELU 1
@@ -291,6 +295,8 @@ typedef struct sc2_tc_split_ex_desc {
     int in_nhwc;
     int act;
     float slope;
+    int pad_x;
+    int out_stride, out_py, out_px;
 } sc2_tc_split_ex_desc;
 
 SC2_API int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const void *x_lo, const void *w_hi,

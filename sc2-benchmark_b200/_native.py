@@ -32,7 +32,8 @@ class TcSplitDesc(_c.Structure):
 class TcSplitExDesc(_c.Structure):
     """struct sc2_tc_split_ex_desc"""
     _fields_ = [(n, i32) for n in ('images', 'h_in', 'w_in', 'c_in', 'c_out', 'kh', 'kw', 'stride', 'pad', 'mode', 'h_out', 'w_out',
-                                    'out_pitch', 'n_off', 'c_total', 'in_nhwc', 'act')] + [('slope', _c.c_float)]
+                                    'out_pitch', 'n_off', 'c_total', 'in_nhwc', 'act')] + [('slope', _c.c_float)] + \
+               [(n, i32) for n in ('pad_x', 'out_stride', 'out_py', 'out_px')]
 
 
 class TcConvExDesc(_c.Structure):

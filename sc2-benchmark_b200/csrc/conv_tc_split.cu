@@ -66,6 +66,7 @@ struct Params {
     int sym_c_off;
     int act;            // STORE: activation after the bias (ReLU / LeakyReLU of the hyper-analysis h_a)
     float slope;
+    int out5d, out_py;  // the tile goes to the pixels of row parity out_py of a 2x larger tensor (transposed-convolution sub-grid)
 };
 
 // B_RES: 1x1 convolutions (one tap, <= 2 K chunks) keep the whole weight matrix resident in shared memory for the life of
@@ -375,8 +376,13 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 fence_proxy_async();
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (issuer) {
-                    tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
-                    tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
+                    if (p.out5d) {
+                        tma_store_5d(&map_o_hi, st_hi, 0, x0, p.out_py, y0, img);
+                        tma_store_5d(&map_o_lo, st_lo, 0, x0, p.out_py, y0, img);
+                    } else {
+                        tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
+                        tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
+                    }
                     tma_store_commit();
                 }
             }
@@ -533,6 +539,10 @@ int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const 
     if (d->mode == MODE_QUANT && (d->c_total < d->n_off + d->c_out)) return SC2_ERR_INVALID_ARG;
     if (d->in_nhwc && (d->stride != 2 || (d->h_in & 1) || (d->w_in & 1))) return SC2_ERR_UNSUPPORTED;
     if (d->act < ACT_NONE || d->act > ACT_LEAKY) return SC2_ERR_INVALID_ARG;
+    const bool interleave = d->out_stride == 2;
+    if (d->out_stride != 1 && d->out_stride != 2) return SC2_ERR_INVALID_ARG;
+    if (interleave && (d->mode != MODE_STORE_SPLIT || d->stride != 1 || (d->out_py | d->out_px) & ~1)) return SC2_ERR_INVALID_ARG;
+    const int pad_x = d->pad_x < 0 ? d->pad : d->pad_x;
     // channels of the output planes this launch owns: [n_off, n_off + out_ext); a launch that does not reach the end of the
     // pixel (an inner N tile) must fill its tile completely
     int out_ext = 0;
@@ -559,7 +569,7 @@ int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const 
     for (int dy = 0; dy < d->kh; ++dy)
         for (int dx = 0; dx < d->kw; ++dx) {
             Tap t;
-            const int sy = dy - d->pad, sx = dx - d->pad;
+            const int sy = dy - d->pad, sx = dx - pad_x;
             if (d->stride == 2) {
                 const int py = ((sy % 2) + 2) % 2, px = ((sx % 2) + 2) % 2;
                 t.plane = static_cast<int8_t>(py * 2 + px);
@@ -586,10 +596,16 @@ int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const 
         p.groups = groups;
     }
     p.c_out = d->c_out;
+    p.out5d = interleave ? 1 : 0;
+    p.out_py = d->out_py;
     p.beta = vec ? vec + d->n_off : nullptr;
     p.medians = medians ? medians + d->n_off : nullptr;
     __half *o_hi = static_cast<__half *>(out_hi), *o_lo = static_cast<__half *>(out_lo);
-    if (o_hi) { o_hi += d->n_off; o_lo += d->n_off; }
+    if (o_hi) {
+        const int shift = d->n_off + (interleave ? d->out_px * d->out_pitch : 0);
+        o_hi += shift;
+        o_lo += shift;
+    }
     p.out_hi = o_hi; p.out_lo = o_lo;
     p.out_c = out_ext;
     p.stage_c = (out_ext / 8) % 2 == 0 ? out_ext + 8 : out_ext;  // odd number of 16-byte units per staging row
@@ -631,11 +647,17 @@ int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const 
         // dense (unswizzled) boxes {stage_c, tw, th, 1}: bulk-store sources / x-tile destinations in the staging buffer; the
         // box is wider than the tensor view when the row pitch is padded (channels beyond the view: skipped / zero-filled)
         const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-        rc = make_nhwc_map_pitch(&maps[4], o_hi, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
-                                 CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc) return rc;
-        rc = make_nhwc_map_pitch(&maps[5], o_lo, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
-                                 CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (interleave) {
+            rc = make_nhwc_parity_out_map(&maps[4], o_hi, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th);
+            if (rc) return rc;
+            rc = make_nhwc_parity_out_map(&maps[5], o_lo, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th);
+        } else {
+            rc = make_nhwc_map_pitch(&maps[4], o_hi, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+            rc = make_nhwc_map_pitch(&maps[5], o_lo, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE);
+        }
         if (rc) return rc;
         if (gdn) {
             rc = make_nhwc_map_pitch(&maps[6], gx_hi, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
@@ -668,6 +690,7 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     e.mode = d->mode;
     e.h_out = d->h_out; e.w_out = d->w_out;
     e.out_pitch = d->out_c; e.n_off = 0; e.c_total = d->c_out; e.in_nhwc = 0; e.act = 0; e.slope = 0.0f;
+    e.pad_x = -1; e.out_stride = 1; e.out_py = 0; e.out_px = 0;
     return sc2_tc_split_conv_ex(&e, x_hi, x_lo, w_hi, w_lo, beta, medians, gdn_x_hi, gdn_x_lo, out_hi, out_lo, out_sym, tile_counter,
                                 stream);
 }

@@ -157,6 +157,7 @@ class SplitAnalysisPlan:
         Conv2d(k <= 5, stride 1 | 2) with bias, optional ReLU / LeakyReLU in the epilogue; stride-2 layers read the NHWC planes of the
             layer before through a 5-D tensor map (pixel parity = a coordinate), layers wider than 128 channels run as N tiles
         GDN / GDN1: a 1x1 gamma GEMM on x^2 / |x| formed in shared memory, y = x * rsqrt(beta + acc) / x / (beta + acc)
+        ConvTranspose2d(k5, s2, p2, op1) (hyper-synthesis h_s): 4 parity sub-convolutions writing interleaved pixels
         the last conv can quantise straight to coder symbols (round(y + bias - median), NCHW order)."""
 
     def __init__(self, seq):
@@ -167,12 +168,20 @@ class SplitAnalysisPlan:
     def why_not(seq, x_shape, planes_in=False):
         """None when the plan covers `seq` for an input of shape x_shape (NCHW), else the reason."""
         mods = list(seq)
-        if not mods or not isinstance(mods[0], nn.Conv2d):
-            return 'does not start with a Conv2d'
+        if not mods or not isinstance(mods[0], (nn.Conv2d, nn.ConvTranspose2d)):
+            return 'does not start with a convolution'
         C, H, W = x_shape[-3:]
         prev_conv = False
         for i, m in enumerate(mods):
-            if isinstance(m, nn.Conv2d):
+            if isinstance(m, nn.ConvTranspose2d):
+                if (tuple(m.kernel_size), tuple(m.stride), tuple(m.padding), tuple(m.output_padding), m.groups, tuple(m.dilation)) != \
+                        ((5, 5), (2, 2), (2, 2), (1, 1), 1, (1, 1)):
+                    return 'transposed convolution %d is not (k5, s2, p2, op1)' % i
+                if m.in_channels != C or C % 16:
+                    return 'transposed convolution %d: c_in %d' % (i, C)
+                H, W, C = 2 * H, 2 * W, m.out_channels
+                prev_conv = True
+            elif isinstance(m, nn.Conv2d):
                 k, st = m.kernel_size[0], m.stride[0]
                 if (m.groups != 1 or tuple(m.dilation) != (1, 1) or m.kernel_size[0] != m.kernel_size[1] or isinstance(m.padding, str)
                         or m.padding[0] != m.padding[1] or m.stride[0] != m.stride[1] or st not in (1, 2) or k > 5
@@ -214,17 +223,20 @@ class SplitAnalysisPlan:
         i = 0
         while i < len(mods):
             m = mods[i]
-            if isinstance(m, nn.Conv2d):
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
                 act, slope = _native.TCS_ACT_NONE, 0.0
                 if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
                     act = _native.TCS_ACT_RELU
                 elif i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU):
                     act, slope = _native.TCS_ACT_LEAKY, mods[i + 1].negative_slope
-                patches = i == 0 and not planes_in and m.in_channels * m.kernel_size[0] ** 2 <= 128
-                k_pad = (m.in_channels * m.kernel_size[0] ** 2 + 15) // 16 * 16 if patches else None
-                tiles = ops.pack_conv_weight_split_tiles(m.weight, c_in_pad=k_pad, as_patches=patches)
                 bias = m.bias.detach().float().contiguous() if m.bias is not None else None
-                steps.append(('conv', m, tiles, bias, act, slope, k_pad))
+                if isinstance(m, nn.ConvTranspose2d):
+                    steps.append(('deconv', m, ops.pack_deconv5_weight_split_tiles(m.weight), bias, act, slope, None))
+                else:
+                    patches = i == 0 and not planes_in and m.in_channels * m.kernel_size[0] ** 2 <= 128
+                    k_pad = (m.in_channels * m.kernel_size[0] ** 2 + 15) // 16 * 16 if patches else None
+                    tiles = ops.pack_conv_weight_split_tiles(m.weight, c_in_pad=k_pad, as_patches=patches)
+                    steps.append(('conv', m, tiles, bias, act, slope, k_pad))
                 i += 2 if act != _native.TCS_ACT_NONE else 1
             else:
                 gamma, beta = m.effective_params()
@@ -265,6 +277,17 @@ class SplitAnalysisPlan:
                 if mode == T.TCS_QUANT:
                     return res
                 h, l = res
+            elif step[0] == 'deconv':
+                _, m, packs, bias, act, slope, _ = step
+                B, H, W, _ = h.shape
+                pitch = (m.out_channels + 7) // 8 * 8
+                out = (torch.empty((B, 2 * H, 2 * W, pitch), dtype=torch.float16, device=h.device),
+                       torch.empty((B, 2 * H, 2 * W, pitch), dtype=torch.float16, device=h.device))
+                for (py, px), tiles in packs.items():
+                    (ky, pad_y), (kx, pad_x) = ops.DECONV5_TAPS[py], ops.DECONV5_TAPS[px]
+                    ops.tc_split_conv_tiled(h, l, tiles, len(ky), len(kx), 1, pad_y, T.TCS_STORE, vec=bias, act=act, slope=slope,
+                                            pad_x=pad_x, out=out, out_parity=(py, px), name='tcs_deconv5')
+                h, l = out
             else:
                 _, m, tiles, beta, mode = step
                 h, l = ops.tc_split_conv_tiled(h, l, tiles, 1, 1, 1, 0, mode, vec=beta, gdn_x=(h, l), name='tcs_gdn')
@@ -272,7 +295,7 @@ class SplitAnalysisPlan:
             raise NotImplementedError('the transform does not end with a convolution')
         if out == 'planes':
             return h, l
-        c_out = [st for st in steps if st[0] == 'conv'][-1][1].out_channels
+        c_out = [st for st in steps if st[0] in ('conv', 'deconv')][-1][1].out_channels
         return ops.unsplit_to_nchw(h, l, c_out)
 
 
@@ -514,7 +537,7 @@ class ScaleHyperprior(CompressionModel):
         z_streams = eb.compress_symbols(z_symbols, spatial=z_symbols[0, 0].numel())
         # the encoder decodes z itself so that both sides derive the scales from identical values
         z_hat = eb.decompress_packed(z_streams, tuple(z_symbols.size()[-2:]))
-        indexes = gc.build_indexes(run_transform(self.h_s, z_hat))
+        indexes = gc.build_indexes(run_analysis(self, 'h_s', self.h_s, z_hat))
         y_symbols = ops.quantize_symbols(y.reshape(y.size(0), 1, -1))
         y_streams = ops.rans_encode(y_symbols, gc.coder_tables(), indexes=indexes)
         return {'strings': [y_streams.tolist(), z_streams.tolist()], 'shape': z_symbols.size()[-2:]}
@@ -525,7 +548,7 @@ class ScaleHyperprior(CompressionModel):
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         device = eb._quantized_cdf.device
         z_hat = eb.decompress_packed(ops.PackedStreams.from_list(strings[1], device), tuple(shape), check_status=True)
-        indexes = gc.build_indexes(run_transform(self.h_s, z_hat))
+        indexes = gc.build_indexes(run_analysis(self, 'h_s', self.h_s, z_hat))
         y_streams = ops.PackedStreams.from_list(strings[0], device)
         y_hat = ops.rans_decode(y_streams, indexes[0].numel(), gc.coder_tables(), indexes=indexes, want='values')
         return {'x_hat': run_synthesis(self, self.g_s, y_hat.view(indexes.size()))}

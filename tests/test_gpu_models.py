@@ -82,7 +82,7 @@ def test_neural_input_compression_classifier_q8(s2, oracle_compressai, arch):
         y_want = ref.g_a(xp)
     assert rel_err(y_got, y_want) < LATENT_TOL
     # ... and on the route compress() takes: the split tensor-core plan (no fp32 CUDA-core fallback for g_a / h_a)
-    assert 'g_a' in codec.__dict__['_tc_analysis'] and (arch == 'bmshj2018_factorized' or 'h_a' in codec.__dict__['_tc_analysis'])
+    assert set(codec.__dict__['_tc_analysis']) == ({'g_a'} if arch == 'bmshj2018_factorized' else {'g_a', 'h_a', 'h_s'})
     y_tc = s2.models.run_analysis(codec, 'g_a', codec.g_a, xp.to(dev)).cpu()
     assert rel_err(y_tc, y_want) < LATENT_TOL
     # (2) the last string list is the EntropyBottleneck stream (y for factorized, z for the hyperprior): decode both sides'

@@ -380,3 +380,33 @@ def test_patchify_nhwc_and_abs_split(s2):
     ah, al = s2.ops.abs_split(h, l)
     assert torch.equal(ah.float() + al.float() / 2048.0, (h.float() + l.float() / 2048.0).abs())
     assert float(ah.min()) >= 0
+
+
+@pytest.mark.parametrize('cin,cout,H,W,act', [(192, 192, 4, 4, 1), (192, 192, 8, 12, 1), (64, 200, 5, 7, 2), (16, 24, 9, 3, 0)])
+def test_tc_split_deconv5_matches_fp64(s2, cin, cout, H, W, act):
+    """ConvTranspose2d(k5, s2, p2, op1) + bias + activation in split precision (h_s of the scale-hyperprior codec): four parity
+    sub-convolutions writing interleaved pixels through a 5-D tensor map."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(cin + cout + H)
+    x = torch.randn(2, cin, H, W) * 2
+    w = torch.randn(cin, cout, 5, 5) / (cin * 6.25) ** 0.5
+    b = torch.randn(cout)
+    ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2, padding=2, output_padding=1)
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = F.leaky_relu(ref, 0.01)
+    xh, xl = _planes(s2, x, dev)
+    packs = s2.ops.pack_deconv5_weight_split_tiles(w.to(dev))
+    pitch = (cout + 7) // 8 * 8
+    out = (torch.full((2, 2 * H, 2 * W, pitch), float('nan'), dtype=torch.float16, device=dev),
+           torch.full((2, 2 * H, 2 * W, pitch), float('nan'), dtype=torch.float16, device=dev))
+    for (py, px), tiles in packs.items():
+        (ky, pad_y), (kx, pad_x) = s2.ops.DECONV5_TAPS[py], s2.ops.DECONV5_TAPS[px]
+        s2.ops.tc_split_conv_tiled(xh, xl, tiles, len(ky), len(kx), 1, pad_y, s2._native.TCS_STORE, vec=b.to(dev), act=act, slope=0.01,
+                                   pad_x=pad_x, out=out, out_parity=(py, px))
+    got = _unsplit(*out)
+    assert not torch.isnan(got).any()
+    assert got[:, :cout].shape == ref.shape
+    assert rel_err(got[:, :cout], ref.float()) < SPLIT_TOL, rel_err(got[:, :cout], ref.float())
+    assert float(got[:, cout:].abs().max()) == 0.0 if pitch > cout else True
