@@ -21,7 +21,12 @@ namespace sc2 {
 namespace {
 
 constexpr uint64_t kL = 1ull << 31;
-constexpr int kRingWords = 64;
+// Decoder word ring: 4 blocks of 32 words.  Crossing into block B waits for every refill issued so far (words < B + 64 are then
+// in shared memory) and requests [B + 64, B + 96) into the block just left: any word up to 32 ahead of the read position is
+// always valid, so the hot loop may look two words ahead and may notice a crossing a few words late.
+constexpr int kRingWords = 128;
+constexpr uint32_t kRefillAhead = 64;
+constexpr int kSpecGroup = 8;   // symbols decoded speculatively per group (see the hot loop)
 
 struct Tables {
     const int32_t *sizes, *offsets, *dec;
@@ -232,7 +237,7 @@ __device__ __noinline__ void dec_refill(const uint32_t *words, uint32_t n_words,
 // consume next_w and fetch the following word from the ring
 __device__ __forceinline__ void dec_advance_word(DecChain &s, const DecStream &st, int lane) {
     ++s.p;
-    if (__builtin_expect((s.p & 31u) == 0u, 0)) dec_refill(st.words, st.n_words, st.ring, s.p + 32u, lane);
+    if (__builtin_expect((s.p & 31u) == 0u, 0)) dec_refill(st.words, st.n_words, st.ring, s.p + kRefillAhead, lane);
     s.next_w = st.ring[s.p & (kRingWords - 1)];
 }
 
@@ -351,6 +356,7 @@ rans_decode_fast_kernel(const uint8_t *__restrict__ packed, const int64_t *__res
     st.ring = s_ring;
     ring_fill(st, 0, lane);
     ring_fill(st, 32, lane);
+    ring_fill(st, 64, lane);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     DecChain s;
@@ -373,6 +379,7 @@ rans_decode_fast_kernel(const uint8_t *__restrict__ packed, const int64_t *__res
         // speculation state: the last regular symbol decoded in this row (freq 0 = nothing yet -> first symbol misses)
         uint32_t sp_start = 0, sp_freq = 0;
         int32_t sp_value = 0;
+        int streak = 0;  // symbols since the last speculation miss (run mode from kSpecGroup on)
         for (uint32_t base = 0; base < row_n; base += 32) {
             const int cnt = (row_n - base) >= 32 ? 32 : static_cast<int>(row_n - base);
             // ---- hot loop: nothing but the hit chain on 32-bit halves of the state; a rare event (speculation miss,
@@ -398,24 +405,63 @@ rans_decode_fast_kernel(const uint8_t *__restrict__ packed, const int64_t *__res
         }                                                                                            \
     }
         resume:
-            while (j + 4 <= cnt) {
-                SC2_DEC_STEP(0)
-                SC2_DEC_STEP(1)
-                SC2_DEC_STEP(2)
-                SC2_DEC_STEP(3)
-                j += 4;
-            }
             while (j < cnt) {
-                SC2_DEC_STEP(0)
-                j += 1;
+                if (streak >= kSpecGroup && j + kSpecGroup <= cnt) {
+                    // ---- run mode: the last symbols all hit the speculation.  Decode a GROUP on copies of the state with no branch at
+                    // all (miss flags are OR-ed, renormalisation is select-only, the two next words sit in registers) and commit it
+                    // if every symbol hit; otherwise drop the copies and take the checked steps below.  Chain per symbol:
+                    //   LOP -> IADD -> IMAD.WIDE -> IMAD -> LOP/ISETP -> SEL
+                    uint32_t gxl = xl, gxh = xh, gp = s.p, w0 = s.next_w, w1 = s_ring[(s.p + 1u) & (kRingWords - 1)];
+                    bool bad = false;
+#pragma unroll
+                    for (int k = 0; k < kSpecGroup; ++k) {
+                        const uint32_t d = (gxl & 0xffffu) - sp_start;
+                        bad |= d >= sp_freq;
+                        const uint64_t prod = static_cast<uint64_t>(sp_freq) * __funnelshift_r(gxl, gxh, 16) + d;
+                        const uint32_t nl = static_cast<uint32_t>(prod);
+                        const uint32_t nh = static_cast<uint32_t>(prod >> 32) + sp_freq * (gxh >> 16);
+                        const bool ren = (nh | (nl >> 31)) == 0u;
+                        gxl = ren ? w0 : nl;
+                        gxh = ren ? nl : nh;
+                        gp += ren ? 1u : 0u;
+                        w0 = ren ? w1 : w0;
+                        w1 = s_ring[(gp + 1u) & (kRingWords - 1)];
+                    }
+                    if (!bad) {
+#pragma unroll
+                        for (int k = 0; k < kSpecGroup; ++k) s_out[j + k] = sp_value;
+                        j += kSpecGroup;
+                        xl = gxl;
+                        xh = gxh;
+                        const bool crossed = ((gp ^ s.p) & 32u) != 0u;
+                        s.p = gp;
+                        s.next_w = w0;
+                        if (crossed) dec_refill(st.words, st.n_words, st.ring, (gp & ~31u) + kRefillAhead, lane);
+                        continue;
+                    }
+                    streak = 0;
+                }
+                if (j + 4 <= cnt) {
+                    SC2_DEC_STEP(0)
+                    SC2_DEC_STEP(1)
+                    SC2_DEC_STEP(2)
+                    SC2_DEC_STEP(3)
+                    j += 4;
+                    streak += 4;
+                } else {
+                    SC2_DEC_STEP(0)
+                    j += 1;
+                    streak += 1;
+                }
             }
             goto chunk_done;
         refill_event:
             // the word index crossed a ring half: top up the half that was just left, then re-read next_w
-            dec_refill(st.words, st.n_words, st.ring, s.p + 32u, lane);
+            dec_refill(st.words, st.n_words, st.ring, s.p + kRefillAhead, lane);
             s.next_w = s_ring[s.p & (kRingWords - 1)];
             goto resume;
         miss_event : {
+            streak = 0;
             s.x = (static_cast<uint64_t>(xh) << 32) | xl;
             const DecMissResult r = dec_miss(s, st.words, st.n_words, st.ring, drow, c0, c1, max_value, sp_start, sp_freq,
                                              sp_value, lane);
