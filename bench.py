@@ -337,7 +337,8 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-threads', type=int, default=0, help='host threads (one CUDA stream each) driving the e2e steps')
     ap.add_argument('--max-ahead', type=int, default=4, help='batches the host may run ahead of the GPU beyond the pipeline depth')
-    ap.add_argument('--inflight', type=int, default=8, help='config 2: depth of the batch pipeline')
+    ap.add_argument('--inflight', type=int, default=16, help='config 2: depth of the batch pipeline')
+    ap.add_argument('--coder-sms', type=int, default=12, help='config 2: SMs the persistent transform kernels leave to the coder blocks')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -402,7 +403,7 @@ def main():
             # (sc2bench_b200/pipeline.py): every g_a / g_s on ONE transform stream, g_a(i + depth) ahead of g_s(i), coders on
             # per-batch streams in the lane-per-stream layout.  Every step does all of its work inside the timed region; the
             # region ends when the pipeline has drained.
-            pipe = s2.pipeline.CodecPipeline(model, depth=max(1, args.inflight), max_ahead=args.max_ahead)
+            pipe = s2.pipeline.CodecPipeline(model, depth=max(1, args.inflight), max_ahead=args.max_ahead, coder_sms=args.coder_sms)
 
             def run_steps(n, first=0):
                 main_s = torch.cuda.current_stream()
@@ -541,6 +542,8 @@ def main():
 
             if use_transform_stream:
                 model.use_transform_stream(True, host_wait=True)
+                if args.coder_sms > 0:  # as CodecPipeline does: the persistent transform kernels leave SMs to the coder blocks
+                    s2._native.check(s2._native.load().sc2_set_persistent_ctas(148 - args.coder_sms), 'sc2_set_persistent_ctas')
             with concurrent.futures.ThreadPoolExecutor(max_workers=n_thr) as pool:
                 list(pool.map(e2e_step, range(max(args.warmup, 4 * n_thr))))  # (fills the allocator pools of every stream / thread)
                 barrier()
@@ -553,6 +556,7 @@ def main():
                 barrier()
             if use_transform_stream:
                 model.use_transform_stream(None)
+                s2._native.check(s2._native.load().sc2_set_persistent_ctas(0), 'sc2_set_persistent_ctas')
             te = torch.tensor([wall], dtype=torch.float64, device=device)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -610,7 +614,8 @@ def main():
     line = {'metric': METRICS[cfg], 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f32-grade (g_a: split-f16 operands, 3 tensor-core passes, f32 accumulate) / f16 operands with f32 accumulate (g_s) / u64 (coder)'
-                     if cfg in (1, 2, 5) else 'f32 (g_a, h_a, h_s: CUDA-core FFMA kernels) / u64 (coder)',
+                     if cfg in (1, 2, 5) else 'f32-grade (g_a, h_a, h_s: split-f16 operands, 3 tensor-core passes) / f16 operands with f32 accumulate, '
+                                              'split activations in the last stage (g_s) / u64 (coder)',
             'data': 'synthetic',
             'config': {'workload': desc + ', batch %d per GPU' % B, 'bench_config': cfg,
                        'images_per_gpu_per_step': B, 'global_images_per_step': B_global, 'symbols_per_image': sym_per_image,

@@ -66,22 +66,38 @@ struct Params {
 
 constexpr int kMaxBeta = 512;  // channels of a GDN layer held in shared memory
 
-template <int N_TILE, int STAGES>
+// STAGED epilogue (fp16 outputs): results leave through 64-channel staging blocks [128 rows][128 bytes] in the SWIZZLE_128B layout
+// (16-byte unit j of row r sits at unit j ^ (r & 7): conflict-free for one row per thread) and TMA bulk stores; the x tile of the GDN
+// epilogue arrives in the same block by TMA and y overwrites it in place.  Three blocks rotate: while block g is computed, the
+// store of g - 1 drains and the x tile of g + 1 loads.  (Per-thread 16-byte global loads / stores at a 512..1024-byte stride
+// between lanes were 32 sectors per request: IGDN1(512) moved 7.9 GB through L2 for 4.8 GB of operands, profiles/r4_*.)
+constexpr int kStageBlocks = 3;
+constexpr int kStageBlockBytes = kTileM * 128;
+
+template <int N_TILE, int STAGES, bool STAGED = false>
 struct Smem {
     static constexpr int kBBytes = N_TILE * 128;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kRingBytes = STAGES * kStageBytes;
-    // full[STAGES], empty[STAGES], xform[STAGES], acc_full[2], acc_empty[2] : 8 bytes each; then the TMEM base address
-    static constexpr int kSchedOffset = kRingBytes + (3 * STAGES + 4) * 8 + 16;
+    static constexpr int kOutOffset = kRingBytes;  // (1024-byte aligned: every ring stage is a multiple of 1024 bytes)
+    static constexpr int kOutBytes = STAGED ? kStageBlocks * kStageBlockBytes : 0;
+    // full[STAGES], empty[STAGES], xform[STAGES], acc_full[2], acc_empty[2], x_full[3] : 8 bytes each; then the TMEM base address
+    static constexpr int kBarOffset = kOutOffset + kOutBytes;
+    static constexpr int kSchedOffset = kBarOffset + (3 * STAGES + 4 + kStageBlocks) * 8 + 16;
     static constexpr int kBetaOffset = (kSchedOffset + kTileSchedBytes + 15) / 16 * 16;  // float[kMaxBeta] (GDN modes)
     static constexpr int kTotal = kBetaOffset + kMaxBeta * 4;
 };
 
-template <int N_TILE, int STAGES, int MODE>
+__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
+
+template <int N_TILE, int STAGES, int MODE, bool STAGED>
 __global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16) ? 448 : 320, 1)  // + 4 |x| transform warps
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ Params p) {
-    using L = Smem<N_TILE, STAGES>;
+               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ Params p) {
+    using L = Smem<N_TILE, STAGES, STAGED>;
+    static_assert(!STAGED || MODE == MODE_STORE_F16 || MODE == MODE_STORE_ABS_F16 || MODE == MODE_IGDN1_ABS_F16, "staged epilogue: fp16 outputs");
+    static_assert(!STAGED || N_TILE % 64 == 0, "staged epilogue works on 64-channel blocks");
     constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;  // |x| formed in shared memory by 4 extra warps
     constexpr bool kGdn = kXform || MODE == MODE_IGDN1_ABS_F16 || MODE == MODE_IGDN_SQ_F16;  // GDN epilogue
     constexpr bool kSigned = MODE == MODE_IGDN1_ABS_F16;                      // x = sign word * |x|
@@ -90,12 +106,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     static_assert(2 * N_TILE <= 512, "two accumulator stages must fit TMEM");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kRingBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + L::kBarOffset);
     uint64_t *empty = full + STAGES;
     uint64_t *xform = empty + STAGES;
     uint64_t *acc_full = xform + STAGES;
     uint64_t *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *x_full = acc_empty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(x_full + kStageBlocks);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -127,6 +144,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 256);
+        }
+        for (int s = 0; s < kStageBlocks; ++s) mbar_init(&x_full[s], 1);
+        if (STAGED) {
+            tma_prefetch_desc(&map_o);
+            tma_prefetch_desc(&map_x);
         }
         fence_barrier_init();
     }
@@ -194,6 +216,111 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int quarter = warp & 3;         // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;  // tile row = TMEM lane = pixel index inside the tile
         const int ty = row / p.tw, tx = row - ty * p.tw;
+        if constexpr (STAGED) {
+            constexpr int kChunks = N_TILE / 64;
+            const bool issuer = threadIdx.x == 64;  // first epilogue thread: owns the bulk-store groups and the x-tile loads
+            uint8_t *blocks = smem + L::kOutOffset;
+            const uint32_t x_bytes = static_cast<uint32_t>(rows * 128);
+            uint32_t g = 0;  // 64-channel blocks processed so far (the same in every epilogue thread): block g uses buffer g % 3
+            for (uint32_t lt = 0;; ++lt) {
+                const int tile = sched.next(lt, lane);
+                if (tile < 0) break;
+                ++trace_tiles;
+                const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+                const int sp = tile % tiles_xy, rest = tile / tiles_xy;
+                const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
+                const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
+                const int oy = y0 + ty, ox = x0 + tx;
+                const bool valid = row < rows && oy < p.h_out && ox < p.w_out;
+                const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
+                uint32_t spre[kSigned ? kChunks : 1];
+                if (kSigned && valid) {
+#pragma unroll
+                    for (int ci = 0; ci < kChunks; ++ci) spre[ci] = __ldg(p.signs + pix * (p.n_total >> 5) + ((n0 + half * 32 + ci * 64) >> 5));
+                }
+                if (kGdn && issuer) {  // x tile of the first block: requested before the accumulator is complete
+                    tma_store_wait_read_1();
+                    mbar_expect_tx(&x_full[g % kStageBlocks], x_bytes);
+                    tma_load_4d(&map_x, &x_full[g % kStageBlocks], blocks + (g % kStageBlocks) * kStageBlockBytes, n0, x0, y0, img);
+                }
+                mbar_wait(&acc_full[as], aph);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + as * N_TILE + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+                for (int ci = 0; ci < kChunks; ++ci, ++g) {
+                    const uint32_t b = g % kStageBlocks;
+                    uint8_t *blk = blocks + b * kStageBlockBytes;
+                    if (kGdn) {
+                        if (issuer && ci + 1 < kChunks) {  // x tile of the next block (its buffer was last stored two blocks ago)
+                            const uint32_t nb = (g + 1) % kStageBlocks;
+                            tma_store_wait_read_1();
+                            mbar_expect_tx(&x_full[nb], x_bytes);
+                            tma_load_4d(&map_x, &x_full[nb], blocks + nb * kStageBlockBytes, n0 + (ci + 1) * 64, x0, y0, img);
+                        }
+                        mbar_wait(&x_full[b], (g / kStageBlocks) & 1u);
+                    } else {
+                        if (issuer) tma_store_wait_read_2();  // the store that read this buffer three blocks ago is done with it
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
+                    uint32_t v[32];
+                    tmem_ld32(taddr + half * 32 + ci * 64, v);
+                    if (row < rows) {
+                        uint32_t sign_word = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            // 16-byte unit (half * 4 + c) of this row's 128-byte line, swizzled
+                            uint4 *slot = reinterpret_cast<uint4 *>(blk + row * 128 + (((half * 4 + c) ^ (row & 7)) << 4));
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * c + e]);
+                            if (kGdn) {
+                                uint4 xv = *slot;
+                                const uint32_t sw = spre[kSigned ? ci : 0];  // x = sign * |x|: half2 word k = 4c + e takes (S << k) & 0x80008000
+                                xv.x |= (sw << (4 * c)) & 0x80008000u;
+                                xv.y |= (sw << (4 * c + 1)) & 0x80008000u;
+                                xv.z |= (sw << (4 * c + 2)) & 0x80008000u;
+                                xv.w |= (sw << (4 * c + 3)) & 0x80008000u;
+                                const __half2 *xh = reinterpret_cast<const __half2 *>(&xv);
+                                const float4 ba = *reinterpret_cast<const float4 *>(s_beta + n0 + half * 32 + ci * 64 + 8 * c);
+                                const float4 bb = *reinterpret_cast<const float4 *>(s_beta + n0 + half * 32 + ci * 64 + 8 * c + 4);
+                                const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 xf = __half22float2(xh[e]);
+                                    f[2 * e] = xf.x * (f[2 * e] + bv[2 * e]);
+                                    f[2 * e + 1] = xf.y * (f[2 * e + 1] + bv[2 * e + 1]);
+                                }
+                            } else if (has_vec) {  // bias of the convolution
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] += s_beta[n0 + half * 32 + ci * 64 + 8 * c + e];
+                            }
+                            uint4 ov;
+                            __half2 h;
+                            h = __floats2half2_rn(f[0], f[1]); ov.x = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2half2_rn(f[2], f[3]); ov.y = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2half2_rn(f[4], f[5]); ov.z = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2half2_rn(f[6], f[7]); ov.w = *reinterpret_cast<uint32_t *>(&h);
+                            if (MODE == MODE_STORE_ABS_F16) {
+                                sign_word |= ((ov.x & 0x80008000u) >> (4 * c)) | ((ov.y & 0x80008000u) >> (4 * c + 1)) |
+                                             ((ov.z & 0x80008000u) >> (4 * c + 2)) | ((ov.w & 0x80008000u) >> (4 * c + 3));
+                                ov.x &= 0x7fff7fffu; ov.y &= 0x7fff7fffu; ov.z &= 0x7fff7fffu; ov.w &= 0x7fff7fffu;
+                            }
+                            *slot = ov;
+                        }
+                        if (MODE == MODE_STORE_ABS_F16 && valid) p.signs[pix * (p.n_total >> 5) + ((n0 + half * 32 + ci * 64) >> 5)] = sign_word;
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (issuer) {
+                        tma_store_4d(&map_o, blk, n0 + ci * 64, x0, y0, img);
+                        tma_store_commit();
+                    }
+                }
+                tcgen05_fence_before();
+                mbar_arrive(&acc_empty[as]);  // 256 arrivals release the accumulator stage to the MMA warp
+            }
+            if (issuer) tma_store_wait_all();
+        } else
         for (uint32_t lt = 0;; ++lt) {
             const int tile = sched.next(lt, lane);
             if (tile < 0) break;
@@ -366,18 +493,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (threadIdx.x == 64) trace_emit(p.trace, TRACE_CONV_TC, trace_t0, trace_tiles);
 }
 
-template <int N_TILE, int STAGES, int MODE>
-static int launch(const CUtensorMap &ma, const CUtensorMap &ma2, const CUtensorMap &mb, const Params &p, cudaStream_t st) {
-    using L = Smem<N_TILE, STAGES>;
+template <int N_TILE, int STAGES, int MODE, bool STAGED = false>
+static int launch(const CUtensorMap &ma, const CUtensorMap &ma2, const CUtensorMap &mb, const Params &p, cudaStream_t st,
+                  const CUtensorMap *mo = nullptr, const CUtensorMap *mx = nullptr) {
+    using L = Smem<N_TILE, STAGES, STAGED>;
     constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
+    static_assert(L::kTotal + 1024 <= 227 * 1024, "shared memory budget");
     const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
     static std::atomic<uint64_t> configured{0};  // per device ordinal
-    if (int rc = ensure_dyn_smem(tc_conv_kernel<N_TILE, STAGES, MODE>, smem, configured)) return rc;
+    if (int rc = ensure_dyn_smem(tc_conv_kernel<N_TILE, STAGES, MODE, STAGED>, smem, configured)) return rc;
     const int total = p.tiles_x * p.tiles_y * p.n_tiles * p.batch;
     const int grid = total < persistent_grid() ? total : persistent_grid();
-    tc_conv_kernel<N_TILE, STAGES, MODE><<<grid, kXform ? 448 : 320, smem, st>>>(ma, ma2, mb, p);
+    tc_conv_kernel<N_TILE, STAGES, MODE, STAGED><<<grid, kXform ? 448 : 320, smem, st>>>(ma, ma2, mb, mo ? *mo : ma, mx ? *mx : ma, p);
     SC2_LAUNCH_CHECK("tc_conv_kernel");
     return SC2_OK;
+}
+
+// experiments: SC2_TC_UNSTAGED=1 keeps the per-thread global loads / stores of the first version
+bool unstaged_epilogue() {
+    static const bool v = [] { const char *e = std::getenv("SC2_TC_UNSTAGED"); return e && e[0] == '1'; }();
+    return v;
 }
 
 // NCHW fp32 -> NHWC fp16 with the channel dimension zero-padded to c_pad (feeds the first tensor-core layer).
@@ -507,6 +642,21 @@ int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *x_lo
         rc = make_weight_map(&mb64, w_packed, d->c_in_pad, d->kh * d->kw * n_rows, 64);
         if (rc) return rc;
         return d->mode == MODE_STORE_SQ_F16 ? launch<64, 8, MODE_STORE_SQ_F16>(ma, ma2, mb64, p, st) : launch<64, 8, MODE_IGDN_SQ_F16>(ma, ma2, mb64, p, st);
+    }
+    if (n_tile == 256 && d->out_stride == 1 && !x_lo &&
+        (d->mode == MODE_STORE_F16 || d->mode == MODE_STORE_ABS_F16 || d->mode == MODE_IGDN1_ABS_F16) && !sc2::tc::unstaged_epilogue()) {
+        // fp16 outputs through shared-memory staging blocks and TMA stores (3 ring stages leave room for them)
+        CUtensorMap mo, mx;
+        rc = make_nhwc_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, n_rows, w_out, h_out, d->batch, 64, tw, th);
+        if (rc) return rc;
+        mx = mo;
+        if (d->mode == MODE_IGDN1_ABS_F16) {
+            rc = make_nhwc_map(&mx, gdn_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, n_rows, w_out, h_out, d->batch, 64, tw, th);
+            if (rc) return rc;
+            return launch<256, 3, MODE_IGDN1_ABS_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
+        }
+        if (d->mode == MODE_STORE_ABS_F16) return launch<256, 3, MODE_STORE_ABS_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
+        return launch<256, 3, MODE_STORE_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
     }
     if (n_tile == 256) { SC2_TC_DISPATCH(256, 4) }
     if (n_tile == 128) { SC2_TC_DISPATCH(128, 6) }

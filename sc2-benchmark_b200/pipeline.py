@@ -48,7 +48,7 @@ class CodecPipeline:
     result are then VIEWS of ring buffers, valid until `depth + 1` more batches have been submitted (clone to keep them).
     coder_sms: SMs left to the coder blocks while the pipeline exists (sc2_set_persistent_ctas; 0 = none)."""
 
-    def __init__(self, layer, depth=8, max_ahead=4, native=True, coder_sms=8):
+    def __init__(self, layer, depth=16, max_ahead=4, native=True, coder_sms=12):
         if depth < 1:
             raise ValueError('depth must be >= 1')
         self.layer, self.depth, self.max_ahead = layer, depth, max(0, max_ahead)
