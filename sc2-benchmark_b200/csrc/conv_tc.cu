@@ -96,7 +96,8 @@ __global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ Params p) {
     using L = Smem<N_TILE, STAGES, STAGED>;
-    static_assert(!STAGED || MODE == MODE_STORE_F16 || MODE == MODE_STORE_ABS_F16 || MODE == MODE_IGDN1_ABS_F16, "staged epilogue: fp16 outputs");
+    static_assert(!STAGED || MODE == MODE_STORE_F16 || MODE == MODE_STORE_ABS_F16 || MODE == MODE_IGDN1_ABS_F16 || MODE == MODE_STORE_F32,
+                  "staged epilogue: dense NHWC outputs");
     static_assert(!STAGED || N_TILE % 64 == 0, "staged epilogue works on 64-channel blocks");
     constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;  // |x| formed in shared memory by 4 extra warps
     constexpr bool kGdn = kXform || MODE == MODE_IGDN1_ABS_F16 || MODE == MODE_IGDN_SQ_F16;  // GDN epilogue
@@ -216,7 +217,56 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int quarter = warp & 3;         // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;  // tile row = TMEM lane = pixel index inside the tile
         const int ty = row / p.tw, tx = row - ty * p.tw;
-        if constexpr (STAGED) {
+        if constexpr (STAGED && MODE == MODE_STORE_F32) {
+            // fp32 output (the last g_s layer): a thread holds 32 channels = one 128-byte piece of its pixel's row.  Written directly,
+            // a warp store touches 32 pixel rows 1 KB apart (32 sectors in 32 lines per request); instead every warp transposes its
+            // 32 rows x 128 bytes through a private 4 KB block (swizzled: conflict-free both ways, __syncwarp only) so that one
+            // store instruction writes four complete 128-byte lines.
+            uint4 *wblk = reinterpret_cast<uint4 *>(smem + L::kOutOffset) + (warp - 2) * 256;
+            float *outf = static_cast<float *>(p.out);
+            for (uint32_t lt = 0;; ++lt) {
+                const int tile = sched.next(lt, lane);
+                if (tile < 0) break;
+                ++trace_tiles;
+                const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+                const int sp = tile % tiles_xy, rest = tile / tiles_xy;
+                const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
+                const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
+                // read-back phase: instruction k moves rows quarter * 32 + 4 k + (lane >> 3), unit lane & 7
+                const int r0 = quarter * 32 + (lane >> 3);
+                const int ty0 = r0 / p.tw, tx0 = r0 - ty0 * p.tw;
+                mbar_wait(&acc_full[as], aph);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + as * N_TILE + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < N_TILE; c0 += 64) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (has_vec) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + s_beta[n0 + c0 + e]);
+                    }
+                    __syncwarp();  // the previous piece has been read back
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) wblk[lane * 8 + (u ^ (lane & 7))] = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    __syncwarp();
+                    int tyk = ty0, txk = tx0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int rl = 4 * k + (lane >> 3);  // row inside the warp's block
+                        const int oy = y0 + tyk, ox = x0 + txk;
+                        if (quarter * 32 + rl < rows && oy < p.h_out && ox < p.w_out) {
+                            const int64_t pix = (static_cast<int64_t>(img) * p.h_out + oy) * p.w_out + ox;
+                            reinterpret_cast<uint4 *>(outf + pix * p.n_total + n0 + c0)[lane & 7] = wblk[rl * 8 + ((lane & 7) ^ (rl & 7))];
+                        }
+                        txk += 4;
+                        if (txk >= p.tw) { txk -= p.tw; ++tyk; }
+                    }
+                }
+                tcgen05_fence_before();
+                mbar_arrive(&acc_empty[as]);
+            }
+        } else if constexpr (STAGED) {
             constexpr int kChunks = N_TILE / 64;
             const bool issuer = threadIdx.x == 64;  // first epilogue thread: owns the bulk-store groups and the x-tile loads
             uint8_t *blocks = smem + L::kOutOffset;
@@ -532,6 +582,42 @@ __global__ void nchw_f32_to_nhwc_f16_kernel(const float *__restrict__ x, __half 
     }
 }
 
+// The same for c_pad == 64 (the bottleneck's latent: 24 channels in front of the first g_s layer) as a tiled transpose: coalesced
+// 128-byte reads along the pixels of one channel, 8 channels packed per thread into a 16-byte unit, units staged in shared memory
+// (swizzled like the tensor-core tiles: conflict-free) and written back as whole 128-byte pixel rows.  The one-thread-per-channel-pair
+// version above read 12 different cache lines per warp load: 0.135 ms for 130 MB (13 % of the copy bandwidth).
+__global__ void __launch_bounds__(256) nchw_f32_to_nhwc64_f16_kernel(const float *__restrict__ x, __half *__restrict__ y, int c, int hw) {
+    __shared__ __align__(128) uint4 tile[64 * 8];
+    const int b = blockIdx.y, p0 = blockIdx.x * 64;
+    const int px = threadIdx.x & 63, cg0 = threadIdx.x >> 6;
+    const float *xb = x + static_cast<int64_t>(b) * c * hw;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int cg = cg0 + 4 * r;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ch = cg * 8 + e;
+            f[e] = (ch < c && p0 + px < hw) ? __ldg(xb + static_cast<int64_t>(ch) * hw + p0 + px) : 0.0f;
+        }
+        uint4 v;
+        __half2 h;
+        h = __floats2half2_rn(f[0], f[1]); v.x = *reinterpret_cast<uint32_t *>(&h);
+        h = __floats2half2_rn(f[2], f[3]); v.y = *reinterpret_cast<uint32_t *>(&h);
+        h = __floats2half2_rn(f[4], f[5]); v.z = *reinterpret_cast<uint32_t *>(&h);
+        h = __floats2half2_rn(f[6], f[7]); v.w = *reinterpret_cast<uint32_t *>(&h);
+        tile[px * 8 + (cg ^ (px & 7))] = v;
+    }
+    __syncthreads();
+    uint4 *yb = reinterpret_cast<uint4 *>(y) + (static_cast<int64_t>(b) * hw + p0) * 8;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = threadIdx.x + 256 * r;  // unit index inside the 64-pixel tile: pixel i / 8, unit i % 8
+        const int q = i >> 3, u = i & 7;
+        if (p0 + q < hw) yb[i] = tile[q * 8 + (u ^ (q & 7))];
+    }
+}
+
 }  // namespace tc
 }  // namespace sc2
 
@@ -541,6 +627,13 @@ int sc2_nchw_f32_to_nhwc_f16(const float *x, void *y, int batch, int channels, i
     if (!x || !y || batch < 0 || channels < 1 || c_pad < channels || (c_pad & 1) || spatial < 0) return SC2_ERR_INVALID_ARG;
     const int64_t total = static_cast<int64_t>(batch) * spatial * (c_pad / 2);
     if (total == 0) return SC2_OK;
+    if (c_pad == 64 && spatial <= 0x7fffffff - 64 && batch <= 65535) {
+        const dim3 grid(static_cast<unsigned>((spatial + 63) / 64), static_cast<unsigned>(batch));
+        sc2::tc::nchw_f32_to_nhwc64_f16_kernel<<<grid, 256, 0, sc2::as_stream(stream)>>>(x, static_cast<__half *>(y), channels,
+                                                                                         static_cast<int>(spatial));
+        SC2_LAUNCH_CHECK("nchw_f32_to_nhwc64_f16_kernel");
+        return SC2_OK;
+    }
     int64_t blocks = (total + 255) / 256;
     if (blocks > sc2::kNumSMs * 32) blocks = sc2::kNumSMs * 32;
     sc2::tc::nchw_f32_to_nhwc_f16_kernel<<<static_cast<int>(blocks), 256, 0, sc2::as_stream(stream)>>>(
@@ -658,6 +751,8 @@ int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *x_lo
         if (d->mode == MODE_STORE_ABS_F16) return launch<256, 3, MODE_STORE_ABS_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
         return launch<256, 3, MODE_STORE_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
     }
+    if (n_tile == 256 && d->out_stride == 1 && !x_lo && d->mode == MODE_STORE_F32 && !sc2::tc::unstaged_epilogue())
+        return launch<256, 3, MODE_STORE_F32, true>(ma, ma2, mb, p, st);
     if (n_tile == 256) { SC2_TC_DISPATCH(256, 4) }
     if (n_tile == 128) { SC2_TC_DISPATCH(128, 6) }
     SC2_TC_DISPATCH(64, 8)

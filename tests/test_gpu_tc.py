@@ -410,3 +410,15 @@ def test_tc_split_deconv5_matches_fp64(s2, cin, cout, H, W, act):
     assert got[:, :cout].shape == ref.shape
     assert rel_err(got[:, :cout], ref.float()) < SPLIT_TOL, rel_err(got[:, :cout], ref.float())
     assert float(got[:, cout:].abs().max()) == 0.0 if pitch > cout else True
+
+
+@pytest.mark.parametrize('B,C,H,W,cp', [(3, 24, 55, 55, 64), (2, 64, 9, 13, 64), (1, 3, 5, 5, 64), (2, 24, 8, 8, 32), (2, 320, 4, 4, 320)])
+def test_nchw_to_nhwc_f16_layouts(s2, B, C, H, W, cp):
+    """fp32 NCHW -> fp16 NHWC with zero-padded channels: the tiled-transpose kernel (c_pad = 64) and the generic one."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(B + C + H)
+    x = torch.randn(B, C, H, W)
+    got = s2.ops.nchw_to_nhwc_f16(x.to(dev), cp).cpu()
+    assert got.shape == (B, H, W, cp) and got.dtype == torch.float16
+    assert torch.equal(got[..., :C], x.permute(0, 2, 3, 1).half())
+    assert float(got[..., C:].abs().max()) == 0.0 if cp > C else True
