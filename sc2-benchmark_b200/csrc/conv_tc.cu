@@ -83,9 +83,7 @@ struct Smem {
     static constexpr int kOutBytes = STAGED ? kStageBlocks * kStageBlockBytes : 0;
     // full[STAGES], empty[STAGES], xform[STAGES], acc_full[2], acc_empty[2], x_full[3] : 8 bytes each; then the TMEM base address
     static constexpr int kBarOffset = kOutOffset + kOutBytes;
-    // (+ the pair mailbox of the cluster variant: kTileQ mbarriers and tile ids)
-    static constexpr int kMailOffset = kBarOffset + (3 * STAGES + 4 + kStageBlocks) * 8 + 16;
-    static constexpr int kSchedOffset = kMailOffset + kTileQ * 8 + kTileQ * 4;
+    static constexpr int kSchedOffset = kBarOffset + (3 * STAGES + 4 + kStageBlocks) * 8 + 16;
     static constexpr int kBetaOffset = (kSchedOffset + kTileSchedBytes + 15) / 16 * 16;  // float[kMaxBeta] (GDN modes)
     static constexpr int kTotal = kBetaOffset + kMaxBeta * 4;
 };
@@ -93,18 +91,11 @@ struct Smem {
 __device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read_2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
 
-// CL (cluster of 2 CTAs): both CTAs work on the SAME output channels and taps of two neighbouring pixel tiles; every B (weight / gamma)
-// tile is loaded once per pair -- each CTA fetches one half of its rows and TMA-multicasts it into both shared memories -- and a ring
-// stage is recycled when BOTH MMA warps have committed it (tcgen05.commit multicast onto both `empty` barriers).  The g_s layers are
-// bound by L2 -> SM operand traffic (gamma of IGDN1(512) is 512 KB per 128-pixel tile): this halves the larger part of it.
-// Tiles are claimed in pairs by the rank-0 producer, which mails the pair id to its peer through distributed shared memory.
-template <int N_TILE, int STAGES, int MODE, bool STAGED, bool CL>
+template <int N_TILE, int STAGES, int MODE, bool STAGED>
 __global__ void __launch_bounds__((MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16) ? 448 : 320, 1)  // + 4 |x| transform warps
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_bh,
-               const __grid_constant__ Params p) {
+               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ Params p) {
     using L = Smem<N_TILE, STAGES, STAGED>;
-    static_assert(!CL || STAGED, "the cluster variant exists for the staged kernels");
     static_assert(!STAGED || MODE == MODE_STORE_F16 || MODE == MODE_STORE_ABS_F16 || MODE == MODE_IGDN1_ABS_F16 || MODE == MODE_STORE_F32,
                   "staged epilogue: dense NHWC outputs");
     static_assert(!STAGED || N_TILE % 64 == 0, "staged epilogue works on 64-channel blocks");
@@ -129,23 +120,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int rows = p.tw * p.th;
     const int k_iters = p.a_passes * p.taps_x * p.taps_y * p.k_chunks;
     const int tiles_xy = p.tiles_x * p.tiles_y;
-    // CL: the scheduler hands out PAIRS of neighbouring pixel tiles of one (image, channel tile); CTA rank r takes tile 2 j + r (the
-    // last pair of an odd row repeats its tile: both CTAs then write the same values)
-    const uint32_t crank = CL ? cluster_ctarank() : 0u;
-    const int pairs_xy = (tiles_xy + 1) >> 1;
-    const int total_tiles = (CL ? pairs_xy : tiles_xy) * p.n_tiles * p.batch;
-    auto split_tile = [&](int t, int &sp, int &rest) {
-        if (CL) {
-            rest = t / pairs_xy;
-            const int j2 = 2 * (t - rest * pairs_xy) + static_cast<int>(crank);
-            sp = j2 < tiles_xy ? j2 : tiles_xy - 1;
-        } else {
-            rest = t / tiles_xy;
-            sp = t - rest * tiles_xy;
-        }
-    };
-    uint64_t *mail_full = reinterpret_cast<uint64_t *>(smem + L::kMailOffset);
-    int *mail_q = reinterpret_cast<int *>(mail_full + kTileQ);
+    const int total_tiles = tiles_xy * p.n_tiles * p.batch;
     const unsigned long long trace_t0 = p.trace.buf ? trace_now() : 0ull;
     int trace_tiles = 0;
     TileSched sched;
@@ -164,10 +139,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CL ? 2 : 1);  // CL: the MMA warps of both CTAs
+            mbar_init(&empty[s], 1);
             mbar_init(&xform[s], 128);
         }
-        for (int s = 0; s < kTileQ; ++s) mbar_init(&mail_full[s], 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 256);
@@ -181,8 +155,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     tcgen05_fence_before();
-    if (CL) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
-    else __syncthreads();
+    __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -191,37 +164,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (elect_one()) {
             const uint32_t stage_tx = static_cast<uint32_t>(rows * 128 + L::kBBytes);
             uint32_t it = 0;
-            // CL: rank 0 claims and mails the pair to rank 1 (slot n % kTileQ of the peer's mailbox, then a remote arrive); rank 1 never
-            // lags more than two entries behind (a stage is reloaded only after BOTH MMA warps released it, and k_iters >= STAGES)
-            auto mail_send = [&](uint32_t n, int q) {
-                const uint32_t slot = n % kTileQ;
-                st_cluster_u32(mapa_shared(smem_u32(mail_q + slot), 1u), static_cast<uint32_t>(q));
-                mbar_arrive_cluster(mapa_shared(smem_u32(mail_full + slot), 1u));
-            };
-            auto mail_read = [&](uint32_t n) {
-                const uint32_t slot = n % kTileQ;
-                mbar_wait_cluster(&mail_full[slot], (n / kTileQ) & 1u);
-                return *reinterpret_cast<volatile int *>(mail_q + slot);
-            };
-            int tile;
-            if (!CL || crank == 0u) {
-                tile = sched.claim(0);
-                if (CL) mail_send(0, tile);
-            } else {
-                tile = mail_read(0);
-            }
+            int tile = sched.claim(0);
             for (uint32_t qn = 0;; ++qn) {
                 sched.publish(qn, tile);
                 if (tile < 0) break;
-                int next_tile;  // claimed early: the atomic's latency hides behind this tile's loads
-                if (!CL || crank == 0u) {
-                    next_tile = sched.claim(qn + 1);
-                    if (CL) mail_send(qn + 1, next_tile);
-                } else {
-                    next_tile = mail_read(qn + 1);
-                }
-                int sp, rest;
-                split_tile(tile, sp, rest);
+                const int next_tile = sched.claim(qn + 1);  // claimed early: the atomic's latency hides behind this tile's loads
+                const int sp = tile % tiles_xy, rest = tile / tiles_xy;
                 const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
                 const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
                 for (int pass = 0; pass < p.a_passes; ++pass)
@@ -233,11 +181,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 uint8_t *dst = smem + s * L::kStageBytes;
                                 mbar_expect_tx(&full[s], stage_tx);
                                 tma_load_4d(pass == 0 ? &map_a : &map_a2, &full[s], dst, kc * kBlockK, x0 + tx - p.pad_x, y0 + ty - p.pad_y, img);
-                                if (CL)  // this CTA's half of the B rows, into both CTAs (map_x's slot carries the half-height B map)
-                                    tma_load_2d_multicast(&map_bh, &full[s], dst + kABytes + crank * (L::kBBytes / 2), kc * kBlockK,
-                                                          (ty * p.taps_x + tx) * p.n_total + n0 + static_cast<int>(crank) * (N_TILE / 2), 0x3);
-                                else
-                                    tma_load_2d(&map_b, &full[s], dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
+                                tma_load_2d(&map_b, &full[s], dst + kABytes, kc * kBlockK, (ty * p.taps_x + tx) * p.n_total + n0);
                             }
                 tile = next_tile;
             }
@@ -261,8 +205,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k)
                         umma_f16(tmem_base + as * N_TILE, a_desc + 2 * k, b_desc + 2 * k, idesc, (k_it > 0 || k > 0) ? 1u : 0u);
-                    if (CL) umma_commit_multicast(&empty[s], 0x3);        // (both CTAs' producers wait for both MMA warps)
-                    else umma_commit(&empty[s]);                          // frees the smem stage once these MMAs have read it
+                    umma_commit(&empty[s]);                               // frees the smem stage once these MMAs have read it
                     if (k_it == k_iters - 1) umma_commit(&acc_full[as]);  // accumulator complete
                 }
                 __syncwarp();
@@ -286,8 +229,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (tile < 0) break;
                 ++trace_tiles;
                 const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
-                int sp, rest;
-                split_tile(tile, sp, rest);
+                const int sp = tile % tiles_xy, rest = tile / tiles_xy;
                 const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
                 const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
                 // read-back phase: instruction k moves rows quarter * 32 + 4 k + (lane >> 3), unit lane & 7
@@ -335,8 +277,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (tile < 0) break;
                 ++trace_tiles;
                 const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
-                int sp, rest;
-                split_tile(tile, sp, rest);
+                const int sp = tile % tiles_xy, rest = tile / tiles_xy;
                 const int n0 = (rest % p.n_tiles) * N_TILE, img = rest / p.n_tiles;
                 const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
                 const int oy = y0 + ty, ox = x0 + tx;
@@ -594,8 +535,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     }
-    if (CL) cluster_sync_all();  // the peer may still multicast into this CTA's shared memory / arrive on its barriers
-    else __syncthreads();
+    __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -603,39 +543,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (threadIdx.x == 64) trace_emit(p.trace, TRACE_CONV_TC, trace_t0, trace_tiles);
 }
 
-template <int N_TILE, int STAGES, int MODE, bool STAGED = false, bool CL = false>
+template <int N_TILE, int STAGES, int MODE, bool STAGED = false>
 static int launch(const CUtensorMap &ma, const CUtensorMap &ma2, const CUtensorMap &mb, const Params &p, cudaStream_t st,
-                  const CUtensorMap *mo = nullptr, const CUtensorMap *mx = nullptr, const CUtensorMap *mbh = nullptr) {
+                  const CUtensorMap *mo = nullptr, const CUtensorMap *mx = nullptr) {
     using L = Smem<N_TILE, STAGES, STAGED>;
     constexpr bool kXform = MODE == MODE_IGDN1_F16 || MODE == MODE_GDN1_F16;
     static_assert(L::kTotal + 1024 <= 227 * 1024, "shared memory budget");
     const int smem = uniform_smem(L::kTotal + 1024);  // + slack for the manual 1024-byte alignment
     static std::atomic<uint64_t> configured{0};  // per device ordinal
-    auto kernel = tc_conv_kernel<N_TILE, STAGES, MODE, STAGED, CL>;
-    if (int rc = ensure_dyn_smem(kernel, smem, configured)) return rc;
-    const int tiles_xy = p.tiles_x * p.tiles_y;
-    if (CL) {
-        const int64_t pairs = static_cast<int64_t>((tiles_xy + 1) / 2) * p.n_tiles * p.batch;
-        int grid = persistent_grid() & ~1;
-        if (2 * pairs < grid) grid = static_cast<int>(2 * pairs);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(static_cast<unsigned>(grid));
-        cfg.blockDim = dim3(kXform ? 448 : 320);
-        cfg.dynamicSmemBytes = static_cast<size_t>(smem);
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        SC2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, ma, ma2, mb, mo ? *mo : ma, mx ? *mx : ma, mbh ? *mbh : mb, p));
-        return SC2_OK;
-    }
-    const int total = tiles_xy * p.n_tiles * p.batch;
+    if (int rc = ensure_dyn_smem(tc_conv_kernel<N_TILE, STAGES, MODE, STAGED>, smem, configured)) return rc;
+    const int total = p.tiles_x * p.tiles_y * p.n_tiles * p.batch;
     const int grid = total < persistent_grid() ? total : persistent_grid();
-    kernel<<<grid, kXform ? 448 : 320, smem, st>>>(ma, ma2, mb, mo ? *mo : ma, mx ? *mx : ma, mb, p);
+    tc_conv_kernel<N_TILE, STAGES, MODE, STAGED><<<grid, kXform ? 448 : 320, smem, st>>>(ma, ma2, mb, mo ? *mo : ma, mx ? *mx : ma, p);
     SC2_LAUNCH_CHECK("tc_conv_kernel");
     return SC2_OK;
 }
@@ -643,12 +562,6 @@ static int launch(const CUtensorMap &ma, const CUtensorMap &ma2, const CUtensorM
 // experiments: SC2_TC_UNSTAGED=1 keeps the per-thread global loads / stores of the first version
 bool unstaged_epilogue() {
     static const bool v = [] { const char *e = std::getenv("SC2_TC_UNSTAGED"); return e && e[0] == '1'; }();
-    return v;
-}
-
-// experiments: SC2_TC_NOCLUSTER=1 launches the staged kernels without CTA pairs
-bool cluster_pairs() {
-    static const bool v = [] { const char *e = std::getenv("SC2_TC_NOCLUSTER"); return !(e && e[0] == '1'); }();
     return v;
 }
 
@@ -826,34 +739,20 @@ int sc2_tc_conv_ex(const sc2_tc_conv_ex_desc *d, const void *x, const void *x_lo
     if (n_tile == 256 && d->out_stride == 1 && !x_lo &&
         (d->mode == MODE_STORE_F16 || d->mode == MODE_STORE_ABS_F16 || d->mode == MODE_IGDN1_ABS_F16) && !sc2::tc::unstaged_epilogue()) {
         // fp16 outputs through shared-memory staging blocks and TMA stores (3 ring stages leave room for them)
-        CUtensorMap mo, mx, mbh;
+        CUtensorMap mo, mx;
         rc = make_nhwc_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, n_rows, w_out, h_out, d->batch, 64, tw, th);
         if (rc) return rc;
         mx = mo;
-        // CTA pairs sharing the B tiles: needs the dynamic tile schedule and enough K iterations per tile (the pair mailbox relies on it)
-        const bool pair = tile_counter && d->kh * d->kw * p.k_chunks >= 3 && p.tiles_x * p.tiles_y * p.n_tiles * d->batch >= 2 && sc2::tc::cluster_pairs();
-        rc = make_weight_map(&mbh, w_packed, d->c_in_pad, d->kh * d->kw * n_rows, 128);
-        if (rc) return rc;
         if (d->mode == MODE_IGDN1_ABS_F16) {
             rc = make_nhwc_map(&mx, gdn_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, n_rows, w_out, h_out, d->batch, 64, tw, th);
             if (rc) return rc;
-            return pair ? launch<256, 3, MODE_IGDN1_ABS_F16, true, true>(ma, ma2, mb, p, st, &mo, &mx, &mbh)
-                        : launch<256, 3, MODE_IGDN1_ABS_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
+            return launch<256, 3, MODE_IGDN1_ABS_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
         }
-        if (d->mode == MODE_STORE_ABS_F16)
-            return pair ? launch<256, 3, MODE_STORE_ABS_F16, true, true>(ma, ma2, mb, p, st, &mo, &mx, &mbh)
-                        : launch<256, 3, MODE_STORE_ABS_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
-        return pair ? launch<256, 3, MODE_STORE_F16, true, true>(ma, ma2, mb, p, st, &mo, &mx, &mbh)
-                    : launch<256, 3, MODE_STORE_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
+        if (d->mode == MODE_STORE_ABS_F16) return launch<256, 3, MODE_STORE_ABS_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
+        return launch<256, 3, MODE_STORE_F16, true>(ma, ma2, mb, p, st, &mo, &mx);
     }
-    if (n_tile == 256 && d->out_stride == 1 && !x_lo && d->mode == MODE_STORE_F32 && !sc2::tc::unstaged_epilogue()) {
-        const bool pair = tile_counter && d->kh * d->kw * p.k_chunks >= 3 && p.tiles_x * p.tiles_y * p.n_tiles * d->batch >= 2 && sc2::tc::cluster_pairs();
-        CUtensorMap mbh;
-        rc = make_weight_map(&mbh, w_packed, d->c_in_pad, d->kh * d->kw * n_rows, 128);
-        if (rc) return rc;
-        return pair ? launch<256, 3, MODE_STORE_F32, true, true>(ma, ma2, mb, p, st, nullptr, nullptr, &mbh)
-                    : launch<256, 3, MODE_STORE_F32, true>(ma, ma2, mb, p, st);
-    }
+    if (n_tile == 256 && d->out_stride == 1 && !x_lo && d->mode == MODE_STORE_F32 && !sc2::tc::unstaged_epilogue())
+        return launch<256, 3, MODE_STORE_F32, true>(ma, ma2, mb, p, st);
     if (n_tile == 256) { SC2_TC_DISPATCH(256, 4) }
     if (n_tile == 128) { SC2_TC_DISPATCH(128, 6) }
     SC2_TC_DISPATCH(64, 8)
