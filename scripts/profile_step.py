@@ -14,6 +14,7 @@ torch.manual_seed(0)
 layer = s2.get_layer('FPBasedResNetBottleneck').eval()
 layer.update()
 layer.to(dev)
+layer.native_calls = False  # per-kernel route: the coder layout below is honoured per call
 x = torch.randn(batch, 3, 224, 224, device=dev)
 with torch.inference_mode():
     for layout in (None, None, 'lanes', 'lanes'):
