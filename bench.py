@@ -325,7 +325,9 @@ def pick_roofline(kernels, peaks, traffic_src):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--steps', type=int, default=None,
+                    help='timed steps (default 40; the reference arm: 3).  Config 2 at 200 steps (0.8 s of sustained load) runs into the '
+                         'board power cap: 1770 MHz instead of 1965, 64 k instead of 68 k images/s (profiles/r4_pipeline_depth.md)')
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', type=int, default=2, help='workload, numbered like SURVEY.md 8d (2 = BASELINE.json configs[1], the metric)')
@@ -340,6 +342,8 @@ def main():
     ap.add_argument('--inflight', type=int, default=16, help='config 2: depth of the batch pipeline')
     ap.add_argument('--coder-sms', type=int, default=12, help='config 2: SMs the persistent transform kernels leave to the coder blocks')
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 3 if args.impl == 'reference' else 40
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
 
