@@ -326,7 +326,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None,
-                    help='timed steps (default 40; the reference arm: 3).  Config 2 at 200 steps (0.8 s of sustained load) runs into the '
+                    help='timed steps (default 40, config 5: 160; the reference arm: 3).  Config 2 at 200 steps (0.8 s of sustained load) runs into the '
                          'board power cap: 1770 MHz instead of 1965, 64 k instead of 68 k images/s (profiles/r4_pipeline_depth.md)')
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
@@ -339,11 +339,12 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-threads', type=int, default=0, help='host threads (one CUDA stream each) driving the e2e steps')
     ap.add_argument('--max-ahead', type=int, default=4, help='batches the host may run ahead of the GPU beyond the pipeline depth')
-    ap.add_argument('--inflight', type=int, default=16, help='config 2: depth of the batch pipeline')
-    ap.add_argument('--coder-sms', type=int, default=12, help='config 2: SMs the persistent transform kernels leave to the coder blocks')
+    ap.add_argument('--inflight', type=int, default=None, help='configs 2 / 5: depth of the batch pipeline (default 16 / 32)')
+    ap.add_argument('--coder-sms', type=int, default=None,
+                    help='configs 2 / 5: SMs the persistent transform kernels leave to the coder blocks (default 12)')
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 3 if args.impl == 'reference' else 40
+        args.steps = 3 if args.impl == 'reference' else (160 if args.config == 5 else 40)  # config 5: 5 x its pipeline depth
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
 
@@ -374,15 +375,23 @@ def main():
         B_global = B * world
     model = build_product_model(cfg, device)
     encode, decode = make_step_fns(cfg, model)
-    pipelined = cfg == 2
+    # config 2 (the headline) and config 5 (COCO shape) are throughput measurements: batches in flight (CodecPipeline); config 5 also
+    # reports the latency of one image (`one_batch_latency_ms`)
+    pipelined = cfg in (2, 5)
+    if args.inflight is None:
+        args.inflight = 16 if cfg == 2 else 32
+    if args.coder_sms is None:
+        args.coder_sms = 12
 
     # inputs: two distinct batches alternate between steps; where a batch is smaller than L2 (126 MB) the L2 is flushed between
     # timed iterations instead (a 256 MB write), each iteration timed by its own event pair
     gen = torch.Generator(device='cpu').manual_seed(1 + rank)
     rnd = torch.randn if cfg in (1, 2, 5) else torch.rand
-    host_inputs = [rnd(B, *shape, generator=gen).pin_memory() for _ in range(2)]
+    input_bytes = B * shape[0] * shape[1] * shape[2] * 4
+    # pipelined configs cannot flush L2 between steps: they alternate between enough distinct batches to exceed it (126 MB)
+    n_in = max(2, -(-140_000_000 // input_bytes)) if pipelined else 2
+    host_inputs = [rnd(B, *shape, generator=gen).pin_memory() for _ in range(n_in)]
     dev_inputs = [h.to(device) for h in host_inputs]
-    input_bytes = host_inputs[0].numel() * 4
     flush_l2 = input_bytes < 160e6 and not pipelined
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device) if flush_l2 else None
 
@@ -392,7 +401,7 @@ def main():
         torch.cuda.synchronize()
 
     def device_step(i):
-        obj = encode(dev_inputs[i & 1])
+        obj = encode(dev_inputs[i % n_in])
         return obj, decode(obj)
 
     def n_symbols(obj):
@@ -415,7 +424,7 @@ def main():
                 start.record(main_s)
                 last = None
                 for i in range(first, first + n):
-                    last = pipe.submit(dev_inputs[i & 1]) or last
+                    last = pipe.submit(dev_inputs[i % n_in]) or last
                 for r in pipe.drain():
                     last = r
                 main_s.wait_stream(pipe.transform_stream)
@@ -447,7 +456,7 @@ def main():
             sym_per_image = int(torch.tensor(last.shape).prod()) * model.entropy_bottleneck.channels
             pipe.close()
             extra['priming_steps'] = n_prime
-            model.entropy_bottleneck.coder_layout = 'lanes'  # the accounting pass keeps the layout of the timed region
+            model.entropy_bottleneck.coder_layout = 'throughput'  # the accounting pass keeps the layout of the timed region
         else:
             for i in range(args.warmup):
                 device_step(i)
@@ -536,7 +545,7 @@ def main():
 
             def e2e_step(i):
                 with torch.inference_mode(), torch.cuda.stream(streams[i % n_thr]):
-                    x = inputs[i & 1].to(device, non_blocking=True)
+                    x = inputs[i % len(inputs)].to(device, non_blocking=True)
                     obj = encode(x)                             # {'strings': [list[bytes]], 'shape'}: bitstreams land on the host
                     feat = decode(obj)                          # list[bytes] -> device -> features
                     res = feat.mean(dim=(1, 2, 3))
@@ -623,7 +632,7 @@ def main():
             'data': 'synthetic',
             'config': {'workload': desc + ', batch %d per GPU' % B, 'bench_config': cfg,
                        'images_per_gpu_per_step': B, 'global_images_per_step': B_global, 'symbols_per_image': sym_per_image,
-                       'l2_policy': 'two alternating input batches of %.0f MB (> 126 MB L2)' % (input_bytes / 1e6) if not flush_l2 else
+                       'l2_policy': '%d alternating input batches of %.0f MB (%.0f MB > 126 MB L2)' % (n_in, input_bytes / 1e6, n_in * input_bytes / 1e6) if not flush_l2 else
                                     'L2 flushed (256 MB write) between timed iterations, each iteration timed by its own event pair',
                        'parallelism': 'dp%d (batch sharded, one counter all-reduce per evaluation)' % world,
                        'schedule': ('software pipeline, %d batches in flight: transforms on one stream, g_a(i + depth) ahead of g_s(i); '

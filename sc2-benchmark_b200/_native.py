@@ -105,6 +105,14 @@ TCS_STORE, TCS_GDN1, TCS_QUANT, TCS_GDN = 0, 1, 2, 3
 TCS_ACT_NONE, TCS_ACT_RELU, TCS_ACT_LEAKY = 0, 1, 2
 RANS_LAYOUTS = {None: 0, 'auto': 0, 'warp': 1, 'lanes': 2}
 
+
+def rans_layout(layout, n_streams):
+    """`layout` argument of sc2_rans_*_batch.  'throughput' (what batches in flight ask for) resolves per call: a lane per stream when
+    the batch fills at least one warp, else a warp per stream (one lane of 32 working would be the slowest choice)."""
+    if layout == 'throughput':
+        layout = 'lanes' if n_streams >= 32 else 'warp'
+    return RANS_LAYOUTS[layout]
+
 _lib = None
 
 

@@ -406,8 +406,9 @@ class FPBasedResNetBottleneck(BaseBottleneck):
             # 7.7-10 ms per step instead of 5.9 (with the coder streams at HIGH priority, seven in ten); 10 of 10 runs with this.
             stream = torch.cuda.Stream(device=self.entropy_bottleneck._quantized_cdf.device, priority=-1)
         self._transform_stream = stream or None
-        # batches in flight: the coder layout that leaves the SMs to the transforms (sc2_rans_encode_batch, `layout`)
-        self.entropy_bottleneck.coder_layout = 'lanes' if self._transform_stream is not None else None
+        # batches in flight: the coder layout that leaves the SMs to the transforms (sc2_rans_encode_batch, `layout`): a lane per stream
+        # for batches of at least one warp of streams, else a warp per stream (_native.rans_layout)
+        self.entropy_bottleneck.coder_layout = 'throughput' if self._transform_stream is not None else None
         return self._transform_stream
 
     def _on_transform_stream(self, fn, *tensors):
@@ -486,7 +487,7 @@ class FPBasedResNetBottleneck(BaseBottleneck):
                     codecs[key] = codec
         if codec is False:
             return None
-        wanted = _native.RANS_LAYOUTS[getattr(self.entropy_bottleneck, 'coder_layout', None)]
+        wanted = _native.rans_layout(getattr(self.entropy_bottleneck, 'coder_layout', None), codec.batch)
         codec.coder_layout = wanted
         # one slot per CUDA stream (all work on a slot's buffers is ordered by its stream, whichever host thread issues it)
         slots = codec.__dict__.setdefault('_stream_slots', {})

@@ -61,7 +61,7 @@ def _ev(e):
 
 
 class FpNativeCodec:
-    def __init__(self, layer, batch, h_in, w_in, device, coder_layout='lanes'):
+    def __init__(self, layer, batch, h_in, w_in, device, coder_layout='throughput'):
         from .bottleneck import TensorCoreAnalysis, TensorCoreTransform, _param_key
         device = torch.device(device)
         if device.type != 'cuda':
@@ -70,7 +70,7 @@ class FpNativeCodec:
         if why is not None or layer.encoder_precision != 'split-tc' or layer.decoder_precision != 'fp16-tc':
             raise ValueError('the fused tensor-core plans do not cover this layer: %s' % (why or 'precision settings'))
         self.layer, self.batch, self.device = layer, int(batch), device
-        self.coder_layout = _native.RANS_LAYOUTS[coder_layout]
+        self.coder_layout = _native.rans_layout(coder_layout, int(batch))
         if layer._tc_encoder is None:
             layer._tc_encoder = TensorCoreAnalysis(layer.encoder)
         if layer._tc_decoder is None:

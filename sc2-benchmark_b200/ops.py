@@ -319,7 +319,7 @@ def rans_encode(symbols, tables, indexes=None, spatial=None, slot_bytes=None, la
         with _launch('rans_encode', 1 if B else 0, nbytes=4.0 * B * n, symbols=(B, n)):
             check(lib.sc2_rans_encode_batch(_ptr(sym), _ptr(idx), B, n, int(spatial or 0), _ptr(tab), tables.n_rows,
                                             tables.cdf_stride, _ptr(arena), slot_bytes, _ptr(lengths), _ptr(status),
-                                            _native.RANS_LAYOUTS[layout], st),
+                                            _native.rans_layout(layout, B), st),
                   'sc2_rans_encode_batch')
         with _launch('rans_pack', 2 if B else 1):
             check(lib.sc2_rans_pack(_ptr(arena), slot_bytes, _ptr(lengths), B, _ptr(packed), _ptr(offsets), st), 'sc2_rans_pack')
@@ -358,7 +358,7 @@ def rans_decode(streams, n_per_stream, tables, indexes=None, spatial=None, means
                                          symbols=(B, n_per_stream)):
         check(_lib().sc2_rans_decode_batch(_ptr(streams.packed), _ptr(streams.offsets), B, n_per_stream, _ptr(idx),
                                            int(spatial or 0), _ptr(tab), tables.n_rows, tables.cdf_stride, _ptr(out_sym),
-                                           _ptr(out_val), _ptr(m), _ptr(status), _native.RANS_LAYOUTS[layout], _stream_ptr()),
+                                           _ptr(out_val), _ptr(m), _ptr(status), _native.rans_layout(layout, B), _stream_ptr()),
               'sc2_rans_decode_batch')
     if check_status:
         torch.cuda.current_stream(dev).synchronize()  # (not a blocking copy: see PackedStreams._host_offsets)

@@ -303,7 +303,7 @@ def test_transform_stream_pipeline_matches_serial(s2):
             want.append((st.tolist(), layer.decode_packed(st, shape).clone()))
         assert layer.entropy_bottleneck.coder_layout is None if hasattr(layer.entropy_bottleneck, 'coder_layout') else True
         ts = layer.use_transform_stream(True)
-        assert ts is not None and layer.entropy_bottleneck.coder_layout == 'lanes'
+        assert ts is not None and layer.entropy_bottleneck.coder_layout == 'throughput'
         side = [torch.cuda.Stream(device=dev) for _ in range(3)]
         depth, enc, got = 2, {}, {}
         for i in range(len(xs) + depth):
