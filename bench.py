@@ -340,6 +340,7 @@ def main():
     ap.add_argument('--e2e-threads', type=int, default=0, help='host threads (one CUDA stream each) driving the e2e steps')
     ap.add_argument('--max-ahead', type=int, default=4, help='batches the host may run ahead of the GPU beyond the pipeline depth')
     ap.add_argument('--inflight', type=int, default=None, help='configs 2 / 5: depth of the batch pipeline (default 16 / 32)')
+    ap.add_argument('--streams', type=int, default=8, help='configs 3 / 4: CUDA streams the batches round-robin over (1: one batch at a time)')
     ap.add_argument('--coder-sms', type=int, default=None,
                     help='configs 2 / 5: SMs the persistent transform kernels leave to the coder blocks (default 12)')
     args = ap.parse_args()
@@ -378,6 +379,9 @@ def main():
     # config 2 (the headline) and config 5 (COCO shape) are throughput measurements: batches in flight (CodecPipeline); config 5 also
     # reports the latency of one image (`one_batch_latency_ms`)
     pipelined = cfg in (2, 5)
+    # configs 3 / 4 (zoo codecs): batches round-robin over a few CUDA streams through the device-resident calls (compress_packed /
+    # decompress on PackedStreams), so that one batch's coder chains overlap the transforms of the others
+    multistream = cfg in (3, 4) and args.streams > 1
     if args.inflight is None:
         args.inflight = 16 if cfg == 2 else 32
     if args.coder_sms is None:
@@ -389,10 +393,10 @@ def main():
     rnd = torch.randn if cfg in (1, 2, 5) else torch.rand
     input_bytes = B * shape[0] * shape[1] * shape[2] * 4
     # pipelined configs cannot flush L2 between steps: they alternate between enough distinct batches to exceed it (126 MB)
-    n_in = max(2, -(-140_000_000 // input_bytes)) if pipelined else 2
+    n_in = max(2, -(-140_000_000 // input_bytes)) if (pipelined or multistream) else 2
     host_inputs = [rnd(B, *shape, generator=gen).pin_memory() for _ in range(n_in)]
     dev_inputs = [h.to(device) for h in host_inputs]
-    flush_l2 = input_bytes < 160e6 and not pipelined
+    flush_l2 = input_bytes < 160e6 and not pipelined and not multistream
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=device) if flush_l2 else None
 
     def barrier():
@@ -457,6 +461,49 @@ def main():
             pipe.close()
             extra['priming_steps'] = n_prime
             model.entropy_bottleneck.coder_layout = 'throughput'  # the accounting pass keeps the layout of the timed region
+        elif multistream:
+            pad = s2.AdaptivePad(fill=0, factor=64)
+            rr = [torch.cuda.Stream(device=device) for _ in range(args.streams)]
+
+            def packed_step(i):
+                strs, shp = model.compress_packed(pad(dev_inputs[i % n_in]))
+                return strs, model.decompress(list(strs) if isinstance(strs, tuple) else [strs], shp)['x_hat']
+
+            def run_rr(n, first=0):
+                main_s = torch.cuda.current_stream()
+                start = torch.cuda.Event(enable_timing=True)
+                start.record(main_s)
+                last = None
+                for st_ in rr:
+                    st_.wait_stream(main_s)
+                for i in range(first, first + n):
+                    with torch.cuda.stream(rr[i % len(rr)]):
+                        last = packed_step(i)
+                for st_ in rr:
+                    main_s.wait_stream(st_)
+                stop = torch.cuda.Event(enable_timing=True)
+                stop.record(main_s)
+                return start, stop, last
+
+            run_rr(max(args.warmup, 2 * len(rr)))
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            launches0 = s2.ops.STATS['launches']
+            allocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
+            t0 = time.perf_counter()
+            e0, e1, last = run_rr(args.steps, first=max(args.warmup, 2 * len(rr)))
+            t_issue = (time.perf_counter() - t0) * 1e3
+            barrier()
+            launches = s2.ops.STATS['launches'] - launches0
+            allocs = torch.cuda.memory_stats(device).get('num_device_alloc', 0) - allocs0
+            ms = e0.elapsed_time(e1)
+            clocks = sampler.stop()
+            model.entropy_bottleneck.check_faults()
+            strs = last[0]
+            total_bytes = sum(ps.total_bytes() for ps in (strs if isinstance(strs, tuple) else (strs,)))
+            sym_per_image = None
+            extra['streams'] = len(rr)
         else:
             for i in range(args.warmup):
                 device_step(i)
@@ -506,8 +553,9 @@ def main():
         if cfg in (1, 2, 5):
             model.native_calls = True
         latency_ms = None
-        if pipelined:  # the latency of ONE batch with the low-latency coder layout (a warp per stream), for reference
-            model.entropy_bottleneck.coder_layout = None
+        if pipelined or multistream:  # the latency of ONE batch (low-latency coder layout: a warp per stream), for reference
+            if pipelined:
+                model.entropy_bottleneck.coder_layout = None
             device_step(0)
             l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             l0.record()
@@ -636,7 +684,9 @@ def main():
                                     'L2 flushed (256 MB write) between timed iterations, each iteration timed by its own event pair',
                        'parallelism': 'dp%d (batch sharded, one counter all-reduce per evaluation)' % world,
                        'schedule': ('software pipeline, %d batches in flight: transforms on one stream, g_a(i + depth) ahead of g_s(i); '
-                                    'coders on per-batch streams' % args.inflight) if pipelined else 'one batch at a time (latency)'},
+                                    'coders on per-batch streams' % args.inflight) if pipelined else
+                                   ('%d batches in flight, round-robin over %d CUDA streams (device-resident compress_packed / decompress)'
+                                    % (args.streams, args.streams)) if multistream else 'one batch at a time (latency)'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'coder': coder, 'cpu_baseline': cpu_baseline,
             'serial_ms_per_step': serial_ms, 'one_batch_latency_ms': latency_ms, 'ms_per_image': ms / args.steps / max(B, 1),
             'host_issue_ms_per_step': t_issue / args.steps, 'cudaMalloc_calls_in_timed_region': allocs, 'per_rank_ms': per_rank_ms,

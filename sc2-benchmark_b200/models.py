@@ -491,7 +491,7 @@ class FactorizedPrior(CompressionModel):
 
     @torch.no_grad()
     def decompress(self, strings, shape):
-        assert isinstance(strings, list) and len(strings) == 1
+        assert isinstance(strings, (list, tuple)) and len(strings) == 1
         first = strings[0]
         streams = first if isinstance(first, ops.PackedStreams) else \
             ops.PackedStreams.from_list(first, self.entropy_bottleneck._quantized_cdf.device)
@@ -529,6 +529,13 @@ class ScaleHyperprior(CompressionModel):
 
     @torch.no_grad()
     def compress(self, x):
+        (y_streams, z_streams), shape = self.compress_packed(x)
+        return {'strings': [y_streams.tolist(), z_streams.tolist()], 'shape': shape}
+
+    @torch.no_grad()
+    def compress_packed(self, x):
+        """compress() with the bitstreams left on the device: ((y PackedStreams, z PackedStreams), latent (H, W)); nothing synchronises,
+        so batches issued on different CUDA streams overlap (a batch's coder is a serial chain per image)."""
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         y_planes = run_analysis(self, 'g_a', self.g_a, x, out='planes')
         y = ops.unsplit_to_nchw(y_planes[0], y_planes[1], self.M)
@@ -540,17 +547,22 @@ class ScaleHyperprior(CompressionModel):
         indexes = gc.build_indexes(run_analysis(self, 'h_s', self.h_s, z_hat))
         y_symbols = ops.quantize_symbols(y.reshape(y.size(0), 1, -1))
         y_streams = ops.rans_encode(y_symbols, gc.coder_tables(), indexes=indexes)
-        return {'strings': [y_streams.tolist(), z_streams.tolist()], 'shape': z_symbols.size()[-2:]}
+        return (y_streams, z_streams), z_symbols.size()[-2:]
 
     @torch.no_grad()
     def decompress(self, strings, shape):
-        assert isinstance(strings, list) and len(strings) == 2
+        """strings: [y, z] as list[bytes] each (the CompressAI contract; decode faults raise here) or as PackedStreams from
+        compress_packed (device resident; faults accumulate in the entropy bottleneck's fault word, see check_faults())."""
+        assert isinstance(strings, (list, tuple)) and len(strings) == 2
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         device = eb._quantized_cdf.device
-        z_hat = eb.decompress_packed(ops.PackedStreams.from_list(strings[1], device), tuple(shape), check_status=True)
+        packed = isinstance(strings[0], ops.PackedStreams) and isinstance(strings[1], ops.PackedStreams)
+        z_streams = strings[1] if packed else ops.PackedStreams.from_list(strings[1], device)
+        y_streams = strings[0] if packed else ops.PackedStreams.from_list(strings[0], device)
+        z_hat = eb.decompress_packed(z_streams, tuple(shape), check_status=not packed)
         indexes = gc.build_indexes(run_analysis(self, 'h_s', self.h_s, z_hat))
-        y_streams = ops.PackedStreams.from_list(strings[0], device)
-        y_hat = ops.rans_decode(y_streams, indexes[0].numel(), gc.coder_tables(), indexes=indexes, want='values')
+        y_hat = ops.rans_decode(y_streams, indexes[0].numel(), gc.coder_tables(), indexes=indexes, want='values', check_status=not packed,
+                                status=eb._fault_word(device) if packed else None)
         return {'x_hat': run_synthesis(self, self.g_s, y_hat.view(indexes.size()))}
 
 
