@@ -70,15 +70,20 @@ __device__ __forceinline__ void enc_emit_checked(EncChain &s) {
 
 // one regular symbol, unchecked (caller guarantees s.pw > 0): the dependent chain is
 //   ISETP -> SEL -> IMAD.WIDE x3 (mul.hi.u64) -> SHF -> IMAD.WIDE -> IADD
+// The renormalisation's side effects (the emitted word, the write position) are issued AFTER the division chain: a single warp issues
+// in order, so with the store first (as the source reads) its address arithmetic and the register hand-over between the stored word
+// and the selected state sat in front of the chain and cost ~25 of 112 cycles per symbol (ncu source view, profiles/r4_coder_*).
 __device__ __forceinline__ void enc_step(EncChain &s, const uint4 a, const uint4 b) {
     const uint32_t xl = static_cast<uint32_t>(s.x), xh = static_cast<uint32_t>(s.x >> 32);
     const bool ren = xh >= a.z;  // x >= freq << 47
-    if (ren) s.words[s.pw - 1] = xl;
-    s.pw -= ren ? 1u : 0u;
+    const uint32_t emit = xl;
     const uint64_t y = ren ? static_cast<uint64_t>(xh) : s.x;
     const uint64_t rcp = (static_cast<uint64_t>(a.y) << 32) | a.x;
     const uint64_t q = __umul64hi(y, rcp) >> b.y;
     s.x = y + b.x + q * static_cast<uint64_t>(a.w);
+    asm volatile("" ::: "memory");  // keep the store below the chain
+    if (ren) s.words[s.pw - 1] = emit;
+    s.pw -= ren ? 1u : 0u;
 }
 
 // cold path: a chunk that contains escapes, is the (short) last chunk, or runs close to the end of the arena slot

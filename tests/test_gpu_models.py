@@ -108,6 +108,21 @@ def test_neural_input_compression_classifier_q8(s2, oracle_compressai, arch):
     # (5) ... and this implementation decodes the ORACLE's bytes (cross-implementation decode)
     assert rel_err(cross.cpu(), want) < FEATURE_TOL
     assert float(got.min()) >= 0 and float(got.max()) <= 1
+    # (6) the device-resident calls (bitstreams stay PackedStreams, nothing synchronises) give the same bytes and the same x_hat,
+    # also when two batches are issued on different CUDA streams
+    with torch.inference_mode():
+        outs = []
+        for st in (torch.cuda.Stream(dev), torch.cuda.Stream(dev)):
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                strs, shp = codec.compress_packed(xp.to(dev))
+                strs = list(strs) if isinstance(strs, tuple) else [strs]
+                outs.append((strs, shp, codec.decompress(strs, shp)['x_hat']))
+        torch.cuda.synchronize(dev)
+        codec.entropy_bottleneck.check_faults()
+    for strs, shp, x_hat in outs:
+        assert [ps.tolist() for ps in strs] == got_obj['strings'] and tuple(shp) == tuple(got_obj['shape'])
+        assert torch.equal(x_hat, got)
 
 
 def test_feature_extraction_backbone_coco_shape(s2):
