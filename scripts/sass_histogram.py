@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel SASS opcode histogram of libsc2b200.so: the evidence that the kernels are Blackwell-native (UTCHMMA = tcgen05.mma,
 LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA, UTCBAR = tcgen05.commit; HMMA would be the legacy mma.sync path).
-    python scripts/sass_histogram.py > profiles/r2_sass_histogram.md"""
+    python scripts/sass_histogram.py > profiles/r4_sass_histogram.md"""
 import collections
 import os
 import re
