@@ -53,7 +53,7 @@ METRICS = {
 }
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 # Kernels whose tensor-core work is three fp16 MMA passes per algorithmic MAC (split fp16 = fp32-grade)
-THREE_PASS_PREFIXES = ('tc_split', 'tc_first', 'ga_halo', 'ga_first')
+THREE_PASS_PREFIXES = ('tc_split', 'tc_first', 'ga_halo', 'ga_first', 'tcs_conv', 'tcs_gdn', 'tcs_deconv5')
 
 
 def load_traffic():
