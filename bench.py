@@ -383,7 +383,9 @@ def main():
     # decompress on PackedStreams), so that one batch's coder chains overlap the transforms of the others
     multistream = cfg in (3, 4) and args.streams > 1
     if args.inflight is None:
-        args.inflight = 16 if cfg == 2 else 32
+        # the serial coder chains of a batch take ~20 ms whatever its size, so the depth that keeps the transform stream busy grows as
+        # the per-GPU batch shrinks (strong scaling: 128 / 64 / 32 images per GPU at N = 2 / 4 / 8): profiles/r4_pipeline_depth.md
+        args.inflight = min(96, max(16, 16 * 256 // max(B, 1))) if cfg == 2 else 32
     if args.coder_sms is None:
         args.coder_sms = 12
 
