@@ -206,6 +206,12 @@ rans_encode_lanes_kernel(const int32_t *__restrict__ symbols, int batch, uint32_
             bool esc_next = false;
             if (!esc_cur && I >= 23 && cur.rem >= 8u && cc.rem >= 8u && s.pw >= 8u) {
                 // ---- fast block: 8 regular symbols of one row, no bounds to check; nothing but the chain and the rings
+                // The 8 symbols a lane loads per block share one 32-byte sector (a new one every block); the compiler sinks those loads
+                // towards their first use, so the sector miss (L2 / HBM, 32 different sectors per warp) was waited for at the top of
+                // every block: 41 % of the kernel's stall samples on one move (ncu source view, profiles/r4_lanes_*).  The sector
+                // of the block after next is therefore requested here, two blocks (~3.5 k cycles) early: 8.46 -> 7.77 ms per batch of 256.
+                // (a prefetch, not a load into an unused register: that load shares a scoreboard with the ones the chain waits for)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(sp - (I >= 32 ? 32 : 0)));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint4 e = ent[j];
@@ -464,6 +470,7 @@ rans_decode_lanes_kernel(const uint8_t *__restrict__ packed, const int64_t *__re
                     s.xh = ren ? nl : nh;
                     // predicated refill of next_w, written so that no branch (and no move that would wait for the
                     // load) lands on the chain: the loaded word is first needed at the next renormalisation
+                    // (tried: taking next_w from a second register and merging the requested word one step later -- 11.7 -> 12.9 ms)
                     s.p += ren ? 1u : 0u;
                     const uint32_t *wp = words + min(s.p, n_words - 1u);
                     asm volatile(
