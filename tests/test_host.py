@@ -360,3 +360,38 @@ def test_ctypes_signatures_match_the_header(s2):
                 assert a is ctypes.c_size_t, (name, p, a)
             else:
                 assert a is ctypes.c_int, (name, p, a)
+
+
+def test_coder_layout_resolution_and_channel_tiles():
+    """Host logic behind the round-2 entry points: the 'throughput' coder layout resolves per batch; output-channel tiles of the
+    extended split convolution cover c_out exactly with tiles the kernel has (sc2_tc_split_n_tile)."""
+    import sc2bench_b200 as s2
+    N = s2._native
+    assert N.rans_layout('throughput', 256) == N.RANS_LAYOUTS['lanes'] and N.rans_layout('throughput', 32) == N.RANS_LAYOUTS['lanes']
+    assert N.rans_layout('throughput', 31) == N.RANS_LAYOUTS['warp'] and N.rans_layout('throughput', 1) == N.RANS_LAYOUTS['warp']
+    assert N.rans_layout(None, 5) == 0 and N.rans_layout('lanes', 1) == 2 and N.rans_layout('warp', 999) == 1
+    lib = N.load()
+    for c_out in (8, 24, 96, 128, 144, 192, 200, 256, 320, 384, 512):
+        tiles = s2.ops.split_n_tiles(c_out)
+        assert tiles[0][0] == 0 and sum(n for _, n in tiles) == c_out
+        assert all(a + n == b for (a, n), (b, _) in zip(tiles, tiles[1:]))
+        for c0, n in tiles[:-1]:
+            assert lib.sc2_tc_split_n_tile(n) == n and c0 % 8 == 0  # inner tiles are full tiles of a size the kernel has
+        assert 0 < lib.sc2_tc_split_n_tile(tiles[-1][1]) <= 128
+
+
+def test_split_analysis_plan_coverage_rules():
+    """SplitAnalysisPlan.why_not: which transforms of the zoo codecs / hyperprior bottlenecks the tensor-core plan takes (no GPU needed)."""
+    import sc2bench_b200 as s2
+    P = s2.models.SplitAnalysisPlan
+    m = s2.models.bmshj2018_hyperprior(8)
+    assert P.why_not(m.g_a, (3, 256, 256)) is None
+    assert P.why_not(m.h_a, (320, 16, 16), planes_in=True) is None
+    assert P.why_not(m.h_s, (192, 4, 4)) is None
+    assert 'odd' in P.why_not(m.g_a, (3, 250, 250))          # 125 x 125 after the first layer: stride 2 needs even sizes
+    f = s2.models.bmshj2018_factorized(1)
+    assert P.why_not(f.g_a, (3, 64, 64)) is None and P.why_not(f.g_s, (192, 4, 4)) is not None  # g_s has inverse GDNs: ZooSynthesisPlan's job
+    assert s2.models.ZooSynthesisPlan.why_not(f.g_s) is None
+    shp = s2.get_layer('SHPBasedResNetBottleneck', num_latent_channels=16, num_bottleneck_channels=24, num_target_channels=256)
+    assert P.why_not(shp.h_s, (16, 7, 7)) is not None         # k5 s2 p1 transposed convolutions: fp32 kernels (logged)
+    assert s2.bottleneck.TensorCoreAnalysis.why_not(shp.g_a, (2, 3, 224, 224)) is None
