@@ -418,4 +418,12 @@ class GaussianConditional(EntropyModel):
 
     def build_indexes(self, scales):
         """Index of the first table entry >= max(scale, bound) (one pass on the device instead of 63)."""
-        return ops.gc_build_indexes(scales, self.scale_table, float(self.scale_bound))
+        # (scale_bound is a registered buffer: float() of it on the device is a blocking copy that drains the stream -- 10 ms per call in
+        # the hyperprior's compress / decompress; its host value is cached until the buffer is written again)
+        sb = self.scale_bound
+        key = (sb.data_ptr(), sb._version, sb.device)
+        cached = self.__dict__.get('_scale_bound_host')
+        if cached is None or cached[0] != key:
+            cached = (key, float(sb))
+            self.__dict__['_scale_bound_host'] = cached
+        return ops.gc_build_indexes(scales, self.scale_table, cached[1])
