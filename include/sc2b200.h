@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SC2_ABI_VERSION 9
+#define SC2_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define SC2_API __attribute__((visibility("default")))
@@ -279,8 +279,9 @@ SC2_API int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, cons
  *   mode 3      GDN proper: y = x / sqrt(beta + gamma . x^2) (1x1: w = gamma, the squares are formed in shared memory)
  *   pad_x       horizontal padding when it differs from pad (< 0: pad_x = pad)
  *   out_stride  2 (mode 0, stride 1): the h_out x w_out results are the pixels (2Y + out_py, 2X + out_px) of planes
- *               [images, 2 h_out, 2 w_out, out_pitch] -- one of the four stride-1 sub-convolutions of a ConvTranspose2d(k5, s2, p2, op1)
- *               (hyper-synthesis h_s, sc2bench/models/layer.py:611-617; taps as in sc2_tc_conv_ex) */
+ *               [images, out_h, out_w, out_pitch] (out_h = out_w = 0: 2 h_out x 2 w_out; h_out, w_out must be the pixel counts of that
+ *               parity) -- one of the four stride-1 sub-convolutions of a ConvTranspose2d(k5, s2): p2 / op1 in the zoo codecs' h_s,
+ *               p1 / op0 (odd output sizes) in the hyperprior bottlenecks' h_s (sc2bench/models/layer.py:611-617) */
 #define SC2_TCS_GDN 3
 #define SC2_TCS_ACT_NONE 0
 #define SC2_TCS_ACT_RELU 1
@@ -297,6 +298,7 @@ typedef struct sc2_tc_split_ex_desc {
     float slope;
     int pad_x;
     int out_stride, out_py, out_px;
+    int out_h, out_w;
 } sc2_tc_split_ex_desc;
 
 SC2_API int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const void *x_lo, const void *w_hi,

@@ -33,7 +33,7 @@ class TcSplitExDesc(_c.Structure):
     """struct sc2_tc_split_ex_desc"""
     _fields_ = [(n, i32) for n in ('images', 'h_in', 'w_in', 'c_in', 'c_out', 'kh', 'kw', 'stride', 'pad', 'mode', 'h_out', 'w_out',
                                     'out_pitch', 'n_off', 'c_total', 'in_nhwc', 'act')] + [('slope', _c.c_float)] + \
-               [(n, i32) for n in ('pad_x', 'out_stride', 'out_py', 'out_px')]
+               [(n, i32) for n in ('pad_x', 'out_stride', 'out_py', 'out_px', 'out_h', 'out_w')]
 
 
 class TcConvExDesc(_c.Structure):
@@ -95,7 +95,7 @@ SIGNATURES = {
 }
 
 SC2_OK = 0
-ABI_VERSION = 9  # include/sc2b200.h SC2_ABI_VERSION
+ABI_VERSION = 10  # include/sc2b200.h SC2_ABI_VERSION
 FAULT_ARENA_OVERFLOW, FAULT_STREAM_TRUNCATED, FAULT_BAD_STREAM, FAULT_BAD_INDEX = 1, 2, 4, 8
 EPI_NONE, EPI_RELU, EPI_CLAMP01, EPI_QUANTIZE, EPI_ABS, EPI_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 IN_NONE, IN_ABS = 0, 1

@@ -20,7 +20,7 @@ from torch import nn
 from . import _native, ops
 from .entropy_models import GaussianConditional
 from .layers import GDN1
-from .models import CompressionModel, get_scale_table, run_transform, update_registered_buffers
+from .models import CompressionModel, get_scale_table, run_analysis, run_transform, update_registered_buffers
 
 
 
@@ -682,14 +682,14 @@ class SHPBasedResNetBottleneck(BaseBottleneck):
 
     @torch.no_grad()
     def _scales_to_indexes(self, z_hat):
-        return self.gaussian_conditional.build_indexes(run_transform(self.h_s, z_hat))
+        return self.gaussian_conditional.build_indexes(run_analysis(self, 'h_s', self.h_s, z_hat))
 
     @torch.no_grad()
     def encode(self, x, **kwargs):
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         y = self._analysis(x)
-        z_symbols = run_transform(self.h_a, y, final_epilogue=_native.EPI_QUANTIZE,
-                                  final_aux=eb._get_medians().detach().reshape(-1), in_abs=True)  # h_a(|y|), |.| on load
+        z_symbols = run_analysis(self, 'h_a', self.h_a, y, medians=eb._get_medians().detach().reshape(-1), out='symbols',
+                                 in_abs=True)  # h_a(|y|)
         z_shape = z_symbols.size()[-2:]
         z_streams = eb.compress_symbols(z_symbols, spatial=z_symbols[0, 0].numel())
         z_hat = eb.decompress_packed(z_streams, tuple(z_shape))  # the encoder decodes z itself, like the decoder will
@@ -768,15 +768,14 @@ class MSHPBasedResNetBottleneck(SHPBasedResNetBottleneck):
 
     @torch.no_grad()
     def _gaussian_params(self, z_hat):
-        scales_hat, means_hat = run_transform(self.h_s, z_hat).chunk(2, 1)
+        scales_hat, means_hat = run_analysis(self, 'h_s', self.h_s, z_hat).chunk(2, 1)
         return self.gaussian_conditional.build_indexes(scales_hat), means_hat.contiguous()
 
     @torch.no_grad()
     def encode(self, x, **kwargs):
         eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         y = self._analysis(x)
-        z_symbols = run_transform(self.h_a, y, final_epilogue=_native.EPI_QUANTIZE,
-                                  final_aux=eb._get_medians().detach().reshape(-1))
+        z_symbols = run_analysis(self, 'h_a', self.h_a, y, medians=eb._get_medians().detach().reshape(-1), out='symbols')
         z_shape = z_symbols.size()[-2:]
         z_streams = eb.compress_symbols(z_symbols, spatial=z_symbols[0, 0].numel())
         z_hat = eb.decompress_packed(z_streams, tuple(z_shape))

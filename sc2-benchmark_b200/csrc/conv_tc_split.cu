@@ -66,7 +66,6 @@ struct Params {
     int sym_c_off;
     int act;            // STORE: activation after the bias (ReLU / LeakyReLU of the hyper-analysis h_a)
     float slope;
-    int out5d, out_py;  // the tile goes to the pixels of row parity out_py of a 2x larger tensor (transposed-convolution sub-grid)
 };
 
 // B_RES: 1x1 convolutions (one tap, <= 2 K chunks) keep the whole weight matrix resident in shared memory for the life of
@@ -376,13 +375,9 @@ tc_split_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 fence_proxy_async();
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (issuer) {
-                    if (p.out5d) {
-                        tma_store_5d(&map_o_hi, st_hi, 0, x0, p.out_py, y0, img);
-                        tma_store_5d(&map_o_lo, st_lo, 0, x0, p.out_py, y0, img);
-                    } else {
-                        tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
-                        tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
-                    }
+                    // (a transposed convolution's parity sub-grid is the same store through a strided view of the output)
+                    tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
+                    tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
                     tma_store_commit();
                 }
             }
@@ -542,6 +537,9 @@ int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const 
     const bool interleave = d->out_stride == 2;
     if (d->out_stride != 1 && d->out_stride != 2) return SC2_ERR_INVALID_ARG;
     if (interleave && (d->mode != MODE_STORE_SPLIT || d->stride != 1 || (d->out_py | d->out_px) & ~1)) return SC2_ERR_INVALID_ARG;
+    // full-resolution output of an interleaved store: out_h x out_w (0: 2 h_out x 2 w_out); this launch owns the pixels of its parity
+    const int full_h = d->out_h > 0 ? d->out_h : 2 * d->h_out, full_w = d->out_w > 0 ? d->out_w : 2 * d->w_out;
+    if (interleave && ((full_h - d->out_py + 1) / 2 != d->h_out || (full_w - d->out_px + 1) / 2 != d->w_out)) return SC2_ERR_INVALID_ARG;
     const int pad_x = d->pad_x < 0 ? d->pad : d->pad_x;
     // channels of the output planes this launch owns: [n_off, n_off + out_ext); a launch that does not reach the end of the
     // pixel (an inner N tile) must fill its tile completely
@@ -596,13 +594,11 @@ int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const 
         p.groups = groups;
     }
     p.c_out = d->c_out;
-    p.out5d = interleave ? 1 : 0;
-    p.out_py = d->out_py;
     p.beta = vec ? vec + d->n_off : nullptr;
     p.medians = medians ? medians + d->n_off : nullptr;
     __half *o_hi = static_cast<__half *>(out_hi), *o_lo = static_cast<__half *>(out_lo);
     if (o_hi) {
-        const int shift = d->n_off + (interleave ? d->out_px * d->out_pitch : 0);
+        const int64_t shift = d->n_off + (interleave ? (static_cast<int64_t>(d->out_py) * full_w + d->out_px) * d->out_pitch : 0);
         o_hi += shift;
         o_lo += shift;
     }
@@ -648,9 +644,9 @@ int sc2_tc_split_conv_ex(const sc2_tc_split_ex_desc *d, const void *x_hi, const 
         // box is wider than the tensor view when the row pitch is padded (channels beyond the view: skipped / zero-filled)
         const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
         if (interleave) {
-            rc = make_nhwc_parity_out_map(&maps[4], o_hi, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th);
+            rc = make_nhwc_parity_out_map(&maps[4], o_hi, out_ext, d->out_pitch, full_w, full_h, d->out_py, d->out_px, d->images, p.stage_c, tw, th);
             if (rc) return rc;
-            rc = make_nhwc_parity_out_map(&maps[5], o_lo, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th);
+            rc = make_nhwc_parity_out_map(&maps[5], o_lo, out_ext, d->out_pitch, full_w, full_h, d->out_py, d->out_px, d->images, p.stage_c, tw, th);
         } else {
             rc = make_nhwc_map_pitch(&maps[4], o_hi, f16, 2, out_ext, d->out_pitch, d->w_out, d->h_out, d->images, p.stage_c, tw, th,
                                      CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -690,7 +686,7 @@ int sc2_tc_split_conv(const sc2_tc_split_desc *d, const void *x_hi, const void *
     e.mode = d->mode;
     e.h_out = d->h_out; e.w_out = d->w_out;
     e.out_pitch = d->out_c; e.n_off = 0; e.c_total = d->c_out; e.in_nhwc = 0; e.act = 0; e.slope = 0.0f;
-    e.pad_x = -1; e.out_stride = 1; e.out_py = 0; e.out_px = 0;
+    e.pad_x = -1; e.out_stride = 1; e.out_py = 0; e.out_px = 0; e.out_h = 0; e.out_w = 0;
     return sc2_tc_split_conv_ex(&e, x_hi, x_lo, w_hi, w_lo, beta, medians, gdn_x_hi, gdn_x_lo, out_hi, out_lo, out_sym, tile_counter,
                                 stream);
 }

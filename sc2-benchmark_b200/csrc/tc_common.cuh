@@ -156,10 +156,6 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *s
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all previously committed bulk stores have finished READING shared memory (the staging buffer may be reused)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -405,18 +401,20 @@ inline int make_nhwc_s2_map(CUtensorMap *m, const void *base, int c, int w, int 
     return r == CUDA_SUCCESS ? SC2_OK : SC2_ERR_INVALID_ARG;
 }
 
-// Output pixels of ONE parity (py, px) of an NHWC tensor [batch, 2h, 2w, pitch_c] (a transposed convolution's sub-grid): dims
-// (channel, X, py, Y, image) from a base already offset to pixel column parity px; dense box {box_c, box_w, 1, box_h, 1}.
-inline int make_nhwc_parity_out_map(CUtensorMap *m, const void *base, int c, int pitch_c, int w, int h, int batch, int box_c, int box_w,
-                                    int box_h) {
+// Output pixels of ONE parity (py, px) of an NHWC tensor [batch, out_h, out_w, pitch_c] (a transposed convolution's sub-grid; out_h,
+// out_w may be odd): dims (channel, X, Y, image) with pixel (2Y + py, 2X + px), extents exactly the pixels of that parity, from a base
+// already offset to pixel (py, px); dense box {box_c, box_w, box_h, 1}.
+inline int make_nhwc_parity_out_map(CUtensorMap *m, const void *base, int c, int pitch_c, int out_w, int out_h, int py, int px, int batch,
+                                    int box_c, int box_w, int box_h) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return SC2_ERR_CUDA;
-    const cuuint64_t row = static_cast<cuuint64_t>(2 * w) * pitch_c * 2;  // one full-resolution row, bytes
-    cuuint64_t dims[5] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), 2, static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(batch)};
-    cuuint64_t strides[4] = {static_cast<cuuint64_t>(2 * pitch_c) * 2, row, 2 * row, static_cast<cuuint64_t>(2 * h) * row};
-    cuuint32_t box[5] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), 1, static_cast<cuuint32_t>(box_h), 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void *>(base), dims, strides, box, estr,
+    const cuuint64_t row = static_cast<cuuint64_t>(out_w) * pitch_c * 2;  // one full-resolution row, bytes
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>((out_w - px + 1) / 2), static_cast<cuuint64_t>((out_h - py + 1) / 2),
+                          static_cast<cuuint64_t>(batch)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(2 * pitch_c) * 2, 2 * row, static_cast<cuuint64_t>(out_h) * row};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SC2_OK : SC2_ERR_INVALID_ARG;

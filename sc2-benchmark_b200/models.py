@@ -157,7 +157,8 @@ class SplitAnalysisPlan:
         Conv2d(k <= 5, stride 1 | 2) with bias, optional ReLU / LeakyReLU in the epilogue; stride-2 layers read the NHWC planes of the
             layer before through a 5-D tensor map (pixel parity = a coordinate), layers wider than 128 channels run as N tiles
         GDN / GDN1: a 1x1 gamma GEMM on x^2 / |x| formed in shared memory, y = x * rsqrt(beta + acc) / x / (beta + acc)
-        ConvTranspose2d(k5, s2, p2, op1) (hyper-synthesis h_s): 4 parity sub-convolutions writing interleaved pixels
+        ConvTranspose2d(k5, s2, p2, op1 | p1, op0) (hyper-synthesis h_s): 4 parity sub-convolutions writing interleaved pixels
+        channel counts that are not multiples of 16 and odd sizes in front of a stride-2 layer are zero-padded (torch pads of small planes)
         the last conv can quantise straight to coder symbols (round(y + bias - median), NCHW order)."""
 
     def __init__(self, seq):
@@ -174,12 +175,13 @@ class SplitAnalysisPlan:
         prev_conv = False
         for i, m in enumerate(mods):
             if isinstance(m, nn.ConvTranspose2d):
-                if (tuple(m.kernel_size), tuple(m.stride), tuple(m.padding), tuple(m.output_padding), m.groups, tuple(m.dilation)) != \
-                        ((5, 5), (2, 2), (2, 2), (1, 1), 1, (1, 1)):
-                    return 'transposed convolution %d is not (k5, s2, p2, op1)' % i
-                if m.in_channels != C or C % 16:
-                    return 'transposed convolution %d: c_in %d' % (i, C)
-                H, W, C = 2 * H, 2 * W, m.out_channels
+                geo = (tuple(m.kernel_size), tuple(m.stride), tuple(m.padding), tuple(m.output_padding), m.groups, tuple(m.dilation))
+                if geo not in (((5, 5), (2, 2), (2, 2), (1, 1), 1, (1, 1)), ((5, 5), (2, 2), (1, 1), (0, 0), 1, (1, 1))):
+                    return 'transposed convolution %d is not (k5, s2, p2, op1) or (k5, s2, p1, op0)' % i
+                if m.in_channels != C:
+                    return 'transposed convolution %d expects %d channels, gets %d' % (i, m.in_channels, C)
+                grow = 0 if m.padding[0] == 2 else 1
+                H, W, C = 2 * H + grow, 2 * W + grow, m.out_channels
                 prev_conv = True
             elif isinstance(m, nn.Conv2d):
                 k, st = m.kernel_size[0], m.stride[0]
@@ -189,12 +191,6 @@ class SplitAnalysisPlan:
                     return 'convolution %d: groups / dilation / kernel / stride outside the kernel' % i
                 if m.in_channels != C:
                     return 'convolution %d expects %d channels, gets %d' % (i, m.in_channels, C)
-                if i == 0 and not planes_in and C * k * k <= 128:
-                    pass  # im2col + 1x1 GEMM
-                elif C % 16:
-                    return 'convolution %d: c_in %d is not a multiple of 16' % (i, C)
-                elif st == 2 and (H % 2 or W % 2):
-                    return 'convolution %d: stride 2 on an odd %d x %d input' % (i, H, W)
                 H, W = (H + 2 * m.padding[0] - k) // st + 1, (W + 2 * m.padding[0] - k) // st + 1
                 if H < 1 or W < 1:
                     return 'empty output'
@@ -204,7 +200,7 @@ class SplitAnalysisPlan:
                 if m.inverse:
                     return 'layer %d is an inverse GDN' % i
                 if C % 16 or m.beta.numel() != C:
-                    return 'GDN over %d channels' % C
+                    return 'GDN over %d channels (not a multiple of 16)' % C
                 prev_conv = False
             elif isinstance(m, (nn.ReLU, nn.LeakyReLU)):
                 if not prev_conv:
@@ -230,12 +226,14 @@ class SplitAnalysisPlan:
                 elif i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU):
                     act, slope = _native.TCS_ACT_LEAKY, mods[i + 1].negative_slope
                 bias = m.bias.detach().float().contiguous() if m.bias is not None else None
+                c_in_pad = (m.in_channels + 15) // 16 * 16  # K of the tensor-core kernel: planes are zero-padded to it
                 if isinstance(m, nn.ConvTranspose2d):
-                    steps.append(('deconv', m, ops.pack_deconv5_weight_split_tiles(m.weight), bias, act, slope, None))
+                    steps.append(('deconv', m, ops.pack_deconv5_weight_split_tiles(m.weight, padding=m.padding[0], c_in_pad=c_in_pad),
+                                  bias, act, slope, None))
                 else:
                     patches = i == 0 and not planes_in and m.in_channels * m.kernel_size[0] ** 2 <= 128
                     k_pad = (m.in_channels * m.kernel_size[0] ** 2 + 15) // 16 * 16 if patches else None
-                    tiles = ops.pack_conv_weight_split_tiles(m.weight, c_in_pad=k_pad, as_patches=patches)
+                    tiles = ops.pack_conv_weight_split_tiles(m.weight, c_in_pad=k_pad if patches else c_in_pad, as_patches=patches)
                     steps.append(('conv', m, tiles, bias, act, slope, k_pad))
                 i += 2 if act != _native.TCS_ACT_NONE else 1
             else:
@@ -260,6 +258,18 @@ class SplitAnalysisPlan:
             h, l = x
         elif steps[0][6] is None:  # an fp32 NCHW activation (not an image): split NHWC planes
             h, l = ops.split_f16(x.permute(0, 2, 3, 1))
+
+        def fit(h, l, c_in, even):
+            # zero-pad the planes to the K the kernel wants (c_in rounded up to 16) and, in front of a stride-2 layer, to even sizes
+            # (the pad row / column is the zero the convolution's own padding would have read)
+            pc = (c_in + 15) // 16 * 16 - h.shape[3]
+            ph, pw = (h.shape[1] & 1, h.shape[2] & 1) if even else (0, 0)
+            if pc < 0:
+                h, l, pc = h[..., :(c_in + 15) // 16 * 16], l[..., :(c_in + 15) // 16 * 16], 0
+            if pc or ph or pw:
+                h, l = torch.nn.functional.pad(h, (0, pc, 0, pw, 0, ph)), torch.nn.functional.pad(l, (0, pc, 0, pw, 0, ph))
+            return h.contiguous(), l.contiguous()
+
         for si, step in enumerate(steps):
             last = si == len(steps) - 1
             if step[0] == 'conv':
@@ -272,19 +282,25 @@ class SplitAnalysisPlan:
                     res = ops.tc_split_conv_tiled(ph, pl, tiles, 1, 1, 1, 0, mode, vec=bias, medians=med, act=act, slope=slope,
                                                   name='tcs_conv_first')
                 else:
+                    H, W = h.shape[1], h.shape[2]
+                    h, l = fit(h, l, m.in_channels, st == 2)
                     res = ops.tc_split_conv_tiled(h, l, tiles, k, k, st, pad, mode, vec=bias, medians=med, act=act, slope=slope,
-                                                  in_nhwc=st == 2, name='tcs_conv')
+                                                  in_nhwc=st == 2, name='tcs_conv',
+                                                  out_hw=((H + 2 * pad - k) // st + 1, (W + 2 * pad - k) // st + 1))
                 if mode == T.TCS_QUANT:
                     return res
                 h, l = res
             elif step[0] == 'deconv':
                 _, m, packs, bias, act, slope, _ = step
+                h, l = fit(h, l, m.in_channels, False)
                 B, H, W, _ = h.shape
                 pitch = (m.out_channels + 7) // 8 * 8
-                out = (torch.empty((B, 2 * H, 2 * W, pitch), dtype=torch.float16, device=h.device),
-                       torch.empty((B, 2 * H, 2 * W, pitch), dtype=torch.float16, device=h.device))
+                grow = 0 if m.padding[0] == 2 else 1  # (k5, s2, p1, op0): 2H + 1 outputs
+                out = (torch.empty((B, 2 * H + grow, 2 * W + grow, pitch), dtype=torch.float16, device=h.device),
+                       torch.empty((B, 2 * H + grow, 2 * W + grow, pitch), dtype=torch.float16, device=h.device))
+                taps = ops.deconv5_parity_taps(m.padding[0])
                 for (py, px), tiles in packs.items():
-                    (ky, pad_y), (kx, pad_x) = ops.DECONV5_TAPS[py], ops.DECONV5_TAPS[px]
+                    (ky, pad_y), (kx, pad_x) = taps[py], taps[px]
                     ops.tc_split_conv_tiled(h, l, tiles, len(ky), len(kx), 1, pad_y, T.TCS_STORE, vec=bias, act=act, slope=slope,
                                             pad_x=pad_x, out=out, out_parity=(py, px), name='tcs_deconv5')
                 h, l = out

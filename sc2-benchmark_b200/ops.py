@@ -612,12 +612,13 @@ def pack_conv_weight_split_tiles(weight, c_in_pad=None, as_patches=False):
 
 
 def tc_split_conv_tiled(x_hi, x_lo, tiles, kh, kw, stride, pad, mode, vec=None, medians=None, gdn_x=None, act=_native.TCS_ACT_NONE,
-                        slope=0.0, in_nhwc=False, name='tc_split', pad_x=None, out=None, out_parity=None):
+                        slope=0.0, in_nhwc=False, name='tc_split', pad_x=None, out=None, out_parity=None, out_hw=None):
     """sc2_tc_split_conv_ex over the output-channel tiles of pack_conv_weight_split_tiles (one launch per tile, all writing the same
     planes).  x planes: [images, H, W, C] (stride 1, or stride 2 with in_nhwc) or parity planes [images * 4, H/2, W/2, C].
     vec: bias (STORE / QUANT) or GDN beta, the full vector; gdn_x: (hi, lo) planes of x for the GDN modes.
-    out_parity=(py, px) with out=(hi, lo) planes [images, 2H, 2W, ceil8(c_out)]: the H x W results are the pixels of that parity
-    (one sub-convolution of a ConvTranspose2d(k5, s2, p2, op1); kh, kw, pad, pad_x from DECONV5_TAPS).
+    out_parity=(py, px) with out=(hi, lo) planes [images, Ho, Wo, ceil8(c_out)]: the results are the pixels (2Y + py, 2X + px) of
+    those planes (one sub-convolution of a ConvTranspose2d(k5, s2); kh, kw, pad, pad_x from deconv5_parity_taps).
+    out_hw: the output size when it is not the one the (possibly zero-padded) input planes imply.
     Returns (hi, lo) planes [images, h_out, w_out, ceil8(c_out)], or int32 symbols [images, c_out, h_out, w_out] (TCS_QUANT)."""
     require_cuda(x_hi, 'tc_split_conv_tiled')
     n_img_planes, H, W, C = x_hi.shape
@@ -631,11 +632,15 @@ def tc_split_conv_tiled(x_hi, x_lo, tiles, kh, kw, stride, pad, mode, vec=None, 
     dev = x_hi.device
     out_hi = out_lo = out_sym = None
     pitch = (c_out + 7) // 8 * 8
+    if out_hw is not None:
+        ho, wo = out_hw
+    full_h = full_w = 0
     if out_parity is not None:
-        ho, wo = H, W
         out_hi, out_lo = out
-        if tuple(out_hi.shape) != (images, 2 * H, 2 * W, pitch) or stride != 1 or mode != _native.TCS_STORE:
-            raise ValueError('out planes %s do not fit a 2x upsampling of %s' % (tuple(out_hi.shape), tuple(x_hi.shape)))
+        full_h, full_w = out_hi.shape[1], out_hi.shape[2]
+        ho, wo = (full_h - out_parity[0] + 1) // 2, (full_w - out_parity[1] + 1) // 2
+        if out_hi.shape[0] != images or out_hi.shape[3] != pitch or stride != 1 or mode != _native.TCS_STORE:
+            raise ValueError('out planes %s do not fit %d channels of %d images' % (tuple(out_hi.shape), c_out, images))
     elif mode == _native.TCS_QUANT:
         out_sym = torch.empty((images, c_out, ho, wo), dtype=torch.int32, device=dev)
     else:
@@ -649,7 +654,7 @@ def tc_split_conv_tiled(x_hi, x_lo, tiles, kh, kw, stride, pad, mode, vec=None, 
     for c0, n, w_hi, w_lo in tiles:
         d = TcSplitExDesc(images, H, W, C, n, kh, kw, stride, pad, mode, ho, wo, pitch, c0, c_out, 1 if in_nhwc else 0, act, float(slope),
                           -1 if pad_x is None else pad_x, 2 if out_parity is not None else 1,
-                          out_parity[0] if out_parity is not None else 0, out_parity[1] if out_parity is not None else 0)
+                          out_parity[0] if out_parity is not None else 0, out_parity[1] if out_parity is not None else 0, full_h, full_w)
         tag = '%s[%d->%d/%d,k%d,s%d,m%d]' % (name, C, n, c_out, kh, stride, mode)
         flops = 2.0 * images * ho * wo * n * C * kh * kw
         nbytes = 4.0 * (x_hi.numel() + images * ho * wo * n)
@@ -660,18 +665,30 @@ def tc_split_conv_tiled(x_hi, x_lo, tiles, kh, kw, stride, pad, mode, vec=None, 
     return out_sym if mode == _native.TCS_QUANT else (out_hi, out_lo)
 
 
-def pack_deconv5_weight_split_tiles(weight):
-    """ConvTranspose2d(k5, s2, p2, output_padding 1) weight [c_in, c_out, 5, 5] -> {(py, px): tiles of the stride-1 sub-convolution
-    that produces the output pixels of that parity} (pack_deconv5_weight_f16 in split precision)."""
+def deconv5_parity_taps(padding):
+    """{output parity: (kernel indexes of the taps, padding)} of the stride-1 sub-convolutions of ConvTranspose2d(k5, s2, padding):
+    from o = 2 i - padding + k, out[2Y + r] = sum_j x[Y + j - pad] * w[taps[j]].  padding 2 (with output_padding 1: 2H outputs) is
+    DECONV5_TAPS; padding 1 (output_padding 0: 2H + 1 outputs, the hyperprior bottlenecks' h_s) has H + 1 even and H odd outputs."""
+    if padding == 2:
+        return DECONV5_TAPS
+    if padding == 1:
+        return {0: ([3, 1], 1), 1: ([4, 2, 0], 1)}
+    raise ValueError('ConvTranspose2d(k5, s2) with padding %d is not covered' % padding)
+
+
+def pack_deconv5_weight_split_tiles(weight, padding=2, c_in_pad=None):
+    """ConvTranspose2d(k5, s2, padding) weight [c_in, c_out, 5, 5] -> {(py, px): tiles of the stride-1 sub-convolution that produces
+    the output pixels of that parity} (pack_deconv5_weight_f16 in split precision)."""
     w = weight.detach().float()
     if tuple(w.shape[2:]) != (5, 5):
         raise ValueError('pack_deconv5_weight_split_tiles is for 5x5 kernels')
+    taps = deconv5_parity_taps(padding)
     packs = {}
     for py in (0, 1):
         for px in (0, 1):
-            ky, kx = DECONV5_TAPS[py][0], DECONV5_TAPS[px][0]
+            ky, kx = taps[py][0], taps[px][0]
             sub = w[:, :, ky][:, :, :, kx].permute(1, 0, 2, 3).contiguous()     # conv weight [c_out, c_in, Ty, Tx]
-            packs[(py, px)] = pack_conv_weight_split_tiles(sub)
+            packs[(py, px)] = pack_conv_weight_split_tiles(sub, c_in_pad=c_in_pad)
     return packs
 
 

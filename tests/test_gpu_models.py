@@ -208,6 +208,7 @@ def test_shp_bottleneck_and_entropy_bottleneck_layer_vs_reference(s2, oracle_com
         enc = shp.encode(x.to(dev))
         dec = shp.decode(**enc)
     assert len(enc['strings']) == 2 and all(len(l) == 2 for l in enc['strings']) and dec.shape == (2, 256, 56, 56)
+    assert set(shp.__dict__['_tc_analysis']) == {'h_a', 'h_s'} and shp.__dict__.get('_tc_encoder') is not None  # no fp32 CUDA-core fallback
     # Oracle pipeline for SHPBasedResNetBottleneck.encode / decode (sc2bench/models/layer.py:631-666), runnable on the GPU box:
     # the module's own layers as plain torch CPU ops + the restated CompressAI entropy models + the C coder.
     import copy

@@ -379,6 +379,8 @@ def test_shp_bottleneck_small_golden(s2, dev, key, fname):
     assert layer.__dict__.get('_tc_encoder') is not None
     assert rel_err(y_tc.cpu(), torch.from_numpy(gs['y'])) < LATENT_TOL
     enc = layer.encode(x)
+    # ... and h_a / h_s on the split tensor-core plan (odd sizes, channel counts that are not multiples of 16, k5 s2 p1 transposed convs)
+    assert set(layer.__dict__['_tc_analysis']) == {'h_a', 'h_s'}
     assert tuple(enc['shape']) == tuple(gs['shape']) and len(enc['strings']) == 2
     want_y = unpack_streams(gs['streams0'], gs['stream_offsets0'])
     want_z = unpack_streams(gs['streams1'], gs['stream_offsets1'])

@@ -422,3 +422,28 @@ def test_nchw_to_nhwc_f16_layouts(s2, B, C, H, W, cp):
     assert got.shape == (B, H, W, cp) and got.dtype == torch.float16
     assert torch.equal(got[..., :C], x.permute(0, 2, 3, 1).half())
     assert float(got[..., C:].abs().max()) == 0.0 if cp > C else True
+
+
+@pytest.mark.parametrize('key,shape', [('h_s', (16, 7, 7)), ('h_a', (24, 55, 55)), ('h_s_mshp', (16, 5, 9)), ('h_a_mshp', (24, 21, 13))])
+def test_split_plan_hyperprior_bottleneck_transforms_match_torch(s2, key, shape):
+    """h_a / h_s of the (mean-)scale-hyperprior bottlenecks on the split tensor-core plan: 24 input channels (zero-padded to 32), odd
+    sizes in front of stride-2 layers, ConvTranspose2d(k5, s2, p1) with 2H + 1 outputs, LeakyReLU -- against torch fp64 on the CPU."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(len(key) + shape[1])
+    name = 'MSHPBasedResNetBottleneck' if key.endswith('mshp') else 'SHPBasedResNetBottleneck'
+    layer = s2.get_layer(name, num_latent_channels=16, num_bottleneck_channels=24, num_target_channels=256).eval()
+    seq = getattr(layer, key[:3])
+    x = torch.randn(2, *shape) * 2
+    with torch.no_grad():
+        ref = seq.double()(x.double()).float()
+        seq.float()
+    assert s2.models.SplitAnalysisPlan.why_not(seq, shape) is None
+    plan = s2.models.SplitAnalysisPlan(seq.to(dev))
+    got = plan(x.to(dev)).cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert rel_err(got, ref) < 2 * SPLIT_TOL, rel_err(got, ref)
+    if key.startswith('h_a'):
+        med = torch.randn(seq[-1].out_channels)
+        sym = plan(x.to(dev), medians=med.to(dev), out='symbols').cpu()
+        want = torch.round(ref - med.view(1, -1, 1, 1)).int()
+        assert int((sym != want).sum()) <= 1

@@ -388,10 +388,12 @@ def test_split_analysis_plan_coverage_rules():
     assert P.why_not(m.g_a, (3, 256, 256)) is None
     assert P.why_not(m.h_a, (320, 16, 16), planes_in=True) is None
     assert P.why_not(m.h_s, (192, 4, 4)) is None
-    assert 'odd' in P.why_not(m.g_a, (3, 250, 250))          # 125 x 125 after the first layer: stride 2 needs even sizes
+    assert P.why_not(m.g_a, (3, 250, 250)) is None           # 125 x 125 after the first layer: odd sizes are zero-padded
     f = s2.models.bmshj2018_factorized(1)
     assert P.why_not(f.g_a, (3, 64, 64)) is None and P.why_not(f.g_s, (192, 4, 4)) is not None  # g_s has inverse GDNs: ZooSynthesisPlan's job
     assert s2.models.ZooSynthesisPlan.why_not(f.g_s) is None
     shp = s2.get_layer('SHPBasedResNetBottleneck', num_latent_channels=16, num_bottleneck_channels=24, num_target_channels=256)
-    assert P.why_not(shp.h_s, (16, 7, 7)) is not None         # k5 s2 p1 transposed convolutions: fp32 kernels (logged)
+    assert P.why_not(shp.h_s, (16, 7, 7)) is None and P.why_not(shp.h_a, (24, 55, 55)) is None  # k5 s2 p1 transposed convs, 24 channels
+    grouped = torch.nn.Sequential(torch.nn.Conv2d(16, 16, 3, groups=2))
+    assert P.why_not(grouped, (16, 8, 8)) is not None
     assert s2.bottleneck.TensorCoreAnalysis.why_not(shp.g_a, (2, 3, 224, 224)) is None
