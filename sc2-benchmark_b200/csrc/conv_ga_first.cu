@@ -116,8 +116,10 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
     uint64_t *ag_full = acc_empty + 1;
     uint64_t *g_full = ag_full + 1;
     uint64_t *w_full = g_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
-    float *s_beta = reinterpret_cast<float *>(tmem_slot + 6);  // 16-byte aligned (11 barriers = 88 bytes, + 24)
+    uint64_t *stage_free = w_full + 1;  // the bulk stores of the previous tile have read the staging tile (= the |x| operand's memory)
+    uint64_t *y_done = stage_free + 1;  // every epilogue thread has written its part of the staging tile
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(y_done + 1);
+    float *s_beta = reinterpret_cast<float *>(tmem_slot + 2);  // 16-byte aligned (13 barriers = 104 bytes, + 8)
     const float *s_lut = reinterpret_cast<const float *>(smem + p.off_lut);
     TileSched sched;
     sched.bind(reinterpret_cast<uint8_t *>(s_beta + N), p.tile_counter, p.tiles_x * p.tiles_y * p.batch * 4);
@@ -151,6 +153,8 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
         mbar_init(ag_full, kEpiThreads);
         mbar_init(g_full, 1);
         mbar_init(w_full, 1);
+        mbar_init(stage_free, 1);
+        mbar_init(y_done, kEpiThreads);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -256,8 +260,12 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             const int sp = tile % tiles_xy, img = tile / tiles_xy;
             const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
             float x[kSubMax][8];
-            if (issuer) tma_store_wait_read();
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            // (mbarriers instead of two block-wide bar.sync per tile: only the store-issuing thread waits for the whole tile; the
+            // other 15 warps go on to the next tile's accumulators -- barrier stalls were 13 % of this kernel's samples)
+            if (issuer) {
+                tma_store_wait_read();
+                mbar_arrive(stage_free);
+            }
             mbar_wait(acc_full, lt & 1u);
             tcgen05_fence_after();
 #pragma unroll
@@ -273,6 +281,7 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             }
             tcgen05_fence_before();
             mbar_arrive(acc_empty);
+            mbar_wait(stage_free, lt & 1u);  // the |x| tile below overwrites the previous tile's staged output
 #pragma unroll
             for (int ui = 0; ui < kSubMax; ++ui) {
                 const int su = s_begin + ui;
@@ -325,8 +334,9 @@ ga_first_gdn_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_co
             }
             tcgen05_fence_before();
             fence_proxy_async();
-            asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+            mbar_arrive(y_done);
             if (issuer) {
+                mbar_wait(y_done, lt & 1u);
                 tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
                 tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
                 tma_store_commit();
