@@ -118,7 +118,9 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     uint64_t *acc_empty = acc_full + 1;
     uint64_t *ag_full = acc_empty + 1;
     uint64_t *g_full = ag_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(g_full + 1);
+    uint64_t *stage_free = g_full + 1;  // the bulk stores of the previous tile have read the staging tile (= the |x| operand's memory)
+    uint64_t *y_done = stage_free + 1;  // every epilogue thread has written its part of the staging tile
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(y_done + 1);
     float *s_beta = reinterpret_cast<float *>(tmem_slot + 4);  // [N]
     TileSched sched;
     sched.bind(reinterpret_cast<uint8_t *>(s_beta + N), p.tile_counter, p.tiles_x * p.tiles_y * p.images);
@@ -151,6 +153,8 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         mbar_init(acc_empty, 256);
         mbar_init(ag_full, 256);
         mbar_init(g_full, 1);
+        mbar_init(stage_free, 1);
+        mbar_init(y_done, 256);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -306,8 +310,11 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const int x0 = (sp % p.tiles_x) * p.tw, y0 = (sp / p.tiles_x) * p.th;
             float x[kUnits0][16];
             // ---- A: conv accumulators -> x (registers), |x| split -> the gamma GEMM's A operand ----
-            if (issuer) tma_store_wait_read();  // the previous tile's bulk stores have read the staging tile (same memory)
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // (mbarriers, not block-wide bar.sync: only the store-issuing thread waits for the whole tile)
+            if (issuer) {
+                tma_store_wait_read();  // the previous tile's bulk stores have read the staging tile (same memory)
+                mbar_arrive(stage_free);
+            }
             mbar_wait(acc_full, lt & 1u);
             tcgen05_fence_after();
 #pragma unroll
@@ -335,6 +342,7 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             }
             tcgen05_fence_before();
             mbar_arrive(acc_empty);  // 256 arrivals: the MMA warp may start the next tile's convolution
+            mbar_wait(stage_free, lt & 1u);  // the |x| tile below overwrites the previous tile's staged output
 #pragma unroll
             for (int ui = 0; ui < kUnits0; ++ui) {
                 const int u = u_begin + ui;
@@ -395,8 +403,9 @@ ga_halo_gdn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             }
             tcgen05_fence_before();
             fence_proxy_async();
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            mbar_arrive(y_done);
             if (issuer) {
+                mbar_wait(y_done, lt & 1u);
                 tma_store_4d(&map_o_hi, st_hi, 0, x0, y0, img);
                 tma_store_4d(&map_o_lo, st_lo, 0, x0, y0, img);
                 tma_store_commit();
@@ -525,7 +534,7 @@ int sc2_ga_halo_conv_gdn(const sc2_ga_halo_desc *d, const void *x_hi, const void
     p.stage_plane = (p.th * p.tw * p.stage_c * 2 + 127) / 128 * 128;
     const int ag_bytes = 2 * gc * kABytes, staging_bytes = 2 * p.stage_plane;
     const int ag_region = ((ag_bytes > staging_bytes ? ag_bytes : staging_bytes) + 1023) / 1024 * 1024;
-    const int tail = (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + n * 4 + kTileSchedBytes + 64;
+    const int tail = (2 * kMaxA + 2 * kMaxB + 6) * 8 + 16 + n * 4 + kTileSchedBytes + 64;
     const int budget = 227 * 1024 - 1024 - tail;  // (1024: slack for the manual alignment of the dynamic shared memory base)
     int n_a = kMaxA, n_b = 0;
     for (; n_a >= 2; --n_a) {
