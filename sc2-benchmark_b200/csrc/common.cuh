@@ -105,9 +105,10 @@ struct __align__(16) RansEncEntry {
     uint32_t freq;        // 1..65535
 };
 
-// channel-mode fast paths (rans_fast.cu)
-int launch_rans_encode_fast(const int32_t *symbols, int batch, int64_t n, int64_t spatial, const void *tables, int n_rows,
-                            int cdf_stride, uint8_t *arena, int64_t slot_bytes, int32_t *lengths, int32_t *status,
+// latency-tuned fast paths (rans_fast.cu): the encoder for channel rows (indexes == nullptr) and per-element rows, the decoder for
+// channel rows
+int launch_rans_encode_fast(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n, int64_t spatial, const void *tables,
+                            int n_rows, int cdf_stride, uint8_t *arena, int64_t slot_bytes, int32_t *lengths, int32_t *status,
                             cudaStream_t st);
 int launch_rans_decode_fast(const uint8_t *packed, const int64_t *offsets, int batch, int64_t n, int64_t spatial,
                             const void *tables, int n_rows, int cdf_stride, int32_t *out_symbols, float *out_values,

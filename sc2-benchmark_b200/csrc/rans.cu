@@ -308,6 +308,93 @@ rans_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restrict
     int32_t *osym = out_symbols ? out_symbols + static_cast<int64_t>(b) * n : nullptr;
     float *oval = out_values ? out_values + static_cast<int64_t>(b) * n : nullptr;
 
+    if (kExplicitIndex) {
+        // ---- per-element rows (GaussianConditional): every symbol has its own CDF row, so there is no "previous symbol of the row"
+        // to speculate on and no row slice worth keeping in registers.  Off the chain, lane l prepares symbol base + l: its row, the
+        // row's CENTRE symbol c (the mode of the quantised Gaussian: value 0 around the mean) with (start, freq) of c.  The chain then
+        // tests cum - start < freq first; only a symbol away from the centre pays for a search, which walks outwards from c in
+        // 32-entry ballots (one or two for a Gaussian) instead of scanning the row from its first entry.
+        for (int64_t base = 0; base < n; base += 32) {
+            const int cnt = (n - base) >= 32 ? 32 : static_cast<int>(n - base);
+            int my_row = lane < cnt ? __ldg(idx + base + lane) : 0;
+            if (static_cast<uint32_t>(my_row) >= static_cast<uint32_t>(t.n_rows)) {
+                atomicOr(status, SC2_FAULT_BAD_INDEX);
+                my_row = 0;
+            }
+            const int32_t *my_drow = dec + static_cast<int64_t>(my_row) * t.dec_stride;
+            const int32_t my_size = __ldg(t.sizes + my_row);
+            const int32_t my_max = my_size - 2, my_off = __ldg(t.offsets + my_row);
+            const int32_t my_c = my_max > 0 ? (my_max - 1) >> 1 : 0;   // pmf_length = my_max + 1 entries: centre (pmf_length - 1) / 2 ... of the regular symbols
+            const uint32_t my_start = static_cast<uint32_t>(my_drow[my_c]);
+            uint32_t my_freq = static_cast<uint32_t>(my_drow[my_c + 1]) - my_start;
+            if (my_c >= my_max) my_freq = 0u;  // (the centre would be the escape symbol: always take the search path)
+            const float my_mean = means ? __ldg(means + my_row) : 0.0f;
+            int32_t my_value = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const uint32_t start = __shfl_sync(0xffffffffu, my_start, j), freq = __shfl_sync(0xffffffffu, my_freq, j);
+                const int32_t c = __shfl_sync(0xffffffffu, my_c, j);
+                const uint32_t cum = static_cast<uint32_t>(s.x) & 0xffffu;
+                int32_t value;
+                if (cum - start < freq) {  // (uniform) the centre symbol
+                    s.x = static_cast<uint64_t>(freq) * (s.x >> kRansPrecision) + (cum - start);
+                    if (s.x < kRansL) s.x = (s.x << 32) | dec_next_word(s, lane);
+                    value = c;
+                } else {
+                    const int r = __shfl_sync(0xffffffffu, my_row, j);
+                    const int32_t max_value = __shfl_sync(0xffffffffu, my_max, j);
+                    const int32_t *drow = dec + static_cast<int64_t>(r) * t.dec_stride;
+                    int32_t sidx;  // largest entry with cdf[sidx] <= cum
+                    if (cum < start) {  // to the left of the centre: entries c - 32 .. c - 1, then further left
+                        for (int32_t hi = c;; hi -= 32) {
+                            const int32_t e = hi - 32 + lane;
+                            const uint32_t mm = __ballot_sync(0xffffffffu, e >= 0 && static_cast<uint32_t>(drow[e < 0 ? 0 : e]) <= cum);
+                            if (mm) {
+                                sidx = hi - 32 + (31 - __clz(mm));
+                                break;
+                            }
+                        }
+                    } else {            // to the right: first entry k > c with cdf[k] > cum (rows are sentinel-padded beyond their size)
+                        for (int32_t lo = c + 1;; lo += 32) {
+                            const int32_t e = lo + lane < t.dec_stride ? lo + lane : t.dec_stride - 1;  // (clamped: the pad entries compare true)
+                            const uint32_t mm = __ballot_sync(0xffffffffu, static_cast<uint32_t>(drow[e]) > cum);
+                            if (mm) {
+                                sidx = lo + __ffs(mm) - 2;
+                                break;
+                            }
+                        }
+                    }
+                    const uint32_t st2 = static_cast<uint32_t>(drow[sidx]);
+                    const uint32_t fr2 = static_cast<uint32_t>(drow[sidx + 1]) - st2;
+                    s.x = static_cast<uint64_t>(fr2) * (s.x >> kRansPrecision) + (cum - st2);
+                    if (s.x < kRansL) s.x = (s.x << 32) | dec_next_word(s, lane);
+                    value = sidx;
+                    if (value == max_value) {
+                        uint32_t val = dec_get_bits(s, lane);
+                        int n_bypass = static_cast<int>(val);
+                        while (val == kMaxBypassVal) {
+                            val = dec_get_bits(s, lane);
+                            n_bypass += static_cast<int>(val);
+                        }
+                        uint32_t raw = 0;
+                        for (int q = 0; q < n_bypass; ++q) {
+                            const uint32_t nib = dec_get_bits(s, lane);
+                            if (q < 8) raw |= nib << (4 * q);
+                        }
+                        value = static_cast<int32_t>(raw >> 1);
+                        value = (raw & 1u) ? -value - 1 : value + max_value;
+                    }
+                }
+                if (j == lane) my_value = value + my_off;
+            }
+            if (lane < cnt) {
+                if (osym) osym[base + lane] = my_value;
+                if (oval) oval[base + lane] = static_cast<float>(my_value) + my_mean;
+            }
+        }
+        if (s.truncated && lane == 0) atomicOr(status, SC2_FAULT_STREAM_TRUNCATED);
+        return;
+    }
+
     int row = -1;
     int32_t c0 = 0, c1 = 0;  // this lane's entries [lane] and [lane + 32] of the current CDF row
     int32_t max_value = 0, offset = 0, row_size = 0;
@@ -453,8 +540,8 @@ int sc2_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int ba
     if (!indexes && spatial <= 0x7fffffff && sc2::rans_use_lanes(layout))
         return sc2::launch_rans_encode_lanes(symbols, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, arena, slot_bytes,
                                              lengths, status, st);
-    if (!indexes && spatial <= 0x7fffffff)
-        return sc2::launch_rans_encode_fast(symbols, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, arena, slot_bytes,
+    if (indexes || spatial <= 0x7fffffff)  // (the latency-tuned chain, for channel rows and for per-element rows alike)
+        return sc2::launch_rans_encode_fast(symbols, indexes, batch, n_per_stream, spatial, tables, n_rows, cdf_stride, arena, slot_bytes,
                                             lengths, status, st);
     const size_t chunk = sc2::kWarpsPerBlock * (32 * 16 + 32 * 4);
     size_t smem = chunk;

@@ -107,8 +107,10 @@ __device__ __noinline__ EncChain enc_chunk_careful(EncChain s, const uint4 *sA, 
     return s;
 }
 
+// IDX: the CDF row of every symbol comes from `indexes` (GaussianConditional: one row per element) instead of i / spatial
+template <bool IDX>
 __global__ void __launch_bounds__(32)
-rans_encode_fast_kernel(const int32_t *__restrict__ symbols, int batch, uint32_t n, uint32_t spatial,
+rans_encode_fast_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int batch, uint32_t n, uint32_t spatial,
                         const void *__restrict__ tables, uint8_t *__restrict__ arena, int64_t slot_bytes,
                         int32_t *__restrict__ lengths, int32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -128,6 +130,7 @@ rans_encode_fast_kernel(const int32_t *__restrict__ symbols, int batch, uint32_t
     __syncwarp();
 
     const int32_t *sym = symbols + static_cast<int64_t>(b) * n;
+    const int32_t *idx = IDX ? indexes + static_cast<int64_t>(b) * n : nullptr;
     EncChain s;
     s.x = kL;
     s.words = reinterpret_cast<uint32_t *>(arena + static_cast<int64_t>(b) * slot_bytes);
@@ -137,17 +140,25 @@ rans_encode_fast_kernel(const int32_t *__restrict__ symbols, int batch, uint32_t
 
     // symbols are consumed back to front; lane l of a chunk ending at `hi` owns symbol hi - 1 - l
     int32_t nxt = (lane < static_cast<int>(n)) ? __ldg(sym + (n - 1 - lane)) : 0;
+    int32_t nxt_row = (IDX && lane < static_cast<int>(n)) ? __ldg(idx + (n - 1 - lane)) : 0;
     for (uint32_t hi = n; hi > 0; hi = hi > 32 ? hi - 32 : 0) {
         const int cnt = hi >= 32 ? 32 : static_cast<int>(hi);
         const int32_t cur = nxt;
+        const int32_t cur_row = nxt_row;
         if (hi > 32) {  // request the next chunk now: its HBM/L2 latency hides behind this chunk's chain
             const uint32_t hn = hi - 32;
             nxt = (static_cast<uint32_t>(lane) < hn) ? __ldg(sym + (hn - 1 - lane)) : 0;
+            if (IDX) nxt_row = (static_cast<uint32_t>(lane) < hn) ? __ldg(idx + (hn - 1 - lane)) : 0;
         }
         uint32_t my_esc = 0;
         if (lane < cnt) {
             const uint32_t i = hi - 1 - lane;
-            const int row = static_cast<int>(i / spatial);
+            int row = IDX ? cur_row : static_cast<int>(i / spatial);
+            if (IDX && static_cast<uint32_t>(row) >= static_cast<uint32_t>(t.n_rows)) {
+                // caller-supplied CDF index out of range: flag it and code the symbol with row 0 instead of reading outside the tables
+                atomicOr(status, SC2_FAULT_BAD_INDEX);
+                row = 0;
+            }
             const int32_t max_value = __ldg(t.sizes + row) - 2;
             int32_t value = cur - __ldg(t.offsets + row);
             uint32_t raw = 0, esc = 0;
@@ -500,16 +511,22 @@ rans_decode_fast_kernel(const uint8_t *__restrict__ packed, const int64_t *__res
 
 }  // namespace
 
-int launch_rans_encode_fast(const int32_t *symbols, int batch, int64_t n, int64_t spatial, const void *tables, int n_rows,
-                            int cdf_stride, uint8_t *arena, int64_t slot_bytes, int32_t *lengths, int32_t *status,
+int launch_rans_encode_fast(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n, int64_t spatial, const void *tables,
+                            int n_rows, int cdf_stride, uint8_t *arena, int64_t slot_bytes, int32_t *lengths, int32_t *status,
                             cudaStream_t st) {
     size_t smem = 64 * 16;
     const size_t table_bytes = static_cast<size_t>(n_rows) * cdf_stride * 16;
     if (table_bytes + smem <= 96 * 1024) smem += table_bytes;
-    static std::atomic<uint64_t> configured{0};  // per device ordinal
-    if (int rc = ensure_dyn_smem(rans_encode_fast_kernel, 100 * 1024, configured)) return rc;
-    rans_encode_fast_kernel<<<batch, 32, smem, st>>>(symbols, batch, static_cast<uint32_t>(n), static_cast<uint32_t>(spatial),
-                                                      tables, arena, slot_bytes, lengths, status);
+    const uint32_t un = static_cast<uint32_t>(n), us = static_cast<uint32_t>(indexes ? 1 : spatial);
+    if (indexes) {
+        static std::atomic<uint64_t> configured{0};  // per device ordinal
+        if (int rc = ensure_dyn_smem(rans_encode_fast_kernel<true>, 100 * 1024, configured)) return rc;
+        rans_encode_fast_kernel<true><<<batch, 32, smem, st>>>(symbols, indexes, batch, un, us, tables, arena, slot_bytes, lengths, status);
+    } else {
+        static std::atomic<uint64_t> configured{0};  // per device ordinal
+        if (int rc = ensure_dyn_smem(rans_encode_fast_kernel<false>, 100 * 1024, configured)) return rc;
+        rans_encode_fast_kernel<false><<<batch, 32, smem, st>>>(symbols, nullptr, batch, un, us, tables, arena, slot_bytes, lengths, status);
+    }
     SC2_LAUNCH_CHECK("rans_encode_fast_kernel");
     return SC2_OK;
 }
