@@ -654,7 +654,8 @@ def main():
             e2e['input'] = 'uint8 images, ToTensor + Normalize on the device (inside the first conv kernel)'
             e2e['fp32_input'] = {k: f32[k] for k in ('value', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'ms_per_step')}
         else:
-            e2e = run_e2e(host_inputs, args.e2e_threads if args.e2e_threads > 0 else (1 if cfg in (1, 5) else 2), False)
+            # config 1: one image at a time (latency); configs 3 / 4: as many host threads as batches the device-timed run keeps in flight
+            e2e = run_e2e(host_inputs, args.e2e_threads if args.e2e_threads > 0 else (1 if cfg in (1, 5) else max(2, args.streams)), False)
 
     if rank != 0:
         if world > 1:
