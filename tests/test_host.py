@@ -397,3 +397,29 @@ def test_split_analysis_plan_coverage_rules():
     grouped = torch.nn.Sequential(torch.nn.Conv2d(16, 16, 3, groups=2))
     assert P.why_not(grouped, (16, 8, 8)) is not None
     assert s2.bottleneck.TensorCoreAnalysis.why_not(shp.g_a, (2, 3, 224, 224)) is None
+
+
+@pytest.mark.parametrize('padding,output_padding', [(2, 1), (1, 0)])
+def test_deconv5_parity_taps_rebuild_the_transposed_convolution(padding, output_padding):
+    """ops.deconv5_parity_taps: ConvTranspose2d(k5, s2, p) as four stride-1 sub-convolutions, checked with torch CPU convolutions
+    (the tap lists and paddings are what the tensor-core plans launch; no GPU needed)."""
+    import torch.nn.functional as F
+    import sc2bench_b200 as s2
+    torch.manual_seed(padding)
+    x = torch.randn(2, 3, 5, 7, dtype=torch.float64)
+    w = torch.randn(3, 4, 5, 5, dtype=torch.float64)
+    ref = F.conv_transpose2d(x, w, stride=2, padding=padding, output_padding=output_padding)
+    taps = s2.ops.deconv5_parity_taps(padding)
+    out = torch.full_like(ref, float('nan'))
+    Ho, Wo = ref.shape[-2:]
+    for py in (0, 1):
+        for px in (0, 1):
+            (ky, pad_y), (kx, pad_x) = taps[py], taps[px]
+            sub = w[:, :, ky][:, :, :, kx].permute(1, 0, 2, 3)                      # conv weight [c_out, c_in, Ty, Tx]
+            hs, ws = (Ho - py + 1) // 2, (Wo - px + 1) // 2                         # pixels of this parity
+            # out[Y] = sum_j x[Y + j - pad] * w[taps[j]] for Y in [0, hs): pad the input so that every tap position exists
+            xp = F.pad(x, (pad_x, ws + len(kx) - 1 - pad_x - x.shape[3], pad_y, hs + len(ky) - 1 - pad_y - x.shape[2]))
+            y = F.conv2d(xp, sub)
+            assert y.shape[-2:] == (hs, ws)
+            out[:, :, py::2, px::2] = y
+    assert torch.isfinite(out).all() and float((out - ref).abs().max()) < 1e-12
